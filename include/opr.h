@@ -1,0 +1,106 @@
+/*
+ * opr.h — the C-ABI drop-in boundary of the B200 light-transport path.
+ *
+ * Every entry point replaces one member of the reference's renderer-facing C++ surface
+ * (class OptixRenderer, RenderEngine/renderer/OptixRenderer.h:21-44, exported from RenderEngine.dll
+ * through RenderEngine/render_engine_export_api.h:8-16).  Plain pointers and sizes only; no exceptions
+ * cross this boundary: functions return 0 on success and non-zero on failure, with the message (the
+ * text the reference would have thrown as std::exception) available from opr_last_error().
+ * One host thread per renderer object, as in the reference (Standalone/StandaloneApplication.cpp:23-26).
+ * There is no CPU fallback: without a CUDA device opr_initialize fails.
+ */
+#ifndef OPR_H
+#define OPR_H
+
+#include "opr_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct opr_renderer opr_renderer;
+
+/* message of the last failure on the calling thread */
+const char* opr_last_error(void);
+
+/* OptixRenderer::OptixRenderer() — OptixRenderer.cpp:79-104.  cfg may be NULL (reference constants). */
+int opr_create(opr_renderer** out, const opr_config* cfg);
+/* OptixRenderer::~OptixRenderer() — OptixRenderer.cpp:106-111 */
+void opr_destroy(opr_renderer* r);
+/* OptixRenderer::initialize(const ComputeDevice&) — OptixRenderer.cpp:113-400; only getDeviceId() is used (:416) */
+int opr_initialize(opr_renderer* r, int cuda_device_ordinal);
+/* OptixRenderer::initScene(IScene&) — OptixRenderer.cpp:436-485 (uploads geometry, builds the BVH) */
+int opr_init_scene(opr_renderer* r, const opr_scene_desc* scene);
+/* OptixRenderer::renderNextIteration(iterationNumber, localIterationNumber, PPMRadius, createOutput, details)
+ * — OptixRenderer.cpp:507-821 */
+int opr_render_next_iteration(opr_renderer* r, uint64_t iterationNumber, uint64_t localIterationNumber, float PPMRadius,
+                              int createOutput, const opr_request_details* details);
+/* OptixRenderer::getOutputBuffer(void*) — OptixRenderer.cpp:860-865: copies W*H*3 floats (the un-normalised
+ * running sum over localIterationNumber = 0..k) into caller-owned host memory */
+int opr_get_output_buffer(opr_renderer* r, void* dst);
+/* OptixRenderer::getWidth/getHeight/getScreenBufferSizeBytes — OptixRenderer.cpp:850-870 */
+uint32_t opr_get_width(opr_renderer* r);
+uint32_t opr_get_height(opr_renderer* r);
+uint32_t opr_get_screen_buffer_size_bytes(opr_renderer* r);
+
+/* Multi-GPU (replaces Client/ + Server/ TCP distribution): the running-sum buffer stays in
+ * HBM; the caller reduces it across ranks (NCCL) through this device pointer (W*H*3 floats). */
+void* opr_get_output_device_ptr(opr_renderer* r);
+int opr_synchronize(opr_renderer* r);
+/* Closed form of the driver's radius schedule r_{i+1}^2 = r_i^2 (i+alpha)/(i+1)
+ * (Standalone/StandaloneRenderManager.cpp:105-107, Client/DistributedApplication.cpp:105-113), so that rank g
+ * can render global iterations g, g+G, ... without exchanging radii. */
+double opr_ppm_radius_for_iteration(double initialRadius, uint64_t iteration, double alpha);
+
+/* counters since the last resize: [0] closest-hit rays, [1] any-hit rays, [2] photons stored, [3] kernel launches */
+int opr_get_stats(opr_renderer* r, uint64_t* out, int n);
+/* per-pass CUDA-event timings of the last iteration (opr_set_timing(r,1) first); returns the number written */
+int opr_set_timing(opr_renderer* r, int enabled);
+int opr_get_timings_ms(opr_renderer* r, float* ms, int capacity);
+const char* opr_get_timing_name(opr_renderer* r, int index);
+
+/* Intermediate buffers in the REFERENCE's layouts for stage-by-stage parity tests.  name is one of
+ * "hitpoints" (Hitpoint.h, 64 B x W*H), "photons" (Photon.h, 36 B x 4P, as emitted), "sorted_photons"
+ * (36 B x numValid), "photon_keys" (u32 x 4P, sorted), "offsets" (u32 x numCells+1), "indirect", "direct"
+ * (float3 x W*H), "random_states" ({d,v0..v4} u32 x 6 per state), "grid" (cellSize, gridSize[3], origo[3],
+ * numValid as 8 x 4 bytes), "photon_path_lengths" (u32 x P), "light_vertex_counts" (u32 x W*H). */
+int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t bytes);
+
+/* ---- stand-alone kernels of the path (host buffers in, host buffers out) ------------------------------ */
+/* initRandomStateBuffer (OptixRenderer_SpatialHash.cu:310-317): states6[6*i..] = XORWOW state of seed+first+i */
+int opr_rng_init(uint32_t* states6, uint32_t seed, uint32_t first, uint32_t count);
+/* n draws of getRandomUniformFloat (helpers/random.h:65-69) from one state (updated in place) */
+int opr_rng_uniform(uint32_t* state6, float* out, uint32_t n);
+/* createUniformGridPhotonMap (OptixRenderer_SpatialHash.cu:209-282) on n photons in the reference's AoS layout
+ * (36 B each).  Outputs: sortedPhotons (36 B x n, first numValid entries defined), keys (u32 x n, sorted),
+ * offsets (u32 x numCells+1, capacity 10^6+2).  Returns 2 if the grid would exceed PHOTON_GRID_MAX_SIZE. */
+int opr_build_photon_grid(const float* photonsAoS, uint32_t n, float* sortedPhotonsAoS, uint32_t* keys, uint32_t* offsets,
+                          float* cellSize, uint32_t* gridSize3, float* origo3, uint32_t* numValid);
+/* IndirectRadianceEstimation::kernel (ppm/IndirectRadianceEstimation.cu:69-227) on caller-supplied hitpoints
+ * (64 B x numPixels) and a sorted photon list + offset table as produced by opr_build_photon_grid */
+int opr_gather(uint32_t numPixels, const float* hitpointsAoS, uint32_t numPhotons, const float* sortedPhotonsAoS, const uint32_t* offsets,
+               float cellSize, const uint32_t* gridSize3, const float* origo3, float ppmRadius, float emittedPhotons, float* indirectOut);
+/* closest-hit / any-hit queries against the scene loaded in r.  rays8: n x (o.xyz, tmin, d.xyz, tmax) */
+int opr_trace_closest(opr_renderer* r, const float* rays8, uint32_t n, float* outT, int32_t* outMaterial, float* outGeometricNormal3);
+int opr_trace_any(opr_renderer* r, const float* rays8, uint32_t n, int32_t* outOccluded);
+
+/* ---- host-side pieces of the surface -------------------------------------------------------------------- */
+/* Camera::setup / setAspectRatio (renderer/Camera.cpp:333-345, :294-318) */
+void opr_camera_setup(opr_camera* c);
+void opr_camera_set_aspect_ratio(opr_camera* c, float ratio);
+/* Light::Light area / point constructors (renderer/Light.cpp:14-40) */
+void opr_make_area_light(opr_light* out, const float* power3, const float* position3, const float* v1, const float* v2);
+void opr_make_point_light(opr_light* out, const float* power3, const float* position3);
+/* IScene::getSceneInitialPPMRadiusEstimate (scene/IScene.cpp:23-31) */
+float opr_initial_ppm_radius(const float* aabbMin3, const float* aabbMax3);
+/* Built-in scenes: "Cornell" (scene/Cornell.cpp) and "CornellSmall" (scene/CornellSmall.cpp; config = Config bits,
+ * 0 = Default).  The returned handle owns the description. */
+void* opr_builtin_scene_create(const char* name, uint32_t config);
+void opr_builtin_scene_destroy(void* scene);
+const opr_scene_desc* opr_builtin_scene_desc(void* scene);
+void opr_builtin_scene_camera(void* scene, opr_camera* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

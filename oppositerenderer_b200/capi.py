@@ -119,12 +119,13 @@ def _declare(lib):
         "opr_synchronize": (i32, [vp]),
         "opr_get_stats": (i32, [vp, C.POINTER(C.c_uint64), i32]),
         "opr_get_timings_ms": (i32, [vp, PF, i32]),
+        "opr_get_timing_name": (C.c_char_p, [vp, i32]),
         "opr_set_timing": (i32, [vp, i32]),
         "opr_debug_get_buffer": (i32, [vp, C.c_char_p, vp, u64]),
         "opr_rng_init": (i32, [PU, u32, u32, u32]),
-        "opr_rng_uniform": (i32, [PU, u32, PF, u32]),
+        "opr_rng_uniform": (i32, [PU, PF, u32]),
         "opr_build_photon_grid": (i32, [PF, u32, PF, PU, PU, PF, PU, PF, PU]),
-        "opr_gather": (i32, [vp, u32, PF, u32, PU, f32, PU, PF, f32, f32, PF]),
+        "opr_gather": (i32, [u32, PF, u32, PF, PU, f32, PU, PF, f32, f32, PF]),
         "opr_trace_closest": (i32, [vp, PF, u32, PF, PI, PF]),
         "opr_trace_any": (i32, [vp, PF, u32, PI]),
         "opr_builtin_scene_create": (vp, [C.c_char_p, u32]),

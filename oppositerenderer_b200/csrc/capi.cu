@@ -1,0 +1,371 @@
+// capi.cu — the extern "C" boundary declared in include/opr.h.  No exceptions cross it.
+#include "renderer.h"
+#include "radix_sort.cuh"
+#include "../../include/opr.h"
+#include <cstring>
+#include <memory>
+
+using namespace opr;
+
+struct opr_renderer { Renderer r; };
+
+static thread_local std::string g_lastError;
+#define OPR_TRY(...) try { __VA_ARGS__; return 0; } catch (const std::exception& e) { g_lastError = e.what(); return 1; } catch (...) { g_lastError = "unknown error"; return 1; }
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    explicit DevBuf(size_t bytes) { OPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return (T*)p; }
+};
+void requireDevice()
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        throw std::runtime_error("no CUDA device: the oppositerenderer_b200 kernels have no CPU path");
+}
+template <class T> std::vector<T> download(const T* d, size_t n, cudaStream_t st)
+{
+    std::vector<T> h(n);
+    if (n) { OPR_CUDA_CHECK(cudaMemcpyAsync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, st)); OPR_CUDA_CHECK(cudaStreamSynchronize(st)); }
+    return h;
+}
+}  // namespace
+
+extern "C" {
+
+const char* opr_last_error(void) { return g_lastError.c_str(); }
+
+int opr_create(opr_renderer** out, const opr_config* cfg)
+{
+    OPR_TRY({
+        std::unique_ptr<opr_renderer> h(new opr_renderer());
+        if (cfg) {
+            if (cfg->photonLaunchWidth) h->r.photonLaunchWidth = cfg->photonLaunchWidth;
+            if (cfg->photonLaunchHeight) h->r.photonLaunchHeight = cfg->photonLaunchHeight;
+            if (cfg->vcmMaxPathLength) h->r.vcmMaxPathLength = cfg->vcmMaxPathLength;
+            if (cfg->seedIsSet) h->r.seed = cfg->randomSeed;
+        }
+        *out = h.release();
+    })
+}
+
+void opr_destroy(opr_renderer* r) { delete r; }
+int opr_initialize(opr_renderer* r, int ordinal) { OPR_TRY(r->r.initialize(ordinal)) }
+int opr_init_scene(opr_renderer* r, const opr_scene_desc* scene) { OPR_TRY(r->r.initScene(scene)) }
+int opr_render_next_iteration(opr_renderer* r, uint64_t it, uint64_t lit, float radius, int createOutput, const opr_request_details* d)
+{ OPR_TRY(r->r.renderNextIteration(it, lit, radius, createOutput != 0, *d)) }
+int opr_get_output_buffer(opr_renderer* r, void* dst) { OPR_TRY(r->r.getOutputBuffer(dst)) }
+uint32_t opr_get_width(opr_renderer* r) { return r->r.width; }
+uint32_t opr_get_height(opr_renderer* r) { return r->r.height; }
+uint32_t opr_get_screen_buffer_size_bytes(opr_renderer* r) { return r->r.width * r->r.height * 3u * (uint32_t)sizeof(float); }
+void* opr_get_output_device_ptr(opr_renderer* r) { return r->r.output; }
+int opr_synchronize(opr_renderer* r) { OPR_TRY({ OPR_CUDA_CHECK(cudaSetDevice(r->r.device)); OPR_CUDA_CHECK(cudaStreamSynchronize(r->r.stream)); }) }
+
+int opr_get_stats(opr_renderer* r, uint64_t* out, int n)
+{
+    OPR_TRY({
+        Renderer& R = r->r;
+        uint64_t v[4] = {0, 0, 0, 0};
+        if (R.buffersAllocated) {
+            auto c = download(R.q.counters + 16, STAT_NUM, R.stream);
+            v[0] = c[STAT_CLOSEST_RAYS]; v[1] = c[STAT_ANY_RAYS];
+        }
+        // device counters are 32-bit and accumulate since the last read; fold them into the 64-bit host totals
+        if (R.buffersAllocated) OPR_CUDA_CHECK(cudaMemsetAsync(R.q.counters + 16, 0, STAT_NUM * sizeof(unsigned), R.stream));
+        R.stats[STAT_CLOSEST_RAYS] += v[0]; R.stats[STAT_ANY_RAYS] += v[1];
+        uint64_t all[4] = {R.stats[STAT_CLOSEST_RAYS], R.stats[STAT_ANY_RAYS], R.stats[STAT_PHOTONS_STORED], R.launches};
+        for (int i = 0; i < n && i < 4; i++) out[i] = all[i];
+    })
+}
+
+int opr_set_timing(opr_renderer* r, int enabled) { r->r.timing = enabled != 0; return 0; }
+int opr_get_timings_ms(opr_renderer* r, float* ms, int capacity)
+{
+    int n = (int)r->r.lastTimings.size();
+    for (int i = 0; i < n && i < capacity; i++) ms[i] = r->r.lastTimings[i].second;
+    return n;
+}
+const char* opr_get_timing_name(opr_renderer* r, int index)
+{
+    if (index < 0 || index >= (int)r->r.lastTimings.size()) return "";
+    return r->r.lastTimings[index].first.c_str();
+}
+
+int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t bytes)
+{
+    OPR_TRY({
+        Renderer& R = r->r;
+        OPR_CUDA_CHECK(cudaSetDevice(R.device));
+        cudaStream_t st = R.stream;
+        const std::string n(name);
+        const size_t px = (size_t)R.width * R.height;
+        const size_t P = (size_t)R.photonLaunchWidth * R.photonLaunchHeight;
+        auto need = [&](size_t b) { if (bytes < b) throw std::runtime_error("opr_debug_get_buffer: destination too small for " + n); };
+        if (n == "hitpoints") {
+            need(px * 64);
+            auto pos = download(R.hp.pos, px, st); auto nrm = download(R.hp.nrm, px, st);
+            auto att = download(R.hp.att, px, st); auto rad = download(R.hp.rad, px, st);
+            float* o = (float*)dst;
+            for (size_t i = 0; i < px; i++, o += 16) {
+                o[0] = pos[i].x; o[1] = pos[i].y; o[2] = pos[i].z; o[3] = nrm[i].x; o[4] = nrm[i].y; o[5] = nrm[i].z;
+                o[6] = att[i].x; o[7] = att[i].y; o[8] = att[i].z; o[9] = rad[i].x; o[10] = rad[i].y; o[11] = rad[i].z;
+                memcpy(o + 12, &pos[i].w, 4); o[13] = o[14] = o[15] = 0.f;
+            }
+        } else if (n == "photons" || n == "sorted_photons") {
+            const bool srt = n == "sorted_photons";
+            const size_t cnt = srt ? R.grid.numValid : P * MAX_PHOTON_DEPOSITS;
+            need(cnt * 36);
+            const PhotonBuf& pb = srt ? R.sorted : R.photons;
+            auto a = download(pb.a, cnt, st); auto b = download(pb.b, cnt, st); auto c = download(pb.c, cnt, st);
+            std::vector<unsigned> state;
+            if (!srt) state = download(R.phState, P, st);
+            float* o = (float*)dst;
+            for (size_t i = 0; i < cnt; i++, o += 9) {
+                bool stored = srt || ((i % MAX_PHOTON_DEPOSITS) < ((state[i / MAX_PHOTON_DEPOSITS] >> 8) & 0xffu));
+                if (stored) { o[0] = b[i].x; o[1] = b[i].y; o[2] = b[i].z; o[3] = a[i].x; o[4] = a[i].y; o[5] = a[i].z; o[6] = a[i].w; o[7] = b[i].w; o[8] = c[i]; }
+                else { for (int k = 0; k < 9; k++) o[k] = 0.f; }   // the reference clears power+position of unused slots
+            }
+        } else if (n == "photon_keys") {
+            need(P * MAX_PHOTON_DEPOSITS * 4);
+            OPR_CUDA_CHECK(cudaMemcpyAsync(dst, R.sortedKeys, P * MAX_PHOTON_DEPOSITS * 4, cudaMemcpyDeviceToHost, st));
+            OPR_CUDA_CHECK(cudaStreamSynchronize(st));
+        } else if (n == "offsets") {
+            need(((size_t)R.grid.numCells + 1) * 4);
+            OPR_CUDA_CHECK(cudaMemcpyAsync(dst, R.gridHist, ((size_t)R.grid.numCells + 1) * 4, cudaMemcpyDeviceToHost, st));
+            OPR_CUDA_CHECK(cudaStreamSynchronize(st));
+        } else if (n == "indirect" || n == "direct") {
+            need(px * 12);
+            OPR_CUDA_CHECK(cudaMemcpyAsync(dst, n == "indirect" ? R.indirect : R.direct, px * 12, cudaMemcpyDeviceToHost, st));
+            OPR_CUDA_CHECK(cudaStreamSynchronize(st));
+        } else if (n == "random_states") {
+            const size_t ns = (size_t)R.rsW * R.rsH;
+            need(ns * 24);
+            auto a = download(R.rng.a, ns, st); auto b = download(R.rng.b, ns, st); auto c = download(R.rng.c, ns, st);
+            unsigned* o = (unsigned*)dst;
+            for (size_t i = 0; i < ns; i++, o += 6) { o[0] = a[i].x; o[1] = a[i].y; o[2] = b[i].x; o[3] = b[i].y; o[4] = c[i].x; o[5] = c[i].y; }
+        } else if (n == "grid") {
+            need(32);
+            float* o = (float*)dst; unsigned* u = (unsigned*)dst;
+            o[0] = R.grid.cellSize; u[1] = R.grid.gridSize.x; u[2] = R.grid.gridSize.y; u[3] = R.grid.gridSize.z;
+            o[4] = R.grid.origo.x; o[5] = R.grid.origo.y; o[6] = R.grid.origo.z; u[7] = R.grid.numValid;
+        } else if (n == "photon_path_lengths") {
+            need(P * 4);
+            auto s = download(R.phState, P, st);
+            unsigned* o = (unsigned*)dst;
+            for (size_t i = 0; i < P; i++) o[i] = s[i] & 0xffu;
+        } else {
+            throw std::runtime_error("opr_debug_get_buffer: unknown buffer " + n);
+        }
+    })
+}
+
+// ---- stand-alone kernels ------------------------------------------------------------------------------------
+__global__ void rng_init_range_kernel(unsigned* out6, unsigned seed, unsigned first, unsigned count)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Rng s; rng_seed(s, seed, first + i);
+    unsigned* o = out6 + 6 * (size_t)i;
+    o[0] = s.d; o[1] = s.v0; o[2] = s.v1; o[3] = s.v2; o[4] = s.v3; o[5] = s.v4;
+}
+__global__ void rng_uniform_kernel(unsigned* state6, float* out, unsigned n)
+{
+    Rng s; s.d = state6[0]; s.v0 = state6[1]; s.v1 = state6[2]; s.v2 = state6[3]; s.v3 = state6[4]; s.v4 = state6[5];
+    for (unsigned i = 0; i < n; i++) out[i] = rng_uniform(s);
+    state6[0] = s.d; state6[1] = s.v0; state6[2] = s.v1; state6[3] = s.v2; state6[4] = s.v3; state6[5] = s.v4;
+}
+
+int opr_rng_init(uint32_t* states6, uint32_t seed, uint32_t first, uint32_t count)
+{
+    OPR_TRY({
+        requireDevice();
+        DevBuf d((size_t)count * 24);
+        rng_init_range_kernel<<<(count + 255) / 256, 256>>>(d.as<unsigned>(), seed, first, count);
+        OPR_CUDA_CHECK(cudaMemcpy(states6, d.p, (size_t)count * 24, cudaMemcpyDeviceToHost));
+    })
+}
+
+int opr_rng_uniform(uint32_t* state6, float* out, uint32_t n)
+{
+    OPR_TRY({
+        requireDevice();
+        DevBuf ds(24), dout((size_t)n * 4);
+        OPR_CUDA_CHECK(cudaMemcpy(ds.p, state6, 24, cudaMemcpyHostToDevice));
+        rng_uniform_kernel<<<1, 1>>>(ds.as<unsigned>(), dout.as<float>(), n);
+        OPR_CUDA_CHECK(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        OPR_CUDA_CHECK(cudaMemcpy(state6, ds.p, 24, cudaMemcpyDeviceToHost));
+    })
+}
+
+// AoS (reference layout) -> the SoA slot layout the build kernels consume; every slot counts as "stored"
+__global__ void photons_aos_to_soa_kernel(const float* __restrict__ aos, unsigned n, PhotonBuf pb, unsigned* __restrict__ phState)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* p = aos + 9 * (size_t)i;
+        pb.a[i] = make_float4(p[3], p[4], p[5], p[6]);
+        pb.b[i] = make_float4(p[0], p[1], p[2], p[7]);
+        pb.c[i] = p[8];
+        if ((i % MAX_PHOTON_DEPOSITS) == 0) phState[i / MAX_PHOTON_DEPOSITS] = (MAX_PHOTON_DEPOSITS << 8);
+    }
+}
+__global__ void photons_soa_to_aos_kernel(PhotonBuf pb, unsigned n, float* __restrict__ aos)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float* p = aos + 9 * (size_t)i;
+        const float4 a = pb.a[i], b = pb.b[i];
+        p[0] = b.x; p[1] = b.y; p[2] = b.z; p[3] = a.x; p[4] = a.y; p[5] = a.z; p[6] = a.w; p[7] = b.w; p[8] = pb.c[i];
+    }
+}
+
+int opr_build_photon_grid(const float* photonsAoS, uint32_t n, float* sortedPhotonsAoS, uint32_t* keys, uint32_t* offsets,
+                          float* cellSize, uint32_t* gridSize3, float* origo3, uint32_t* numValid)
+{
+    try {
+        requireDevice();
+        if (n == 0) throw std::runtime_error("opr_build_photon_grid: n == 0");
+        cudaStream_t st = 0;
+        unsigned long long launches = 0;
+        LaunchCtx lc{st, &launches};
+        const unsigned nPad = (n + MAX_PHOTON_DEPOSITS - 1) / MAX_PHOTON_DEPOSITS * MAX_PHOTON_DEPOSITS;
+        DevBuf dAos((size_t)n * 36), a((size_t)nPad * 16), b((size_t)nPad * 16), c((size_t)nPad * 4), state((size_t)nPad);
+        DevBuf sa((size_t)nPad * 16), sb((size_t)nPad * 16), sc_((size_t)nPad * 4);
+        DevBuf k0((size_t)nPad * 4), k1((size_t)nPad * 4), v0((size_t)nPad * 4), v1((size_t)nPad * 4);
+        DevBuf hist(((size_t)PHOTON_GRID_MAX_SIZE + 2) * 4), sortTmp(rs_hist_words(nPad) * 4), scanTmp(scan_tmp_words(PHOTON_GRID_MAX_SIZE + 2) * 4), bbox(32);
+        PhotonBuf pb{a.as<float4>(), b.as<float4>(), c.as<float>()}, sorted{sa.as<float4>(), sb.as<float4>(), sc_.as<float>()};
+        OPR_CUDA_CHECK(cudaMemcpy(dAos.p, photonsAoS, (size_t)n * 36, cudaMemcpyHostToDevice));
+        OPR_CUDA_CHECK(cudaMemset(state.p, 0, nPad));
+        OPR_CUDA_CHECK(cudaMemset(b.p, 0, (size_t)nPad * 16));
+        photons_aos_to_soa_kernel<<<148 * 4, 256>>>(dAos.as<float>(), n, pb, state.as<unsigned>());
+        float init[8] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f, 0.f};
+        OPR_CUDA_CHECK(cudaMemcpy(bbox.p, init, 28, cudaMemcpyHostToDevice));
+        launch_photon_bbox(pb, state.as<unsigned>(), nPad / MAX_PHOTON_DEPOSITS, bbox.as<float>(), lc);
+        float h[8];
+        OPR_CUDA_CHECK(cudaMemcpy(h, bbox.p, 28, cudaMemcpyDeviceToHost));
+        unsigned nv; memcpy(&nv, h + 6, 4);
+        float lo[3] = {h[0], h[1], h[2]}, hi[3] = {h[3], h[4], h[5]};
+        if (nv == 0) { for (int i = 0; i < 3; i++) lo[i] = hi[i] = photonsAoS[3 + i]; }   // init = photons[0] (:125-126)
+        GridParams g;
+        bool ok = compute_grid_params(lo, hi, g);
+        g.numValid = nv;
+        *cellSize = g.cellSize; gridSize3[0] = g.gridSize.x; gridSize3[1] = g.gridSize.y; gridSize3[2] = g.gridSize.z;
+        origo3[0] = g.origo.x; origo3[1] = g.origo.y; origo3[2] = g.origo.z; *numValid = nv;
+        if (!ok) { g_lastError = "Too many cells in SpatialHash.cu, over defined PHOTON_GRID_MAX_SIZE."; return 2; }
+        OPR_CUDA_CHECK(cudaMemset(hist.p, 0, ((size_t)g.numCells + 2) * 4));
+        launch_grid_keys(pb, state.as<unsigned>(), nPad, g, k0.as<unsigned>(), hist.as<unsigned>(), lc);
+        int bits = 1; while ((1ull << bits) <= (unsigned long long)g.numCells + 1) bits++;
+        bool flipped = radix_sort_pairs<unsigned>(k0.as<unsigned>(), v0.as<unsigned>(), k1.as<unsigned>(), v1.as<unsigned>(), nPad, bits,
+                                                  sortTmp.as<unsigned>(), true, st);
+        exclusive_scan_u32(hist.as<unsigned>(), hist.as<unsigned>(), g.numCells + 1, scanTmp.as<unsigned>(), st);
+        const unsigned* sk = flipped ? k1.as<unsigned>() : k0.as<unsigned>();
+        const unsigned* sv = flipped ? v1.as<unsigned>() : v0.as<unsigned>();
+        launch_photon_reorder(pb, sv, nv, sorted, lc);
+        photons_soa_to_aos_kernel<<<148 * 4, 256>>>(sorted, nv, dAos.as<float>());
+        OPR_CUDA_CHECK(cudaDeviceSynchronize());
+        OPR_CUDA_CHECK(cudaGetLastError());
+        OPR_CUDA_CHECK(cudaMemcpy(sortedPhotonsAoS, dAos.p, (size_t)nv * 36, cudaMemcpyDeviceToHost));
+        OPR_CUDA_CHECK(cudaMemcpy(keys, sk, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        OPR_CUDA_CHECK(cudaMemcpy(offsets, hist.p, ((size_t)g.numCells + 1) * 4, cudaMemcpyDeviceToHost));
+        return 0;
+    } catch (const std::exception& e) { g_lastError = e.what(); return 1; }
+}
+
+__global__ void hitpoints_aos_to_soa_kernel(const float* __restrict__ aos, unsigned n, HitpointBuf hp)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* p = aos + 16 * (size_t)i;
+        hp.pos[i] = make_float4(p[0], p[1], p[2], p[12]);
+        hp.nrm[i] = make_float4(p[3], p[4], p[5], 0.f);
+        hp.att[i] = make_float4(p[6], p[7], p[8], 0.f);
+        hp.rad[i] = make_float4(p[9], p[10], p[11], 0.f);
+    }
+}
+
+int opr_gather(uint32_t numPixels, const float* hitpointsAoS, uint32_t numPhotons, const float* photonsAoS, const uint32_t* offsets,
+               float cellSize, const uint32_t* gridSize3, const float* origo3, float ppmRadius, float emittedPhotons, float* indirectOut)
+{
+    OPR_TRY({
+        requireDevice();
+        cudaStream_t st = 0;
+        unsigned long long launches = 0;
+        LaunchCtx lc{st, &launches};
+        GridParams g; g.cellSize = cellSize; g.gridSize = make_uint3(gridSize3[0], gridSize3[1], gridSize3[2]);
+        g.origo = make_float3(origo3[0], origo3[1], origo3[2]); g.numCells = gridSize3[0] * gridSize3[1] * gridSize3[2]; g.numValid = numPhotons;
+        DevBuf dHp((size_t)numPixels * 64), p0((size_t)numPixels * 16), p1((size_t)numPixels * 16), p2((size_t)numPixels * 16), p3((size_t)numPixels * 16);
+        DevBuf dPh((size_t)numPhotons * 36), a((size_t)numPhotons * 16 + 64), b((size_t)numPhotons * 16 + 64), c((size_t)numPhotons * 4 + 64), state((size_t)numPhotons + 64);
+        DevBuf dOff(((size_t)g.numCells + 1) * 4), dOut((size_t)numPixels * 12);
+        HitpointBuf hp{p0.as<float4>(), p1.as<float4>(), p2.as<float4>(), p3.as<float4>()};
+        PhotonBuf pb{a.as<float4>(), b.as<float4>(), c.as<float>()};
+        OPR_CUDA_CHECK(cudaMemcpy(dHp.p, hitpointsAoS, (size_t)numPixels * 64, cudaMemcpyHostToDevice));
+        OPR_CUDA_CHECK(cudaMemcpy(dPh.p, photonsAoS, (size_t)numPhotons * 36, cudaMemcpyHostToDevice));
+        OPR_CUDA_CHECK(cudaMemcpy(dOff.p, offsets, ((size_t)g.numCells + 1) * 4, cudaMemcpyHostToDevice));
+        hitpoints_aos_to_soa_kernel<<<148 * 4, 256>>>(dHp.as<float>(), numPixels, hp);
+        if (numPhotons) photons_aos_to_soa_kernel<<<148 * 4, 256>>>(dPh.as<float>(), numPhotons, pb, state.as<unsigned>());
+        launch_gather(hp, numPixels, pb, dOff.as<unsigned>(), g, ppmRadius, ppmRadius * ppmRadius, emittedPhotons, dOut.as<float>(), lc);
+        OPR_CUDA_CHECK(cudaDeviceSynchronize());
+        OPR_CUDA_CHECK(cudaGetLastError());
+        OPR_CUDA_CHECK(cudaMemcpy(indirectOut, dOut.p, (size_t)numPixels * 12, cudaMemcpyDeviceToHost));
+    })
+}
+
+__global__ void rays8_to_soa_kernel(const float* __restrict__ rays8, unsigned n, float4* __restrict__ o, float4* __restrict__ d)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* p = rays8 + 8 * (size_t)i;
+        o[i] = make_float4(p[0], p[1], p[2], p[3]);
+        d[i] = make_float4(p[4], p[5], p[6], p[7]);
+    }
+}
+
+__global__ void hits_to_host_layout_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD, const float4* __restrict__ hits,
+                                           unsigned n, float* __restrict__ outT, int* __restrict__ outMat, float* __restrict__ outNg)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h4 = hits[i];
+        HitRec hit; hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
+        if (hit.prim < 0) { outT[i] = -1.f; outMat[i] = -1; outNg[3 * i] = outNg[3 * i + 1] = outNg[3 * i + 2] = 0.f; continue; }
+        const Surface s = eval_surface(sc, hit, f3(rayO[i]), f3(rayD[i]));
+        outT[i] = hit.t; outMat[i] = s.material;
+        outNg[3 * i] = s.geometricNormal.x; outNg[3 * i + 1] = s.geometricNormal.y; outNg[3 * i + 2] = s.geometricNormal.z;
+    }
+}
+
+int opr_trace_closest(opr_renderer* r, const float* rays8, uint32_t n, float* outT, int32_t* outMaterial, float* outNg3)
+{
+    OPR_TRY({
+        Renderer& R = r->r;
+        if (!R.sceneLoaded) throw std::runtime_error("opr_trace_closest: no scene loaded");
+        OPR_CUDA_CHECK(cudaSetDevice(R.device));
+        LaunchCtx lc{R.stream, &R.launches};
+        DevBuf dr((size_t)n * 32), o((size_t)n * 16), d((size_t)n * 16), h((size_t)n * 16), t((size_t)n * 4), m((size_t)n * 4), ng((size_t)n * 12);
+        OPR_CUDA_CHECK(cudaMemcpyAsync(dr.p, rays8, (size_t)n * 32, cudaMemcpyHostToDevice, R.stream));
+        rays8_to_soa_kernel<<<148 * 4, 256, 0, R.stream>>>(dr.as<float>(), n, o.as<float4>(), d.as<float4>());
+        launch_trace_closest_raw(R.scene.view, o.as<float4>(), d.as<float4>(), n, h.as<float4>(), lc);
+        hits_to_host_layout_kernel<<<148 * 4, 256, 0, R.stream>>>(R.scene.view, o.as<float4>(), d.as<float4>(), h.as<float4>(), n, t.as<float>(), m.as<int>(), ng.as<float>());
+        OPR_CUDA_CHECK(cudaMemcpyAsync(outT, t.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
+        OPR_CUDA_CHECK(cudaMemcpyAsync(outMaterial, m.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
+        OPR_CUDA_CHECK(cudaMemcpyAsync(outNg3, ng.p, (size_t)n * 12, cudaMemcpyDeviceToHost, R.stream));
+        OPR_CUDA_CHECK(cudaStreamSynchronize(R.stream));
+        OPR_CUDA_CHECK(cudaGetLastError());
+    })
+}
+
+int opr_trace_any(opr_renderer* r, const float* rays8, uint32_t n, int32_t* outOccluded)
+{
+    OPR_TRY({
+        Renderer& R = r->r;
+        if (!R.sceneLoaded) throw std::runtime_error("opr_trace_any: no scene loaded");
+        OPR_CUDA_CHECK(cudaSetDevice(R.device));
+        LaunchCtx lc{R.stream, &R.launches};
+        DevBuf dr((size_t)n * 32), o((size_t)n * 16), d((size_t)n * 16), occ((size_t)n * 4);
+        OPR_CUDA_CHECK(cudaMemcpyAsync(dr.p, rays8, (size_t)n * 32, cudaMemcpyHostToDevice, R.stream));
+        rays8_to_soa_kernel<<<148 * 4, 256, 0, R.stream>>>(dr.as<float>(), n, o.as<float4>(), d.as<float4>());
+        launch_trace_any_raw(R.scene.view, o.as<float4>(), d.as<float4>(), n, occ.as<int>(), lc);
+        OPR_CUDA_CHECK(cudaMemcpyAsync(outOccluded, occ.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
+        OPR_CUDA_CHECK(cudaStreamSynchronize(R.stream));
+        OPR_CUDA_CHECK(cudaGetLastError());
+    })
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// grid.cu — photon uniform-grid build and the radius-bounded gather of Progressive Photon Mapping.
+//
+// Build (replaces thrust in RenderEngine/renderer/OptixRenderer_SpatialHash.cu:209-282):
+//   photon_bbox      AABB + count of valid photons         (getPhotonsBoundingBox :123-128)
+//   [host]           cell size / grid size in fp32         (:62-71, :42-50, :229-248) — on the host, as in the
+//                    reference, so that powf/ceil round identically to the oracle (bit-exact keys)
+//   grid_keys_hist   cell key per slot + histogram         (calculateHashCellsKernel :152-173)
+//   radix sort       (key, slot) pairs, stable             (sortPhotonsByHash :193-196)
+//   exclusive scan   histogram -> offset table             (createHashmapOffsetTable :202-207)
+//   photon_reorder   one gather of the 36-byte payload into sorted order (thrust moved it every pass)
+// Algorithmic bytes: 36N (bbox) + 16N (keys: pos + key + hist) + sort 8N r/w per pass + 72V (reorder) + 8C.
+//
+// Gather (replaces ppm/IndirectRadianceEstimation.cu:69-227, uniform-grid branch):
+// algorithmic bytes 64 B hitpoint + 12 B out per pixel + 36 B per photon touched once + 8 B per cell row.
+#include "renderer.h"
+#include <cmath>
+
+namespace opr {
+
+// ---- float atomics through the ordered-int trick ---------------------------------------------------------
+OPR_DEV void atomicMinFloat(float* addr, float v)
+{
+    v += 0.0f;   // canonicalise -0
+    if (v >= 0.f) atomicMin((int*)addr, __float_as_int(v)); else atomicMax((unsigned*)addr, __float_as_uint(v));
+}
+OPR_DEV void atomicMaxFloat(float* addr, float v)
+{
+    v += 0.0f;
+    if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v)); else atomicMin((unsigned*)addr, __float_as_uint(v));
+}
+
+constexpr int BBOX_THREADS = 256;
+
+// One thread per emitting photon thread; reads its <= 4 deposits.  A photon is valid when it was stored this
+// iteration and fmaxf(power) > 0 (PhotonToAABBConverter :112-119).
+__global__ void __launch_bounds__(BBOX_THREADS) photon_bbox_kernel(PhotonBuf photons, const unsigned* __restrict__ phState, unsigned numThreads,
+                                                                   float* __restrict__ bbox)
+{
+    float3 lo = f3(FLT_MAX), hi = f3(-FLT_MAX);
+    unsigned count = 0;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < numThreads; t += gridDim.x * blockDim.x) {
+        const unsigned numStored = (phState[t] >> 8) & 0xffu;
+        for (unsigned k = 0; k < numStored; k++) {
+            const size_t s = (size_t)t * MAX_PHOTON_DEPOSITS + k;
+            const float4 b = photons.b[s];
+            if (fmaxf(fmaxf(b.x, b.y), b.z) > 0) {
+                const float4 a = photons.a[s];
+                lo = fmin3(lo, f3(a)); hi = fmax3(hi, f3(a));
+                count++;
+            }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o)); hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+        count += __shfl_xor_sync(0xffffffffu, count, o);
+    }
+    if ((threadIdx.x & 31) == 0 && count) {
+        atomicMinFloat(bbox + 0, lo.x); atomicMinFloat(bbox + 1, lo.y); atomicMinFloat(bbox + 2, lo.z);
+        atomicMaxFloat(bbox + 3, hi.x); atomicMaxFloat(bbox + 4, hi.y); atomicMaxFloat(bbox + 5, hi.z);
+        atomicAdd((unsigned*)(bbox + 6), count);
+    }
+}
+
+void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc)
+{
+    int blocks = (int)std::min<unsigned>((numThreads + BBOX_THREADS - 1) / BBOX_THREADS, 148 * 8);
+    photon_bbox_kernel<<<blocks, BBOX_THREADS, 0, lc.st>>>(photons, phState, numThreads, bbox);
+    ++*lc.launches;
+}
+
+// ---- host scalars: getSmallestPossibleCellSize :62-71, calculateGridSize :42-50, :229-248 ---------------
+static inline unsigned f2u_sat(float f) { if (!(f > 0.0f)) return 0u; if (f >= 4294967296.0f) return 0xffffffffu; return (unsigned)f; }
+
+bool compute_grid_params(const float lo[3], const float hi[3], GridParams& g)
+{
+    // padAABB :135-141
+    const float first[3] = {lo[0] - 0.0000001f, lo[1] - 0.0000001f, lo[2] - 0.0000001f};
+    const float second[3] = {hi[0] + 0.0000001f, hi[1] + 0.0000001f, hi[2] + 0.0000001f};
+    const float ext[3] = {second[0] - first[0], second[1] - first[1], second[2] - first[2]};
+    float sceneVolume = ext[0] * ext[1] * ext[2];
+    float minVolumePerCell = sceneVolume / PHOTON_GRID_MAX_SIZE;
+    float smallestPossibleRadiusC = powf(minVolumePerCell, 1.0f / 3.0f);
+    float inv = 1.0f / smallestPossibleRadiusC;                           // float3 / float multiplies by the reciprocal
+    unsigned nc[3] = {f2u_sat(floorf(ext[0] * inv)), f2u_sat(floorf(ext[1] * inv)), f2u_sat(floorf(ext[2] * inv))};
+    float r0 = ext[0] / nc[0], r1 = ext[1] / nc[1], r2 = ext[2] / nc[2];
+    float smallestPossibleCellSize = fmaxf(fmaxf(r0, r1), r2);
+    float cellSize = (float)(smallestPossibleCellSize + 0.001);           // float + double literal (:230)
+    float invc = 1.0f / cellSize;
+    unsigned gs[3] = {f2u_sat(ceilf(ext[0] * invc)), f2u_sat(ceilf(ext[1] * invc)), f2u_sat(ceilf(ext[2] * invc))};
+    for (int i = 0; i < 3; i++) gs[i] = gs[i] < 1u ? 1u : gs[i];
+    g.cellSize = cellSize;
+    g.gridSize = make_uint3(gs[0], gs[1], gs[2]);
+    g.origo = make_float3(first[0], first[1], first[2]);
+    g.numCells = gs[0] * gs[1] * gs[2];
+    return g.numCells <= PHOTON_GRID_MAX_SIZE;                            // :244-248
+}
+
+// ---- keys + histogram: calculateHashCellsKernel :152-173, getPhotonGridIndex(1D) ppm/PhotonGrid.h:19-28 ---
+__global__ void __launch_bounds__(256) grid_keys_hist_kernel(PhotonBuf photons, const unsigned* __restrict__ phState, unsigned numSlots, GridParams g,
+                                                             unsigned* __restrict__ keys, unsigned* __restrict__ hist)
+{
+    const float invCell = 1.f / g.cellSize;
+    const unsigned invalidHashCell = g.numCells + 1;
+    for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < numSlots; s += gridDim.x * blockDim.x) {
+        const unsigned t = s / MAX_PHOTON_DEPOSITS, k = s % MAX_PHOTON_DEPOSITS;
+        const unsigned numStored = (phState[t] >> 8) & 0xffu;
+        unsigned hashCell = invalidHashCell;
+        if (k < numStored) {
+            const float4 b = photons.b[s];
+            if (fmaxf(fmaxf(b.x, b.y), b.z) > 0) {
+                const float4 a = photons.a[s];
+                // (position - origo) * (1/cellSize): a subtraction then a multiplication, nothing to contract
+                const float px = (a.x - g.origo.x) * invCell, py = (a.y - g.origo.y) * invCell, pz = (a.z - g.origo.z) * invCell;
+                const unsigned gx = (unsigned)floorf(px), gy = (unsigned)floorf(py), gz = (unsigned)floorf(pz);
+                hashCell = gx + gy * g.gridSize.x + gz * g.gridSize.x * g.gridSize.y;
+                if (hashCell < g.numCells) atomicAdd(hist + hashCell, 1u);
+            }
+        }
+        keys[s] = hashCell;
+    }
+}
+
+void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, GridParams g, unsigned* keys, unsigned* hist, LaunchCtx lc)
+{
+    int blocks = (int)std::min<unsigned>((numSlots + 255) / 256, 148 * 16);
+    grid_keys_hist_kernel<<<blocks, 256, 0, lc.st>>>(photons, phState, numSlots, g, keys, hist);
+    ++*lc.launches;
+}
+
+__global__ void __launch_bounds__(256) photon_reorder_kernel(PhotonBuf src, const unsigned* __restrict__ sortedSlots, unsigned numValid, PhotonBuf dst)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < numValid; i += gridDim.x * blockDim.x) {
+        const unsigned s = sortedSlots[i];
+        dst.a[i] = src.a[s]; dst.b[i] = src.b[s]; dst.c[i] = src.c[s];
+    }
+}
+
+void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned numValid, const PhotonBuf& dst, LaunchCtx lc)
+{
+    if (!numValid) return;
+    int blocks = (int)std::min<unsigned>((numValid + 255) / 256, 148 * 16);
+    photon_reorder_kernel<<<blocks, 256, 0, lc.st>>>(src, sortedSlots, numValid, dst);
+    ++*lc.launches;
+}
+
+// ---- gather: IndirectRadianceEstimation::kernel (:69-129, :213-220), validPhoton :54-57, photonPower :59-67
+constexpr int GATHER_THREADS = 128;
+
+__global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf hp, unsigned numPixels, PhotonBuf sorted, const unsigned* __restrict__ offsets,
+                                                                    GridParams g, float ppmRadius, float ppmRadiusSquared, float emittedPhotons,
+                                                                    float* __restrict__ indirect)
+{
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < numPixels; p += gridDim.x * blockDim.x) {
+        const float4 pos4 = hp.pos[p];
+        const unsigned flags = __float_as_uint(pos4.w);
+        const float3 attenuation = f3(hp.att[p]);
+        float3 acc = f3(0.f);
+        if (flags & PRD_HIT_NON_SPECULAR) {
+            const float3 pos = f3(pos4), nrm = f3(hp.nrm[p]);
+            const float radius2 = ppmRadiusSquared, radius = ppmRadius;
+            const float invCellSize = 1.f / g.cellSize;
+            const float3 np = pos - g.origo;
+            const unsigned x_lo = (unsigned)max(0, (int)((np.x - radius) * invCellSize));
+            const unsigned y_lo = (unsigned)max(0, (int)((np.y - radius) * invCellSize));
+            const unsigned z_lo = (unsigned)max(0, (int)((np.z - radius) * invCellSize));
+            const unsigned x_hi = min(g.gridSize.x - 1, (unsigned)((np.x + radius) * invCellSize));
+            const unsigned y_hi = min(g.gridSize.y - 1, (unsigned)((np.y + radius) * invCellSize));
+            const unsigned z_hi = min(g.gridSize.z - 1, (unsigned)((np.z + radius) * invCellSize));
+            if (x_lo <= x_hi) {
+                for (unsigned z = z_lo; z <= z_hi; z++) {
+                    for (unsigned y = y_lo; y <= y_hi; y++) {
+                        const unsigned from = x_lo + y * g.gridSize.x + z * g.gridSize.x * g.gridSize.y;
+                        const unsigned to = from + (x_hi - x_lo);
+                        const unsigned begin = __ldg(offsets + from), end = __ldg(offsets + to + 1);
+                        for (unsigned i = begin; i < end; i++) {
+                            const float4 a = __ldg(sorted.a + i);
+                            const float3 diff = pos - f3(a);
+                            const float distance2 = dot(diff, diff);
+                            if (distance2 <= radius2) {
+                                const float4 b = __ldg(sorted.b + i);
+                                const float dz = __ldg(sorted.c + i);
+                                if (dot(-f3(a.w, b.w, dz), nrm) >= 0) {
+                                    const float alpha = 1.818f, beta = 1.953f, expNegativeBeta = 0.141847f;
+                                    const float weight = alpha * (1 - (1 - expf(-beta * distance2 / (2 * radius2))) / (1 - expNegativeBeta));
+                                    acc += f3(b) * weight;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const float3 ind = acc * attenuation * (1.0f / (PI_F * ppmRadiusSquared)) * (1.0f / emittedPhotons);
+        indirect[3 * (size_t)p] = ind.x; indirect[3 * (size_t)p + 1] = ind.y; indirect[3 * (size_t)p + 2] = ind.z;
+    }
+}
+
+void launch_gather(const HitpointBuf& hp, unsigned numPixels, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
+                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, LaunchCtx lc)
+{
+    int blocks = (int)std::min<unsigned>((numPixels + GATHER_THREADS - 1) / GATHER_THREADS, 148 * 16);
+    ppm_gather_kernel<<<blocks, GATHER_THREADS, 0, lc.st>>>(hp, numPixels, sorted, offsets, g, ppmRadius, ppmRadiusSquared, emittedPhotons, indirect);
+    ++*lc.launches;
+}
+
+} // namespace opr

@@ -1,0 +1,503 @@
+// ppm.cu — Progressive Photon Mapping passes as wavefront kernels: camera-ray generation and the
+// RADIANCE material programs, photon emission and the PHOTON material programs, and the fused
+// direct-lighting + output pass.  Each kernel cites the reference device program it replaces.
+//
+// The reference's recursion (rtTrace inside closest-hit programs) becomes an iterative state machine:
+// per-path state lives in HBM (hitpoint SoA for camera paths, phPower/phState for photons) and a shading
+// kernel either terminates the path or pushes ONE continuation ray into the next queue (warp-aggregated).
+// Shading runs bucketed by material kind: blockIdx.y selects the material queue filled by the trace kernel.
+#include "renderer.h"
+
+namespace opr {
+
+constexpr int SHADE_THREADS = 128;
+constexpr int SHADE_BLOCKS_X = 148 * 2;
+
+// ---- helpers -------------------------------------------------------------------------------------------
+OPR_DEV unsigned rng_index(unsigned path, unsigned launchW, unsigned rsW)
+{   // randomStates is a 2-D buffer indexed by launchIndex (x,y): OptixRenderer.cpp:368-373
+    return (path / launchW) * rsW + (path % launchW);
+}
+
+// material/Glass.cu:69-88
+OPR_DEV float reflectionFactor(float cosI, float cosT, float n1, float n2)
+{
+    float rp = (n2 * cosI - n1 * cosT) / (n2 * cosI + n1 * cosT);
+    float rs = (n1 * cosI - n2 * cosT) / (n1 * cosI + n2 * cosT);
+    return (rp * rp + rs * rs) / 2.f;
+}
+
+// Fresnel reflect/refract choice shared by Glass closestHitRadiance (:90-143) and closestHitPhoton (:164-205)
+OPR_DEV float3 glass_scatter(const float3& dir, const float3& worldShadingNormal, float ior, Rng& rng, bool& isReflected, float& n1, float& n2)
+{
+    bool isHitFromOutside = dot(worldShadingNormal, dir) < 0;      // helpers.h:146-149
+    float3 N = isHitFromOutside ? worldShadingNormal : -worldShadingNormal;
+    n1 = isHitFromOutside ? 1.f : ior;
+    n2 = isHitFromOutside ? ior : 1.f;
+    float3 refractionDirection = f3(0.f);
+    bool validRefraction = refract(refractionDirection, dir, N, n2 / n1);
+    float cosThetaI = -dot(dir, N);
+    float cosThetaT = -dot(refractionDirection, N);
+    float reflFactor = validRefraction ? reflectionFactor(cosThetaI, cosThetaT, n1, n2) : 1.f;
+    float sample = rng_uniform(rng);
+    isReflected = (sample <= reflFactor);
+    return isReflected ? reflect(dir, N) : refractionDirection;
+}
+
+// material/Texture.cu:72-80
+OPR_DEV float3 getNormalMappedNormal(const float3& normal, const float3& tangent, const float3& bitangent, const float4& normalMap)
+{
+    float4 nMap = make_float4(2 * normalMap.x - 1, 2 * normalMap.y - 1, 2 * normalMap.z - 1, 2 * normalMap.w - 1);
+    float3 N;
+    N.x = nMap.x * tangent.x + nMap.y * bitangent.x + nMap.z * normal.x;
+    N.y = nMap.x * tangent.y + nMap.y * bitangent.y + nMap.z * normal.y;
+    N.z = nMap.x * tangent.z + nMap.y * bitangent.z + nMap.z * normal.z;
+    return normalize(N);
+}
+
+// ---- RNG state init: initRandomStateBuffer (OptixRenderer_SpatialHash.cu:310-317) ---------------------
+__global__ void rng_init_kernel(RngBuf rng, unsigned seed, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        Rng s; rng_seed(s, seed, (unsigned)i);
+        rng_store(rng, i, s);
+    }
+}
+void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc)
+{
+    rng_init_kernel<<<148 * 8, 256, 0, lc.st>>>(rng, seed, n);
+    ++*lc.launches;
+}
+
+// ---- camera pass: RayGeneratorPPM::generateRay (ppm/RayGeneratorPPM.cu:31-66) + DOF (helpers/camera.h:11-27)
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_gen_kernel(opr_camera cam, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf,
+                                                                       HitpointBuf hp, float4* __restrict__ rayO, float4* __restrict__ rayD,
+                                                                       unsigned* __restrict__ rayPath)
+{
+    const unsigned n = w * h;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const unsigned x = p % w, y = p / w;
+        const size_t ri = (size_t)y * rsW + x;
+        Rng rng = rng_load(rngBuf, ri);
+        const float3 eye = f3(cam.eye[0], cam.eye[1], cam.eye[2]);
+        const float3 cu = f3(cam.camera_u[0], cam.camera_u[1], cam.camera_u[2]);
+        const float3 cv = f3(cam.camera_v[0], cam.camera_v[1], cam.camera_v[2]);
+        const float3 lookdir = f3(cam.lookdir[0], cam.lookdir[1], cam.lookdir[2]);
+        float2 sample = rng_uniform2(rng);
+        float dx = ((float)x + sample.x) / (float)w * 2.0f - 1.0f;
+        float dy = ((float)y + sample.y) / (float)h * 2.0f - 1.0f;
+        float3 rayOrigin = eye;
+        float3 rayDirection = normalize(dx * cu + dy * cv + lookdir);
+        if (cam.aperture > 0) {
+            float3 focalPlaneCenterPoint = eye + lookdir;
+            float3 camLookDir = normalize(lookdir);
+            float focalPlaneT = (dot(camLookDir, focalPlaneCenterPoint) - dot(camLookDir, eye)) / dot(camLookDir, rayDirection);
+            float3 lookAt = rayOrigin + focalPlaneT * rayDirection;
+            float2 dofSample = rng_uniform2(rng);
+            float2 disc = sampleUnitDisc(dofSample);
+            rayOrigin += disc.x * cu * cam.aperture + disc.y * cv * cam.aperture;
+            rayDirection = normalize(lookAt - rayOrigin);
+        }
+        rng_store(rngBuf, ri, rng);
+        // RadiancePRD initial state (:33-37); position/normal are uninitialised in the reference, 0 here
+        hp.pos[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        hp.nrm[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        hp.att[p] = make_float4(1.f, 1.f, 1.f, 0.f);
+        hp.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rayO[p] = make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, 0.001f);
+        rayD[p] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, RT_DEFAULT_MAX);
+        rayPath[p] = p;
+    }
+}
+
+void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
+                           const RayQueues& q, LaunchCtx lc)
+{
+    unsigned n = w * h;
+    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
+    ppm_camera_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(cam, w, h, rsW, rng, hp, q.rayO[0], q.rayD[0], q.rayPath[0]);
+    ++*lc.launches;
+}
+
+// RADIANCE closest-hit programs, one material kind per blockIdx.y.
+//   Diffuse.cu:71-87, Glossy.cu:74-90, Texture.cu:83-110, DiffuseEmitter.cu:40-51, Mirror.cu:50-63,
+//   Glass.cu:90-143, miss RayGeneratorPPM.cu:72-77.
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneView sc, unsigned w, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
+                                                                         const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+                                                                         const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
+                                                                         const unsigned* __restrict__ matQueue, const unsigned* __restrict__ matCount,
+                                                                         unsigned capacity, float4* __restrict__ nextO, float4* __restrict__ nextD,
+                                                                         unsigned* __restrict__ nextPath, unsigned* __restrict__ nextCount)
+{
+    const int kind = blockIdx.y;
+    const unsigned n = matCount[kind];
+    const unsigned* queue = matQueue + (size_t)kind * capacity;
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned qi = base + threadIdx.x;
+        const bool active = qi < n;
+        bool push = false;
+        float3 newO = f3(0.f), newD = f3(0.f);
+        unsigned p = 0;
+        if (active) {
+            const unsigned slot = queue[qi];
+            p = rayPath[slot];
+            if (kind == QUEUE_MISS) {
+                hp.pos[p].w = __uint_as_float(PRD_MISS);
+                hp.att[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                hp.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const float4 o4 = rayO[slot], d4 = rayD[slot], h4 = hits[slot];
+                const float3 o = f3(o4), d = f3(d4);
+                HitRec hit; hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
+                const Surface sf = eval_surface(sc, hit, o, d);
+                const DMaterial& m = sc.materials[sf.material];
+                const float tHit = hit.t;
+                unsigned flags = __float_as_uint(hp.pos[p].w);
+                unsigned depth = __float_as_uint(hp.nrm[p].w);
+                float3 att = f3(hp.att[p]);
+                const float3 worldShadingNormal = normalize(sf.shadingNormal);
+                const float3 hitPoint = o + tHit * d;
+                if (kind == OPR_MAT_DIFFUSE || kind == OPR_MAT_GLOSSY) {
+                    flags |= PRD_HIT_NON_SPECULAR;
+                    att *= m.Kd;
+                    depth++;
+                    hp.pos[p] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, __uint_as_float(flags));
+                    hp.nrm[p] = make_float4(worldShadingNormal.x, worldShadingNormal.y, worldShadingNormal.z, __uint_as_float(depth));
+                    hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
+                } else if (kind == OPR_MAT_TEXTURE) {
+                    float3 normal = worldShadingNormal;
+                    if (m.hasNormalTex) {
+                        float3 worldTangent = normalize(sf.tangent), worldBitangent = normalize(sf.bitangent);
+                        normal = getNormalMappedNormal(worldShadingNormal, worldTangent, worldBitangent, tex2D<float4>(m.normalTex, sf.uv.x, sf.uv.y));
+                    }
+                    flags |= PRD_HIT_NON_SPECULAR;
+                    float4 value = tex2D<float4>(m.diffuseTex, sf.uv.x, sf.uv.y);
+                    att *= f3(value.x, value.y, value.z);
+                    hp.pos[p] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, __uint_as_float(flags));
+                    hp.nrm[p] = make_float4(normal.x, normal.y, normal.z, __uint_as_float(depth));   // no depth++ (Texture.cu:83-110)
+                    hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
+                } else if (kind == OPR_MAT_DIFFUSE_EMITTER) {
+                    flags |= PRD_HIT_EMITTER;
+                    hp.pos[p].w = __uint_as_float(flags);
+                    if (!(dot(worldShadingNormal, -d) < 0.f)) {
+                        float3 Le = m.powerPerArea / PI_F;
+                        float3 rad = f3(hp.rad[p]);
+                        rad += att * Le;
+                        hp.rad[p] = make_float4(rad.x, rad.y, rad.z, 0.f);
+                    }
+                } else if (kind == OPR_MAT_MIRROR) {
+                    depth++;
+                    hp.nrm[p].w = __uint_as_float(depth);
+                    if (depth <= MAX_RADIANCE_TRACE_DEPTH) {
+                        att *= m.Kr;
+                        hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
+                        newO = hitPoint; newD = reflect(d, worldShadingNormal);
+                        push = true;
+                    }
+                } else {   // OPR_MAT_GLASS
+                    const size_t ri = rng_index(p, w, rsW);
+                    Rng rng = rng_load(rngBuf, ri);
+                    bool isReflected; float n1, n2;
+                    newD = glass_scatter(d, worldShadingNormal, m.ior, rng, isReflected, n1, n2);
+                    rng_store(rngBuf, ri, rng);
+                    if (!isReflected) att *= (n2 * n2) / (n1 * n1);
+                    flags |= PRD_HIT_SPECULAR;
+                    flags &= ~PRD_HIT_NON_SPECULAR;
+                    depth++;
+                    newO = hitPoint;
+                    if (depth <= MAX_RADIANCE_TRACE_DEPTH) push = true;
+                    else att *= 0.f;
+                    hp.pos[p].w = __uint_as_float(flags);
+                    hp.nrm[p].w = __uint_as_float(depth);
+                    hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
+                }
+            }
+        }
+        // ray regeneration: one atomicAdd per warp
+        const unsigned dst = warp_append(nextCount, push);
+        if (push) {
+            nextO[dst] = make_float4(newO.x, newO.y, newO.z, 0.0001f);
+            nextD[dst] = make_float4(newD.x, newD.y, newD.z, RT_DEFAULT_MAX);
+            nextPath[dst] = p;
+        }
+    }
+}
+
+void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
+                             const RayQueues& q, int cur, LaunchCtx lc)
+{
+    dim3 grid(SHADE_BLOCKS_X, NUM_QUEUES);
+    const int nxt = cur ^ 1;
+    ppm_camera_shade_kernel<<<grid, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
+                                                               q.counters + 2, q.capacity, q.rayO[nxt], q.rayD[nxt], q.rayPath[nxt], q.counters + nxt);
+    ++*lc.launches;
+}
+
+// ---- photon pass: PhotonGenerator::generator (ppm/PhotonGenerator.cu:40-128) ----------------------------
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_gen_kernel(SceneView sc, unsigned pw, unsigned ph, unsigned rsW, RngBuf rngBuf,
+                                                                       float4* __restrict__ phPower, unsigned* __restrict__ phState,
+                                                                       float4* __restrict__ rayO, float4* __restrict__ rayD, unsigned* __restrict__ rayPath)
+{
+    const unsigned n = pw * ph;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const unsigned x = t % pw, y = t / pw;
+        const size_t ri = (size_t)y * rsW + x;
+        Rng rng = rng_load(rngBuf, ri);
+        int lightIndex = 0;
+        if (sc.numLights > 1) {
+            float sample = rng_uniform(rng);
+            lightIndex = min((int)(sample * sc.numLights), sc.numLights - 1);
+        }
+        const opr_light light = sc.lights[lightIndex];
+        float powerScale = (float)sc.numLights;
+        float3 power = f3(light.power[0], light.power[1], light.power[2]) * powerScale;
+        float3 origin = f3(light.position[0], light.position[1], light.position[2]);
+        float3 direction = f3(0.f);
+        float photonPowerFactor = 1.f;
+        float2 sample1 = rng_uniform2(rng);
+        if (light.lightType == OPR_LIGHT_AREA) {
+            float2 sample2 = rng_uniform2(rng);
+            origin += sample1.x * f3(light.v1[0], light.v1[1], light.v1[2]) + sample1.y * f3(light.v2[0], light.v2[1], light.v2[2]);
+            direction = sampleUnitHemisphere(f3(light.normal[0], light.normal[1], light.normal[2]), sample2);
+        } else if (light.lightType == OPR_LIGHT_POINT) {
+            float3 sceneCenterToLight = origin - sc.boundingSphere.center;
+            float lightDistance = length(sceneCenterToLight);
+            sceneCenterToLight /= lightDistance;
+            bool lightWellOutsideSphere = ((double)lightDistance > 1.5 * (double)sc.boundingSphere.radius);
+            if (lightWellOutsideSphere) {
+                float3 pointOnDisc = sampleDisc(sample1, sc.boundingSphere.center, sc.boundingSphere.radius, sceneCenterToLight);
+                direction = normalize(pointOnDisc - origin);
+                float r = sc.boundingSphere.radius;
+                photonPowerFactor = (1 - lightDistance * (1.0f / sqrtf(r * r + lightDistance * lightDistance))) / 2.f;
+            } else {
+                direction = sampleUnitSphere(sample1);
+            }
+        } else {
+            float3 ldir = f3(light.normal[0], light.normal[1], light.normal[2]);
+            float3 pointOnDisc = sampleDisc(sample1, origin + ldir, sinf(light.area_or_angle / 2), ldir);
+            direction = normalize(pointOnDisc - origin);
+        }
+        power *= photonPowerFactor;
+        rng_store(rngBuf, ri, rng);
+        phPower[t] = make_float4(power.x, power.y, power.z, 1.0f);
+        phState[t] = 0u;    // depth 0, numStoredPhotons 0 (also "clears" the 4 slots this thread owns)
+        rayO[t] = make_float4(origin.x, origin.y, origin.z, 0.0001f);
+        rayD[t] = make_float4(direction.x, direction.y, direction.z, RT_DEFAULT_MAX);
+        rayPath[t] = t;
+    }
+}
+
+void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsigned rsW, const RngBuf& rng, float4* phPower,
+                           unsigned* phState, const RayQueues& q, LaunchCtx lc)
+{
+    unsigned n = pw * ph;
+    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
+    ppm_photon_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, pw, ph, rsW, rng, phPower, phState, q.rayO[0], q.rayD[0], q.rayPath[0]);
+    ++*lc.launches;
+}
+
+// PHOTON closest-hit programs: Diffuse.cu:92-135, Glossy.cu:94-137, Texture.cu:116-175, Mirror.cu:65-77,
+// Glass.cu:164-205, DiffuseEmitter.cu:56-59; miss is a no-op (PhotonGenerator.cu:132-135).
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf,
+                                                                         float4* __restrict__ phPower, unsigned* __restrict__ phState, PhotonBuf photons,
+                                                                         const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+                                                                         const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
+                                                                         const unsigned* __restrict__ matQueue, const unsigned* __restrict__ matCount,
+                                                                         unsigned capacity, float4* __restrict__ nextO, float4* __restrict__ nextD,
+                                                                         unsigned* __restrict__ nextPath, unsigned* __restrict__ nextCount)
+{
+    const int kind = blockIdx.y;
+    if (kind == QUEUE_MISS) return;
+    const unsigned n = matCount[kind];
+    const unsigned* queue = matQueue + (size_t)kind * capacity;
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned qi = base + threadIdx.x;
+        const bool active = qi < n;
+        bool push = false;
+        float3 newO = f3(0.f), newD = f3(0.f);
+        float newTmin = 0.0001f;
+        unsigned t = 0;
+        if (active) {
+            const unsigned slot = queue[qi];
+            t = rayPath[slot];
+            unsigned state = phState[t];
+            unsigned depth = state & 0xffu, numStored = (state >> 8) & 0xffu;
+            if (kind == OPR_MAT_DIFFUSE_EMITTER) {
+                depth++;
+            } else {
+                const float4 o4 = rayO[slot], d4 = rayD[slot], h4 = hits[slot];
+                const float3 o = f3(o4), d = f3(d4);
+                HitRec hit; hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
+                const Surface sf = eval_surface(sc, hit, o, d);
+                const DMaterial& m = sc.materials[sf.material];
+                const float3 worldShadingNormal = normalize(sf.shadingNormal);
+                const float3 hitPoint = o + hit.t * d;
+                float4 pw4 = phPower[t];
+                float3 power = f3(pw4);
+                float weight = pw4.w;
+                if (kind == OPR_MAT_MIRROR) {
+                    depth++;
+                    if (depth <= MAX_PHOTON_TRACE_DEPTH) {
+                        power *= m.Kr;
+                        newO = hitPoint; newD = reflect(d, worldShadingNormal); push = true;
+                    }
+                } else if (kind == OPR_MAT_GLASS) {
+                    const size_t ri = rng_index(t, pw, rsW);
+                    Rng rng = rng_load(rngBuf, ri);
+                    bool isReflected; float n1, n2;
+                    newD = glass_scatter(d, worldShadingNormal, m.ior, rng, isReflected, n1, n2);
+                    rng_store(rngBuf, ri, rng);
+                    depth++;
+                    newO = hitPoint;
+                    if (depth <= MAX_PHOTON_TRACE_DEPTH) push = true;
+                } else {   // Diffuse / Glossy / Texture
+                    const bool tex = (kind == OPR_MAT_TEXTURE);
+                    if (depth >= 1 && numStored < MAX_PHOTON_DEPOSITS) {
+                        // STORE_PHOTON (helpers/store_photon.h:12-15): slot pm_index + numStoredPhotons
+                        const size_t ps = (size_t)t * MAX_PHOTON_DEPOSITS + numStored;
+                        photons.a[ps] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, d.x);
+                        photons.b[ps] = make_float4(power.x, power.y, power.z, d.y);
+                        photons.c[ps] = d.z;
+                        numStored++;
+                    }
+                    float3 albedo;
+                    if (tex) { float4 v = tex2D<float4>(m.diffuseTex, sf.uv.x, sf.uv.y); albedo = f3(v.x, v.y, v.z); }
+                    else albedo = m.Kd;
+                    power *= albedo;
+                    weight *= fmax3(albedo);
+                    bool alive = true;
+                    Rng rng; bool rngLoaded = false;
+                    const size_t ri = rng_index(t, pw, rsW);
+                    if (depth >= PHOTON_TRACING_RR_START_DEPTH) {
+                        rng = rng_load(rngBuf, ri); rngLoaded = true;
+                        float probContinue = favgf(albedo);
+                        float probSample = rng_uniform(rng);
+                        if (probSample >= probContinue) alive = false;
+                        else power /= probContinue;
+                    }
+                    if (alive) {
+                        depth++;
+                        if (depth >= MAX_PHOTON_TRACE_DEPTH || (double)weight < (tex ? 0.01 : 0.001)) alive = false;
+                    }
+                    if (alive && numStored >= MAX_PHOTON_DEPOSITS) alive = false;
+                    if (alive) {
+                        if (!rngLoaded) { rng = rng_load(rngBuf, ri); rngLoaded = true; }
+                        float2 s = rng_uniform2(rng);
+                        newD = sampleUnitHemisphereCos(worldShadingNormal, s);
+                        newO = hitPoint;
+                        newTmin = tex ? 0.01f : 0.0001f;
+                        push = true;
+                    }
+                    if (rngLoaded) rng_store(rngBuf, ri, rng);
+                }
+                phPower[t] = make_float4(power.x, power.y, power.z, weight);
+            }
+            phState[t] = depth | (numStored << 8);
+        }
+        const unsigned dst = warp_append(nextCount, push);
+        if (push) {
+            nextO[dst] = make_float4(newO.x, newO.y, newO.z, newTmin);
+            nextD[dst] = make_float4(newD.x, newD.y, newD.z, RT_DEFAULT_MAX);
+            nextPath[dst] = t;
+        }
+    }
+}
+
+void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
+                             const PhotonBuf& photons, const RayQueues& q, int cur, LaunchCtx lc)
+{
+    dim3 grid(SHADE_BLOCKS_X, NUM_QUEUES);
+    const int nxt = cur ^ 1;
+    ppm_photon_shade_kernel<<<grid, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
+                                                               q.hits, q.matQueue, q.counters + 2, q.capacity, q.rayO[nxt], q.rayD[nxt], q.rayPath[nxt],
+                                                               q.counters + nxt);
+    ++*lc.launches;
+}
+
+// ---- direct lighting + output: DirectRadianceEstimation::kernel (ppm/DirectRadianceEstimation.cu:29-77),
+// getLightContribution (helpers/light.h:29-87), gatherAnyHitOnNonEmitter (:79-83), Output::kernel
+// (ppm/Output.cu:32-37).  One thread per pixel; the four shadow rays are any-hit traversals issued in place
+// (the RNG draws of the four samples are sequential on one state, DirectRadianceEstimation.cu:62,66).
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_output_kernel(SceneView sc, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
+                                                                          const float* __restrict__ indirect, float* __restrict__ direct,
+                                                                          float* __restrict__ output, unsigned localIteration, unsigned* __restrict__ stat)
+{
+    const unsigned n = w * h;
+    unsigned shadowRays = 0;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const float4 pos4 = hp.pos[p];
+        const unsigned flags = __float_as_uint(pos4.w);
+        float3 directRadiance;
+        if (!(flags & PRD_HIT_NON_SPECULAR)) {
+            float3 rad = f3(hp.rad[p]);
+            if ((flags & PRD_HIT_EMITTER) && !(flags & PRD_HIT_SPECULAR)) directRadiance = fmin3(rad, f3(1.f));
+            else directRadiance = rad;
+        } else {
+            const float3 rec_position = f3(pos4), rec_normal = f3(hp.nrm[p]), attenuation = f3(hp.att[p]);
+            const size_t ri = (size_t)(p / w) * rsW + (p % w);
+            Rng rng = rng_load(rngBuf, ri);
+            const int numLights = sc.numLights;
+            float3 avgLightRadiance = f3(0.f);
+            #pragma unroll 1
+            for (int shadowSample = 0; shadowSample < 4; shadowSample++) {
+                float sample = rng_uniform(rng);
+                int randomLightIndex = min(int(sample * numLights), numLights - 1);
+                const opr_light& light = sc.lights[randomLightIndex];
+                float scale = (float)numLights;
+                // getLightContribution
+                float lightFactor = 1;
+                float3 pointOnLight = f3(0.f);
+                const int lightType = light.lightType;
+                if (lightType == OPR_LIGHT_AREA) {
+                    float2 s = rng_uniform2(rng);
+                    pointOnLight = f3(light.position[0], light.position[1], light.position[2]) + s.x * f3(light.v1[0], light.v1[1], light.v1[2]) +
+                                   s.y * f3(light.v2[0], light.v2[1], light.v2[2]);
+                } else if (lightType == OPR_LIGHT_POINT) {
+                    pointOnLight = f3(light.position[0], light.position[1], light.position[2]);
+                    lightFactor *= 1.f / 4.f;
+                } else {
+                    lightFactor = 0;
+                }
+                float3 towardsLight = pointOnLight - rec_position;
+                float lightDistance = length(towardsLight);
+                towardsLight = towardsLight / lightDistance;
+                float n_dot_l = maxf_(0, dot(rec_normal, towardsLight));
+                lightFactor *= n_dot_l / (PI_F * lightDistance * lightDistance);
+                if (lightType == OPR_LIGHT_AREA)
+                    lightFactor *= maxf_(0, dot(-towardsLight, f3(light.normal[0], light.normal[1], light.normal[2])));
+                float3 lightContrib = f3(0.f);
+                if (lightFactor > 0.0f) {
+                    HitRec hit;
+                    shadowRays++;
+                    bool occluded = traverse<true>(sc, rec_position, towardsLight, 0.0001f, (float)((double)lightDistance - 0.0001), hit);
+                    lightFactor *= occluded ? 0.0f : 1.0f;
+                    lightContrib = f3(light.power[0], light.power[1], light.power[2]) * lightFactor;
+                }
+                avgLightRadiance += scale * lightContrib;
+            }
+            rng_store(rngBuf, ri, rng);
+            directRadiance = attenuation * avgLightRadiance / 4.0f;
+        }
+        const float3 ind = f3(indirect[3 * (size_t)p], indirect[3 * (size_t)p + 1], indirect[3 * (size_t)p + 2]);
+        if (direct) { direct[3 * (size_t)p] = directRadiance.x; direct[3 * (size_t)p + 1] = directRadiance.y; direct[3 * (size_t)p + 2] = directRadiance.z; }
+        const float3 finalRadiance = directRadiance + ind;
+        float3 out = finalRadiance;
+        if (localIteration != 0) out = f3(output[3 * (size_t)p], output[3 * (size_t)p + 1], output[3 * (size_t)p + 2]) + finalRadiance;
+        output[3 * (size_t)p] = out.x; output[3 * (size_t)p + 1] = out.y; output[3 * (size_t)p + 2] = out.z;
+    }
+    // shadow-ray count for the Mrays/s metric: warp-reduce, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) shadowRays += __shfl_xor_sync(0xffffffffu, shadowRays, o);
+    if ((threadIdx.x & 31) == 0 && shadowRays) atomicAdd(stat, shadowRays);
+}
+
+void launch_ppm_direct_output(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
+                              const float* indirect, float* direct, float* output, unsigned localIteration, unsigned* statCounters, LaunchCtx lc)
+{
+    unsigned n = w * h;
+    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
+    ppm_direct_output_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, w, h, rsW, rng, hp, indirect, direct, output, localIteration,
+                                                                  statCounters + STAT_ANY_RAYS);
+    ++*lc.launches;
+}
+
+} // namespace opr

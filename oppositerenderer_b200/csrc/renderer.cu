@@ -1,0 +1,252 @@
+// renderer.cu — host orchestration of one iteration (the body of OptixRenderer::renderNextIteration,
+// RenderEngine/renderer/OptixRenderer.cpp:507-821) over the wavefront kernels, buffer management
+// (resizeBuffers :828-848) and RNG (re)seeding (OptixRenderer_SpatialHash.cu:319-347).
+#include "renderer.h"
+#include "radix_sort.cuh"
+#include <algorithm>
+#include <cstring>
+
+namespace opr {
+
+void vcm_free(Renderer& r);   // vcm.cu
+
+template <class T> static void dalloc(T*& p, size_t count)
+{
+    OPR_CUDA_CHECK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+}
+template <class T> static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+Renderer::~Renderer()
+{
+    if (device >= 0) cudaSetDevice(device);
+    vcm_free(*this);
+    freeBuffers();
+    dfree(phPower); dfree(phState); dfree(photons.a); dfree(photons.b); dfree(photons.c);
+    dfree(sorted.a); dfree(sorted.b); dfree(sorted.c);
+    dfree(gridKeys[0]); dfree(gridKeys[1]); dfree(gridVals[0]); dfree(gridVals[1]); dfree(gridHist); dfree(sortTmp); dfree(scanTmp);
+    dfree(gridBBox);
+    if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
+    scene.release();
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Renderer::initialize(int cudaOrdinal)
+{
+    if (initialized) throw std::runtime_error("ERROR: Multiple OptixRenderer::initialize!\n");   // OptixRenderer.cpp:115-118
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw std::runtime_error("Did not find a CUDA device: this renderer has no CPU path");
+    if (cudaOrdinal < 0 || cudaOrdinal >= count)
+        throw std::runtime_error("Did not find OptiX device Number for given device. OptiX may not support this device.");   // :427-431 (message kept)
+    device = cudaOrdinal;
+    OPR_CUDA_CHECK(cudaSetDevice(device));
+    OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+    const size_t P = (size_t)photonLaunchWidth * photonLaunchHeight;
+    const size_t N = P * MAX_PHOTON_DEPOSITS;
+    dalloc(phPower, P); dalloc(phState, P);
+    dalloc(photons.a, N); dalloc(photons.b, N); dalloc(photons.c, N);
+    dalloc(sorted.a, N); dalloc(sorted.b, N); dalloc(sorted.c, N);
+    dalloc(gridKeys[0], N); dalloc(gridKeys[1], N); dalloc(gridVals[0], N); dalloc(gridVals[1], N);
+    dalloc(gridHist, (size_t)PHOTON_GRID_MAX_SIZE + 2);
+    dalloc(sortTmp, rs_hist_words((unsigned)N));
+    dalloc(scanTmp, scan_tmp_words(PHOTON_GRID_MAX_SIZE + 2));
+    dalloc(gridBBox, 8);
+    OPR_CUDA_CHECK(cudaMallocHost((void**)&gridBBoxHost, 16 * sizeof(float)));
+    OPR_CUDA_CHECK(cudaMemsetAsync(phState, 0, P * sizeof(unsigned), stream));
+    initialized = true;
+}
+
+void Renderer::initScene(const opr_scene_desc* d)
+{
+    if (!initialized) throw std::runtime_error("Cannot initialize scene before OptixRenderer.");   // :438-441
+    if (!d || d->numLights == 0) throw std::runtime_error("No lights exists in this scene.");     // :443-447
+    OPR_CUDA_CHECK(cudaSetDevice(device));
+    lightVertexCountEstimated = false;
+    scene.load(d, stream);
+    sceneLoaded = true;
+}
+
+void Renderer::freeBuffers()
+{
+    dfree(rng.a); dfree(rng.b); dfree(rng.c);
+    dfree(hp.pos); dfree(hp.nrm); dfree(hp.att); dfree(hp.rad);
+    for (int i = 0; i < 2; i++) { dfree(q.rayO[i]); dfree(q.rayD[i]); dfree(q.rayPath[i]); }
+    dfree(q.hits); dfree(q.matQueue); dfree(q.counters);
+    dfree(indirect); dfree(direct); dfree(output);
+    buffersAllocated = false;
+}
+
+void Renderer::resizeBuffers(unsigned w, unsigned h)
+{   // OptixRenderer.cpp:828-848
+    OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    freeBuffers();
+    const size_t px = (size_t)w * h;
+    rsW = std::max(photonLaunchWidth, w); rsH = std::max(photonLaunchHeight, h);
+    const size_t ns = (size_t)rsW * rsH;
+    dalloc(rng.a, ns); dalloc(rng.b, ns); dalloc(rng.c, ns);
+    dalloc(hp.pos, px); dalloc(hp.nrm, px); dalloc(hp.att, px); dalloc(hp.rad, px);
+    const size_t cap = std::max(px, (size_t)photonLaunchWidth * photonLaunchHeight);
+    q.capacity = (unsigned)cap;
+    for (int i = 0; i < 2; i++) { dalloc(q.rayO[i], cap); dalloc(q.rayD[i], cap); dalloc(q.rayPath[i], cap); }
+    dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, 32);
+    dalloc(indirect, px * 3); dalloc(direct, px * 3); dalloc(output, px * 3);
+    OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, 32 * sizeof(unsigned), stream));
+    OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, px * 3 * sizeof(float), stream));
+    buffersAllocated = true;
+    LaunchCtx lc{stream, &launches};
+    launch_rng_init(rng, seed, ns, lc);    // initializeRandomStates(): every resize re-seeds (:835)
+    width = w; height = h;
+    lightVertexCountEstimated = false;      // :847
+}
+
+struct ScopedTimer {
+    Renderer& r; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+    ScopedTimer(Renderer& r_, const char* n) : r(r_), name(n)
+    {
+        if (!r.timing) return;
+        cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, r.stream);
+    }
+    ~ScopedTimer()
+    {
+        if (!r.timing) return;
+        cudaEventRecord(b, r.stream); cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        r.lastTimings.emplace_back(name, ms);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
+void Renderer::buildPhotonGrid()
+{   // createUniformGridPhotonMap, OptixRenderer_SpatialHash.cu:209-282
+    LaunchCtx lc{stream, &launches};
+    const unsigned P = photonLaunchWidth * photonLaunchHeight;
+    const unsigned N = P * MAX_PHOTON_DEPOSITS;
+    {
+        ScopedTimer t(*this, "grid.bbox");
+        float* h = gridBBoxHost;
+        h[8] = FLT_MAX; h[9] = FLT_MAX; h[10] = FLT_MAX; h[11] = -FLT_MAX; h[12] = -FLT_MAX; h[13] = -FLT_MAX; h[14] = 0.f; h[15] = 0.f;
+        OPR_CUDA_CHECK(cudaMemcpyAsync(gridBBox, h + 8, 7 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        launch_photon_bbox(photons, phState, P, gridBBox, lc);
+        OPR_CUDA_CHECK(cudaMemcpyAsync(h, gridBBox, 7 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        OPR_CUDA_CHECK(cudaStreamSynchronize(stream));   // the reference syncs here too (:222)
+    }
+    unsigned numValid; memcpy(&numValid, gridBBoxHost + 6, 4);
+    float lo[3] = {gridBBoxHost[0], gridBBoxHost[1], gridBBoxHost[2]}, hi[3] = {gridBBoxHost[3], gridBBoxHost[4], gridBBoxHost[5]};
+    if (numValid == 0) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.f; }   // photons[0] is a cleared slot
+    if (!compute_grid_params(lo, hi, grid))
+        throw std::runtime_error("Too many cells in SpatialHash.cu, over defined PHOTON_GRID_MAX_SIZE.");   // :246
+    grid.numValid = numValid;
+    stats[STAT_PHOTONS_STORED] += numValid;
+    {
+        ScopedTimer t(*this, "grid.keys");
+        OPR_CUDA_CHECK(cudaMemsetAsync(gridHist, 0, ((size_t)grid.numCells + 2) * sizeof(unsigned), stream));
+        launch_grid_keys(photons, phState, N, grid, gridKeys[0], gridHist, lc);
+    }
+    bool flipped;
+    {
+        ScopedTimer t(*this, "grid.sort");
+        int bits = 1; while ((1ull << bits) <= (unsigned long long)grid.numCells + 1) bits++;
+        int nl = 0;
+        flipped = radix_sort_pairs<unsigned>(gridKeys[0], gridVals[0], gridKeys[1], gridVals[1], N, bits, sortTmp, true, stream, &nl);
+        launches += nl;
+    }
+    sortedKeys = flipped ? gridKeys[1] : gridKeys[0];
+    const unsigned* sortedSlots = flipped ? gridVals[1] : gridVals[0];
+    {
+        ScopedTimer t(*this, "grid.offsets");
+        exclusive_scan_u32(gridHist, gridHist, grid.numCells + 1, scanTmp, stream);
+        launches += 3;
+    }
+    {
+        ScopedTimer t(*this, "grid.reorder");
+        launch_photon_reorder(photons, sortedSlots, numValid, sorted, lc);
+    }
+}
+
+void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localIterationNumber, float PPMRadius, const opr_request_details& details)
+{
+    LaunchCtx lc{stream, &launches};
+    const SceneView& sc = scene.view;
+    // ---- PPM_RAYTRACE_PASS (:576)
+    {
+        ScopedTimer t(*this, "ppm.camera");
+        unsigned c[2 + NUM_QUEUES + 1] = {0};
+        c[0] = width * height;
+        OPR_CUDA_CHECK(cudaMemcpyAsync(q.counters, c, sizeof(unsigned) * (2 + NUM_QUEUES), cudaMemcpyHostToDevice, stream));
+        launch_ppm_camera_gen(details.camera, width, height, rsW, rng, hp, q, lc);
+        int cur = 0;
+        // depth <= MAX_RADIANCE_TRACE_DEPTH specular continuations + the primary ray
+        for (unsigned bounce = 0; bounce <= MAX_RADIANCE_TRACE_DEPTH; bounce++) {
+            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
+            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
+            launch_trace_closest(sc, q, cur, lc);
+            launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, cur, lc);
+            cur ^= 1;
+        }
+    }
+    const float ppmRadiusSquared = PPMRadius * PPMRadius;   // :585
+    // ---- PPM_PHOTON_PASS (:612)
+    {
+        ScopedTimer t(*this, "ppm.photon");
+        unsigned c[2 + NUM_QUEUES + 1] = {0};
+        c[0] = photonLaunchWidth * photonLaunchHeight;
+        OPR_CUDA_CHECK(cudaMemcpyAsync(q.counters, c, sizeof(unsigned) * (2 + NUM_QUEUES), cudaMemcpyHostToDevice, stream));
+        launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, lc);
+        int cur = 0;
+        for (unsigned bounce = 0; bounce <= MAX_PHOTON_TRACE_DEPTH; bounce++) {
+            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
+            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
+            launch_trace_closest(sc, q, cur, lc);
+            launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, cur, lc);
+            cur ^= 1;
+        }
+    }
+    // ---- createUniformGridPhotonMap (:628)
+    buildPhotonGrid();
+    // ---- PPM_INDIRECT_RADIANCE_ESTIMATION_PASS (:657)
+    {
+        ScopedTimer t(*this, "ppm.gather");
+        launch_gather(hp, width * height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
+                      float(photonLaunchWidth * photonLaunchHeight), indirect, lc);
+    }
+    // ---- PPM_DIRECT_RADIANCE_ESTIMATION_PASS + PPM_OUTPUT_PASS (:664, :670)
+    {
+        ScopedTimer t(*this, "ppm.direct_output");
+        launch_ppm_direct_output(sc, width, height, rsW, rng, hp, indirect, keepDebugBuffers ? direct : nullptr, output, localIterationNumber,
+                                 q.counters + 16, lc);
+    }
+    (void)iterationNumber;
+}
+
+void Renderer::renderNextIteration(unsigned long long iterationNumber, unsigned long long localIterationNumber, float PPMRadius,
+                                   bool /*createOutput — accepted and ignored, as in the reference*/, const opr_request_details& details)
+{
+    if (!initialized) throw std::runtime_error("Traced before OptixRenderer was initialized.");   // :513-516
+    if (!sceneLoaded) throw std::runtime_error("Traced before a scene was initialized.");
+    OPR_CUDA_CHECK(cudaSetDevice(device));
+    if (details.width == 0 || details.height == 0) throw std::runtime_error("zero-sized render request");
+    lastTimings.clear();
+    if (!buffersAllocated || details.width != width || details.height != height) resizeBuffers(details.width, details.height);   // :534-537
+    if (localIterationNumber == 0)                                                                                               // :540-545
+        OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, (size_t)width * height * 3 * sizeof(float), stream));
+
+    if (details.renderMethod == OPR_PROGRESSIVE_PHOTON_MAPPING)
+        renderPPM(iterationNumber, (unsigned)localIterationNumber, PPMRadius, details);
+    else if (details.renderMethod == OPR_VCM_BIDIRECTIONAL_PATH_TRACING)
+        renderVCM(iterationNumber, (unsigned)localIterationNumber, PPMRadius, details);
+    else
+        throw std::runtime_error("RenderMethod not on the accelerated path (PATH_TRACING is out of scope)");
+    OPR_CUDA_CHECK(cudaGetLastError());
+}
+
+void Renderer::getOutputBuffer(void* dst)
+{   // OptixRenderer.cpp:860-865: copies W*H*12 bytes into a caller-owned buffer
+    if (!buffersAllocated) throw std::runtime_error("getOutputBuffer before the first iteration");
+    OPR_CUDA_CHECK(cudaSetDevice(device));
+    OPR_CUDA_CHECK(cudaMemcpyAsync(dst, output, (size_t)width * height * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+} // namespace opr

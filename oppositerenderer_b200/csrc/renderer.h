@@ -1,0 +1,132 @@
+// renderer.h — device buffers and host-side state of the B200 renderer behind the OptixRenderer surface
+// (RenderEngine/renderer/OptixRenderer.h:21-115).  Buffer roles follow SURVEY.md Appendix C; layouts are
+// SoA / 16-byte vectors instead of the reference's AoS user-format buffers.
+#pragma once
+#include "device_scene.h"
+#include <string>
+#include <vector>
+
+namespace opr {
+
+constexpr int NUM_QUEUES = 7;     // six material kinds + miss
+constexpr int QUEUE_MISS = 6;
+
+// Wavefront ray queue state (all device pointers)
+struct RayQueues {
+    float4* rayO[2];        // origin.xyz, tmin
+    float4* rayD[2];        // direction.xyz, tmax
+    unsigned* rayPath[2];   // owning path (pixel / photon thread / subpath) of each ray slot
+    float4* hits;           // HitRec per ray slot of the current queue
+    unsigned* matQueue;     // NUM_QUEUES x capacity ray-slot indices, bucketed by material kind
+    unsigned* counters;     // [0],[1] ray counts (ping-pong); [2..2+NUM_QUEUES) material queue counts; [16..] stats
+    unsigned capacity;
+};
+
+struct HitpointBuf {        // raytracePassOutputBuffer (Hitpoint.h:10-18) as four float4 arrays, 64 B/pixel
+    float4* pos;            // position.xyz, flags (uint bits)
+    float4* nrm;            // normal.xyz, depth (uint bits)
+    float4* att;            // attenuation.xyz
+    float4* rad;            // radiance.xyz
+};
+
+struct PhotonBuf {          // `photons` (ppm/Photon.h:10-33, 36 B) as three arrays; slot = 4*thread + k
+    float4* a;              // position.xyz, rayDirection.x
+    float4* b;              // power.xyz, rayDirection.y
+    float* c;               // rayDirection.z
+};
+
+struct GridParams { float cellSize; uint3 gridSize; float3 origo; unsigned numCells; unsigned numValid; };
+
+enum StatSlot { STAT_CLOSEST_RAYS = 0, STAT_ANY_RAYS = 1, STAT_PHOTONS_STORED = 2, STAT_NUM = 8 };
+
+struct Renderer {
+    // configuration (runtime versions of OptixRenderer.cpp:44-53 / config.h:50)
+    unsigned photonLaunchWidth = 1024, photonLaunchHeight = 1024;
+    unsigned vcmMaxPathLength = 10;
+    unsigned seed = 1645301512u;
+
+    bool initialized = false, sceneLoaded = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    DeviceScene scene;
+
+    unsigned width = 10, height = 10;     // OptixRenderer.cpp:84-85: the first request always resizes
+    bool buffersAllocated = false;
+    unsigned rsW = 0, rsH = 0;
+    RngBuf rng{};
+    HitpointBuf hp{};
+    RayQueues q{};
+    // photon pass
+    float4* phPower = nullptr;            // power.xyz, weight   (PhotonPRD.h:11-12)
+    unsigned* phState = nullptr;          // depth | numStored << 8
+    PhotonBuf photons{};                  // 4*P slots
+    // photon grid
+    unsigned* gridKeys[2] = {nullptr, nullptr};
+    unsigned* gridVals[2] = {nullptr, nullptr};
+    unsigned* gridHist = nullptr;         // PHOTON_GRID_MAX_SIZE + 2 entries: histogram, then offsets in place
+    unsigned* sortTmp = nullptr;
+    unsigned* scanTmp = nullptr;
+    float* gridBBox = nullptr;            // device: 6 ordered-int floats + valid count
+    float* gridBBoxHost = nullptr;        // pinned
+    PhotonBuf sorted{};                   // compacted + sorted photons
+    unsigned* sortedKeys = nullptr;       // alias of gridKeys[x] after the sort
+    GridParams grid{};
+    // radiance
+    float* indirect = nullptr;            // float3 per pixel
+    float* direct = nullptr;
+    float* output = nullptr;              // running sum, float3 per pixel == reference outputBuffer
+    bool keepDebugBuffers = true;
+
+    // VCM state lives in vcm.cu
+    struct VcmState* vcm = nullptr;
+    bool lightVertexCountEstimated = false;
+
+    // statistics / timing
+    unsigned long long stats[STAT_NUM] = {0};
+    unsigned long long launches = 0;
+    bool timing = false;
+    std::vector<std::pair<std::string, float>> lastTimings;
+    std::string lastError;
+
+    ~Renderer();
+    void initialize(int cudaOrdinal);
+    void initScene(const opr_scene_desc* d);
+    void resizeBuffers(unsigned w, unsigned h);
+    void freeBuffers();
+    void renderNextIteration(unsigned long long iterationNumber, unsigned long long localIterationNumber, float PPMRadius,
+                             bool createOutput, const opr_request_details& details);
+    void renderPPM(unsigned long long iterationNumber, unsigned localIterationNumber, float PPMRadius, const opr_request_details& details);
+    void renderVCM(unsigned long long iterationNumber, unsigned localIterationNumber, float PPMRadius, const opr_request_details& details);
+    void buildPhotonGrid();
+    void getOutputBuffer(void* dst);
+};
+
+// ---- kernel launchers (ppm.cu, trace.cu, grid.cu) -------------------------------------------------------
+struct LaunchCtx { cudaStream_t st; unsigned long long* launches; };
+
+void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc);
+void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc);
+void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, float4* hits, LaunchCtx lc);
+void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, int* occluded, LaunchCtx lc);
+
+void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
+                           const RayQueues& q, LaunchCtx lc);
+void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
+                             const RayQueues& q, int cur, LaunchCtx lc);
+void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsigned rsW, const RngBuf& rng, float4* phPower,
+                           unsigned* phState, const RayQueues& q, LaunchCtx lc);
+void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
+                             const PhotonBuf& photons, const RayQueues& q, int cur, LaunchCtx lc);
+void launch_ppm_direct_output(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
+                              const float* indirect, float* direct, float* output, unsigned localIteration, unsigned* statCounters, LaunchCtx lc);
+
+void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc);
+void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, GridParams g, unsigned* keys, unsigned* hist, LaunchCtx lc);
+void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned numValid, const PhotonBuf& dst, LaunchCtx lc);
+void launch_gather(const HitpointBuf& hp, unsigned numPixels, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
+                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, LaunchCtx lc);
+
+// host-side restatement of createUniformGridPhotonMap's scalar part (OptixRenderer_SpatialHash.cu:209-250)
+bool compute_grid_params(const float lo[3], const float hi[3], GridParams& g);
+
+} // namespace opr

@@ -1,0 +1,350 @@
+// scene.cu — scene upload and the GPU LBVH build (Morton codes -> stable radix sort -> Karras hierarchy
+// -> bottom-up refit that emits the 64-byte traversal nodes).  Replaces the OptiX "Trbvh"/"Bvh"/"NoAccel"
+// builders the reference requests in scene/Scene.cpp:353,513,547 and scene/Cornell.cpp:183,188.
+#include "device_scene.h"
+#include "radix_sort.cuh"
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+
+namespace opr {
+
+// ---- build kernels ---------------------------------------------------------------------------------------
+struct BuildPrim { float4 lo; float4 hi; };   // w of lo = leaf ref bits
+
+__device__ __forceinline__ unsigned long long expandBits21(unsigned v)
+{
+    unsigned long long x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void bvh_morton_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, unsigned n,
+                                  float3 cmin, float3 cinv, unsigned long long* __restrict__ keys)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = lo[i], b = hi[i];
+    float cx = ((a.x + b.x) * 0.5f - cmin.x) * cinv.x;
+    float cy = ((a.y + b.y) * 0.5f - cmin.y) * cinv.y;
+    float cz = ((a.z + b.z) * 0.5f - cmin.z) * cinv.z;
+    unsigned ix = (unsigned)fminf(fmaxf(cx * 2097152.0f, 0.0f), 2097151.0f);
+    unsigned iy = (unsigned)fminf(fmaxf(cy * 2097152.0f, 0.0f), 2097151.0f);
+    unsigned iz = (unsigned)fminf(fmaxf(cz * 2097152.0f, 0.0f), 2097151.0f);
+    keys[i] = (expandBits21(ix) << 2) | (expandBits21(iy) << 1) | expandBits21(iz);
+}
+
+__device__ __forceinline__ int lbvh_delta(const unsigned long long* keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((unsigned)i ^ (unsigned)j);
+    return __clzll((long long)(a ^ b));
+}
+
+// Karras 2012: one thread per internal node i in [0, n-1)
+__global__ void bvh_karras_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ childL, int* __restrict__ childR,
+                                  int* __restrict__ nodeParent, int* __restrict__ leafParent)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    // child encoding here: >= 0 internal, < 0 : ~leafSortedIndex
+    int left = (lo == gamma) ? ~gamma : gamma;
+    int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    childL[i] = left; childR[i] = right;
+    if (left >= 0) nodeParent[left] = i; else leafParent[~left] = i;
+    if (right >= 0) nodeParent[right] = i; else leafParent[~right] = i;
+    if (i == 0) nodeParent[0] = -1;
+}
+
+// Bottom-up refit.  boxLo/boxHi: [0,n-1) internal, [n-1, 2n-1) leaves in sorted order.
+__global__ void bvh_refit_kernel(const unsigned* __restrict__ sortedPrim, const float4* __restrict__ primLo, const float4* __restrict__ primHi,
+                                 int n, const int* __restrict__ childL, const int* __restrict__ childR,
+                                 const int* __restrict__ nodeParent, const int* __restrict__ leafParent,
+                                 float4* __restrict__ boxLo, float4* __restrict__ boxHi, unsigned* __restrict__ flags,
+                                 float4* __restrict__ nodes)
+{
+    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    unsigned p = sortedPrim[leaf];
+    boxLo[n - 1 + leaf] = primLo[p];
+    boxHi[n - 1 + leaf] = primHi[p];
+    __threadfence();
+    int cur = leafParent[leaf];
+    while (cur >= 0) {
+        if (atomicAdd(&flags[cur], 1u) == 0u) return;   // first arrival: the sibling subtree is not done yet
+        __threadfence();
+        int l = childL[cur], r = childR[cur];
+        int li = l >= 0 ? l : (n - 1 + ~l), ri = r >= 0 ? r : (n - 1 + ~r);
+        volatile float4* vlo = boxLo; volatile float4* vhi = boxHi;
+        float4 llo, lhi, rlo, rhi;
+        llo.x = vlo[li].x; llo.y = vlo[li].y; llo.z = vlo[li].z; llo.w = vlo[li].w;
+        lhi.x = vhi[li].x; lhi.y = vhi[li].y; lhi.z = vhi[li].z;
+        rlo.x = vlo[ri].x; rlo.y = vlo[ri].y; rlo.z = vlo[ri].z; rlo.w = vlo[ri].w;
+        rhi.x = vhi[ri].x; rhi.y = vhi[ri].y; rhi.z = vhi[ri].z;
+        // leaf boxes carry the (negative) leaf reference ~((index << 2) | type) in lo.w
+        int lref = l >= 0 ? l : __float_as_int(llo.w);
+        int rref = r >= 0 ? r : __float_as_int(rlo.w);
+        nodes[4 * cur + 0] = make_float4(llo.x, lhi.x, llo.y, lhi.y);
+        nodes[4 * cur + 1] = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
+        nodes[4 * cur + 2] = make_float4(llo.z, lhi.z, rlo.z, rhi.z);
+        nodes[4 * cur + 3] = make_float4(__int_as_float(lref), __int_as_float(rref), 0.f, 0.f);
+        boxLo[cur] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
+        boxHi[cur] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+        __threadfence();
+        cur = nodeParent[cur];
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+template <class T> static T* upload(const std::vector<T>& v, std::vector<void*>& owned)
+{
+    T* d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    OPR_CUDA_CHECK(cudaMalloc(&d, bytes));
+    if (!v.empty()) OPR_CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    owned.push_back(d);
+    return d;
+}
+
+static inline float3 h3(const float* p) { return make_float3(p[0], p[1], p[2]); }
+
+DeviceScene::~DeviceScene() { release(); }
+
+void DeviceScene::release()
+{
+    for (void* p : owned) cudaFree(p);
+    owned.clear();
+    for (auto t : texObjects) cudaDestroyTextureObject(t);
+    texObjects.clear();
+    for (auto a : texArrays) cudaFreeArray(a);
+    texArrays.clear();
+    memset(&view, 0, sizeof view);
+}
+
+void DeviceScene::load(const opr_scene_desc* d, cudaStream_t st)
+{
+    release();
+    if (d->numLights <= 0) throw std::runtime_error("No lights exists in this scene.");   // OptixRenderer.cpp:443-447
+
+    // ---- textures (material/Texture.cpp:109-130): RGBA8, wrap repeat, bilinear, normalised float reads
+    std::vector<cudaTextureObject_t> tex(d->numTextures);
+    for (int i = 0; i < d->numTextures; i++) {
+        const opr_texture& t = d->textures[i];
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr;
+        OPR_CUDA_CHECK(cudaMallocArray(&arr, &cd, t.width, t.height));
+        OPR_CUDA_CHECK(cudaMemcpy2DToArray(arr, 0, 0, t.rgba, (size_t)t.width * 4, (size_t)t.width * 4, t.height, cudaMemcpyHostToDevice));
+        texArrays.push_back(arr);
+        cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+        cudaTextureDesc td; memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 1;
+        OPR_CUDA_CHECK(cudaCreateTextureObject(&tex[i], &rd, &td, nullptr));
+        texObjects.push_back(tex[i]);
+    }
+
+    // ---- materials (values of registerGeometryInstanceValues, see include/opr_scene.h)
+    std::vector<DMaterial> mats(d->numMaterials);
+    for (int i = 0; i < d->numMaterials; i++) {
+        const opr_material& m = d->materials[i];
+        DMaterial& o = mats[i]; memset(&o, 0, sizeof o);
+        o.kind = m.kind;
+        o.Kd = h3(m.Kd); o.Ks = h3(m.Ks); o.exponent = m.exponent; o.Kr = h3(m.Kr); o.Kt = h3(m.Kt); o.ior = m.indexOfRefraction;
+        float3 ppa = h3(m.power); ppa.x *= m.inverseArea; ppa.y *= m.inverseArea; ppa.z *= m.inverseArea;   // DiffuseEmitter.cpp:52-56
+        o.powerPerArea = ppa;
+        o.Lemit = make_float3(m.power[0] * m.inverseArea * INV_PI_F, m.power[1] * m.inverseArea * INV_PI_F, m.power[2] * m.inverseArea * INV_PI_F);   // :61
+        o.inverseArea = m.inverseArea;
+        if (m.kind == OPR_MAT_TEXTURE) {
+            if (m.diffuseTexture < 0 || m.diffuseTexture >= d->numTextures) throw std::runtime_error("Texture material without a diffuse texture");
+            o.diffuseTex = tex[m.diffuseTexture];
+            o.hasNormalTex = (m.normalTexture >= 0);
+            if (o.hasNormalTex) o.normalTex = tex[m.normalTexture];
+        }
+    }
+
+    // ---- primitives.  Degenerate ones are dropped exactly as the bounds programs invalidate them
+    // (TriangleMesh.cu:105-117, parallelogram.cu:89-97).
+    std::vector<float4> triRec, pgramRec, sphereRec, vN, vT, vB;
+    std::vector<int4> triShade;
+    std::vector<float2> vUV;
+    std::vector<int> pgramMat, sphereMat;
+    std::vector<float4> primLo, primHi;
+    size_t totalV = 0;
+    for (int m = 0; m < d->numMeshes; m++) totalV += d->meshes[m].numVertices;
+    vN.assign(std::max<size_t>(totalV, 1), make_float4(0, 0, 0, 0)); vT = vN; vB = vN;
+    vUV.assign(std::max<size_t>(totalV, 1), make_float2(0, 0));
+    auto addPrim = [&](float3 lo, float3 hi, int ref) {
+        // conservative inflation: the fp32 slab test must never cull a box whose primitive test would pass
+        float3 ext = make_float3(hi.x - lo.x, hi.y - lo.y, hi.z - lo.z);
+        float scale = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+        float eps = 4e-6f * fmaxf(scale, fmaxf(ext.x, fmaxf(ext.y, ext.z))) + 1e-30f;
+        primLo.push_back(make_float4(lo.x - eps, lo.y - eps, lo.z - eps, __builtin_bit_cast(float, ~ref)));
+        primHi.push_back(make_float4(hi.x + eps, hi.y + eps, hi.z + eps, 0.f));
+    };
+    size_t vbase = 0;
+    for (int m = 0; m < d->numMeshes; m++) {
+        const opr_mesh& me = d->meshes[m];
+        int flags = (me.normals ? TRI_HAS_NORMALS : 0) | (me.uvs ? TRI_HAS_UVS : 0) | ((me.normals && me.tangents && me.bitangents) ? TRI_HAS_TANGENTS : 0);
+        for (int v = 0; v < me.numVertices; v++) {
+            if (me.normals) vN[vbase + v] = make_float4(me.normals[3 * v], me.normals[3 * v + 1], me.normals[3 * v + 2], 0);
+            if (me.uvs) vUV[vbase + v] = make_float2(me.uvs[2 * v], me.uvs[2 * v + 1]);
+            if (flags & TRI_HAS_TANGENTS) {
+                vT[vbase + v] = make_float4(me.tangents[3 * v], me.tangents[3 * v + 1], me.tangents[3 * v + 2], 0);
+                vB[vbase + v] = make_float4(me.bitangents[3 * v], me.bitangents[3 * v + 1], me.bitangents[3 * v + 2], 0);
+            }
+        }
+        for (int t = 0; t < me.numTriangles; t++) {
+            const int i0 = me.indices[3 * t], i1 = me.indices[3 * t + 1], i2 = me.indices[3 * t + 2];
+            const float3 p0 = h3(me.vertices + 3 * i0), p1 = h3(me.vertices + 3 * i1), p2 = h3(me.vertices + 3 * i2);
+            const float3 a = p1 - p0, b = p2 - p0;
+            const float area = length(cross(a, b));
+            if (!(area > 0.0f) || std::isinf(area)) continue;
+            const float3 e0 = p1 - p0, e1 = p0 - p2;
+            const float3 n = cross(e1, e0);
+            int idx = (int)triShade.size();
+            triRec.push_back(make_float4(p0.x, p0.y, p0.z, e0.x));
+            triRec.push_back(make_float4(e0.y, e0.z, e1.x, e1.y));
+            triRec.push_back(make_float4(e1.z, n.x, n.y, n.z));
+            triShade.push_back(make_int4((int)vbase + i0, (int)vbase + i1, (int)vbase + i2, me.material | (flags << 24)));
+            addPrim(fmin3(fmin3(p0, p1), p2), fmax3(fmax3(p0, p1), p2), (idx << 2) | PRIM_TRIANGLE);
+        }
+        vbase += me.numVertices;
+    }
+    for (int i = 0; i < d->numParallelograms; i++) {
+        // Cornell::createParallelogram, scene/Cornell.cpp:46-58
+        const opr_parallelogram& s = d->parallelograms[i];
+        const float3 anchor = h3(s.anchor), o1 = h3(s.offset1), o2 = h3(s.offset2);
+        const float3 normal = normalize(cross(o1, o2));
+        const float dd = dot(normal, anchor);
+        const float3 v1 = o1 / dot(o1, o1), v2 = o2 / dot(o2, o2);
+        const float3 tv1 = v1 / dot(v1, v1), tv2 = v2 / dot(v2, v2);     // bounds program rescales back
+        const float area = length(cross(tv1, tv2));
+        if (!(area > 0.0f) || std::isinf(area)) continue;
+        int idx = (int)pgramMat.size();
+        pgramRec.push_back(make_float4(normal.x, normal.y, normal.z, dd));
+        pgramRec.push_back(make_float4(v1.x, v1.y, v1.z, 0.f));
+        pgramRec.push_back(make_float4(v2.x, v2.y, v2.z, 0.f));
+        pgramRec.push_back(make_float4(anchor.x, anchor.y, anchor.z, 0.f));
+        pgramMat.push_back(s.material);
+        const float3 p00 = anchor, p01 = anchor + tv1, p10 = anchor + tv2, p11 = anchor + tv1 + tv2;
+        addPrim(fmin3(fmin3(p00, p01), fmin3(p10, p11)), fmax3(fmax3(p00, p01), fmax3(p10, p11)), (idx << 2) | PRIM_PARALLELOGRAM);
+    }
+    for (int i = 0; i < d->numSpheres; i++) {
+        const opr_sphere& s = d->spheres[i];
+        int idx = (int)sphereMat.size();
+        sphereRec.push_back(make_float4(s.center[0], s.center[1], s.center[2], s.radius));
+        sphereMat.push_back(s.material);
+        const float3 c = h3(s.center);
+        addPrim(c - f3(s.radius), c + f3(s.radius), (idx << 2) | PRIM_SPHERE);
+    }
+    numTriangles = (unsigned)triShade.size();
+    numPrims = (unsigned)primLo.size();
+    if (numPrims == 0) throw std::runtime_error("scene has no intersectable geometry");
+
+    view.triRec = upload(triRec, owned); view.triShade = upload(triShade, owned);
+    view.pgramRec = upload(pgramRec, owned); view.pgramMat = upload(pgramMat, owned);
+    view.sphereRec = upload(sphereRec, owned); view.sphereMat = upload(sphereMat, owned);
+    view.vNormal = upload(vN, owned); view.vUV = upload(vUV, owned); view.vTangent = upload(vT, owned); view.vBitangent = upload(vB, owned);
+    view.materials = upload(mats, owned);
+    std::vector<opr_light> lights(d->lights, d->lights + d->numLights);
+    view.lights = upload(lights, owned);
+    view.numLights = d->numLights;
+    hostLights = lights;
+
+    // sceneBoundingSphere: AAB::getBoundingSphere (math/AAB.cpp:31-38) through Vector3::dot, which
+    // multiplies a.z*b.x (math/Vector3.cpp:30-33).  Kept: it feeds point-light emission.
+    {
+        float3 mn = h3(d->aabbMin), mx = h3(d->aabbMax);
+        float3 center = (mn + mx) * 0.5f;
+        float3 dd = mx - center;
+        float dotbug = dd.x * dd.x + dd.y * dd.y + dd.z * dd.x;
+        view.boundingSphere.center = center;
+        view.boundingSphere.radius = sqrtf(dotbug);
+        aabbMin = mn; aabbMax = mx;
+    }
+
+    buildBvh(primLo, primHi, st);
+}
+
+void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<float4>& primHi, cudaStream_t st)
+{
+    const int n = (int)primLo.size();
+    if (n == 1) {   // a single leaf: the root reference is the leaf itself
+        float4* nodes = nullptr;
+        OPR_CUDA_CHECK(cudaMalloc(&nodes, 64)); owned.push_back(nodes);
+        view.nodes = nodes;
+        view.rootRef = __builtin_bit_cast(int, primLo[0].w);
+        numNodes = 0;
+        return;
+    }
+    // centroid bounds on the host (n is known here and this is a one-off per scene)
+    float3 cmin = f3(FLT_MAX), cmax = f3(-FLT_MAX);
+    for (int i = 0; i < n; i++) {
+        float3 c = f3((primLo[i].x + primHi[i].x) * 0.5f, (primLo[i].y + primHi[i].y) * 0.5f, (primLo[i].z + primHi[i].z) * 0.5f);
+        cmin = fmin3(cmin, c); cmax = fmax3(cmax, c);
+    }
+    float3 ext = cmax - cmin;
+    float3 cinv = f3(ext.x > 0 ? 1.0f / ext.x : 0.f, ext.y > 0 ? 1.0f / ext.y : 0.f, ext.z > 0 ? 1.0f / ext.z : 0.f);
+
+    std::vector<void*> tmp;
+    auto dalloc = [&](size_t bytes) { void* p; OPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); tmp.push_back(p); return p; };
+    float4* dLo = (float4*)dalloc(sizeof(float4) * n);
+    float4* dHi = (float4*)dalloc(sizeof(float4) * n);
+    OPR_CUDA_CHECK(cudaMemcpyAsync(dLo, primLo.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, st));
+    OPR_CUDA_CHECK(cudaMemcpyAsync(dHi, primHi.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, st));
+    unsigned long long* keys = (unsigned long long*)dalloc(8 * (size_t)n);
+    unsigned long long* keysAlt = (unsigned long long*)dalloc(8 * (size_t)n);
+    unsigned* vals = (unsigned*)dalloc(4 * (size_t)n);
+    unsigned* valsAlt = (unsigned*)dalloc(4 * (size_t)n);
+    unsigned* hist = (unsigned*)dalloc(4 * rs_hist_words(n));
+    const int T = 256, B = (n + T - 1) / T;
+    bvh_morton_kernel<<<B, T, 0, st>>>(dLo, dHi, n, cmin, cinv, keys);
+    bool flipped = radix_sort_pairs<unsigned long long>(keys, vals, keysAlt, valsAlt, n, 64, hist, true, st);
+    unsigned long long* sk = flipped ? keysAlt : keys;
+    unsigned* sv = flipped ? valsAlt : vals;
+
+    int* childL = (int*)dalloc(4 * (size_t)n); int* childR = (int*)dalloc(4 * (size_t)n);
+    int* nodeParent = (int*)dalloc(4 * (size_t)n); int* leafParent = (int*)dalloc(4 * (size_t)n);
+    float4* boxLo = (float4*)dalloc(sizeof(float4) * (2 * (size_t)n)); float4* boxHi = (float4*)dalloc(sizeof(float4) * (2 * (size_t)n));
+    unsigned* flags = (unsigned*)dalloc(4 * (size_t)n);
+    OPR_CUDA_CHECK(cudaMemsetAsync(flags, 0, 4 * (size_t)n, st));
+    float4* nodes = nullptr;
+    OPR_CUDA_CHECK(cudaMalloc(&nodes, 64 * (size_t)(n - 1))); owned.push_back(nodes);
+    bvh_karras_kernel<<<B, T, 0, st>>>(sk, n, childL, childR, nodeParent, leafParent);
+    bvh_refit_kernel<<<B, T, 0, st>>>(sv, dLo, dHi, n, childL, childR, nodeParent, leafParent, boxLo, boxHi, flags, nodes);
+    OPR_CUDA_CHECK(cudaStreamSynchronize(st));
+    OPR_CUDA_CHECK(cudaGetLastError());
+    for (void* p : tmp) cudaFree(p);
+    view.nodes = nodes;
+    view.rootRef = 0;
+    numNodes = n - 1;
+}
+
+} // namespace opr

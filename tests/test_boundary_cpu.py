@@ -1,0 +1,113 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol the headers
+declare, fails loudly on compute calls without a device, and its host-side helpers (Camera, Light, built-in
+scenes, radius schedule) agree with the oracle's independent restatement of the same reference code."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oppositerenderer_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "opr.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(opr_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(product):
+    lib = capi.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), "include/opr.h declares %s but the library does not export it" % s
+
+
+def test_no_cpu_fallback(product):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = product.OptixRenderer()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r.initialize(product.ComputeDevice(0))
+    lib = capi.load_library()
+    st = (C.c_uint32 * 6)()
+    assert lib.opr_rng_init(st, 1, 0, 1) != 0
+    assert b"no CPU path" in lib.opr_last_error()
+
+
+def test_state_rules(product):
+    # OptixRenderer.cpp:438-441 / :513-516: initScene and renderNextIteration require initialize()
+    r = product.OptixRenderer()
+    scene = product.Cornell()
+    with pytest.raises(RuntimeError, match="Cannot initialize scene before OptixRenderer"):
+        r.initScene(scene)
+    det = product.RenderServerRenderRequestDetails(scene.getDefaultCamera(), "Cornell", product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, 8, 8, 2 / 3)
+    with pytest.raises(RuntimeError, match="Traced before OptixRenderer was initialized"):
+        r.renderNextIteration(0, 0, 1.0, True, det)
+
+
+def _bytes(x):
+    return bytes(memoryview(x).cast("B"))
+
+
+@pytest.mark.parametrize("name,config", [("Cornell", 0), ("CornellSmall", 0), ("CornellSmall", (1 << 0) | (1 << 1) | (1 << 9)),
+                                         ("CornellSmall", (1 << 3) | (1 << 7) | (1 << 11)), ("CornellSmall", (1 << 5) | (1 << 8) | (1 << 12) | (1 << 13)),
+                                         ("CornellSmall", (1 << 2) | (1 << 6) | (1 << 10))])
+def test_builtin_scene_tables_match_oracle(product, oracle, name, config):
+    lib = capi.load_library()
+    h = lib.opr_builtin_scene_create(name.encode(), config)
+    a = lib.opr_builtin_scene_desc(h).contents
+    osc = oracle.BuiltinScene(name, config)
+    b = osc.desc.contents
+    assert (a.numParallelograms, a.numSpheres, a.numMaterials, a.numLights) == (b.numParallelograms, b.numSpheres, b.numMaterials, b.numLights)
+    assert list(a.aabbMin) == list(b.aabbMin) and list(a.aabbMax) == list(b.aabbMax)
+    for i in range(a.numLights):
+        assert _bytes(a.lights[i]) == _bytes(b.lights[i])
+
+    def resolved(d, i):  # geometry with its material record (material ids may be numbered differently)
+        p = d.parallelograms[i]
+        return _bytes(p)[:36], _bytes(d.materials[p.material])
+
+    assert [resolved(a, i) for i in range(a.numParallelograms)] == [resolved(b, i) for i in range(b.numParallelograms)]
+    for i in range(a.numSpheres):
+        assert _bytes(a.spheres[i])[:16] == _bytes(b.spheres[i])[:16]
+        assert _bytes(a.materials[a.spheres[i].material]) == _bytes(b.materials[b.spheres[i].material])
+    ca, cb = capi.opr_camera(), osc.camera()
+    lib.opr_builtin_scene_camera(h, C.byref(ca))
+    assert _bytes(ca) == _bytes(cb)
+    lib.opr_builtin_scene_destroy(h)
+
+
+def test_camera_aspect_ratio_and_radius(product, oracle):
+    lib, olib = capi.load_library(), oracle.load("oracle")
+    for ratio in (1.0, 16 / 9, 0.5):
+        for mode in (0, 1, 2):
+            a = product.Camera((1.25, 1.25, -2.85), (1.25, 1.25, 0), (0, 1, 0), 45, 45, 0.1, mode).pod
+            b = capi.opr_camera.from_buffer_copy(_bytes(a))
+            lib.opr_camera_set_aspect_ratio(C.byref(a), ratio)
+            olib.ora_camera_set_aspect_ratio(C.byref(b), ratio)
+            assert _bytes(a) == _bytes(b)
+    mn, mx = (C.c_float * 3)(-5, -5, -5), (C.c_float * 3)(561, 553.85, 564.2)
+    assert lib.opr_initial_ppm_radius(mn, mx) == olib.ora_initial_ppm_radius(mn, mx)
+    r0 = 7.5
+    sched = oracle.ppm_radius_schedule(r0, 40)
+    for i in (0, 1, 7, 39):
+        assert lib.opr_ppm_radius_for_iteration(r0, i, 2.0 / 3.0) == sched[i]
+
+
+def test_light_constructors(product, oracle):
+    olib = oracle.load("oracle")
+    a = product.Light((0.5e6, 0.4e6, 0.2e6), (343.0, 548.7999, 227.0), (0, 0, 105.0), (-130.0, 0, 0)).pod
+    b = capi.opr_light()
+    f3 = lambda *v: (C.c_float * 3)(*v)
+    olib.ora_make_area_light(C.byref(b), f3(0.5e6, 0.4e6, 0.2e6), f3(343.0, 548.7999, 227.0), f3(0, 0, 105.0), f3(-130.0, 0, 0))
+    assert _bytes(a) == _bytes(b)
+    assert list(a.normal) == [0.0, -1.0, 0.0] or np.allclose(list(a.normal), [0, -1, 0])
+    a = product.Light((30, 30, 30), (1.25, 2.25, 1.25)).pod
+    olib.ora_make_point_light(C.byref(b), f3(30, 30, 30), f3(1.25, 2.25, 1.25))
+    assert _bytes(a) == _bytes(b)

@@ -1,0 +1,191 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Integer/index results (RNG words, photon cell keys, sorted order, offset table) must be
+bit-exact; float images must match per pixel within rel 1e-3 + abs 1e-5 on identical paths, for at least the
+stated fraction of pixels (the remainder are paths that diverged at a discrete decision — Russian roulette,
+Fresnel choice, cell boundary — because sinf/cosf/expf differ by ulps between CUDA and glibc)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import util
+from oppositerenderer_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-5
+
+
+def test_rng_bit_exact(product, oracle):
+    lib, olib = capi.load_library(), oracle.load("oracle")
+    n = 4096
+    for first in (0, 1920 * 1080 - 100, 0xfffffff0):
+        a, b = np.zeros(6 * n, np.uint32), np.zeros(6 * n, np.uint32)
+        assert lib.opr_rng_init(ol.uptr(a), util.SEED, first, n) == 0, lib.opr_last_error()
+        olib.ora_rng_init(ol.uptr(b), util.SEED, first, n)
+        assert (a == b).all()
+    st_a, st_b = a[:6].copy(), b[:6].copy()
+    ua, ub = np.zeros(1000, np.float32), np.zeros(1000, np.float32)
+    assert lib.opr_rng_uniform(ol.uptr(st_a), ol.fptr(ua), 1000) == 0
+    olib.ora_rng_uniform(ol.uptr(st_b), ol.fptr(ub), 1000)
+    assert (ua.view(np.uint32) == ub.view(np.uint32)).all() and (st_a == st_b).all()
+
+
+@pytest.mark.parametrize("n,seed,invalid", [(1, 11, 0.0), (3, 12, 0.5), (4096, 13, 0.4), (100000, 14, 0.4), (4 * 316 * 316, 15, 0.55),
+                                            (5000, 16, 1.1), (70000, 17, 0.0)])
+def test_photon_grid_bit_exact(product, oracle, n, seed, invalid):
+    """createUniformGridPhotonMap: cell size, grid size, origin, cell keys, sorted photon order and the offset
+    table are bit-identical to the reference logic on the same photons (empty, ragged, all-invalid included)."""
+    ph = util.synthetic_photons(n, seed, invalid_fraction=invalid)
+    o = util.oracle_grid(ph)
+    p = util.product_grid(ph)
+    assert p["rc"] == o["rc"] == 0
+    assert p["cellSize"].view(np.uint32) == o["cellSize"].view(np.uint32)
+    assert p["gridSize"] == o["gridSize"]
+    assert (p["origo"].view(np.uint32) == o["origo"].view(np.uint32)).all()
+    assert p["numValid"] == o["numValid"]
+    assert (p["keys"] == o["keys"]).all()
+    assert (p["offsets"] == o["offsets"]).all()
+    nv = o["numValid"]
+    assert (p["photons"][:nv].view(np.uint32) == o["photons"][:nv].view(np.uint32)).all()
+
+
+def test_photon_grid_full_size_properties(product):
+    """BASELINE size (4 x 1024 x 1024 slots): size-independent properties — sortedness, permutation (checksum of
+    checksums), offsets consistent with keys."""
+    n = 4 * 1024 * 1024
+    ph = util.synthetic_photons(n, 21, extent=(3000.0, 1200.0, 1500.0))
+    p = util.product_grid(ph)
+    assert p["rc"] == 0
+    nv = p["numValid"]
+    valid = ph["power"].max(axis=1) > 0
+    assert nv == valid.sum()
+    k = p["keys"].astype(np.int64)
+    assert (np.diff(k) >= 0).all()
+    ncell = p["gridSize"][0] * p["gridSize"][1] * p["gridSize"][2]
+    assert (np.diff(p["offsets"].astype(np.int64)) == np.bincount(k[:nv], minlength=ncell)[:ncell]).all()
+    a = np.sort(ph[valid].view(np.uint32).reshape(-1, 9).astype(np.uint64).sum(axis=1))
+    b = np.sort(p["photons"][:nv].view(np.uint32).reshape(-1, 9).astype(np.uint64).sum(axis=1))
+    assert (a == b).all()
+
+
+def _renderers(product, oracle, scene_name, config, size, pl, maxlen=10):
+    scene = product.Cornell() if scene_name == "Cornell" else product.CornellSmall(config)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(1.0)
+    r = product.OptixRenderer(photon_launch=pl, vcm_max_path_length=maxlen, seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    o = oracle.OracleRenderer("oracle", pl, maxlen, util.SEED)
+    osc = oracle.BuiltinScene(scene_name, config or 0)
+    o.init_scene(osc.desc)
+    return scene, cam, r, o, osc
+
+
+@pytest.mark.parametrize("scene_name,config", [("Cornell", 0), ("CornellSmall", 0), ("CornellSmall", (1 << 1) | (1 << 7) | (1 << 11)),
+                                               ("CornellSmall", (1 << 3) | (1 << 12) | (1 << 13))])
+def test_traversal_matches_oracle(product, oracle, scene_name, config):
+    """Closest-hit (t, material, geometric normal) and any-hit against the oracle's CPU BVH, ray by ray."""
+    scene, cam, r, o, osc = _renderers(product, oracle, scene_name, config, 64, (16, 16))
+    rng = np.random.default_rng(5)
+    mn, mx = scene.getSceneAABB()
+    rays = np.concatenate([util.camera_rays(cam.pod, 96, 96, rng), util.random_rays_in_box(20000, mn, mx, rng)])
+    t, mat, ng = r.trace_closest(rays)
+    t0, mat0, ng0 = o.trace_closest(rays)
+    d = scene.getSceneDescription().contents
+    od = osc.desc.contents
+    # material ids are numbered per scene table: compare material kinds + records
+    def rec(desc, ids):
+        return [bytes(memoryview(desc.materials[i]).cast("B")) if i >= 0 else b"" for i in ids]
+    hit, hit0 = t >= 0, t0 >= 0
+    assert (hit == hit0).mean() > 0.9999
+    both = hit & hit0
+    assert np.allclose(t[both], t0[both], rtol=1e-5, atol=1e-6)
+    assert rec(d, mat[both][:2000]) == rec(od, mat0[both][:2000])
+    assert np.allclose(ng[both], ng0[both], atol=1e-5)
+    # any-hit: shadow segments between random points
+    a = (rng.random((20000, 3)) * (mx - mn) + mn).astype(np.float32)
+    b = (rng.random((20000, 3)) * (mx - mn) + mn).astype(np.float32)
+    dist = np.linalg.norm(b - a, axis=1).astype(np.float32)
+    sh = np.zeros((20000, 8), np.float32)
+    sh[:, 0:3], sh[:, 3], sh[:, 4:7], sh[:, 7] = a, 1e-4, (b - a) / dist[:, None], dist - 1e-4
+    occ, occ0 = r.trace_any(sh), o.trace_any(sh)
+    assert (occ == occ0).mean() > 0.9995
+
+
+@pytest.mark.parametrize("scene_name,config,size,pl,iters,minfrac", [
+    ("Cornell", 0, 64, (64, 64), 3, 0.98),
+    ("CornellSmall", 0, 48, (64, 64), 2, 0.97),
+    ("CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 48, (64, 64), 2, 0.95),   # area light, mirror floor, large glass sphere, blocks
+    ("CornellSmall", (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 48, (64, 64), 2, 0.95),   # point light, glossy floor, small mirror + glass spheres
+])
+def test_ppm_stage_parity(product, oracle, scene_name, config, size, pl, iters, minfrac):
+    """One PPM iteration stage by stage (hitpoints, photons, grid, indirect, direct, sum buffer) and the RNG
+    states afterwards, on identical paths (same per-pixel XORWOW seeding)."""
+    scene, cam, r, o, osc = _renderers(product, oracle, scene_name, config, size, pl)
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, size, size, 2.0 / 3.0)
+    odet = oracle.make_details(osc.camera(1.0), capi.PROGRESSIVE_PHOTON_MAPPING, size, size)
+    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), iters)
+    if scene_name == "CornellSmall":
+        radii = [0.05 * (x / radii[0]) for x in radii]   # the scene-extent estimate (1.7e-4) finds no photons at this photon count
+    for i in range(iters):
+        r.renderNextIteration(i, i, radii[i], True, det)
+        o.render_next_iteration(i, i, radii[i], odet)
+        hp = r.debug_buffer("hitpoints", ol.HITPOINT_DT, size * size)
+        hp0 = o.hitpoints()
+        same_flags = hp["flags"] == hp0["flags"]
+        assert same_flags.mean() > minfrac
+        m = same_flags & ((hp0["flags"] & ol.PRD_HIT_NON_SPECULAR) != 0)
+        assert np.allclose(hp["position"][m], hp0["position"][m], rtol=1e-4, atol=1e-4 * float(np.abs(hp0["position"]).max()))
+        assert np.allclose(hp["attenuation"][m], hp0["attenuation"][m], rtol=1e-5)
+        # photons as emitted (reference layout: thread t owns slots 4t..4t+3)
+        ph = r.debug_buffer("photons", ol.PHOTON_DT, pl[0] * pl[1] * 4)
+        ph0 = o.photons()   # sorted in place by the oracle's grid build: compare as multisets through the sorted lists
+        g = r.debug_buffer("grid", np.uint32, 8)
+        og = o.grid()
+        nv, nv0 = int(g[7]), og["numValid"]
+        assert abs(nv - nv0) <= max(4, 0.02 * nv0)
+        sp = r.debug_buffer("sorted_photons", ol.PHOTON_DT, nv)
+        if nv == nv0 and (g[0:7] == np.concatenate([[og["cellSize"].view(np.uint32)], np.array(og["gridSize"], np.uint32), og["origo"].view(np.uint32)])).all():
+            same = np.isclose(sp["position"], ph0["position"][:nv], rtol=1e-4, atol=1e-3).all(axis=1)
+            assert same.mean() > minfrac
+        assert (ph["power"].max(axis=1) > 0).sum() == nv
+        ind, ind0 = r.debug_buffer("indirect", np.float32, size * size * 3).reshape(size, size, 3), o.indirect()
+        dr, dr0 = r.debug_buffer("direct", np.float32, size * size * 3).reshape(size, size, 3), o.direct()
+        assert util.rel_close_fraction(dr.reshape(-1, 3), dr0.reshape(-1, 3), RTOL, ATOL) > minfrac
+        assert util.rel_close_fraction(ind.reshape(-1, 3), ind0.reshape(-1, 3), 5e-3, 1e-5 * float(ind0.max() + 1e-20)) > minfrac - 0.03
+    out, out0 = r.getOutputBuffer(), o.output()
+    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 1e-5 * float(out0.max()))
+    assert frac > minfrac - 0.03, frac
+    # whole-image agreement far below the Monte Carlo noise of a %d-iteration render
+    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
+    assert rel < 2e-2, rel
+    st = r.stats()
+    assert st["closest_rays"] > 0 and st["any_rays"] > 0 and st["launches"] > 0
+
+
+def test_state_rules_gpu(product):
+    r = product.OptixRenderer(photon_launch=(16, 16))
+    r.initialize(product.ComputeDevice(0))
+    with pytest.raises(RuntimeError, match="Multiple OptixRenderer::initialize"):
+        r.initialize(product.ComputeDevice(0))
+    scene = product.Cornell()
+    r.initScene(scene)
+    cam = scene.getDefaultCamera()
+    det = product.RenderServerRenderRequestDetails(cam, "Cornell", product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, 32, 24, 2 / 3)
+    r.renderNextIteration(0, 0, 7.5, True, det)
+    assert (r.getWidth(), r.getHeight(), r.getScreenBufferSizeBytes()) == (32, 24, 32 * 24 * 12)
+    a = r.getOutputBuffer().copy()
+    r.renderNextIteration(1, 1, 7.0, True, det)
+    b = r.getOutputBuffer().copy()
+    assert (b >= a - 1e-6).all() and b.sum() > a.sum()          # running SUM over local iterations (Output.cu:36)
+    r.renderNextIteration(2, 0, 7.0, True, det)                  # localIterationNumber == 0 zeroes the sum (:540-545)
+    c = r.getOutputBuffer()
+    assert c.sum() < b.sum()
+    det2 = product.RenderServerRenderRequestDetails(cam, "Cornell", product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, 40, 40, 2 / 3)
+    r.renderNextIteration(0, 0, 7.5, True, det2)                 # resize (:534-537)
+    assert r.getOutputBuffer().shape == (40, 40, 3)
+    bad = product.RenderServerRenderRequestDetails(cam, "Cornell", product.RenderMethod.PATH_TRACING, 40, 40, 2 / 3)
+    with pytest.raises(RuntimeError):
+        r.renderNextIteration(0, 0, 7.5, True, bad)
