@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the light-transport hot path (BASELINE.json: Mrays/s + PPM iterations/s at
+1080p, 1M photons/iteration, 1/2/4/8 B200).
+
+A "step" is one PPM iteration (camera pass, photon pass, photon-grid build, gather, direct + output) of the
+synthetic ~1M-triangle textured scene at 1920x1080 with a 1024x1024 photon launch, through the C ABI
+(opr_render_next_iteration).  With N > 1 ranks (torchrun, one process per GPU) rank g renders the global
+iterations g, g+N, ... with the closed-form radius schedule and the per-GPU running sums are combined with one
+NCCL reduce inside the timed region; value = rays of all ranks / max-over-ranks device time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sponza|conference|cornell]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sponza", choices=["sponza", "conference", "cornell"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--photons", type=int, default=1024, help="photon launch is photons x photons")
+    ap.add_argument("--detail", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", default="480x270:256", help="WxH:photonLaunch of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.maxmhz = [], set(), 0
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append(float(f[0]))
+                self.maxmhz = max(self.maxmhz, float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxmhz or None, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def build_scene(args):
+    import oppositerenderer_b200 as opr
+    if args.workload == "cornell":
+        scene = opr.Cornell()
+        cam = scene.getDefaultCamera()
+    else:
+        from oppositerenderer_b200 import synthetic
+        scene = synthetic.make_scene(args.workload, seed=1, detail=args.detail)
+        cam = scene.getDefaultCamera()
+    cam.setAspectRatio(args.width / args.height)
+    return scene, cam
+
+
+def cpu_reference_run(args, scene, cam, sample, steps, warmup, which):
+    """The reference's CPU implementation of the path (oracle/_ref when built, else the oracle port) on a bounded
+    sample of the same workload, all host threads.  Returns (Mrays/s, it/s, cores, description)."""
+    import oracle_lib as ol
+    from oppositerenderer_b200 import capi
+    wh, pl = sample.split(":")
+    w, h = (int(x) for x in wh.split("x"))
+    pl = int(pl)
+    o = ol.OracleRenderer(which, (pl, pl), 10, 1645301512)
+    o.init_scene(scene.getSceneDescription())
+    det = ol.make_details(cam.pod, capi.PROGRESSIVE_PHOTON_MAPPING, w, h)
+    r0 = scene.getSceneInitialPPMRadiusEstimate()
+    radii = ol.ppm_radius_schedule(r0, steps + warmup)
+    for i in range(warmup):
+        o.render_next_iteration(i, i, radii[i], det)
+    c0 = o.ray_counts()
+    t0 = time.perf_counter()
+    for i in range(warmup, warmup + steps):
+        o.render_next_iteration(i, i, radii[i], det)
+    dt = time.perf_counter() - t0
+    c1 = o.ray_counts()
+    rays = (c1[0] - c0[0]) + (c1[1] - c0[1])
+    cores = ol.load(which).ora_max_threads()
+    desc = "%d PPM iteration(s) of the same scene at %dx%d with a %dx%d photon launch (OpenMP, %d threads)" % (steps, w, h, pl, pl, cores)
+    return rays / dt / 1e6, steps / dt, cores, desc
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload_name = {"sponza": "synthetic ~1M-tri Sponza-scale textured scene, PPM %dx%d, %dx%d photon launch" % (args.width, args.height, args.photons, args.photons),
+                     "conference": "synthetic ~300K-tri Conference-scale scene with glass/mirror caustics, PPM %dx%d, %dx%d photon launch" % (args.width, args.height, args.photons, args.photons),
+                     "cornell": "built-in Cornell box, PPM %dx%d, %dx%d photon launch" % (args.width, args.height, args.photons, args.photons)}[args.workload]
+    config = {"workload": workload_name, "width": args.width, "height": args.height, "photons_per_iteration": args.photons * args.photons,
+              "detail": args.detail, "l2": "per-iteration working set (photon slots 151 MB + hitpoints 133 MB + ray queues) exceeds the 126 MB L2",
+              "parallelism": "iterations partitioned over %d GPU(s), scene replicated, one NCCL reduce of the sum buffer" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle_lib as ol
+        scene, cam = build_scene(args)
+        which = "ref" if ol.have_ref() else "oracle"
+        steps = max(1, min(args.steps, 2))
+        v, its, cores, desc = cpu_reference_run(args, scene, cam, args.cpu_sample, steps, min(args.warmup, 1), which)
+        line = {"impl": "reference", "metric": "ppm_rays_per_second", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+                "ms_per_step": 1000.0 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "iterations_per_s": its,
+                "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "reference" if which == "ref" else "port", "sample": desc},
+                "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import oppositerenderer_b200 as opr
+    from oppositerenderer_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t0 = time.perf_counter()
+    scene, cam = build_scene(args)
+    t_scene = time.perf_counter() - t0
+    W, H = args.width, args.height
+    # distinct RNG streams per rank (the reference's servers got this from wall-clock seeds, SpatialHash.cu:322)
+    r = opr.OptixRenderer(photon_launch=(args.photons, args.photons), seed=(1645301512 + rank * 104729) & 0xffffffff)
+    r.initialize(opr.ComputeDevice(local_rank))
+    t0 = time.perf_counter()
+    r.initScene(scene)
+    r.synchronize()
+    t_init = time.perf_counter() - t0
+    details = opr.RenderServerRenderRequestDetails(cam, scene.getSceneName(), opr.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, W, H, 2.0 / 3.0)
+    pod = details.pod()
+    r0 = scene.getSceneInitialPPMRadiusEstimate()
+    lib = capi.load_library()
+    radius = lambda it: float(lib.opr_ppm_radius_for_iteration(r0, it, 2.0 / 3.0))
+    stream = torch.cuda.ExternalStream(lib.opr_get_stream(r._h), device=torch.device("cuda", local_rank))
+
+    def out_tensor():
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f4", "data": (r.output_device_ptr(), False), "version": 2}
+        return torch.as_tensor(_Arr(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(steps, first_local, readback=None):
+        for k in range(steps):
+            local = first_local + k
+            it = local * world + rank
+            r.renderNextIteration(it, local, radius(it), True, pod)
+            if readback is not None:
+                r.getOutputBuffer(readback)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.reduce(out_tensor(), dst=0)
+
+    # ---- warm-up, then the device-timed region (inputs resident in HBM)
+    run(args.warmup, 0)
+    launches0 = r.stats()["launches"]
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record()
+    run(args.steps, args.warmup)
+    with torch.cuda.stream(stream):
+        e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    st = r.stats()
+    rays = st["closest_rays"] + st["any_rays"]
+
+    # ---- end to end through the C ABI with host buffers: request struct in, W*H*3 floats out every step
+    host_out = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()
+    barrier()
+    t0 = time.perf_counter()
+    run(args.steps, args.warmup + args.steps, readback=host_out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    st2 = r.stats()
+    rays_e2e = st2["closest_rays"] + st2["any_rays"] - rays
+
+    t = torch.tensor([ms, float(rays), e2e_s, float(rays_e2e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(tmax[0]), float(tmax[2])
+        rays, rays_e2e = float(tsum[1]), float(tsum[3])
+    total_steps = args.steps * world
+
+    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline of the dominant kernel
+    roof = None
+    kernel_ms = {}
+    if rank == 0:
+        r.set_timing(True)
+        acc = {}
+        nprof = 3
+        for k in range(nprof):
+            local = args.warmup + 2 * args.steps + k
+            it = local * world + rank
+            r.renderNextIteration(it, local, radius(it), True, pod)
+            for name, v in r.timings():
+                acc[name] = acc.get(name, 0.0) + v / nprof
+        r.set_timing(False)
+        kernel_ms = acc
+        stp = r.stats()
+        g = r.debug_buffer("grid", np.uint32, 8)
+        V = int(g[7])
+        ncells = int(g[1]) * int(g[2]) * int(g[3])
+        px = W * H
+        N = args.photons * args.photons * 4
+        peak, how = peaks()
+        alg = {
+            "ppm.gather": 76.0 * px + 36.0 * V + 8.0 * ncells,
+            "ppm.direct_output": (64 + 12 + 12 + 12 + 24) * px + 36.0 * (stp["any_rays"] - st2["any_rays"]) / nprof,
+            "trace.camera0": 52.0 * px,
+            "trace.photon0": 52.0 * args.photons * args.photons,
+        }
+        cands = [(acc.get(k, 0.0), k) for k in alg if acc.get(k, 0.0) > 0]
+        if cands:
+            dur, name = max(cands)
+            achieved = alg[name] / (dur * 1e-3) / 1e9
+            roof = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": how, "kernel_ms": dur, "algorithmic_bytes": alg[name],
+                    "note": "traversal/gather are L2- and latency-bound by construction (SURVEY.md §8d); see profiles/ for dram/L2 bytes"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            import oracle_lib as ol
+            which = "ref" if ol.have_ref() else "oracle"
+            v, its, cores, desc = cpu_reference_run(args, scene, cam, args.cpu_sample, 1, 0, which)
+            cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "reference" if which == "ref" else "port", "sample": desc, "iterations_per_s": its}
+        except Exception as e:  # the oracle is a reported baseline, never a dependency of the product numbers
+            cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+
+    if rank == 0:
+        line = {"metric": "ppm_rays_per_second", "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "iterations_per_s": total_steps / (ms * 1e-3), "rays_per_iteration": rays / total_steps,
+                "photons_stored_per_iteration": st["photons_stored"] / max(1, (args.warmup + args.steps)),
+                "e2e": {"value": rays_e2e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.opr_request_details),
+                        "d2h_bytes_per_step": W * H * 12, "iterations_per_s": total_steps / e2e_s,
+                        "how": "opr_render_next_iteration + opr_get_output_buffer into pinned host memory every step, wall clock, max over ranks"},
+                "gpu_launches": int(st["launches"] - launches0), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "kernel_ms": kernel_ms, "scene": {"triangles": scene.getNumTriangles(), "meshes": scene.getNumMeshes(), "generate_s": t_scene, "init_scene_s": t_init}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

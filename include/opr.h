@@ -47,6 +47,8 @@ uint32_t opr_get_screen_buffer_size_bytes(opr_renderer* r);
  * HBM; the caller reduces it across ranks (NCCL) through this device pointer (W*H*3 floats). */
 void* opr_get_output_device_ptr(opr_renderer* r);
 int opr_synchronize(opr_renderer* r);
+/* the CUDA stream (cudaStream_t) every kernel of r is launched on — for event timing and for ordering the NCCL reduce */
+void* opr_get_stream(opr_renderer* r);
 /* Closed form of the driver's radius schedule r_{i+1}^2 = r_i^2 (i+alpha)/(i+1)
  * (Standalone/StandaloneRenderManager.cpp:105-107, Client/DistributedApplication.cpp:105-113), so that rank g
  * can render global iterations g, g+G, ... without exchanging radii. */

@@ -61,6 +61,7 @@ uint32_t opr_get_width(opr_renderer* r) { return r->r.width; }
 uint32_t opr_get_height(opr_renderer* r) { return r->r.height; }
 uint32_t opr_get_screen_buffer_size_bytes(opr_renderer* r) { return r->r.width * r->r.height * 3u * (uint32_t)sizeof(float); }
 void* opr_get_output_device_ptr(opr_renderer* r) { return r->r.output; }
+void* opr_get_stream(opr_renderer* r) { return (void*)r->r.stream; }
 int opr_synchronize(opr_renderer* r) { OPR_TRY({ OPR_CUDA_CHECK(cudaSetDevice(r->r.device)); OPR_CUDA_CHECK(cudaStreamSynchronize(r->r.stream)); }) }
 
 int opr_get_stats(opr_renderer* r, uint64_t* out, int n)

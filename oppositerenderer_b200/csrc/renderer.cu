@@ -181,7 +181,8 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         for (unsigned bounce = 0; bounce <= MAX_RADIANCE_TRACE_DEPTH; bounce++) {
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
-            launch_trace_closest(sc, q, cur, lc);
+            if (bounce == 0) { ScopedTimer t0(*this, "trace.camera0"); launch_trace_closest(sc, q, cur, lc); }
+            else launch_trace_closest(sc, q, cur, lc);
             launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, cur, lc);
             cur ^= 1;
         }
@@ -198,7 +199,8 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         for (unsigned bounce = 0; bounce <= MAX_PHOTON_TRACE_DEPTH; bounce++) {
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
-            launch_trace_closest(sc, q, cur, lc);
+            if (bounce == 0) { ScopedTimer t0(*this, "trace.photon0"); launch_trace_closest(sc, q, cur, lc); }
+            else launch_trace_closest(sc, q, cur, lc);
             launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, cur, lc);
             cur ^= 1;
         }
