@@ -1,0 +1,66 @@
+"""Summarise ncu outputs brought back in gpurun_out/ into small text files under profiles/.
+usage: python scripts/ncu_summary.py <tag> [launches.csv] [name=report.ncu-rep ...]"""
+import collections
+import csv
+import subprocess
+import sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__occupancy_limit_registers", "sm__inst_executed.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct",
+        "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct"]
+
+
+def launches(path, out):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except Exception:
+            continue
+        u = row["Metric Unit"]
+        v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
+        a = agg.setdefault(row["Kernel Name"].split("(")[0][:70], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    out.write("# per-kernel device time from `ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare SHARES)\n")
+    out.write("%-72s %6s %12s %7s\n" % ("kernel", "n", "total_us", "share"))
+    for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+        out.write("%-72s %6d %12.1f %6.1f%%\n" % (k, a[0], a[1], 100 * a[1] / tot))
+    out.write("%-72s %6s %12.1f\n\n" % ("TOTAL", "", tot))
+
+
+def report(name, path, out):
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    if len(rows) < 3:
+        out.write("# %s: could not read %s\n" % (name, path))
+        return
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        kn = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else name
+        out.write("# %s — `ncu --set full --clock-control none` — %s\n" % (name, kn[:90]))
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                out.write("%-78s %18s %s\n" % (w, vals[i], units[i]))
+        out.write("\n")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1]
+    with open("profiles/%s_ncu_summary.txt" % tag, "w") as out:
+        for a in sys.argv[2:]:
+            if "=" in a:
+                n, p = a.split("=", 1)
+                report(n, p, out)
+            else:
+                launches(a, out)
+    print(open("profiles/%s_ncu_summary.txt" % tag).read())
