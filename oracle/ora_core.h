@@ -91,6 +91,33 @@ struct Scene {
     bool intersectPrim(int primIndex, const Ray& ray, float tmax, Hit& hit) const;
     bool closestHit(const Ray& ray, Hit& hit) const;
     bool anyHit(const Ray& ray) const;
+
+    // Generic front-to-back candidate enumeration: leaf(primIndex, tmax) may shrink tmax and returns true to stop.
+    // Used by oracle/refshim to call the reference's own intersection programs at the leaves.
+    template <class Leaf> void forEachCandidate(const Ray& ray, float& tmax, Leaf&& leaf) const
+    {
+        if (nodes.empty()) return;
+        const float3 inv = {1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z};
+        int stack[128]; int sp = 0; stack[sp++] = 0;
+        while (sp) {
+            const BvhNode& nd = nodes[stack[--sp]];
+            if (!slabTest(nd.box, ray.origin, inv, ray.tmin, tmax)) continue;
+            if (nd.count > 0) { for (int i = nd.first; i < nd.first + nd.count; i++) if (leaf(i, tmax)) return; }
+            else { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+        }
+    }
+    static inline bool slabTest(const Aabb& b, const float3& o, const float3& inv, float tmin, float tmax)
+    {
+        float t0 = (b.lo.x - o.x) * inv.x, t1 = (b.hi.x - o.x) * inv.x;
+        float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
+        t0 = (b.lo.y - o.y) * inv.y; t1 = (b.hi.y - o.y) * inv.y;
+        lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+        t0 = (b.lo.z - o.z) * inv.z; t1 = (b.hi.z - o.z) * inv.z;
+        lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+        lo = lo - fabsf(lo) * 1e-4f - 1e-6f;   // conservative: never cull a primitive lying exactly on a box face
+        hi = hi + fabsf(hi) * 1e-4f + 1e-6f;
+        return lo <= hi && hi >= tmin && lo <= tmax;
+    }
 };
 
 // host helpers restated from the reference's scene/camera/light classes

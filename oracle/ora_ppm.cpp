@@ -79,29 +79,8 @@ static float3 sampleDisc(const float2& sample, const float3& center, const float
     return center + radius * (U * unitDisc.x + V * unitDisc.y);
 }
 
-// ---- texture fetch: rtTextureSampler<uchar4,2,cudaReadModeNormalizedFloat>, wrap=repeat, linear,
-// normalised coordinates (material/Texture.cpp:109-121).  The reference uses the hardware texture unit;
-// this follows the CUDA programming guide's "Texture Fetching" appendix: xB = N*frac(x) - 0.5,
-// i = floor(xB), alpha = frac(xB) kept in 1.8 fixed point, tex = (1-a)(1-b)T[i,j] + ...
-float4 tex2D(const Texture& t, float u, float v)
-{
-    if (t.width <= 0 || t.height <= 0) return make_float4(0, 0, 0, 0);
-    float x = (u - floorf(u)) * t.width - 0.5f;
-    float y = (v - floorf(v)) * t.height - 0.5f;
-    float fx = floorf(x), fy = floorf(y);
-    float a = floorf((x - fx) * 256.0f + 0.5f) * (1.0f / 256.0f);
-    float b = floorf((y - fy) * 256.0f + 0.5f) * (1.0f / 256.0f);
-    int i0 = (int)fx, j0 = (int)fy;
-    auto wrap = [](int i, int n) { i %= n; return i < 0 ? i + n : i; };
-    int i1 = wrap(i0 + 1, t.width), j1 = wrap(j0 + 1, t.height);
-    i0 = wrap(i0, t.width); j0 = wrap(j0, t.height);
-    auto T = [&](int i, int j, int c) { return t.rgba[((size_t)j * t.width + i) * 4 + c] * (1.0f / 255.0f); };
-    float4 r;
-    float* rp = &r.x;
-    for (int c = 0; c < 4; c++)
-        rp[c] = (1 - a) * (1 - b) * T(i0, j0, c) + a * (1 - b) * T(i1, j0, c) + (1 - a) * b * T(i0, j1, c) + a * b * T(i1, j1, c);
-    return r;
-}
+float4 tex2D(const Texture& t, float u, float v);   // ora_tex.cpp
+void pass_begin(Renderer&) {}                         // hook used by the oracle/_ref build only
 
 // ---- payloads ------------------------------------------------------------------------------------------
 struct RadiancePRD {   // renderer/RadiancePRD.h:11-29

@@ -8,7 +8,8 @@
 
 namespace ora {
 
-Renderer::Renderer() {}
+static std::atomic<unsigned long long> g_nextUid{1};
+Renderer::Renderer() { uid = g_nextUid.fetch_add(1); }
 Renderer::~Renderer() { vcm_free(*this); }
 
 void Renderer::initialize()
@@ -32,6 +33,7 @@ void Renderer::initScene(const opr_scene_desc* d)
 void Renderer::initializeRandomStates()
 {   // OptixRenderer_SpatialHash.cu:310-347
     const size_t num = (size_t)rsW * rsH;
+    rngEpoch++;
     randomStates.resize(num);
     #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)num; i++) rng_init(&randomStates[i], seed, (unsigned)i);
@@ -55,6 +57,7 @@ void Renderer::resizeBuffers(uint w, uint h)
 template <class F> static void launch2D(Renderer& r, uint w, uint h, F f)
 {
     const long long n = (long long)w * h;
+    pass_begin(r);
     #pragma omp parallel for schedule(dynamic, 64)
     for (long long i = 0; i < n; i++) f(r, (uint)(i % w), (uint)(i / w));
 }

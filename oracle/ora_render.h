@@ -14,11 +14,13 @@ struct Renderer {
     uint vcmMaxPathLength = 10;
     uint seed = 1645301512u;    // config.h:50
 
+    unsigned long long uid = 0;   // unique per Renderer object (the oracle/_ref build keys its OptiX-style context on it)
     bool initialized = false;
     bool sceneLoaded = false;
     Scene scene;
 
     uint width = 10, height = 10;           // OptixRenderer.cpp:84-85
+    unsigned rngEpoch = 0;                  // bumped by initializeRandomStates (oracle/refshim keeps curandState copies)
     uint rsW = 0, rsH = 0;                  // randomStates dims: max(photonLaunchW, W) x max(photonLaunchH, H)
     std::vector<RandomState> randomStates;
     std::vector<Hitpoint> hitpoints;        // raytracePassOutputBuffer
@@ -64,6 +66,9 @@ struct Renderer {
                              float PPMRadius, bool createOutput, const opr_request_details& details);
     inline RandomState& rs(uint x, uint y) { return randomStates[(size_t)y * rsW + x]; }
 };
+
+// called once, serially, before every pass launch (no-op in the restatement; the _ref build refreshes its OptiX-style context)
+void pass_begin(Renderer& r);
 
 // PPM programs (ora_ppm.cpp)
 void ppm_generateRay(Renderer& r, uint x, uint y);       // ppm/RayGeneratorPPM.cu:31-66

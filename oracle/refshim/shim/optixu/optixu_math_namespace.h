@@ -1,0 +1,2 @@
+#pragma once
+#include "../shim_optix.h"

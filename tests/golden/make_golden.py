@@ -1,0 +1,50 @@
+"""Generates the golden fixtures in this directory by running the REFERENCE's own device programs (host-compiled
+behind oracle/refshim into oracle/_ref/liboppref.so) on the built-in scenes.  Only possible where /root/reference
+exists (the build container); the fixtures travel, the reference does not.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle_lib as ol  # noqa: E402
+
+SEED = 1645301512
+CASES = [  # name, scene, CornellSmall config, method (2 = PPM, 1 = BDPT), size, photon launch, iterations, max path length, fixed r0
+    ("cornell_ppm_64x64_p64x64_it3", "Cornell", 0, 2, 64, 64, 3, 10, None),
+    ("cornellsmall_ppm_48x48_p48x48_it2", "CornellSmall", 0, 2, 48, 48, 2, 10, 0.05),
+    ("cornellsmall_mirrorfloor_glass_ppm_48x48_p48x48_it2", "CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 2, 48, 48, 2, 10, 0.05),
+    ("cornellsmall_point_glossy_spheres_ppm_48x48_p48x48_it2", "CornellSmall", (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 2, 48, 48, 2, 10, 0.05),
+    ("cornellsmall_bdpt_48x48_it3_len8", "CornellSmall", 0, 1, 48, 48, 3, 8, None),
+    ("cornellsmall_mirrorfloor_glass_bdpt_48x48_it2_len8", "CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 1, 48, 48, 2, 8, None),
+    ("cornellsmall_point_glossy_spheres_bdpt_48x48_it2_len10", "CornellSmall", (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 1, 48, 48, 2, 10, None),
+]
+
+
+def render(which, scene, cfg, method, size, pl, iters, maxlen, r0):
+    sc = ol.BuiltinScene(scene, cfg, which)
+    r = ol.OracleRenderer(which, (pl, pl), maxlen, SEED)
+    r.init_scene(sc.desc)
+    det = ol.make_details(sc.camera(1.0), method, size, size)
+    radii = ol.ppm_radius_schedule(sc.initial_radius() if r0 is None else r0, iters)
+    for i in range(iters):
+        r.render_next_iteration(i, i, radii[i], det)
+    out = dict(output=r.output(), rays=np.array(r.ray_counts(), np.uint64))
+    if method == 2:
+        out["photon_keys"] = r.photon_keys()
+        out["offsets"] = r.offsets()
+        out["hitpoint_flags"] = r.hitpoints()["flags"]
+    return out
+
+
+if __name__ == "__main__":
+    assert ol.have_ref(), "build oracle/_ref first: make -C oracle/refshim"
+    for case in CASES:
+        data = render("ref", *case[1:])
+        np.savez_compressed(os.path.join(HERE, case[0] + ".npz"), **data)
+        print(case[0], "rays", data["rays"], "mean", data["output"].mean())
