@@ -28,7 +28,8 @@ CASES = [  # name, scene, CornellSmall config, method (2 = PPM, 1 = BDPT), size,
 
 def render(which, scene, cfg, method, size, pl, iters, maxlen, r0):
     sc = ol.BuiltinScene(scene, cfg, which)
-    r = ol.OracleRenderer(which, (pl, pl), maxlen, SEED)
+    # the reference's light-tracing splat is a plain `+=` (vcm.h:159): run its programs on one thread so that no update is lost
+    r = ol.OracleRenderer(which, (pl, pl), maxlen, SEED, threads=1 if (which == "ref" and method == 1) else 0)
     r.init_scene(sc.desc)
     det = ol.make_details(sc.camera(1.0), method, size, size)
     radii = ol.ppm_radius_schedule(sc.initial_radius() if r0 is None else r0, iters)
