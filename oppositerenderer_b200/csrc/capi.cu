@@ -156,6 +156,9 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
             auto s = download(R.phState, P, st);
             unsigned* o = (unsigned*)dst;
             for (size_t i = 0; i < P; i++) o[i] = s[i] & 0xffu;
+        } else if (n == "light_vertex_counts") {
+            need(px * 4);
+            if (R.debugLightVertexCounts((unsigned*)dst)) throw std::runtime_error("no BDPT iteration has run yet");
         } else {
             throw std::runtime_error("opr_debug_get_buffer: unknown buffer " + n);
         }

@@ -101,23 +101,6 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     lightVertexCountEstimated = false;      // :847
 }
 
-struct ScopedTimer {
-    Renderer& r; const char* name; cudaEvent_t a = nullptr, b = nullptr;
-    ScopedTimer(Renderer& r_, const char* n) : r(r_), name(n)
-    {
-        if (!r.timing) return;
-        cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, r.stream);
-    }
-    ~ScopedTimer()
-    {
-        if (!r.timing) return;
-        cudaEventRecord(b, r.stream); cudaEventSynchronize(b);
-        float ms = 0; cudaEventElapsedTime(&ms, a, b);
-        r.lastTimings.emplace_back(name, ms);
-        cudaEventDestroy(a); cudaEventDestroy(b);
-    }
-};
-
 void Renderer::buildPhotonGrid()
 {   // createUniformGridPhotonMap, OptixRenderer_SpatialHash.cu:209-282
     LaunchCtx lc{stream, &launches};

@@ -79,6 +79,7 @@ struct Renderer {
 
     // VCM state lives in vcm.cu
     struct VcmState* vcm = nullptr;
+    int debugLightVertexCounts(unsigned* dstHost);
     bool lightVertexCountEstimated = false;
 
     // statistics / timing
@@ -99,6 +100,24 @@ struct Renderer {
     void renderVCM(unsigned long long iterationNumber, unsigned localIterationNumber, float PPMRadius, const opr_request_details& details);
     void buildPhotonGrid();
     void getOutputBuffer(void* dst);
+};
+
+// CUDA-event timer around one pass (enabled by opr_set_timing)
+struct ScopedTimer {
+    Renderer& r; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+    ScopedTimer(Renderer& r_, const char* n) : r(r_), name(n)
+    {
+        if (!r.timing) return;
+        cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, r.stream);
+    }
+    ~ScopedTimer()
+    {
+        if (!r.timing) return;
+        cudaEventRecord(b, r.stream); cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        r.lastTimings.emplace_back(name, ms);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
 };
 
 // ---- kernel launchers (ppm.cu, trace.cu, grid.cu) -------------------------------------------------------

@@ -190,3 +190,63 @@ def test_state_rules_gpu(product):
     bad = product.RenderServerRenderRequestDetails(cam, "Cornell", product.RenderMethod.PATH_TRACING, 40, 40, 2 / 3)
     with pytest.raises(RuntimeError):
         r.renderNextIteration(0, 0, 7.5, True, bad)
+
+
+@pytest.mark.parametrize("config,maxlen,iters,minfrac", [
+    (0, 8, 3, 0.95),                                            # BASELINE config 2: CornellSmall default, max path length 8
+    ((1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 8, 2, 0.92),   # mirror floor + large glass sphere + blocks
+    ((1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 10, 2, 0.92),  # point light, glossy floor (Lambertian+Phong), mirror + glass spheres
+    ((1 << 5) | (1 << 10), 10, 2, 0.92),                        # distant point light (cone emission), large mirror sphere, no ceiling
+])
+def test_bdpt_parity(product, oracle, config, maxlen, iters, minfrac):
+    """Vertex-connection BDPT (light pass with camera splats, camera pass with S0/S1/vertex connections, recursive MIS)
+    against the oracle on identical paths: per-path stored light-vertex counts, then the sum buffer per pixel."""
+    size = 48
+    scene, cam, r, o, osc = _renderers(product, oracle, "CornellSmall", config, size, (16, 16), maxlen)
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.VCM_BIDIRECTIONAL_PATH_TRACING, size, size, 2.0 / 3.0)
+    odet = oracle.make_details(osc.camera(1.0), capi.VCM_BIDIRECTIONAL_PATH_TRACING, size, size)
+    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), iters)
+    for i in range(iters):
+        r.renderNextIteration(i, i, radii[i], True, det)
+        o.render_next_iteration(i, i, radii[i], odet)
+        cnt = r.debug_buffer("light_vertex_counts", np.uint32, size * size)
+        cnt0 = np.zeros(size * size, np.uint32)
+        o.lib.ora_get_light_vertex_counts(o.h, cnt0.ctypes.data_as(C.c_void_p))
+        assert (cnt == cnt0).mean() > minfrac, (cnt == cnt0).mean()
+    out, out0 = r.getOutputBuffer(), o.output()
+    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
+    assert frac > minfrac - 0.07, frac
+    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
+    assert rel < 3e-2, rel
+    st = r.stats()
+    assert st["closest_rays"] > 0 and st["any_rays"] > 0
+
+
+def test_cuda_matches_reference_golden(product):
+    """The CUDA path against the committed outputs of the reference's own device programs (tests/golden/*.npz,
+    generated by tests/golden/make_golden.py from oracle/_ref): no oracle code runs in this test."""
+    import os
+    from golden.make_golden import CASES, SEED
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name, scene_name, cfg, method, size, pl, iters, maxlen, r0 in CASES:
+        gold = np.load(os.path.join(gdir, name + ".npz"))
+        scene = product.Cornell() if scene_name == "Cornell" else product.CornellSmall(cfg or None)
+        cam = scene.getDefaultCamera()
+        cam.setAspectRatio(1.0)
+        r = product.OptixRenderer(photon_launch=(pl, pl), vcm_max_path_length=maxlen, seed=SEED)
+        r.initialize(product.ComputeDevice(0))
+        r.initScene(scene)
+        det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, size, size, 2.0 / 3.0)
+        radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate() if r0 is None else r0, iters)
+        for i in range(iters):
+            r.renderNextIteration(i, i, radii[i], True, det)
+        out = r.getOutputBuffer()
+        frac = util.rel_close_fraction(out.reshape(-1, 3), gold["output"].reshape(-1, 3), 5e-3, 2e-5 * float(gold["output"].max()))
+        rel = np.abs(out - gold["output"]).sum() / np.abs(gold["output"]).sum()
+        assert frac > 0.85 and rel < 3e-2, (name, frac, rel)
+        st = r.stats()
+        rays = st["closest_rays"] + st["any_rays"]
+        assert abs(rays - int(gold["rays"].sum())) <= 0.02 * int(gold["rays"].sum()), (name, rays, gold["rays"])
+        if method == 2:
+            flags = r.debug_buffer("hitpoints", ol.HITPOINT_DT, size * size)["flags"]
+            assert (flags == gold["hitpoint_flags"]).mean() > 0.97
