@@ -306,7 +306,7 @@ int opr_gather(uint32_t numPixels, const float* hitpointsAoS, uint32_t numPhoton
         OPR_CUDA_CHECK(cudaMemcpy(dOff.p, offsets, ((size_t)g.numCells + 1) * 4, cudaMemcpyHostToDevice));
         hitpoints_aos_to_soa_kernel<<<148 * 4, 256>>>(dHp.as<float>(), numPixels, hp);
         if (numPhotons) photons_aos_to_soa_kernel<<<148 * 4, 256>>>(dPh.as<float>(), numPhotons, pb, state.as<unsigned>());
-        launch_gather(hp, numPixels, pb, dOff.as<unsigned>(), g, ppmRadius, ppmRadius * ppmRadius, emittedPhotons, dOut.as<float>(), lc);
+        launch_gather(hp, numPixels, 0, 0, pb, dOff.as<unsigned>(), g, ppmRadius, ppmRadius * ppmRadius, emittedPhotons, dOut.as<float>(), lc);
         OPR_CUDA_CHECK(cudaDeviceSynchronize());
         OPR_CUDA_CHECK(cudaGetLastError());
         OPR_CUDA_CHECK(cudaMemcpy(indirectOut, dOut.p, (size_t)numPixels * 12, cudaMemcpyDeviceToHost));

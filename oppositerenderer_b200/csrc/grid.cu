@@ -148,62 +148,102 @@ void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, un
 }
 
 // ---- gather: IndirectRadianceEstimation::kernel (:69-129, :213-220), validPhoton :54-57, photonPower :59-67
+//
+// One warp gathers for an 8x4 pixel tile.  The reference lets every pixel walk its own cube of cells and read each
+// photon through the cache (13 of 32 lanes active on average, profiles/r1_baseline_ncu_summary.txt).  Here the
+// warp walks the UNION of its lanes' cell rows in the reference's order (z, then y, then the contiguous x-run of
+// sorted photons), stages 32 photons at a time in shared memory with coalesced 16-byte loads, and every lane that
+// needs the row tests the staged photons against its own hit point (shared-memory broadcast reads).  A lane
+// accumulates exactly the photons the reference accumulates, in the same order, so the sum is unchanged.
 constexpr int GATHER_THREADS = 128;
+constexpr int GATHER_WARPS = GATHER_THREADS / 32;
 
-__global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf hp, unsigned numPixels, PhotonBuf sorted, const unsigned* __restrict__ offsets,
-                                                                    GridParams g, float ppmRadius, float ppmRadiusSquared, float emittedPhotons,
-                                                                    float* __restrict__ indirect)
+__global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf hp, unsigned numPixels, unsigned width, unsigned height, PhotonBuf sorted,
+                                                                    const unsigned* __restrict__ offsets, GridParams g, float ppmRadius, float ppmRadiusSquared,
+                                                                    float emittedPhotons, float* __restrict__ indirect)
 {
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < numPixels; p += gridDim.x * blockDim.x) {
-        const float4 pos4 = hp.pos[p];
-        const unsigned flags = __float_as_uint(pos4.w);
-        const float3 attenuation = f3(hp.att[p]);
-        float3 acc = f3(0.f);
-        if (flags & PRD_HIT_NON_SPECULAR) {
-            const float3 pos = f3(pos4), nrm = f3(hp.nrm[p]);
-            const float radius2 = ppmRadiusSquared, radius = ppmRadius;
-            const float invCellSize = 1.f / g.cellSize;
+    __shared__ float4 sA[GATHER_WARPS][32];
+    __shared__ float4 sB[GATHER_WARPS][32];
+    __shared__ float sC[GATHER_WARPS][32];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned tilesX = width ? (width + 7) / 8 : 0;
+    const unsigned numTiles = width ? tilesX * ((height + 3) / 4) : (numPixels + 31) / 32;
+    const float radius2 = ppmRadiusSquared, radius = ppmRadius;
+    const float invCellSize = 1.f / g.cellSize;
+    const unsigned gx = g.gridSize.x, gxy = g.gridSize.x * g.gridSize.y;
+    for (unsigned tile = blockIdx.x * GATHER_WARPS + w; tile < numTiles; tile += gridDim.x * GATHER_WARPS) {
+        unsigned p; bool inImage;
+        if (width) {
+            const unsigned x = (tile % tilesX) * 8 + (lane & 7), y = (tile / tilesX) * 4 + (lane >> 3);
+            inImage = x < width && y < height; p = y * width + x;
+        } else { p = tile * 32 + lane; inImage = p < numPixels; }
+        float3 pos = f3(0.f), nrm = f3(0.f), attenuation = f3(0.f);
+        bool active = false;
+        if (inImage) {
+            const float4 pos4 = hp.pos[p];
+            attenuation = f3(hp.att[p]);
+            if (__float_as_uint(pos4.w) & PRD_HIT_NON_SPECULAR) { active = true; pos = f3(pos4); nrm = f3(hp.nrm[p]); }
+        }
+        unsigned x_lo = 0xffffffffu, y_lo = 0xffffffffu, z_lo = 0xffffffffu, x_hi = 0, y_hi = 0, z_hi = 0;
+        if (active) {
             const float3 np = pos - g.origo;
-            const unsigned x_lo = (unsigned)max(0, (int)((np.x - radius) * invCellSize));
-            const unsigned y_lo = (unsigned)max(0, (int)((np.y - radius) * invCellSize));
-            const unsigned z_lo = (unsigned)max(0, (int)((np.z - radius) * invCellSize));
-            const unsigned x_hi = min(g.gridSize.x - 1, (unsigned)((np.x + radius) * invCellSize));
-            const unsigned y_hi = min(g.gridSize.y - 1, (unsigned)((np.y + radius) * invCellSize));
-            const unsigned z_hi = min(g.gridSize.z - 1, (unsigned)((np.z + radius) * invCellSize));
-            if (x_lo <= x_hi) {
-                for (unsigned z = z_lo; z <= z_hi; z++) {
-                    for (unsigned y = y_lo; y <= y_hi; y++) {
-                        const unsigned from = x_lo + y * g.gridSize.x + z * g.gridSize.x * g.gridSize.y;
-                        const unsigned to = from + (x_hi - x_lo);
-                        const unsigned begin = __ldg(offsets + from), end = __ldg(offsets + to + 1);
-                        for (unsigned i = begin; i < end; i++) {
-                            const float4 a = __ldg(sorted.a + i);
-                            const float3 diff = pos - f3(a);
-                            const float distance2 = dot(diff, diff);
-                            if (distance2 <= radius2) {
-                                const float4 b = __ldg(sorted.b + i);
-                                const float dz = __ldg(sorted.c + i);
-                                if (dot(-f3(a.w, b.w, dz), nrm) >= 0) {
-                                    const float alpha = 1.818f, beta = 1.953f, expNegativeBeta = 0.141847f;
-                                    const float weight = alpha * (1 - (1 - expf(-beta * distance2 / (2 * radius2))) / (1 - expNegativeBeta));
-                                    acc += f3(b) * weight;
+            x_lo = (unsigned)max(0, (int)((np.x - radius) * invCellSize));
+            y_lo = (unsigned)max(0, (int)((np.y - radius) * invCellSize));
+            z_lo = (unsigned)max(0, (int)((np.z - radius) * invCellSize));
+            x_hi = min(g.gridSize.x - 1, (unsigned)((np.x + radius) * invCellSize));
+            y_hi = min(g.gridSize.y - 1, (unsigned)((np.y + radius) * invCellSize));
+            z_hi = min(g.gridSize.z - 1, (unsigned)((np.z + radius) * invCellSize));
+            if (!(x_lo <= x_hi) || !(y_lo <= y_hi) || !(z_lo <= z_hi)) active = false;
+        }
+        float3 acc = f3(0.f);
+        if (__any_sync(0xffffffffu, active)) {
+            const unsigned uy_lo = __reduce_min_sync(0xffffffffu, active ? y_lo : 0xffffffffu), uy_hi = __reduce_max_sync(0xffffffffu, active ? y_hi : 0u);
+            const unsigned uz_lo = __reduce_min_sync(0xffffffffu, active ? z_lo : 0xffffffffu), uz_hi = __reduce_max_sync(0xffffffffu, active ? z_hi : 0u);
+            for (unsigned z = uz_lo; z <= uz_hi; z++) {
+                for (unsigned y = uy_lo; y <= uy_hi; y++) {
+                    const bool need = active && z >= z_lo && z <= z_hi && y >= y_lo && y <= y_hi;   // the rows the reference visits for this lane
+                    if (!__any_sync(0xffffffffu, need)) continue;
+                    const unsigned rx_lo = __reduce_min_sync(0xffffffffu, need ? x_lo : 0xffffffffu), rx_hi = __reduce_max_sync(0xffffffffu, need ? x_hi : 0u);
+                    const unsigned from = rx_lo + y * gx + z * gxy;
+                    const unsigned begin = __ldg(offsets + from), end = __ldg(offsets + from + (rx_hi - rx_lo) + 1);
+                    for (unsigned base = begin; base < end; base += 32) {
+                        const unsigned i = base + lane;
+                        if (i < end) { sA[w][lane] = __ldg(sorted.a + i); sB[w][lane] = __ldg(sorted.b + i); sC[w][lane] = __ldg(sorted.c + i); }
+                        __syncwarp();
+                        const unsigned cnt = min(32u, end - base);
+                        if (need) {
+                            for (unsigned j = 0; j < cnt; j++) {
+                                const float4 a = sA[w][j];
+                                const float3 diff = pos - f3(a);
+                                const float distance2 = dot(diff, diff);
+                                if (distance2 <= radius2) {
+                                    const float4 b = sB[w][j];
+                                    if (dot(-f3(a.w, b.w, sC[w][j]), nrm) >= 0) {
+                                        const float alpha = 1.818f, beta = 1.953f, expNegativeBeta = 0.141847f;
+                                        const float weight = alpha * (1 - (1 - expf(-beta * distance2 / (2 * radius2))) / (1 - expNegativeBeta));
+                                        acc += f3(b) * weight;
+                                    }
                                 }
                             }
                         }
+                        __syncwarp();
                     }
                 }
             }
         }
-        const float3 ind = acc * attenuation * (1.0f / (PI_F * ppmRadiusSquared)) * (1.0f / emittedPhotons);
-        indirect[3 * (size_t)p] = ind.x; indirect[3 * (size_t)p + 1] = ind.y; indirect[3 * (size_t)p + 2] = ind.z;
+        if (inImage) {
+            const float3 ind = acc * attenuation * (1.0f / (PI_F * ppmRadiusSquared)) * (1.0f / emittedPhotons);
+            indirect[3 * (size_t)p] = ind.x; indirect[3 * (size_t)p + 1] = ind.y; indirect[3 * (size_t)p + 2] = ind.z;
+        }
     }
 }
 
-void launch_gather(const HitpointBuf& hp, unsigned numPixels, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
+void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
                    float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, LaunchCtx lc)
 {
-    int blocks = (int)std::min<unsigned>((numPixels + GATHER_THREADS - 1) / GATHER_THREADS, 148 * 16);
-    ppm_gather_kernel<<<blocks, GATHER_THREADS, 0, lc.st>>>(hp, numPixels, sorted, offsets, g, ppmRadius, ppmRadiusSquared, emittedPhotons, indirect);
+    const unsigned numTiles = width ? ((width + 7) / 8) * ((height + 3) / 4) : (numPixels + 31) / 32;
+    int blocks = (int)std::min<unsigned>((numTiles + GATHER_WARPS - 1) / GATHER_WARPS, 148 * 16);
+    ppm_gather_kernel<<<blocks, GATHER_THREADS, 0, lc.st>>>(hp, numPixels, width, height, sorted, offsets, g, ppmRadius, ppmRadiusSquared, emittedPhotons, indirect);
     ++*lc.launches;
 }
 

@@ -193,7 +193,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     // ---- PPM_INDIRECT_RADIANCE_ESTIMATION_PASS (:657)
     {
         ScopedTimer t(*this, "ppm.gather");
-        launch_gather(hp, width * height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
+        launch_gather(hp, width * height, width, height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
                       float(photonLaunchWidth * photonLaunchHeight), indirect, lc);
     }
     // ---- PPM_DIRECT_RADIANCE_ESTIMATION_PASS + PPM_OUTPUT_PASS (:664, :670)

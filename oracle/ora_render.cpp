@@ -194,6 +194,28 @@ int ora_build_photon_grid(float* photonsAoS, unsigned n, unsigned* keys, unsigne
     return 0;
 }
 
+// IndirectRadianceEstimation::kernel on caller-supplied hitpoints (64 B each) + sorted photons (36 B each) + offset table
+int ora_gather(unsigned numPixels, const float* hitpointsAoS, unsigned numPhotons, const float* photonsAoS, const unsigned* offsets,
+               float cellSize, const unsigned* gridSize3, const float* origo3, float ppmRadius, float emittedPhotons, float* indirectOut)
+{
+    Renderer r;
+    r.width = numPixels; r.height = 1;
+    r.hitpoints.assign((const Hitpoint*)hitpointsAoS, (const Hitpoint*)hitpointsAoS + numPixels);
+    r.photons.assign((const Photon*)photonsAoS, (const Photon*)photonsAoS + numPhotons);
+    r.grid.cellSize = cellSize; r.grid.gridSize = {gridSize3[0], gridSize3[1], gridSize3[2]}; r.grid.origo = f3(origo3);
+    r.grid.numCells = gridSize3[0] * gridSize3[1] * gridSize3[2];
+    r.offsets.assign(offsets, offsets + r.grid.numCells + 1);
+    r.indirect.assign(numPixels, make_float3(0.f));
+    r.direct.assign(numPixels, make_float3(0.f)); r.output.assign(numPixels, make_float3(0.f));
+    r.ppmRadius = ppmRadius; r.ppmRadiusSquared = ppmRadius * ppmRadius; r.emittedPhotonsPerIterationFloat = emittedPhotons;
+    r.rsW = 1; r.rsH = 1; r.randomStates.resize(1);
+    pass_begin(r);
+    #pragma omp parallel for schedule(dynamic, 64)
+    for (long long i = 0; i < (long long)numPixels; i++) ppm_indirect(r, (uint)i, 0);
+    memcpy(indirectOut, r.indirect.data(), sizeof(float3) * numPixels);
+    return 0;
+}
+
 // closest-hit / any-hit queries against the loaded scene.  rays: n x 8 floats (o.xyz,tmin,d.xyz,tmax);
 // out hits: n x {t (float), prim-kind (int), material (int), geometric normal xyz}
 int ora_trace_closest(void* h, const float* rays8, unsigned n, float* outT, int* outMaterial, float* outNg3)

@@ -51,6 +51,7 @@ def _declare(lib):
         "ora_rng_init": (None, [PU, u32, u32, u32]),
         "ora_rng_uniform": (None, [PU, PF, u32]),
         "ora_build_photon_grid": (i32, [PF, u32, PU, PU, PF, PU, PF, PU]),
+        "ora_gather": (i32, [u32, PF, u32, PF, PU, f32, PU, PF, f32, f32, PF]),
         "ora_trace_closest": (i32, [vp, PF, u32, PF, PI, PF]),
         "ora_trace_any": (i32, [vp, PF, u32, PI]),
         "ora_camera_setup": (None, [C.POINTER(capi.opr_camera)]),

@@ -250,3 +250,36 @@ def test_cuda_matches_reference_golden(product):
         if method == 2:
             flags = r.debug_buffer("hitpoints", ol.HITPOINT_DT, size * size)["flags"]
             assert (flags == gold["hitpoint_flags"]).mean() > 0.97
+
+
+@pytest.mark.parametrize("npix,nph,radius,coherent", [(1, 500, 30.0, True), (4096, 60000, 25.0, True), (5000, 60000, 40.0, False), (777, 3, 10.0, False)])
+def test_gather_matches_oracle(product, oracle, npix, nph, radius, coherent):
+    """The fixed-radius gather through the C ABI (opr_gather) against IndirectRadianceEstimation restated, on the same
+    hitpoints / sorted photons / offset table; incoherent hitpoints stress the per-warp cell-row union."""
+    lib, olib = capi.load_library(), oracle.load("oracle")
+    rng = np.random.default_rng(7)
+    ph = util.synthetic_photons(nph, 31, invalid_fraction=0.3)
+    g = util.oracle_grid(ph)
+    nv = g["numValid"]
+    sorted_ph = np.ascontiguousarray(g["photons"][:max(nv, 1)])
+    hp = np.zeros(npix, ol.HITPOINT_DT)
+    ext = np.array([556.0, 548.8, 559.2], np.float32)
+    if coherent:   # a camera-like sweep over the floor
+        u = np.linspace(0, 1, npix, dtype=np.float32)
+        hp["position"] = np.stack([u * ext[0], np.zeros(npix, np.float32), (0.3 + 0.4 * u) * ext[2]], 1)
+        hp["normal"] = np.array([0, 1, 0], np.float32)
+    else:
+        hp["position"] = rng.random((npix, 3), dtype=np.float32) * ext
+        n = rng.normal(size=(npix, 3)).astype(np.float32)
+        hp["normal"] = n / np.linalg.norm(n, axis=1, keepdims=True)
+    hp["attenuation"] = rng.random((npix, 3), dtype=np.float32)
+    hp["flags"] = np.where(rng.random(npix) < 0.85, ol.PRD_HIT_NON_SPECULAR, ol.PRD_MISS).astype(np.uint32)
+    gs = (C.c_uint32 * 3)(*g["gridSize"])
+    org = (C.c_float * 3)(*[float(x) for x in g["origo"]])
+    out, out0 = np.zeros((npix, 3), np.float32), np.zeros((npix, 3), np.float32)
+    args = lambda o: (npix, ol.fptr(hp.view(np.float32)), nv, ol.fptr(sorted_ph.view(np.float32)), ol.uptr(g["offsets"]), float(g["cellSize"]), gs, org,
+                      radius, 1000.0, ol.fptr(o))
+    assert lib.opr_gather(*args(out)) == 0, lib.opr_last_error()
+    assert olib.ora_gather(*args(out0)) == 0
+    assert np.allclose(out, out0, rtol=2e-5, atol=1e-7 * float(out0.max() + 1e-30))
+    assert (out[hp["flags"] != ol.PRD_HIT_NON_SPECULAR] == 0).all()
