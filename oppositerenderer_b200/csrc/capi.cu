@@ -298,7 +298,7 @@ int opr_gather(uint32_t numPixels, const float* hitpointsAoS, uint32_t numPhoton
         g.origo = make_float3(origo3[0], origo3[1], origo3[2]); g.numCells = gridSize3[0] * gridSize3[1] * gridSize3[2]; g.numValid = numPhotons;
         DevBuf dHp((size_t)numPixels * 64), p0((size_t)numPixels * 16), p1((size_t)numPixels * 16), p2((size_t)numPixels * 16), p3((size_t)numPixels * 16);
         DevBuf dPh((size_t)numPhotons * 36), a((size_t)numPhotons * 16 + 64), b((size_t)numPhotons * 16 + 64), c((size_t)numPhotons * 4 + 64), state((size_t)numPhotons + 64);
-        DevBuf dOff(((size_t)g.numCells + 1) * 4), dOut((size_t)numPixels * 12);
+        DevBuf dOff(((size_t)g.numCells + 1) * 4), dOut((size_t)numPixels * 12), dCounter(16);
         HitpointBuf hp{p0.as<float4>(), p1.as<float4>(), p2.as<float4>(), p3.as<float4>()};
         PhotonBuf pb{a.as<float4>(), b.as<float4>(), c.as<float>()};
         OPR_CUDA_CHECK(cudaMemcpy(dHp.p, hitpointsAoS, (size_t)numPixels * 64, cudaMemcpyHostToDevice));
@@ -306,7 +306,7 @@ int opr_gather(uint32_t numPixels, const float* hitpointsAoS, uint32_t numPhoton
         OPR_CUDA_CHECK(cudaMemcpy(dOff.p, offsets, ((size_t)g.numCells + 1) * 4, cudaMemcpyHostToDevice));
         hitpoints_aos_to_soa_kernel<<<148 * 4, 256>>>(dHp.as<float>(), numPixels, hp);
         if (numPhotons) photons_aos_to_soa_kernel<<<148 * 4, 256>>>(dPh.as<float>(), numPhotons, pb, state.as<unsigned>());
-        launch_gather(hp, numPixels, 0, 0, pb, dOff.as<unsigned>(), g, ppmRadius, ppmRadius * ppmRadius, emittedPhotons, dOut.as<float>(), lc);
+        launch_gather(hp, numPixels, 0, 0, pb, dOff.as<unsigned>(), g, ppmRadius, ppmRadius * ppmRadius, emittedPhotons, dOut.as<float>(), dCounter.as<unsigned>(), lc);
         OPR_CUDA_CHECK(cudaDeviceSynchronize());
         OPR_CUDA_CHECK(cudaGetLastError());
         OPR_CUDA_CHECK(cudaMemcpy(indirectOut, dOut.p, (size_t)numPixels * 12, cudaMemcpyDeviceToHost));

@@ -149,39 +149,55 @@ void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, un
 
 // ---- gather: IndirectRadianceEstimation::kernel (:69-129, :213-220), validPhoton :54-57, photonPower :59-67
 //
-// One warp gathers for an 8x4 pixel tile.  The reference lets every pixel walk its own cube of cells and read each
-// photon through the cache (13 of 32 lanes active on average, profiles/r1_baseline_ncu_summary.txt).  Here the
-// warp walks the UNION of its lanes' cell rows in the reference's order (z, then y, then the contiguous x-run of
-// sorted photons), stages 32 photons at a time in shared memory with coalesced 16-byte loads, and every lane that
-// needs the row tests the staged photons against its own hit point (shared-memory broadcast reads).  A lane
-// accumulates exactly the photons the reference accumulates, in the same order, so the sum is unchanged.
+// One 128-thread block gathers for an 8x4 pixel tile; lane l of every warp owns pixel l of the tile and the four
+// warps split the tile's cell rows between them.  The reference lets every pixel walk its own cube of cells and
+// read each photon through the cache (13 of 32 lanes active, SMs idle half of the kernel: profiles/r1_*).  Here a
+// warp walks rows of the UNION of its lanes' cubes in the reference's order (z, then y, then the contiguous x-run
+// of sorted photons), stages 32 photons at a time in shared memory with coalesced 16-byte loads, and every lane
+// that needs the row tests the staged photons against its own hit point (shared-memory broadcast reads).  A lane
+// accumulates exactly the photons the reference accumulates; the four per-warp partial sums are added in a fixed
+// order.  Tiles are handed out through an atomic counter so that photon-dense tiles do not leave SMs idle.
+OPR_DEV float exp2f_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 constexpr int GATHER_THREADS = 128;
 constexpr int GATHER_WARPS = GATHER_THREADS / 32;
 
 __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf hp, unsigned numPixels, unsigned width, unsigned height, PhotonBuf sorted,
                                                                     const unsigned* __restrict__ offsets, GridParams g, float ppmRadius, float ppmRadiusSquared,
-                                                                    float emittedPhotons, float* __restrict__ indirect)
+                                                                    float emittedPhotons, float* __restrict__ indirect, unsigned* __restrict__ tileCounter)
 {
     __shared__ float4 sA[GATHER_WARPS][32];
     __shared__ float4 sB[GATHER_WARPS][32];
     __shared__ float sC[GATHER_WARPS][32];
+    __shared__ float sAcc[GATHER_WARPS][32][3];
+    __shared__ unsigned sTile;
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned tilesX = width ? (width + 7) / 8 : 0;
     const unsigned numTiles = width ? tilesX * ((height + 3) / 4) : (numPixels + 31) / 32;
     const float radius2 = ppmRadiusSquared, radius = ppmRadius;
     const float invCellSize = 1.f / g.cellSize;
     const unsigned gx = g.gridSize.x, gxy = g.gridSize.x * g.gridSize.y;
-    for (unsigned tile = blockIdx.x * GATHER_WARPS + w; tile < numTiles; tile += gridDim.x * GATHER_WARPS) {
+    // photonPower (:59-67): alpha*(1 - (1 - exp(-beta d2 / 2r2)) / (1 - e^-beta)) = w0 + w1*exp2(kexp*d2).  The two IEEE
+    // divisions and expf per photon saturated the XU pipe in the first version; one ex2.approx remains — the reference
+    // itself was built with -use_fast_math (RenderEngine.vcxproj:129).
+    const float alpha = 1.818f, beta = 1.953f, expNegativeBeta = 0.141847f;
+    const float w1 = alpha / (1 - expNegativeBeta), w0 = alpha - w1;
+    const float kexp = -beta / (2 * radius2) * 1.44269504088896341f;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTile = atomicAdd(tileCounter, 1u);
+        __syncthreads();
+        const unsigned tile = sTile;
+        if (tile >= numTiles) break;
         unsigned p; bool inImage;
         if (width) {
             const unsigned x = (tile % tilesX) * 8 + (lane & 7), y = (tile / tilesX) * 4 + (lane >> 3);
             inImage = x < width && y < height; p = y * width + x;
         } else { p = tile * 32 + lane; inImage = p < numPixels; }
-        float3 pos = f3(0.f), nrm = f3(0.f), attenuation = f3(0.f);
+        float3 pos = f3(0.f), nrm = f3(0.f);
         bool active = false;
         if (inImage) {
             const float4 pos4 = hp.pos[p];
-            attenuation = f3(hp.att[p]);
             if (__float_as_uint(pos4.w) & PRD_HIT_NON_SPECULAR) { active = true; pos = f3(pos4); nrm = f3(hp.nrm[p]); }
         }
         unsigned x_lo = 0xffffffffu, y_lo = 0xffffffffu, z_lo = 0xffffffffu, x_hi = 0, y_hi = 0, z_hi = 0;
@@ -199,51 +215,59 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
         if (__any_sync(0xffffffffu, active)) {
             const unsigned uy_lo = __reduce_min_sync(0xffffffffu, active ? y_lo : 0xffffffffu), uy_hi = __reduce_max_sync(0xffffffffu, active ? y_hi : 0u);
             const unsigned uz_lo = __reduce_min_sync(0xffffffffu, active ? z_lo : 0xffffffffu), uz_hi = __reduce_max_sync(0xffffffffu, active ? z_hi : 0u);
-            for (unsigned z = uz_lo; z <= uz_hi; z++) {
-                for (unsigned y = uy_lo; y <= uy_hi; y++) {
-                    const bool need = active && z >= z_lo && z <= z_hi && y >= y_lo && y <= y_hi;   // the rows the reference visits for this lane
-                    if (!__any_sync(0xffffffffu, need)) continue;
-                    const unsigned rx_lo = __reduce_min_sync(0xffffffffu, need ? x_lo : 0xffffffffu), rx_hi = __reduce_max_sync(0xffffffffu, need ? x_hi : 0u);
-                    const unsigned from = rx_lo + y * gx + z * gxy;
-                    const unsigned begin = __ldg(offsets + from), end = __ldg(offsets + from + (rx_hi - rx_lo) + 1);
-                    for (unsigned base = begin; base < end; base += 32) {
-                        const unsigned i = base + lane;
-                        if (i < end) { sA[w][lane] = __ldg(sorted.a + i); sB[w][lane] = __ldg(sorted.b + i); sC[w][lane] = __ldg(sorted.c + i); }
-                        __syncwarp();
-                        const unsigned cnt = min(32u, end - base);
-                        if (need) {
-                            for (unsigned j = 0; j < cnt; j++) {
-                                const float4 a = sA[w][j];
-                                const float3 diff = pos - f3(a);
-                                const float distance2 = dot(diff, diff);
-                                if (distance2 <= radius2) {
-                                    const float4 b = sB[w][j];
-                                    if (dot(-f3(a.w, b.w, sC[w][j]), nrm) >= 0) {
-                                        const float alpha = 1.818f, beta = 1.953f, expNegativeBeta = 0.141847f;
-                                        const float weight = alpha * (1 - (1 - expf(-beta * distance2 / (2 * radius2))) / (1 - expNegativeBeta));
-                                        acc += f3(b) * weight;
-                                    }
+            const unsigned ny = uy_hi - uy_lo + 1, numRows = ny * (uz_hi - uz_lo + 1);
+            for (unsigned row = w; row < numRows; row += GATHER_WARPS) {   // rows in (z, y) order, interleaved over the warps
+                const unsigned z = uz_lo + row / ny, y = uy_lo + row % ny;
+                const bool need = active && z >= z_lo && z <= z_hi && y >= y_lo && y <= y_hi;   // the rows the reference visits for this lane
+                if (!__any_sync(0xffffffffu, need)) continue;
+                const unsigned rx_lo = __reduce_min_sync(0xffffffffu, need ? x_lo : 0xffffffffu), rx_hi = __reduce_max_sync(0xffffffffu, need ? x_hi : 0u);
+                const unsigned from = rx_lo + y * gx + z * gxy;
+                const unsigned begin = __ldg(offsets + from), end = __ldg(offsets + from + (rx_hi - rx_lo) + 1);
+                for (unsigned base = begin; base < end; base += 32) {
+                    const unsigned i = base + lane;
+                    if (i < end) { sA[w][lane] = __ldg(sorted.a + i); sB[w][lane] = __ldg(sorted.b + i); sC[w][lane] = __ldg(sorted.c + i); }
+                    __syncwarp();
+                    const unsigned cnt = min(32u, end - base);
+                    if (need) {
+                        #pragma unroll 4
+                        for (unsigned j = 0; j < cnt; j++) {
+                            const float4 a = sA[w][j];
+                            const float dx = pos.x - a.x, dy = pos.y - a.y, dz = pos.z - a.z;
+                            const float distance2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            if (distance2 <= radius2) {
+                                const float4 b = sB[w][j];
+                                if (fmaf(sC[w][j], nrm.z, fmaf(b.w, nrm.y, a.w * nrm.x)) <= 0.f) {   // dot(-rayDirection, normal) >= 0
+                                    const float weight = fmaf(w1, exp2f_approx(kexp * distance2), w0);
+                                    acc.x = fmaf(b.x, weight, acc.x); acc.y = fmaf(b.y, weight, acc.y); acc.z = fmaf(b.z, weight, acc.z);
                                 }
                             }
                         }
-                        __syncwarp();
                     }
+                    __syncwarp();
                 }
             }
         }
-        if (inImage) {
-            const float3 ind = acc * attenuation * (1.0f / (PI_F * ppmRadiusSquared)) * (1.0f / emittedPhotons);
+        sAcc[w][lane][0] = acc.x; sAcc[w][lane][1] = acc.y; sAcc[w][lane][2] = acc.z;
+        __syncthreads();
+        if (w == 0 && inImage) {
+            float3 sum = f3(0.f);
+            #pragma unroll
+            for (int ww = 0; ww < GATHER_WARPS; ww++) { sum.x += sAcc[ww][lane][0]; sum.y += sAcc[ww][lane][1]; sum.z += sAcc[ww][lane][2]; }
+            const float3 attenuation = f3(hp.att[p]);
+            const float3 ind = sum * attenuation * (1.0f / (PI_F * ppmRadiusSquared)) * (1.0f / emittedPhotons);
             indirect[3 * (size_t)p] = ind.x; indirect[3 * (size_t)p + 1] = ind.y; indirect[3 * (size_t)p + 2] = ind.z;
         }
     }
 }
 
 void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
-                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, LaunchCtx lc)
+                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc)
 {
     const unsigned numTiles = width ? ((width + 7) / 8) * ((height + 3) / 4) : (numPixels + 31) / 32;
-    int blocks = (int)std::min<unsigned>((numTiles + GATHER_WARPS - 1) / GATHER_WARPS, 148 * 16);
-    ppm_gather_kernel<<<blocks, GATHER_THREADS, 0, lc.st>>>(hp, numPixels, width, height, sorted, offsets, g, ppmRadius, ppmRadiusSquared, emittedPhotons, indirect);
+    int blocks = (int)std::min<unsigned>(numTiles, 148 * 12);
+    OPR_CUDA_CHECK(cudaMemsetAsync(tileCounter, 0, sizeof(unsigned), lc.st));
+    ppm_gather_kernel<<<blocks, GATHER_THREADS, 0, lc.st>>>(hp, numPixels, width, height, sorted, offsets, g, ppmRadius, ppmRadiusSquared, emittedPhotons, indirect,
+                                                            tileCounter);
     ++*lc.launches;
 }
 

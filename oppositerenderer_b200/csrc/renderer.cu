@@ -194,7 +194,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     {
         ScopedTimer t(*this, "ppm.gather");
         launch_gather(hp, width * height, width, height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
-                      float(photonLaunchWidth * photonLaunchHeight), indirect, lc);
+                      float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + 12, lc);
     }
     // ---- PPM_DIRECT_RADIANCE_ESTIMATION_PASS + PPM_OUTPUT_PASS (:664, :670)
     {

@@ -143,7 +143,7 @@ void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsig
 void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, GridParams g, unsigned* keys, unsigned* hist, LaunchCtx lc);
 void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned numValid, const PhotonBuf& dst, LaunchCtx lc);
 void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
-                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, LaunchCtx lc);
+                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc);
 
 // host-side restatement of createUniformGridPhotonMap's scalar part (OptixRenderer_SpatialHash.cu:209-250)
 bool compute_grid_params(const float lo[3], const float hi[3], GridParams& g);
