@@ -212,8 +212,9 @@ def main():
 
     # ---- warm-up, then the device-timed region (inputs resident in HBM)
     run(args.warmup, 0)
-    launches0 = r.stats()["launches"]
     barrier()
+    st0 = r.stats()          # counters are cumulative: everything reported below is the difference over the timed region
+    launches0 = st0["launches"]
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -227,7 +228,7 @@ def main():
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     st = r.stats()
-    rays = st["closest_rays"] + st["any_rays"]
+    rays = (st["closest_rays"] + st["any_rays"]) - (st0["closest_rays"] + st0["any_rays"])
 
     # ---- end to end through the C ABI with host buffers: request struct in, W*H*3 floats out every step
     host_out = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()
@@ -237,7 +238,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     st2 = r.stats()
-    rays_e2e = st2["closest_rays"] + st2["any_rays"] - rays
+    rays_e2e = (st2["closest_rays"] + st2["any_rays"]) - (st["closest_rays"] + st["any_rays"])
 
     t = torch.tensor([ms, float(rays), e2e_s, float(rays_e2e)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -297,7 +298,7 @@ def main():
         line = {"metric": "ppm_rays_per_second", "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "iterations_per_s": total_steps / (ms * 1e-3), "rays_per_iteration": rays / total_steps,
-                "photons_stored_per_iteration": st["photons_stored"] / max(1, (args.warmup + args.steps)),
+                "photons_stored_per_iteration": (st["photons_stored"] - st0["photons_stored"]) / max(1, args.steps),
                 "e2e": {"value": rays_e2e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.opr_request_details),
                         "d2h_bytes_per_step": W * H * 12, "iterations_per_s": total_steps / e2e_s,
                         "how": "opr_render_next_iteration + opr_get_output_buffer into pinned host memory every step, wall clock, max over ranks"},
