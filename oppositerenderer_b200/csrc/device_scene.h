@@ -12,7 +12,8 @@ class DeviceScene {
 public:
     SceneView view{};
     unsigned numPrims = 0, numTriangles = 0;
-    int numNodes = 0;
+    int numNodes = 0, bvhLevels = 0, plocRounds = 0;   // 4-wide nodes, collapse levels, PLOC rounds
+    float sahCost = 0.f;                                // SAH cost of the binary tree / root area
     float3 aabbMin{}, aabbMax{};
     std::vector<opr_light> hostLights;
 

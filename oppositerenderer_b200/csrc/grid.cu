@@ -183,6 +183,9 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
     const float alpha = 1.818f, beta = 1.953f, expNegativeBeta = 0.141847f;
     const float w1 = alpha / (1 - expNegativeBeta), w0 = alpha - w1;
     const float kexp = -beta / (2 * radius2) * 1.44269504088896341f;
+    // cull radius: a relative margin (plus the fp32 error of cell coordinates ~ extent * 2^-22) keeps the cull conservative
+    const float cullRadius = radius * 1.0001f + 1e-6f * g.cellSize * (float)max(max(g.gridSize.x, g.gridSize.y), g.gridSize.z);
+    const float cullRadius2 = cullRadius * cullRadius;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) sTile = atomicAdd(tileCounter, 1u);
@@ -201,8 +204,10 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
             if (__float_as_uint(pos4.w) & PRD_HIT_NON_SPECULAR) { active = true; pos = f3(pos4); nrm = f3(hp.nrm[p]); }
         }
         unsigned x_lo = 0xffffffffu, y_lo = 0xffffffffu, z_lo = 0xffffffffu, x_hi = 0, y_hi = 0, z_hi = 0;
+        float3 npos = f3(0.f);
         if (active) {
             const float3 np = pos - g.origo;
+            npos = np;
             x_lo = (unsigned)max(0, (int)((np.x - radius) * invCellSize));
             y_lo = (unsigned)max(0, (int)((np.y - radius) * invCellSize));
             z_lo = (unsigned)max(0, (int)((np.z - radius) * invCellSize));
@@ -218,9 +223,26 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
             const unsigned ny = uy_hi - uy_lo + 1, numRows = ny * (uz_hi - uz_lo + 1);
             for (unsigned row = w; row < numRows; row += GATHER_WARPS) {   // rows in (z, y) order, interleaved over the warps
                 const unsigned z = uz_lo + row / ny, y = uy_lo + row % ny;
-                const bool need = active && z >= z_lo && z <= z_hi && y >= y_lo && y <= y_hi;   // the rows the reference visits for this lane
+                bool need = active && z >= z_lo && z <= z_hi && y >= y_lo && y <= y_hi;   // the rows the reference visits for this lane
+                // Sphere cull (results unchanged): the reference walks the whole cube of cells and rejects photons one by one with
+                // distance2 <= radius2; cells of this row that lie entirely outside the (slightly inflated) sphere cannot hold an
+                // accepted photon, so the lane's x-run shrinks to the chord of the sphere at this (y, z) slab.
+                unsigned lx_lo = x_lo, lx_hi = x_hi;
+                if (need) {
+                    const float cy0 = (float)y * g.cellSize, cz0 = (float)z * g.cellSize;
+                    const float dy = fmaxf(fmaxf(cy0 - npos.y, npos.y - (cy0 + g.cellSize)), 0.f);
+                    const float dz = fmaxf(fmaxf(cz0 - npos.z, npos.z - (cz0 + g.cellSize)), 0.f);
+                    const float rem = cullRadius2 - dy * dy - dz * dz;
+                    if (rem < 0.f) need = false;
+                    else {
+                        const float hw = sqrtf(rem);
+                        lx_lo = max(x_lo, (unsigned)max(0, (int)((npos.x - hw) * invCellSize)));
+                        lx_hi = min(x_hi, (unsigned)fmaxf((npos.x + hw) * invCellSize, 0.f));
+                        if (lx_lo > lx_hi) need = false;
+                    }
+                }
                 if (!__any_sync(0xffffffffu, need)) continue;
-                const unsigned rx_lo = __reduce_min_sync(0xffffffffu, need ? x_lo : 0xffffffffu), rx_hi = __reduce_max_sync(0xffffffffu, need ? x_hi : 0u);
+                const unsigned rx_lo = __reduce_min_sync(0xffffffffu, need ? lx_lo : 0xffffffffu), rx_hi = __reduce_max_sync(0xffffffffu, need ? lx_hi : 0u);
                 const unsigned from = rx_lo + y * gx + z * gxy;
                 const unsigned begin = __ldg(offsets + from), end = __ldg(offsets + from + (rx_hi - rx_lo) + 1);
                 for (unsigned base = begin; base < end; base += 32) {

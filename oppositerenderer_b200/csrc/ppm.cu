@@ -55,6 +55,14 @@ OPR_DEV float3 getNormalMappedNormal(const float3& normal, const float3& tangent
     return normalize(N);
 }
 
+// Per-bounce queue counters (renderer.h CTR_*): the generation kernel of a pass zeroes them and seeds bounce 0 with the
+// launch size, so the bounce loop needs no memset.  The trace kernel of bounce 0 is stream-ordered after this kernel.
+OPR_DEV void reset_wave_counters(unsigned* __restrict__ counters, unsigned n)
+{
+    if (blockIdx.x == 0)
+        for (unsigned i = CTR_RAYCOUNT + threadIdx.x; i < CTR_TOTAL; i += blockDim.x) counters[i] = (i == CTR_RAYCOUNT) ? n : 0u;
+}
+
 // ---- RNG state init: initRandomStateBuffer (OptixRenderer_SpatialHash.cu:310-317) ---------------------
 __global__ void rng_init_kernel(RngBuf rng, unsigned seed, size_t n)
 {
@@ -72,9 +80,10 @@ void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc)
 // ---- camera pass: RayGeneratorPPM::generateRay (ppm/RayGeneratorPPM.cu:31-66) + DOF (helpers/camera.h:11-27)
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_gen_kernel(opr_camera cam, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf,
                                                                        HitpointBuf hp, float4* __restrict__ rayO, float4* __restrict__ rayD,
-                                                                       unsigned* __restrict__ rayPath)
+                                                                       unsigned* __restrict__ rayPath, unsigned* __restrict__ counters)
 {
     const unsigned n = w * h;
+    reset_wave_counters(counters, n);
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const unsigned x = p % w, y = p / w;
         const size_t ri = (size_t)y * rsW + x;
@@ -115,13 +124,90 @@ void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsign
 {
     unsigned n = w * h;
     int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
-    ppm_camera_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(cam, w, h, rsW, rng, hp, q.rayO[0], q.rayD[0], q.rayPath[0]);
+    ppm_camera_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(cam, w, h, rsW, rng, hp, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters);
     ++*lc.launches;
 }
 
-// RADIANCE closest-hit programs, one material kind per blockIdx.y.
-//   Diffuse.cu:71-87, Glossy.cu:74-90, Texture.cu:83-110, DiffuseEmitter.cu:40-51, Mirror.cu:50-63,
-//   Glass.cu:90-143, miss RayGeneratorPPM.cu:72-77.
+// RADIANCE closest-hit programs (Diffuse.cu:71-87, Glossy.cu:74-90, Texture.cu:83-110, DiffuseEmitter.cu:40-51,
+// Mirror.cu:50-63, Glass.cu:90-143, miss RayGeneratorPPM.cu:72-77) for ONE hit of camera path p.  Path state (the
+// RadiancePRD fields) lives in the hitpoint SoA.  Returns true when the program recursed (rtTrace): the continuation
+// ray is (newO, newD) with tmin 1e-4.
+OPR_DEV bool shade_camera_hit(const SceneView& sc, int kind, unsigned p, const float3& o, const float3& d, const HitRec& hit, unsigned w, unsigned rsW,
+                              const RngBuf& rngBuf, const HitpointBuf& hp, float3& newO, float3& newD)
+{
+    if (kind == QUEUE_MISS) {
+        hp.pos[p].w = __uint_as_float(PRD_MISS);
+        hp.att[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        hp.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return false;
+    }
+    bool push = false;
+    const Surface sf = eval_surface(sc, hit, o, d);
+    const DMaterial& m = sc.materials[sf.material];
+    const float tHit = hit.t;
+    unsigned flags = __float_as_uint(hp.pos[p].w);
+    unsigned depth = __float_as_uint(hp.nrm[p].w);
+    float3 att = f3(hp.att[p]);
+    const float3 worldShadingNormal = normalize(sf.shadingNormal);
+    const float3 hitPoint = o + tHit * d;
+    if (kind == OPR_MAT_DIFFUSE || kind == OPR_MAT_GLOSSY) {
+        flags |= PRD_HIT_NON_SPECULAR;
+        att *= m.Kd;
+        depth++;
+        hp.pos[p] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, __uint_as_float(flags));
+        hp.nrm[p] = make_float4(worldShadingNormal.x, worldShadingNormal.y, worldShadingNormal.z, __uint_as_float(depth));
+        hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
+    } else if (kind == OPR_MAT_TEXTURE) {
+        float3 normal = worldShadingNormal;
+        if (m.hasNormalTex) {
+            float3 worldTangent = normalize(sf.tangent), worldBitangent = normalize(sf.bitangent);
+            normal = getNormalMappedNormal(worldShadingNormal, worldTangent, worldBitangent, tex2D<float4>(m.normalTex, sf.uv.x, sf.uv.y));
+        }
+        flags |= PRD_HIT_NON_SPECULAR;
+        float4 value = tex2D<float4>(m.diffuseTex, sf.uv.x, sf.uv.y);
+        att *= f3(value.x, value.y, value.z);
+        hp.pos[p] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, __uint_as_float(flags));
+        hp.nrm[p] = make_float4(normal.x, normal.y, normal.z, __uint_as_float(depth));   // no depth++ (Texture.cu:83-110)
+        hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
+    } else if (kind == OPR_MAT_DIFFUSE_EMITTER) {
+        flags |= PRD_HIT_EMITTER;
+        hp.pos[p].w = __uint_as_float(flags);
+        if (!(dot(worldShadingNormal, -d) < 0.f)) {
+            float3 Le = m.powerPerArea / PI_F;
+            float3 rad = f3(hp.rad[p]);
+            rad += att * Le;
+            hp.rad[p] = make_float4(rad.x, rad.y, rad.z, 0.f);
+        }
+    } else if (kind == OPR_MAT_MIRROR) {
+        depth++;
+        hp.nrm[p].w = __uint_as_float(depth);
+        if (depth <= MAX_RADIANCE_TRACE_DEPTH) {
+            att *= m.Kr;
+            hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
+            newO = hitPoint; newD = reflect(d, worldShadingNormal);
+            push = true;
+        }
+    } else {   // OPR_MAT_GLASS
+        const size_t ri = rng_index(p, w, rsW);
+        Rng rng = rng_load(rngBuf, ri);
+        bool isReflected; float n1, n2;
+        newD = glass_scatter(d, worldShadingNormal, m.ior, rng, isReflected, n1, n2);
+        rng_store(rngBuf, ri, rng);
+        if (!isReflected) att *= (n2 * n2) / (n1 * n1);
+        flags |= PRD_HIT_SPECULAR;
+        flags &= ~PRD_HIT_NON_SPECULAR;
+        depth++;
+        newO = hitPoint;
+        if (depth <= MAX_RADIANCE_TRACE_DEPTH) push = true;
+        else att *= 0.f;
+        hp.pos[p].w = __uint_as_float(flags);
+        hp.nrm[p].w = __uint_as_float(depth);
+        hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
+    }
+    return push;
+}
+
+// Wavefront shading of one bounce, one material kind per blockIdx.y (the queues the trace kernel filled).
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneView sc, unsigned w, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
                                                                          const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                          const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
@@ -141,77 +227,14 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneVi
         if (active) {
             const unsigned slot = queue[qi];
             p = rayPath[slot];
-            if (kind == QUEUE_MISS) {
-                hp.pos[p].w = __uint_as_float(PRD_MISS);
-                hp.att[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                hp.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
+            HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
+            float3 o = f3(0.f), d = f3(0.f);
+            if (kind != QUEUE_MISS) {
                 const float4 o4 = rayO[slot], d4 = rayD[slot], h4 = hits[slot];
-                const float3 o = f3(o4), d = f3(d4);
-                HitRec hit; hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
-                const Surface sf = eval_surface(sc, hit, o, d);
-                const DMaterial& m = sc.materials[sf.material];
-                const float tHit = hit.t;
-                unsigned flags = __float_as_uint(hp.pos[p].w);
-                unsigned depth = __float_as_uint(hp.nrm[p].w);
-                float3 att = f3(hp.att[p]);
-                const float3 worldShadingNormal = normalize(sf.shadingNormal);
-                const float3 hitPoint = o + tHit * d;
-                if (kind == OPR_MAT_DIFFUSE || kind == OPR_MAT_GLOSSY) {
-                    flags |= PRD_HIT_NON_SPECULAR;
-                    att *= m.Kd;
-                    depth++;
-                    hp.pos[p] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, __uint_as_float(flags));
-                    hp.nrm[p] = make_float4(worldShadingNormal.x, worldShadingNormal.y, worldShadingNormal.z, __uint_as_float(depth));
-                    hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
-                } else if (kind == OPR_MAT_TEXTURE) {
-                    float3 normal = worldShadingNormal;
-                    if (m.hasNormalTex) {
-                        float3 worldTangent = normalize(sf.tangent), worldBitangent = normalize(sf.bitangent);
-                        normal = getNormalMappedNormal(worldShadingNormal, worldTangent, worldBitangent, tex2D<float4>(m.normalTex, sf.uv.x, sf.uv.y));
-                    }
-                    flags |= PRD_HIT_NON_SPECULAR;
-                    float4 value = tex2D<float4>(m.diffuseTex, sf.uv.x, sf.uv.y);
-                    att *= f3(value.x, value.y, value.z);
-                    hp.pos[p] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, __uint_as_float(flags));
-                    hp.nrm[p] = make_float4(normal.x, normal.y, normal.z, __uint_as_float(depth));   // no depth++ (Texture.cu:83-110)
-                    hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
-                } else if (kind == OPR_MAT_DIFFUSE_EMITTER) {
-                    flags |= PRD_HIT_EMITTER;
-                    hp.pos[p].w = __uint_as_float(flags);
-                    if (!(dot(worldShadingNormal, -d) < 0.f)) {
-                        float3 Le = m.powerPerArea / PI_F;
-                        float3 rad = f3(hp.rad[p]);
-                        rad += att * Le;
-                        hp.rad[p] = make_float4(rad.x, rad.y, rad.z, 0.f);
-                    }
-                } else if (kind == OPR_MAT_MIRROR) {
-                    depth++;
-                    hp.nrm[p].w = __uint_as_float(depth);
-                    if (depth <= MAX_RADIANCE_TRACE_DEPTH) {
-                        att *= m.Kr;
-                        hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
-                        newO = hitPoint; newD = reflect(d, worldShadingNormal);
-                        push = true;
-                    }
-                } else {   // OPR_MAT_GLASS
-                    const size_t ri = rng_index(p, w, rsW);
-                    Rng rng = rng_load(rngBuf, ri);
-                    bool isReflected; float n1, n2;
-                    newD = glass_scatter(d, worldShadingNormal, m.ior, rng, isReflected, n1, n2);
-                    rng_store(rngBuf, ri, rng);
-                    if (!isReflected) att *= (n2 * n2) / (n1 * n1);
-                    flags |= PRD_HIT_SPECULAR;
-                    flags &= ~PRD_HIT_NON_SPECULAR;
-                    depth++;
-                    newO = hitPoint;
-                    if (depth <= MAX_RADIANCE_TRACE_DEPTH) push = true;
-                    else att *= 0.f;
-                    hp.pos[p].w = __uint_as_float(flags);
-                    hp.nrm[p].w = __uint_as_float(depth);
-                    hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
-                }
+                o = f3(o4); d = f3(d4);
+                hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
             }
+            push = shade_camera_hit(sc, kind, p, o, d, hit, w, rsW, rngBuf, hp, newO, newD);
         }
         // ray regeneration: one atomicAdd per warp
         const unsigned dst = warp_append(nextCount, push);
@@ -223,22 +246,64 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneVi
     }
 }
 
+// Tail of the camera pass: the few specular continuation rays left after the wavefront bounces are finished here, one
+// thread per path looping trace -> material program until the path ends (the reference's recursion, unrolled in place).
+// A near-empty wavefront bounce costs a full trace + shade launch pair whose duration is one ray's dependent-load
+// latency; this kernel pays that latency once per path instead of once per bounce.
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_tail_kernel(SceneView sc, unsigned w, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
+                                                                        const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+                                                                        const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
+                                                                        unsigned* __restrict__ stat)
+{
+    const unsigned n = *count;
+    unsigned traced = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = rayO[i], d4 = rayD[i];
+        const unsigned p = rayPath[i];
+        float3 o = f3(o4), d = f3(d4);
+        float tmin = o4.w;
+        for (;;) {
+            HitRec hit;
+            traverse<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit);
+            traced++;
+            const int kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
+            float3 newO = f3(0.f), newD = f3(0.f);
+            if (!shade_camera_hit(sc, kind, p, o, d, hit, w, rsW, rngBuf, hp, newO, newD)) break;
+            o = newO; d = newD; tmin = 0.0001f;
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, s);
+    if ((threadIdx.x & 31) == 0 && traced) atomicAdd(stat, traced);
+}
+
 void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
-                             const RayQueues& q, int cur, LaunchCtx lc)
+                             const RayQueues& q, int bounce, LaunchCtx lc)
 {
     dim3 grid(SHADE_BLOCKS_X, NUM_QUEUES);
-    const int nxt = cur ^ 1;
+    const int cur = bounce & 1, nxt = cur ^ 1;
     ppm_camera_shade_kernel<<<grid, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
-                                                               q.counters + 2, q.capacity, q.rayO[nxt], q.rayD[nxt], q.rayPath[nxt], q.counters + nxt);
+                                                               q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.rayO[nxt], q.rayD[nxt], q.rayPath[nxt],
+                                                               q.counters + CTR_RAYCOUNT + bounce + 1);
+    ++*lc.launches;
+}
+
+void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, int bounce,
+                            LaunchCtx lc)
+{
+    const int cur = bounce & 1;
+    ppm_camera_tail_kernel<<<148 * 4, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
+                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS);
     ++*lc.launches;
 }
 
 // ---- photon pass: PhotonGenerator::generator (ppm/PhotonGenerator.cu:40-128) ----------------------------
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_gen_kernel(SceneView sc, unsigned pw, unsigned ph, unsigned rsW, RngBuf rngBuf,
                                                                        float4* __restrict__ phPower, unsigned* __restrict__ phState,
-                                                                       float4* __restrict__ rayO, float4* __restrict__ rayD, unsigned* __restrict__ rayPath)
+                                                                       float4* __restrict__ rayO, float4* __restrict__ rayD, unsigned* __restrict__ rayPath,
+                                                                       unsigned* __restrict__ counters)
 {
     const unsigned n = pw * ph;
+    reset_wave_counters(counters, n);
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const unsigned x = t % pw, y = t / pw;
         const size_t ri = (size_t)y * rsW + x;
@@ -292,12 +357,92 @@ void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsign
 {
     unsigned n = pw * ph;
     int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
-    ppm_photon_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, pw, ph, rsW, rng, phPower, phState, q.rayO[0], q.rayD[0], q.rayPath[0]);
+    ppm_photon_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, pw, ph, rsW, rng, phPower, phState, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters);
     ++*lc.launches;
 }
 
-// PHOTON closest-hit programs: Diffuse.cu:92-135, Glossy.cu:94-137, Texture.cu:116-175, Mirror.cu:65-77,
-// Glass.cu:164-205, DiffuseEmitter.cu:56-59; miss is a no-op (PhotonGenerator.cu:132-135).
+// PHOTON closest-hit programs (Diffuse.cu:92-135, Glossy.cu:94-137, Texture.cu:116-175, Mirror.cu:65-77,
+// Glass.cu:164-205, DiffuseEmitter.cu:56-59; the miss program is a no-op, PhotonGenerator.cu:132-135) for ONE hit of
+// photon thread t.  PhotonPRD lives in phPower / phState.  Returns true when the program recursed.
+OPR_DEV bool shade_photon_hit(const SceneView& sc, int kind, unsigned t, const float3& o, const float3& d, const HitRec& hit, unsigned pw, unsigned rsW,
+                              const RngBuf& rngBuf, float4* __restrict__ phPower, unsigned* __restrict__ phState, const PhotonBuf& photons,
+                              float3& newO, float3& newD, float& newTmin)
+{
+    bool push = false;
+    newTmin = 0.0001f;
+    unsigned state = phState[t];
+    unsigned depth = state & 0xffu, numStored = (state >> 8) & 0xffu;
+    if (kind == OPR_MAT_DIFFUSE_EMITTER) {
+        depth++;
+    } else {
+        const Surface sf = eval_surface(sc, hit, o, d);
+        const DMaterial& m = sc.materials[sf.material];
+        const float3 worldShadingNormal = normalize(sf.shadingNormal);
+        const float3 hitPoint = o + hit.t * d;
+        float4 pw4 = phPower[t];
+        float3 power = f3(pw4);
+        float weight = pw4.w;
+        if (kind == OPR_MAT_MIRROR) {
+            depth++;
+            if (depth <= MAX_PHOTON_TRACE_DEPTH) {
+                power *= m.Kr;
+                newO = hitPoint; newD = reflect(d, worldShadingNormal); push = true;
+            }
+        } else if (kind == OPR_MAT_GLASS) {
+            const size_t ri = rng_index(t, pw, rsW);
+            Rng rng = rng_load(rngBuf, ri);
+            bool isReflected; float n1, n2;
+            newD = glass_scatter(d, worldShadingNormal, m.ior, rng, isReflected, n1, n2);
+            rng_store(rngBuf, ri, rng);
+            depth++;
+            newO = hitPoint;
+            if (depth <= MAX_PHOTON_TRACE_DEPTH) push = true;
+        } else {   // Diffuse / Glossy / Texture
+            const bool tex = (kind == OPR_MAT_TEXTURE);
+            if (depth >= 1 && numStored < MAX_PHOTON_DEPOSITS) {
+                // STORE_PHOTON (helpers/store_photon.h:12-15): slot pm_index + numStoredPhotons
+                const size_t ps = (size_t)t * MAX_PHOTON_DEPOSITS + numStored;
+                photons.a[ps] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, d.x);
+                photons.b[ps] = make_float4(power.x, power.y, power.z, d.y);
+                photons.c[ps] = d.z;
+                numStored++;
+            }
+            float3 albedo;
+            if (tex) { float4 v = tex2D<float4>(m.diffuseTex, sf.uv.x, sf.uv.y); albedo = f3(v.x, v.y, v.z); }
+            else albedo = m.Kd;
+            power *= albedo;
+            weight *= fmax3(albedo);
+            bool alive = true;
+            Rng rng; bool rngLoaded = false;
+            const size_t ri = rng_index(t, pw, rsW);
+            if (depth >= PHOTON_TRACING_RR_START_DEPTH) {
+                rng = rng_load(rngBuf, ri); rngLoaded = true;
+                float probContinue = favgf(albedo);
+                float probSample = rng_uniform(rng);
+                if (probSample >= probContinue) alive = false;
+                else power /= probContinue;
+            }
+            if (alive) {
+                depth++;
+                if (depth >= MAX_PHOTON_TRACE_DEPTH || (double)weight < (tex ? 0.01 : 0.001)) alive = false;
+            }
+            if (alive && numStored >= MAX_PHOTON_DEPOSITS) alive = false;
+            if (alive) {
+                if (!rngLoaded) { rng = rng_load(rngBuf, ri); rngLoaded = true; }
+                float2 s = rng_uniform2(rng);
+                newD = sampleUnitHemisphereCos(worldShadingNormal, s);
+                newO = hitPoint;
+                newTmin = tex ? 0.01f : 0.0001f;
+                push = true;
+            }
+            if (rngLoaded) rng_store(rngBuf, ri, rng);
+        }
+        phPower[t] = make_float4(power.x, power.y, power.z, weight);
+    }
+    phState[t] = depth | (numStored << 8);
+    return push;
+}
+
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf,
                                                                          float4* __restrict__ phPower, unsigned* __restrict__ phState, PhotonBuf photons,
                                                                          const float4* __restrict__ rayO, const float4* __restrict__ rayD,
@@ -320,79 +465,14 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneVi
         if (active) {
             const unsigned slot = queue[qi];
             t = rayPath[slot];
-            unsigned state = phState[t];
-            unsigned depth = state & 0xffu, numStored = (state >> 8) & 0xffu;
-            if (kind == OPR_MAT_DIFFUSE_EMITTER) {
-                depth++;
-            } else {
+            HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
+            float3 o = f3(0.f), d = f3(0.f);
+            if (kind != OPR_MAT_DIFFUSE_EMITTER) {
                 const float4 o4 = rayO[slot], d4 = rayD[slot], h4 = hits[slot];
-                const float3 o = f3(o4), d = f3(d4);
-                HitRec hit; hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
-                const Surface sf = eval_surface(sc, hit, o, d);
-                const DMaterial& m = sc.materials[sf.material];
-                const float3 worldShadingNormal = normalize(sf.shadingNormal);
-                const float3 hitPoint = o + hit.t * d;
-                float4 pw4 = phPower[t];
-                float3 power = f3(pw4);
-                float weight = pw4.w;
-                if (kind == OPR_MAT_MIRROR) {
-                    depth++;
-                    if (depth <= MAX_PHOTON_TRACE_DEPTH) {
-                        power *= m.Kr;
-                        newO = hitPoint; newD = reflect(d, worldShadingNormal); push = true;
-                    }
-                } else if (kind == OPR_MAT_GLASS) {
-                    const size_t ri = rng_index(t, pw, rsW);
-                    Rng rng = rng_load(rngBuf, ri);
-                    bool isReflected; float n1, n2;
-                    newD = glass_scatter(d, worldShadingNormal, m.ior, rng, isReflected, n1, n2);
-                    rng_store(rngBuf, ri, rng);
-                    depth++;
-                    newO = hitPoint;
-                    if (depth <= MAX_PHOTON_TRACE_DEPTH) push = true;
-                } else {   // Diffuse / Glossy / Texture
-                    const bool tex = (kind == OPR_MAT_TEXTURE);
-                    if (depth >= 1 && numStored < MAX_PHOTON_DEPOSITS) {
-                        // STORE_PHOTON (helpers/store_photon.h:12-15): slot pm_index + numStoredPhotons
-                        const size_t ps = (size_t)t * MAX_PHOTON_DEPOSITS + numStored;
-                        photons.a[ps] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, d.x);
-                        photons.b[ps] = make_float4(power.x, power.y, power.z, d.y);
-                        photons.c[ps] = d.z;
-                        numStored++;
-                    }
-                    float3 albedo;
-                    if (tex) { float4 v = tex2D<float4>(m.diffuseTex, sf.uv.x, sf.uv.y); albedo = f3(v.x, v.y, v.z); }
-                    else albedo = m.Kd;
-                    power *= albedo;
-                    weight *= fmax3(albedo);
-                    bool alive = true;
-                    Rng rng; bool rngLoaded = false;
-                    const size_t ri = rng_index(t, pw, rsW);
-                    if (depth >= PHOTON_TRACING_RR_START_DEPTH) {
-                        rng = rng_load(rngBuf, ri); rngLoaded = true;
-                        float probContinue = favgf(albedo);
-                        float probSample = rng_uniform(rng);
-                        if (probSample >= probContinue) alive = false;
-                        else power /= probContinue;
-                    }
-                    if (alive) {
-                        depth++;
-                        if (depth >= MAX_PHOTON_TRACE_DEPTH || (double)weight < (tex ? 0.01 : 0.001)) alive = false;
-                    }
-                    if (alive && numStored >= MAX_PHOTON_DEPOSITS) alive = false;
-                    if (alive) {
-                        if (!rngLoaded) { rng = rng_load(rngBuf, ri); rngLoaded = true; }
-                        float2 s = rng_uniform2(rng);
-                        newD = sampleUnitHemisphereCos(worldShadingNormal, s);
-                        newO = hitPoint;
-                        newTmin = tex ? 0.01f : 0.0001f;
-                        push = true;
-                    }
-                    if (rngLoaded) rng_store(rngBuf, ri, rng);
-                }
-                phPower[t] = make_float4(power.x, power.y, power.z, weight);
+                o = f3(o4); d = f3(d4);
+                hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
             }
-            phState[t] = depth | (numStored << 8);
+            push = shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin);
         }
         const unsigned dst = warp_append(nextCount, push);
         if (push) {
@@ -403,14 +483,53 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneVi
     }
 }
 
+// Tail of the photon pass (see ppm_camera_tail_kernel): photons still alive after the wavefront bounces finish their
+// random walk here, one thread per photon.
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_tail_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf, float4* __restrict__ phPower,
+                                                                        unsigned* __restrict__ phState, PhotonBuf photons, const float4* __restrict__ rayO,
+                                                                        const float4* __restrict__ rayD, const unsigned* __restrict__ rayPath,
+                                                                        const unsigned* __restrict__ count, unsigned* __restrict__ stat)
+{
+    const unsigned n = *count;
+    unsigned traced = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = rayO[i], d4 = rayD[i];
+        const unsigned t = rayPath[i];
+        float3 o = f3(o4), d = f3(d4);
+        float tmin = o4.w;
+        for (;;) {
+            HitRec hit;
+            traverse<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit);
+            traced++;
+            if (hit.prim < 0) break;   // miss: no-op
+            const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+            float3 newO = f3(0.f), newD = f3(0.f);
+            float newTmin;
+            if (!shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin)) break;
+            o = newO; d = newD; tmin = newTmin;
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, s);
+    if ((threadIdx.x & 31) == 0 && traced) atomicAdd(stat, traced);
+}
+
 void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
-                             const PhotonBuf& photons, const RayQueues& q, int cur, LaunchCtx lc)
+                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc)
 {
     dim3 grid(SHADE_BLOCKS_X, NUM_QUEUES);
-    const int nxt = cur ^ 1;
+    const int cur = bounce & 1, nxt = cur ^ 1;
     ppm_photon_shade_kernel<<<grid, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
-                                                               q.hits, q.matQueue, q.counters + 2, q.capacity, q.rayO[nxt], q.rayD[nxt], q.rayPath[nxt],
-                                                               q.counters + nxt);
+                                                               q.hits, q.matQueue, q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.rayO[nxt], q.rayD[nxt],
+                                                               q.rayPath[nxt], q.counters + CTR_RAYCOUNT + bounce + 1);
+    ++*lc.launches;
+}
+
+void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
+                            const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc)
+{
+    const int cur = bounce & 1;
+    ppm_photon_tail_kernel<<<148 * 8, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
+                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS);
     ++*lc.launches;
 }
 

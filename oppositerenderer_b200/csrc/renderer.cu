@@ -5,6 +5,7 @@
 #include "radix_sort.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace opr {
 
@@ -40,6 +41,9 @@ void Renderer::initialize(int cudaOrdinal)
     if (cudaOrdinal < 0 || cudaOrdinal >= count)
         throw std::runtime_error("Did not find OptiX device Number for given device. OptiX may not support this device.");   // :427-431 (message kept)
     device = cudaOrdinal;
+    // tuning knobs (measurement only; results do not depend on them)
+    if (const char* e = getenv("OPR_CAMERA_WAVES")) cameraWaveBounces = (unsigned)std::max(0, atoi(e));
+    if (const char* e = getenv("OPR_PHOTON_WAVES")) photonWaveBounces = (unsigned)std::max(0, atoi(e));
     OPR_CUDA_CHECK(cudaSetDevice(device));
     OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 
@@ -90,9 +94,9 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     const size_t cap = std::max(px, (size_t)photonLaunchWidth * photonLaunchHeight);
     q.capacity = (unsigned)cap;
     for (int i = 0; i < 2; i++) { dalloc(q.rayO[i], cap); dalloc(q.rayD[i], cap); dalloc(q.rayPath[i], cap); }
-    dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, 32);
+    dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, CTR_TOTAL);
     dalloc(indirect, px * 3); dalloc(direct, px * 3); dalloc(output, px * 3);
-    OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, 32 * sizeof(unsigned), stream));
+    OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, CTR_TOTAL * sizeof(unsigned), stream));
     OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, px * 3 * sizeof(float), stream));
     buffersAllocated = true;
     LaunchCtx lc{stream, &launches};
@@ -152,40 +156,32 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
 {
     LaunchCtx lc{stream, &launches};
     const SceneView& sc = scene.view;
-    // ---- PPM_RAYTRACE_PASS (:576)
+    // ---- PPM_RAYTRACE_PASS (:576): wavefront bounces, then one per-path tail kernel for the specular continuations
     {
         ScopedTimer t(*this, "ppm.camera");
-        unsigned c[2 + NUM_QUEUES + 1] = {0};
-        c[0] = width * height;
-        OPR_CUDA_CHECK(cudaMemcpyAsync(q.counters, c, sizeof(unsigned) * (2 + NUM_QUEUES), cudaMemcpyHostToDevice, stream));
         launch_ppm_camera_gen(details.camera, width, height, rsW, rng, hp, q, lc);
-        int cur = 0;
-        // depth <= MAX_RADIANCE_TRACE_DEPTH specular continuations + the primary ray
-        for (unsigned bounce = 0; bounce <= MAX_RADIANCE_TRACE_DEPTH; bounce++) {
-            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
-            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
-            if (bounce == 0) { ScopedTimer t0(*this, "trace.camera0"); launch_trace_closest(sc, q, cur, lc); }
-            else launch_trace_closest(sc, q, cur, lc);
-            launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, cur, lc);
-            cur ^= 1;
+        const unsigned waves = std::min(cameraWaveBounces, MAX_RADIANCE_TRACE_DEPTH + 1);
+        for (unsigned bounce = 0; bounce < waves; bounce++) {
+            if (bounce == 0) { ScopedTimer t0(*this, "trace.camera0"); launch_trace_closest_bounce(sc, q, bounce, lc); }
+            else launch_trace_closest_bounce(sc, q, bounce, lc);
+            launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, bounce, lc);
         }
+        if (waves <= MAX_RADIANCE_TRACE_DEPTH) { ScopedTimer t1(*this, "ppm.camera_tail"); launch_ppm_camera_tail(sc, width, rsW, rng, hp, q, waves, lc); }
     }
     const float ppmRadiusSquared = PPMRadius * PPMRadius;   // :585
     // ---- PPM_PHOTON_PASS (:612)
     {
         ScopedTimer t(*this, "ppm.photon");
-        unsigned c[2 + NUM_QUEUES + 1] = {0};
-        c[0] = photonLaunchWidth * photonLaunchHeight;
-        OPR_CUDA_CHECK(cudaMemcpyAsync(q.counters, c, sizeof(unsigned) * (2 + NUM_QUEUES), cudaMemcpyHostToDevice, stream));
         launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, lc);
-        int cur = 0;
-        for (unsigned bounce = 0; bounce <= MAX_PHOTON_TRACE_DEPTH; bounce++) {
-            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
-            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
-            if (bounce == 0) { ScopedTimer t0(*this, "trace.photon0"); launch_trace_closest(sc, q, cur, lc); }
-            else launch_trace_closest(sc, q, cur, lc);
-            launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, cur, lc);
-            cur ^= 1;
+        const unsigned waves = std::min(photonWaveBounces, MAX_PHOTON_TRACE_DEPTH + 1);
+        for (unsigned bounce = 0; bounce < waves; bounce++) {
+            if (bounce == 0) { ScopedTimer t0(*this, "trace.photon0"); launch_trace_closest_bounce(sc, q, bounce, lc); }
+            else launch_trace_closest_bounce(sc, q, bounce, lc);
+            launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, bounce, lc);
+        }
+        if (waves <= MAX_PHOTON_TRACE_DEPTH) {
+            ScopedTimer t1(*this, "ppm.photon_tail");
+            launch_ppm_photon_tail(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, waves, lc);
         }
     }
     // ---- createUniformGridPhotonMap (:628)
@@ -194,7 +190,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     {
         ScopedTimer t(*this, "ppm.gather");
         launch_gather(hp, width * height, width, height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
-                      float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + 12, lc);
+                      float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lc);
     }
     // ---- PPM_DIRECT_RADIANCE_ESTIMATION_PASS + PPM_OUTPUT_PASS (:664, :670)
     {

@@ -10,6 +10,13 @@ namespace opr {
 
 constexpr int NUM_QUEUES = 7;     // six material kinds + miss
 constexpr int QUEUE_MISS = 6;
+// RayQueues::counters layout (unsigned words).  The PPM passes use one counter set per bounce so that the bounce loop
+// needs no memset: the generation kernel of a pass resets [CTR_RAYCOUNT, CTR_TOTAL) and seeds bounce 0.
+constexpr int CTR_TILE = 12;          // gather tile queue cursor
+constexpr int CTR_STATS = 16;         // StatSlot counters
+constexpr int CTR_RAYCOUNT = 32;      // ray count of bounce b at CTR_RAYCOUNT + b (b < 32)
+constexpr int CTR_MATCOUNT = 64;      // material-queue counts of bounce b at CTR_MATCOUNT + 8 b (b < 24)
+constexpr int CTR_TOTAL = 256;
 
 // Wavefront ray queue state (all device pointers)
 struct RayQueues {
@@ -18,7 +25,7 @@ struct RayQueues {
     unsigned* rayPath[2];   // owning path (pixel / photon thread / subpath) of each ray slot
     float4* hits;           // HitRec per ray slot of the current queue
     unsigned* matQueue;     // NUM_QUEUES x capacity ray-slot indices, bucketed by material kind
-    unsigned* counters;     // [0],[1] ray counts (ping-pong); [2..2+NUM_QUEUES) material queue counts; [16..] stats
+    unsigned* counters;     // CTR_TOTAL words; VCM passes still use [0],[1] ray counts (ping-pong) + [2..2+NUM_QUEUES) material counts
     unsigned capacity;
 };
 
@@ -43,6 +50,8 @@ struct Renderer {
     // configuration (runtime versions of OptixRenderer.cpp:44-53 / config.h:50)
     unsigned photonLaunchWidth = 1024, photonLaunchHeight = 1024;
     unsigned vcmMaxPathLength = 10;
+    // wavefront bounces before the per-path tail kernels take over (camera: specular chains only; photons: after RR starts)
+    unsigned cameraWaveBounces = 1, photonWaveBounces = 4;
     unsigned seed = 1645301512u;
 
     bool initialized = false, sceneLoaded = false;
@@ -125,17 +134,22 @@ struct LaunchCtx { cudaStream_t st; unsigned long long* launches; };
 
 void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc);
 void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc);
+void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc);
 void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, float4* hits, LaunchCtx lc);
 void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, int* occluded, LaunchCtx lc);
 
 void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                            const RayQueues& q, LaunchCtx lc);
 void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
-                             const RayQueues& q, int cur, LaunchCtx lc);
+                             const RayQueues& q, int bounce, LaunchCtx lc);
+void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, int bounce,
+                            LaunchCtx lc);
 void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsigned rsW, const RngBuf& rng, float4* phPower,
                            unsigned* phState, const RayQueues& q, LaunchCtx lc);
 void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
-                             const PhotonBuf& photons, const RayQueues& q, int cur, LaunchCtx lc);
+                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
+void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
+                            const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
 void launch_ppm_direct_output(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                               const float* indirect, float* direct, float* output, unsigned localIteration, unsigned* statCounters, LaunchCtx lc);
 

@@ -1,8 +1,7 @@
-// scene.cu — scene upload and the GPU LBVH build (Morton codes -> stable radix sort -> Karras hierarchy
-// -> bottom-up refit that emits the 64-byte traversal nodes).  Replaces the OptiX "Trbvh"/"Bvh"/"NoAccel"
-// builders the reference requests in scene/Scene.cpp:353,513,547 and scene/Cornell.cpp:183,188.
+// scene.cu — scene upload: geometry records, per-vertex attributes, materials, textures, lights
+// (the values the reference hands to OptiX in scene/Scene.cpp:361-467, scene/Cornell.cpp:46-197, material/*.cpp).
+// The acceleration structure is built in bvh.cu.
 #include "device_scene.h"
-#include "radix_sort.cuh"
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -10,114 +9,6 @@
 #include <string>
 
 namespace opr {
-
-// ---- build kernels ---------------------------------------------------------------------------------------
-struct BuildPrim { float4 lo; float4 hi; };   // w of lo = leaf ref bits
-
-__device__ __forceinline__ unsigned long long expandBits21(unsigned v)
-{
-    unsigned long long x = v & 0x1fffffu;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
-    return x;
-}
-
-__global__ void bvh_morton_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, unsigned n,
-                                  float3 cmin, float3 cinv, unsigned long long* __restrict__ keys)
-{
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 a = lo[i], b = hi[i];
-    float cx = ((a.x + b.x) * 0.5f - cmin.x) * cinv.x;
-    float cy = ((a.y + b.y) * 0.5f - cmin.y) * cinv.y;
-    float cz = ((a.z + b.z) * 0.5f - cmin.z) * cinv.z;
-    unsigned ix = (unsigned)fminf(fmaxf(cx * 2097152.0f, 0.0f), 2097151.0f);
-    unsigned iy = (unsigned)fminf(fmaxf(cy * 2097152.0f, 0.0f), 2097151.0f);
-    unsigned iz = (unsigned)fminf(fmaxf(cz * 2097152.0f, 0.0f), 2097151.0f);
-    keys[i] = (expandBits21(ix) << 2) | (expandBits21(iy) << 1) | expandBits21(iz);
-}
-
-__device__ __forceinline__ int lbvh_delta(const unsigned long long* keys, int n, int i, int j)
-{
-    if (j < 0 || j >= n) return -1;
-    unsigned long long a = keys[i], b = keys[j];
-    if (a == b) return 64 + __clz((unsigned)i ^ (unsigned)j);
-    return __clzll((long long)(a ^ b));
-}
-
-// Karras 2012: one thread per internal node i in [0, n-1)
-__global__ void bvh_karras_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ childL, int* __restrict__ childR,
-                                  int* __restrict__ nodeParent, int* __restrict__ leafParent)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-    int dmin = lbvh_delta(keys, n, i, i - d);
-    int lmax = 2;
-    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
-    int l = 0;
-    for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
-    int j = i + l * d;
-    int dnode = lbvh_delta(keys, n, i, j);
-    int s = 0;
-    int t = l;
-    do {
-        t = (t + 1) >> 1;
-        if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
-    } while (t > 1);
-    int gamma = i + s * d + min(d, 0);
-    int lo = min(i, j), hi = max(i, j);
-    // child encoding here: >= 0 internal, < 0 : ~leafSortedIndex
-    int left = (lo == gamma) ? ~gamma : gamma;
-    int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
-    childL[i] = left; childR[i] = right;
-    if (left >= 0) nodeParent[left] = i; else leafParent[~left] = i;
-    if (right >= 0) nodeParent[right] = i; else leafParent[~right] = i;
-    if (i == 0) nodeParent[0] = -1;
-}
-
-// Bottom-up refit.  boxLo/boxHi: [0,n-1) internal, [n-1, 2n-1) leaves in sorted order.
-__global__ void bvh_refit_kernel(const unsigned* __restrict__ sortedPrim, const float4* __restrict__ primLo, const float4* __restrict__ primHi,
-                                 int n, const int* __restrict__ childL, const int* __restrict__ childR,
-                                 const int* __restrict__ nodeParent, const int* __restrict__ leafParent,
-                                 float4* __restrict__ boxLo, float4* __restrict__ boxHi, unsigned* __restrict__ flags,
-                                 float4* __restrict__ nodes)
-{
-    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
-    if (leaf >= n) return;
-    unsigned p = sortedPrim[leaf];
-    boxLo[n - 1 + leaf] = primLo[p];
-    boxHi[n - 1 + leaf] = primHi[p];
-    __threadfence();
-    int cur = leafParent[leaf];
-    while (cur >= 0) {
-        if (atomicAdd(&flags[cur], 1u) == 0u) return;   // first arrival: the sibling subtree is not done yet
-        __threadfence();
-        int l = childL[cur], r = childR[cur];
-        int li = l >= 0 ? l : (n - 1 + ~l), ri = r >= 0 ? r : (n - 1 + ~r);
-        volatile float4* vlo = boxLo; volatile float4* vhi = boxHi;
-        float4 llo, lhi, rlo, rhi;
-        llo.x = vlo[li].x; llo.y = vlo[li].y; llo.z = vlo[li].z; llo.w = vlo[li].w;
-        lhi.x = vhi[li].x; lhi.y = vhi[li].y; lhi.z = vhi[li].z;
-        rlo.x = vlo[ri].x; rlo.y = vlo[ri].y; rlo.z = vlo[ri].z; rlo.w = vlo[ri].w;
-        rhi.x = vhi[ri].x; rhi.y = vhi[ri].y; rhi.z = vhi[ri].z;
-        // leaf boxes carry the (negative) leaf reference ~((index << 2) | type) in lo.w
-        int lref = l >= 0 ? l : __float_as_int(llo.w);
-        int rref = r >= 0 ? r : __float_as_int(rlo.w);
-        nodes[4 * cur + 0] = make_float4(llo.x, lhi.x, llo.y, lhi.y);
-        nodes[4 * cur + 1] = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
-        nodes[4 * cur + 2] = make_float4(llo.z, lhi.z, rlo.z, rhi.z);
-        nodes[4 * cur + 3] = make_float4(__int_as_float(lref), __int_as_float(rref), 0.f, 0.f);
-        boxLo[cur] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
-        boxHi[cur] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
-        __threadfence();
-        cur = nodeParent[cur];
-    }
-}
 
 // ---- host side ------------------------------------------------------------------------------------------
 template <class T> static T* upload(const std::vector<T>& v, std::vector<void*>& owned)
@@ -291,60 +182,6 @@ void DeviceScene::load(const opr_scene_desc* d, cudaStream_t st)
     }
 
     buildBvh(primLo, primHi, st);
-}
-
-void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<float4>& primHi, cudaStream_t st)
-{
-    const int n = (int)primLo.size();
-    if (n == 1) {   // a single leaf: the root reference is the leaf itself
-        float4* nodes = nullptr;
-        OPR_CUDA_CHECK(cudaMalloc(&nodes, 64)); owned.push_back(nodes);
-        view.nodes = nodes;
-        view.rootRef = __builtin_bit_cast(int, primLo[0].w);
-        numNodes = 0;
-        return;
-    }
-    // centroid bounds on the host (n is known here and this is a one-off per scene)
-    float3 cmin = f3(FLT_MAX), cmax = f3(-FLT_MAX);
-    for (int i = 0; i < n; i++) {
-        float3 c = f3((primLo[i].x + primHi[i].x) * 0.5f, (primLo[i].y + primHi[i].y) * 0.5f, (primLo[i].z + primHi[i].z) * 0.5f);
-        cmin = fmin3(cmin, c); cmax = fmax3(cmax, c);
-    }
-    float3 ext = cmax - cmin;
-    float3 cinv = f3(ext.x > 0 ? 1.0f / ext.x : 0.f, ext.y > 0 ? 1.0f / ext.y : 0.f, ext.z > 0 ? 1.0f / ext.z : 0.f);
-
-    std::vector<void*> tmp;
-    auto dalloc = [&](size_t bytes) { void* p; OPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); tmp.push_back(p); return p; };
-    float4* dLo = (float4*)dalloc(sizeof(float4) * n);
-    float4* dHi = (float4*)dalloc(sizeof(float4) * n);
-    OPR_CUDA_CHECK(cudaMemcpyAsync(dLo, primLo.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, st));
-    OPR_CUDA_CHECK(cudaMemcpyAsync(dHi, primHi.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, st));
-    unsigned long long* keys = (unsigned long long*)dalloc(8 * (size_t)n);
-    unsigned long long* keysAlt = (unsigned long long*)dalloc(8 * (size_t)n);
-    unsigned* vals = (unsigned*)dalloc(4 * (size_t)n);
-    unsigned* valsAlt = (unsigned*)dalloc(4 * (size_t)n);
-    unsigned* hist = (unsigned*)dalloc(4 * rs_hist_words(n));
-    const int T = 256, B = (n + T - 1) / T;
-    bvh_morton_kernel<<<B, T, 0, st>>>(dLo, dHi, n, cmin, cinv, keys);
-    bool flipped = radix_sort_pairs<unsigned long long>(keys, vals, keysAlt, valsAlt, n, 64, hist, true, st);
-    unsigned long long* sk = flipped ? keysAlt : keys;
-    unsigned* sv = flipped ? valsAlt : vals;
-
-    int* childL = (int*)dalloc(4 * (size_t)n); int* childR = (int*)dalloc(4 * (size_t)n);
-    int* nodeParent = (int*)dalloc(4 * (size_t)n); int* leafParent = (int*)dalloc(4 * (size_t)n);
-    float4* boxLo = (float4*)dalloc(sizeof(float4) * (2 * (size_t)n)); float4* boxHi = (float4*)dalloc(sizeof(float4) * (2 * (size_t)n));
-    unsigned* flags = (unsigned*)dalloc(4 * (size_t)n);
-    OPR_CUDA_CHECK(cudaMemsetAsync(flags, 0, 4 * (size_t)n, st));
-    float4* nodes = nullptr;
-    OPR_CUDA_CHECK(cudaMalloc(&nodes, 64 * (size_t)(n - 1))); owned.push_back(nodes);
-    bvh_karras_kernel<<<B, T, 0, st>>>(sk, n, childL, childR, nodeParent, leafParent);
-    bvh_refit_kernel<<<B, T, 0, st>>>(sv, dLo, dHi, n, childL, childR, nodeParent, leafParent, boxLo, boxHi, flags, nodes);
-    OPR_CUDA_CHECK(cudaStreamSynchronize(st));
-    OPR_CUDA_CHECK(cudaGetLastError());
-    for (void* p : tmp) cudaFree(p);
-    view.nodes = nodes;
-    view.rootRef = 0;
-    numNodes = n - 1;
 }
 
 } // namespace opr

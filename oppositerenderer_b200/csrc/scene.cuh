@@ -2,10 +2,10 @@
 // OptiX's acceleration structure + rtTrace.
 //
 // HBM layout
-//   nodes      4 x float4 per internal node (64 B, one 16-byte load each):
-//                n0xy = (L.lo.x, L.hi.x, L.lo.y, L.hi.y)   n1xy = same for the right child
-//                nz   = (L.lo.z, L.hi.z, R.lo.z, R.hi.z)   ch   = (leftRef, rightRef, -, -) as int bits
-//              child ref >= 0: internal node index; < 0: leaf, ~ref = (primIndex << 2) | primType
+//   nodes      8 x float4 per 4-wide node (128 B = one line): lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4] spare
+//              child ref >= 0: node index; < 0: leaf, ~ref = (firstSlot << 4) | ((count-1) << 1) | mixed; empty: box +inf
+//   leafTri    3 x float4 per leaf slot: the triangle record of the slot's primitive (leaf = contiguous run of <= 8 slots)
+//   leafPrim   int per leaf slot: (primIndex << 2) | primType, read once per ray to name the hit
 //   triRec     3 x float4 per triangle (48 B): (p0.xyz, e0.x) (e0.yz, e1.xy) (e1.z, n.xyz) with
 //              e0 = p1-p0, e1 = p0-p2, n = cross(e1,e0) — the operands of OptiX intersect_triangle_branchless
 //              (called from geometry_instance/TriangleMesh.cu:46), precomputed with the same fp32 ops
@@ -35,7 +35,8 @@ struct DMaterial {
 struct DSphere { float3 center; float radius; };
 
 struct SceneView {
-    const float4* nodes; int rootRef;
+    const float4* nodes; int rootRef;                 // 4-wide BVH (bvh.cu), 8 float4 per node
+    const float4* leafTri; const int* leafPrim;       // leaf-slot order: 3 float4 per slot; (primIndex << 2) | primType per slot
     const float4* triRec; const int4* triShade;
     const float4* pgramRec; const int* pgramMat;
     const float4* sphereRec; const int* sphereMat;
@@ -55,22 +56,28 @@ OPR_DEV int prim_material(const SceneView& sc, int prim)
     return __ldg(&sc.sphereMat[idx]);
 }
 
+// Triangle test on one 48-byte record (the operands of OptiX intersect_triangle_branchless, TriangleMesh.cu:46)
+OPR_DEV bool intersect_tri_rec(const float4& a, const float4& b, const float4& c, const float3& o, const float3& d, float tmin, float tcur,
+                               float& tOut, float& uOut, float& vOut)
+{
+    const float3 p0 = f3(a.x, a.y, a.z), e0 = f3(a.w, b.x, b.y), e1 = f3(b.z, b.w, c.x), n = f3(c.y, c.z, c.w);
+    const float3 e2 = (1.0f / dot(n, d)) * (p0 - o);
+    const float3 i = cross(d, e2);
+    const float beta = dot(i, e1);
+    const float gamma = dot(i, e0);
+    const float t = dot(n, e2);
+    if ((t < tcur) & (t > tmin) & (beta >= 0.0f) & (gamma >= 0.0f) & (beta + gamma <= 1)) { tOut = t; uOut = beta; vOut = gamma; return true; }
+    return false;
+}
+
 // Leaf test.  Accepts tmin < t < tcur (rtPotentialIntersection).  Returns true and updates hit on success.
 OPR_DEV bool intersect_prim(const SceneView& sc, int prim, const float3& o, const float3& d, float tmin, float tcur, HitRec& hit)
 {
     const int type = prim & 3, idx = prim >> 2;
     if (type == PRIM_TRIANGLE) {
         const float4 a = __ldg(&sc.triRec[3 * idx]), b = __ldg(&sc.triRec[3 * idx + 1]), c = __ldg(&sc.triRec[3 * idx + 2]);
-        const float3 p0 = f3(a.x, a.y, a.z), e0 = f3(a.w, b.x, b.y), e1 = f3(b.z, b.w, c.x), n = f3(c.y, c.z, c.w);
-        const float3 e2 = (1.0f / dot(n, d)) * (p0 - o);
-        const float3 i = cross(d, e2);
-        const float beta = dot(i, e1);
-        const float gamma = dot(i, e0);
-        const float t = dot(n, e2);
-        if ((t < tcur) & (t > tmin) & (beta >= 0.0f) & (gamma >= 0.0f) & (beta + gamma <= 1)) {
-            hit.t = t; hit.prim = prim; hit.u = beta; hit.v = gamma;
-            return true;
-        }
+        float t, u, v;
+        if (intersect_tri_rec(a, b, c, o, d, tmin, tcur, t, u, v)) { hit.t = t; hit.prim = prim; hit.u = u; hit.v = v; return true; }
         return false;
     }
     if (type == PRIM_PARALLELOGRAM) {
@@ -106,52 +113,93 @@ OPR_DEV bool intersect_prim(const SceneView& sc, int prim, const float3& o, cons
     }
 }
 
-constexpr int TRAVERSAL_STACK = 64;
+constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*levels + 4 > TRAVERSAL_STACK
 
-// While-while BVH2 traversal.  ANY = true returns at the first accepted intersection (shadow rays:
-// ppm/DirectRadianceEstimation.cu:79-83 bound to every material by material/Material.cpp:18-26).
+// Slab test of child c of a wide node: entry distance, or +inf when the ray misses the box within (tmin, tmax).
+// (plane - o) * idir, not the fused plane*idir - o*idir: no cancellation for grazing rays, so the conservatively
+// inflated boxes (scene.cu addPrim) never cull a primitive the exact test would accept.
+#define OPR_SLAB(LX, HX, LY, HY, LZ, HZ, TOUT)                                                                     \
+    {                                                                                                              \
+        const float ax = ((LX) - o.x) * idir.x, bx = ((HX) - o.x) * idir.x;                                        \
+        const float ay = ((LY) - o.y) * idir.y, by = ((HY) - o.y) * idir.y;                                        \
+        const float az = ((LZ) - o.z) * idir.z, bz = ((HZ) - o.z) * idir.z;                                        \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));                   \
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t));                  \
+        TOUT = tn <= tf ? tn : INF;                                                                                \
+    }
+#define OPR_CSWAP(TA, RA, TB, RB) { if (TB < TA) { const float tt = TA; TA = TB; TB = tt; const int rr = RA; RA = RB; RB = rr; } }
+
+// Stack-based traversal of the 4-wide BVH (bvh.cu).  One node visit = one 128-byte line: six float4 of child boxes and one
+// int4 of child refs.  Hit children are visited front to back (5-comparator sorting network); the far ones are pushed with
+// their entry distance so that a pop can discard subtrees already behind the closest hit without fetching their node.
+// ANY = true returns at the first accepted intersection (shadow rays: ppm/DirectRadianceEstimation.cu:79-83, bound to
+// every material by material/Material.cpp:18-26).  On return hit.prim = (primIndex << 2) | primType, or -1.
 template <bool ANY>
 OPR_DEV bool traverse(const SceneView& sc, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
 {
+    const float INF = __int_as_float(0x7f800000);
     hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
-    const float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int stack[TRAVERSAL_STACK];
+    // 1/d with |d| clamped away from zero: keeps every slab product finite-or-inf (never 0 * inf = NaN)
+    const float3 idir = f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
+                           1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
+    int2 stack[TRAVERSAL_STACK];
     int sp = 0;
     int cur = sc.rootRef;
     for (;;) {
-        while (cur >= 0) {
-            const float4 n0 = __ldg(&sc.nodes[4 * cur]), n1 = __ldg(&sc.nodes[4 * cur + 1]), nz = __ldg(&sc.nodes[4 * cur + 2]);
-            const float4 chf = __ldg(&sc.nodes[4 * cur + 3]);
-            const int left = __float_as_int(chf.x), right = __float_as_int(chf.y);
-            // slab tests; (plane - o) * idir keeps +-inf (not NaN) for axis-parallel rays
-            float lx0 = (n0.x - o.x) * idir.x, lx1 = (n0.y - o.x) * idir.x;
-            float ly0 = (n0.z - o.y) * idir.y, ly1 = (n0.w - o.y) * idir.y;
-            float lz0 = (nz.x - o.z) * idir.z, lz1 = (nz.y - o.z) * idir.z;
-            float lmin = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
-            float lmax = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), hit.t));
-            float rx0 = (n1.x - o.x) * idir.x, rx1 = (n1.y - o.x) * idir.x;
-            float ry0 = (n1.z - o.y) * idir.y, ry1 = (n1.w - o.y) * idir.y;
-            float rz0 = (nz.z - o.z) * idir.z, rz1 = (nz.w - o.z) * idir.z;
-            float rmin = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
-            float rmax = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), hit.t));
-            const bool hl = lmin <= lmax, hr = rmin <= rmax;
-            if (!hl && !hr) {
-                if (sp == 0) return hit.prim != -1;
-                cur = stack[--sp];
-            } else {
-                cur = hl ? left : right;
-                if (hl && hr) {
-                    int far = right;
-                    if (rmin < lmin) { far = left; cur = right; }
-                    stack[sp++] = far;
+        if (cur >= 0) {
+            const float4* N = sc.nodes + 8 * (size_t)cur;
+            const float4 lox = __ldg(N + 0), hix = __ldg(N + 1), loy = __ldg(N + 2), hiy = __ldg(N + 3), loz = __ldg(N + 4), hiz = __ldg(N + 5);
+            const float4 rf = __ldg(N + 6);
+            int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
+            float t0, t1, t2, t3;
+            OPR_SLAB(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, t0)
+            OPR_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, t1)
+            OPR_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, t2)
+            OPR_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, t3)
+            OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t2, r2, t3, r3) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t1, r1, t3, r3) OPR_CSWAP(t1, r1, t2, r2)
+            if (t0 < INF) {
+                if (t3 < INF) stack[sp++] = make_int2(r3, __float_as_int(t3));
+                if (t2 < INF) stack[sp++] = make_int2(r2, __float_as_int(t2));
+                if (t1 < INF) stack[sp++] = make_int2(r1, __float_as_int(t1));
+                cur = r0;
+                continue;
+            }
+        } else {
+            const unsigned L = (unsigned)~cur;
+            const unsigned first = L >> 4, cnt = ((L >> 1) & 7u) + 1u;
+            bool found = false;
+            if (!(L & 1u)) {      // all triangles: one contiguous run of 48-byte records
+                for (unsigned k = 0; k < cnt; k++) {
+                    const float4* R = sc.leafTri + 3 * (size_t)(first + k);
+                    const float4 a = __ldg(R), b = __ldg(R + 1), c = __ldg(R + 2);
+                    if (intersect_tri_rec(a, b, c, o, d, tmin, hit.t, hit.t, hit.u, hit.v)) { hit.prim = (int)(first + k); found = true; }
+                }
+            } else {              // analytic primitives of the built-in scenes (parallelogram.cu, Sphere.cu) mixed in
+                for (unsigned k = 0; k < cnt; k++) {
+                    const int prim = __ldg(&sc.leafPrim[first + k]);
+                    if ((prim & 3) == PRIM_TRIANGLE) {
+                        const float4* R = sc.leafTri + 3 * (size_t)(first + k);
+                        const float4 a = __ldg(R), b = __ldg(R + 1), c = __ldg(R + 2);
+                        if (intersect_tri_rec(a, b, c, o, d, tmin, hit.t, hit.t, hit.u, hit.v)) { hit.prim = (int)(first + k); found = true; }
+                    } else if (intersect_prim(sc, prim, o, d, tmin, hit.t, hit)) { hit.prim = (int)(first + k); found = true; }
                 }
             }
+            if (ANY && found) return true;
         }
-        if (intersect_prim(sc, ~cur, o, d, tmin, hit.t, hit) && ANY) return true;
-        if (sp == 0) return hit.prim != -1;
-        cur = stack[--sp];
+        // pop; subtrees that start behind the closest hit so far are dropped unfetched
+        for (;;) {
+            if (sp == 0) {
+                if (hit.prim < 0) return false;
+                hit.prim = __ldg(&sc.leafPrim[hit.prim]);     // leaf slot -> (primIndex << 2) | primType
+                return true;
+            }
+            const int2 e = stack[--sp];
+            if (ANY || __int_as_float(e.y) < hit.t) { cur = e.x; break; }
+        }
     }
 }
+#undef OPR_SLAB
+#undef OPR_CSWAP
 
 // Attributes the reference's intersection programs hand to the material programs
 struct Surface { float3 geometricNormal, shadingNormal, tangent, bitangent; float2 uv; int material; };

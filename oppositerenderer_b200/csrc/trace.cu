@@ -51,6 +51,14 @@ void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, Laun
     ++*lc.launches;
 }
 
+void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc)
+{
+    const int cur = bounce & 1;
+    trace_closest_kernel<<<148 * 16, TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
+                                                                q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS);
+    ++*lc.launches;
+}
+
 // Raw entry points over caller-supplied SoA rays (C-ABI opr_trace_closest / opr_trace_any)
 __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_raw_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                           unsigned n, float4* __restrict__ hits)
