@@ -11,7 +11,7 @@
 //   4. Collapse to 4-wide nodes, top-down, one kernel launch per level: a wide node adopts the two children of its
 //      binary node and keeps replacing the child with the largest area by its own two children until it has four.
 //      Leaves get consecutive slots in a leaf-ordered primitive list.                              (bvh_collapse_kernel)
-//   5. Triangle records are copied into leaf-slot order so that a leaf is one contiguous run of 48-byte records.
+//   5. Triangle records are copied into leaf-slot order (padded to 64 B) so that a leaf is one contiguous run of records.
 //                                                                                                   (bvh_leaf_tri_kernel)
 //
 // Wide node, 128 bytes = one cache line = eight float4:
@@ -224,7 +224,8 @@ __global__ void bvh_leaf_tri_kernel(const int* __restrict__ leafPrim, int n, con
     const int prim = leafPrim[s];
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
     if ((prim & 3) == PRIM_TRIANGLE) { const int idx = prim >> 2; a = triRec[3 * idx]; b = triRec[3 * idx + 1]; c = triRec[3 * idx + 2]; }
-    leafTri[3 * (size_t)s] = a; leafTri[3 * (size_t)s + 1] = b; leafTri[3 * (size_t)s + 2] = c;
+    float4* dst = leafTri + LEAF_TRI_STRIDE * (size_t)s;
+    dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---- host driver -----------------------------------------------------------------------------------------------------
@@ -328,7 +329,7 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
     OPR_CUDA_CHECK(cudaMalloc(&nodes, 128 * (size_t)numWide)); owned.push_back(nodes);
     OPR_CUDA_CHECK(cudaMemcpyAsync(nodes, wideTmp, 128 * (size_t)numWide, cudaMemcpyDeviceToDevice, st));
     float4* leafTri = nullptr;
-    OPR_CUDA_CHECK(cudaMalloc(&leafTri, 48 * (size_t)n)); owned.push_back(leafTri);
+    OPR_CUDA_CHECK(cudaMalloc(&leafTri, sizeof(float4) * LEAF_TRI_STRIDE * (size_t)n)); owned.push_back(leafTri);
     bvh_leaf_tri_kernel<<<B256, 256, 0, st>>>(leafPrim, n, view.triRec, leafTri);
     OPR_CUDA_CHECK(cudaStreamSynchronize(st));
     OPR_CUDA_CHECK(cudaGetLastError());

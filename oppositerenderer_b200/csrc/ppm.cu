@@ -257,19 +257,23 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_tail_kernel(SceneVie
 {
     const unsigned n = *count;
     unsigned traced = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o4 = rayO[i], d4 = rayD[i];
-        const unsigned p = rayPath[i];
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = base + threadIdx.x;
+        bool alive = i < n;
+        const float4 o4 = alive ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = alive ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
+        const unsigned p = alive ? rayPath[i] : 0u;
         float3 o = f3(o4), d = f3(d4);
         float tmin = o4.w;
-        for (;;) {
+        while (__any_sync(0xffffffffu, alive)) {
             HitRec hit;
-            traverse<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit);
-            traced++;
-            const int kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
-            float3 newO = f3(0.f), newD = f3(0.f);
-            if (!shade_camera_hit(sc, kind, p, o, d, hit, w, rsW, rngBuf, hp, newO, newD)) break;
-            o = newO; d = newD; tmin = 0.0001f;
+            traverse_warp<false>(sc, 0xffffffffu, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+            if (alive) {
+                traced++;
+                const int kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
+                float3 newO = f3(0.f), newD = f3(0.f);
+                alive = shade_camera_hit(sc, kind, p, o, d, hit, w, rsW, rngBuf, hp, newO, newD);
+                o = newO; d = newD; tmin = 0.0001f;
+            }
         }
     }
     for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, s);
@@ -492,21 +496,27 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_tail_kernel(SceneVie
 {
     const unsigned n = *count;
     unsigned traced = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o4 = rayO[i], d4 = rayD[i];
-        const unsigned t = rayPath[i];
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = base + threadIdx.x;
+        bool alive = i < n;
+        const float4 o4 = alive ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = alive ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
+        const unsigned t = alive ? rayPath[i] : 0u;
         float3 o = f3(o4), d = f3(d4);
         float tmin = o4.w;
-        for (;;) {
+        while (__any_sync(0xffffffffu, alive)) {
             HitRec hit;
-            traverse<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit);
-            traced++;
-            if (hit.prim < 0) break;   // miss: no-op
-            const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
-            float3 newO = f3(0.f), newD = f3(0.f);
-            float newTmin;
-            if (!shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin)) break;
-            o = newO; d = newD; tmin = newTmin;
+            traverse_warp<false>(sc, 0xffffffffu, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+            if (alive) {
+                traced++;
+                if (hit.prim < 0) alive = false;   // miss: no-op
+                else {
+                    const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+                    float3 newO = f3(0.f), newD = f3(0.f);
+                    float newTmin;
+                    alive = shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin);
+                    o = newO; d = newD; tmin = newTmin;
+                }
+            }
         }
     }
     for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, s);
@@ -543,28 +553,40 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_output_kernel(SceneV
 {
     const unsigned n = w * h;
     unsigned shadowRays = 0;
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const float4 pos4 = hp.pos[p];
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned p = base + threadIdx.x;
+        const bool inImage = p < n;
+        const float4 pos4 = inImage ? hp.pos[p] : make_float4(0.f, 0.f, 0.f, 0.f);
         const unsigned flags = __float_as_uint(pos4.w);
-        float3 directRadiance;
-        if (!(flags & PRD_HIT_NON_SPECULAR)) {
+        const bool diffuse = inImage && (flags & PRD_HIT_NON_SPECULAR);
+        float3 directRadiance = f3(0.f);
+        if (inImage && !diffuse) {
             float3 rad = f3(hp.rad[p]);
             if ((flags & PRD_HIT_EMITTER) && !(flags & PRD_HIT_SPECULAR)) directRadiance = fmin3(rad, f3(1.f));
             else directRadiance = rad;
-        } else {
-            const float3 rec_position = f3(pos4), rec_normal = f3(hp.nrm[p]), attenuation = f3(hp.att[p]);
-            const size_t ri = (size_t)(p / w) * rsW + (p % w);
-            Rng rng = rng_load(rngBuf, ri);
-            const int numLights = sc.numLights;
-            float3 avgLightRadiance = f3(0.f);
-            #pragma unroll 1
-            for (int shadowSample = 0; shadowSample < 4; shadowSample++) {
+        }
+        // the warp walks the four shadow samples together; lanes without a diffuse hit (or with a zero light factor) ride along
+        float3 rec_position = f3(pos4), rec_normal = f3(0.f), attenuation = f3(0.f);
+        size_t ri = 0;
+        Rng rng{};
+        if (diffuse) {
+            rec_normal = f3(hp.nrm[p]); attenuation = f3(hp.att[p]);
+            ri = (size_t)(p / w) * rsW + (p % w);
+            rng = rng_load(rngBuf, ri);
+        }
+        const int numLights = sc.numLights;
+        float3 avgLightRadiance = f3(0.f);
+        #pragma unroll 1
+        for (int shadowSample = 0; shadowSample < 4; shadowSample++) {
+            float lightFactor = 0.f, lightDistance = 1.f, scale = 0.f;
+            float3 towardsLight = f3(0.f, 0.f, 1.f), power = f3(0.f);
+            if (diffuse) {
                 float sample = rng_uniform(rng);
                 int randomLightIndex = min(int(sample * numLights), numLights - 1);
                 const opr_light& light = sc.lights[randomLightIndex];
-                float scale = (float)numLights;
+                scale = (float)numLights;
                 // getLightContribution
-                float lightFactor = 1;
+                lightFactor = 1;
                 float3 pointOnLight = f3(0.f);
                 const int lightType = light.lightType;
                 if (lightType == OPR_LIGHT_AREA) {
@@ -577,32 +599,38 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_output_kernel(SceneV
                 } else {
                     lightFactor = 0;
                 }
-                float3 towardsLight = pointOnLight - rec_position;
-                float lightDistance = length(towardsLight);
+                towardsLight = pointOnLight - rec_position;
+                lightDistance = length(towardsLight);
                 towardsLight = towardsLight / lightDistance;
                 float n_dot_l = maxf_(0, dot(rec_normal, towardsLight));
                 lightFactor *= n_dot_l / (PI_F * lightDistance * lightDistance);
                 if (lightType == OPR_LIGHT_AREA)
                     lightFactor *= maxf_(0, dot(-towardsLight, f3(light.normal[0], light.normal[1], light.normal[2])));
-                float3 lightContrib = f3(0.f);
-                if (lightFactor > 0.0f) {
-                    HitRec hit;
-                    shadowRays++;
-                    bool occluded = traverse<true>(sc, rec_position, towardsLight, 0.0001f, (float)((double)lightDistance - 0.0001), hit);
-                    lightFactor *= occluded ? 0.0f : 1.0f;
-                    lightContrib = f3(light.power[0], light.power[1], light.power[2]) * lightFactor;
-                }
-                avgLightRadiance += scale * lightContrib;
+                power = f3(light.power[0], light.power[1], light.power[2]);
             }
+            const bool cast = diffuse && lightFactor > 0.0f;
+            HitRec hit;
+            const bool occluded = traverse_warp<true>(sc, 0xffffffffu, cast, rec_position, towardsLight, 0.0001f, (float)((double)lightDistance - 0.0001), hit);
+            float3 lightContrib = f3(0.f);
+            if (cast) {
+                shadowRays++;
+                lightFactor *= occluded ? 0.0f : 1.0f;
+                lightContrib = power * lightFactor;
+            }
+            avgLightRadiance += scale * lightContrib;
+        }
+        if (diffuse) {
             rng_store(rngBuf, ri, rng);
             directRadiance = attenuation * avgLightRadiance / 4.0f;
         }
-        const float3 ind = f3(indirect[3 * (size_t)p], indirect[3 * (size_t)p + 1], indirect[3 * (size_t)p + 2]);
-        if (direct) { direct[3 * (size_t)p] = directRadiance.x; direct[3 * (size_t)p + 1] = directRadiance.y; direct[3 * (size_t)p + 2] = directRadiance.z; }
-        const float3 finalRadiance = directRadiance + ind;
-        float3 out = finalRadiance;
-        if (localIteration != 0) out = f3(output[3 * (size_t)p], output[3 * (size_t)p + 1], output[3 * (size_t)p + 2]) + finalRadiance;
-        output[3 * (size_t)p] = out.x; output[3 * (size_t)p + 1] = out.y; output[3 * (size_t)p + 2] = out.z;
+        if (inImage) {
+            const float3 ind = f3(indirect[3 * (size_t)p], indirect[3 * (size_t)p + 1], indirect[3 * (size_t)p + 2]);
+            if (direct) { direct[3 * (size_t)p] = directRadiance.x; direct[3 * (size_t)p + 1] = directRadiance.y; direct[3 * (size_t)p + 2] = directRadiance.z; }
+            const float3 finalRadiance = directRadiance + ind;
+            float3 out = finalRadiance;
+            if (localIteration != 0) out = f3(output[3 * (size_t)p], output[3 * (size_t)p + 1], output[3 * (size_t)p + 2]) + finalRadiance;
+            output[3 * (size_t)p] = out.x; output[3 * (size_t)p + 1] = out.y; output[3 * (size_t)p + 2] = out.z;
+        }
     }
     // shadow-ray count for the Mrays/s metric: warp-reduce, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) shadowRays += __shfl_xor_sync(0xffffffffu, shadowRays, o);

@@ -159,12 +159,11 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     // ---- PPM_RAYTRACE_PASS (:576): wavefront bounces, then one per-path tail kernel for the specular continuations
     {
         ScopedTimer t(*this, "ppm.camera");
-        launch_ppm_camera_gen(details.camera, width, height, rsW, rng, hp, q, lc);
+        { ScopedTimer tg(*this, "camera.gen"); launch_ppm_camera_gen(details.camera, width, height, rsW, rng, hp, q, lc); }
         const unsigned waves = std::min(cameraWaveBounces, MAX_RADIANCE_TRACE_DEPTH + 1);
         for (unsigned bounce = 0; bounce < waves; bounce++) {
-            if (bounce == 0) { ScopedTimer t0(*this, "trace.camera0"); launch_trace_closest_bounce(sc, q, bounce, lc); }
-            else launch_trace_closest_bounce(sc, q, bounce, lc);
-            launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, bounce, lc);
+            { ScopedTimer t0(*this, bounce == 0 ? "trace.camera0" : "trace.camera1+"); launch_trace_closest_bounce(sc, q, bounce, lc); }
+            { ScopedTimer t0(*this, bounce == 0 ? "shade.camera0" : "shade.camera1+"); launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, bounce, lc); }
         }
         if (waves <= MAX_RADIANCE_TRACE_DEPTH) { ScopedTimer t1(*this, "ppm.camera_tail"); launch_ppm_camera_tail(sc, width, rsW, rng, hp, q, waves, lc); }
     }
@@ -172,12 +171,13 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     // ---- PPM_PHOTON_PASS (:612)
     {
         ScopedTimer t(*this, "ppm.photon");
-        launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, lc);
+        { ScopedTimer tg(*this, "photon.gen"); launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, lc); }
         const unsigned waves = std::min(photonWaveBounces, MAX_PHOTON_TRACE_DEPTH + 1);
+        static const char* tn[] = {"trace.photon0", "trace.photon1", "trace.photon2", "trace.photon3", "trace.photon4+"};
+        static const char* sn[] = {"shade.photon0", "shade.photon1", "shade.photon2", "shade.photon3", "shade.photon4+"};
         for (unsigned bounce = 0; bounce < waves; bounce++) {
-            if (bounce == 0) { ScopedTimer t0(*this, "trace.photon0"); launch_trace_closest_bounce(sc, q, bounce, lc); }
-            else launch_trace_closest_bounce(sc, q, bounce, lc);
-            launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, bounce, lc);
+            { ScopedTimer t0(*this, tn[std::min(bounce, 4u)]); launch_trace_closest_bounce(sc, q, bounce, lc); }
+            { ScopedTimer t0(*this, sn[std::min(bounce, 4u)]); launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, bounce, lc); }
         }
         if (waves <= MAX_PHOTON_TRACE_DEPTH) {
             ScopedTimer t1(*this, "ppm.photon_tail");

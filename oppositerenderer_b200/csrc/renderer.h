@@ -16,6 +16,8 @@ constexpr int CTR_TILE = 12;          // gather tile queue cursor
 constexpr int CTR_STATS = 16;         // StatSlot counters
 constexpr int CTR_RAYCOUNT = 32;      // ray count of bounce b at CTR_RAYCOUNT + b (b < 32)
 constexpr int CTR_MATCOUNT = 64;      // material-queue counts of bounce b at CTR_MATCOUNT + 8 b (b < 24)
+constexpr int CTR_FETCH = 192;        // ray-fetch cursor of the persistent trace kernel, bounce b at CTR_FETCH + b (b < 32)
+constexpr int CTR_FETCH_LEGACY = 10;  // same for the ping-pong (VCM) launcher
 constexpr int CTR_TOTAL = 256;
 
 // Wavefront ray queue state (all device pointers)

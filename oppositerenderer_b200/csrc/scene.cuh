@@ -4,7 +4,7 @@
 // HBM layout
 //   nodes      8 x float4 per 4-wide node (128 B = one line): lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4] spare
 //              child ref >= 0: node index; < 0: leaf, ~ref = (firstSlot << 4) | ((count-1) << 1) | mixed; empty: box +inf
-//   leafTri    3 x float4 per leaf slot: the triangle record of the slot's primitive (leaf = contiguous run of <= 8 slots)
+//   leafTri    4 x float4 per leaf slot (48-byte triangle record padded to 64 B; leaf = contiguous run of <= 8 slots)
 //   leafPrim   int per leaf slot: (primIndex << 2) | primType, read once per ray to name the hit
 //   triRec     3 x float4 per triangle (48 B): (p0.xyz, e0.x) (e0.yz, e1.xy) (e1.z, n.xyz) with
 //              e0 = p1-p0, e1 = p0-p2, n = cross(e1,e0) — the operands of OptiX intersect_triangle_branchless
@@ -113,9 +113,34 @@ OPR_DEV bool intersect_prim(const SceneView& sc, int prim, const float3& o, cons
     }
 }
 
+// 256-bit read-only global load (LDG.E.ENL2.256 on sm_100a): a lane's 128-byte node is 4 L1 wavefronts instead of 8, and the
+// L1 data pipe — not DRAM, not issue — is what bounds incoherent traversal (profiles/r1d: l1tex data-pipe wavefronts 72 %).
+struct __align__(32) Float8 { float4 lo, hi; };
+OPR_DEV Float8 ldg256(const float4* p)
+{
+    Float8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+    return r;
+}
+
+constexpr int LEAF_TRI_STRIDE = 4;                 // float4 per leaf slot: 48-byte triangle record padded to 64 B = two 256-bit loads
+constexpr int TRAVERSAL_DONE = (int)0x80000000;   // negative like a leaf ref, never a real one (bvh.cu caps the slot count)
 constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*levels + 4 > TRAVERSAL_STACK
 
-// Slab test of child c of a wide node: entry distance, or +inf when the ray misses the box within (tmin, tmax).
+// ---- traversal of the 4-wide BVH (bvh.cu) -----------------------------------------------------------------------------
+// One node visit = one 128-byte line: six float4 of child boxes and one int4 of child refs.  Hit children are visited front
+// to back (5-comparator sorting network); the far ones are pushed with their entry distance so that a pop can discard
+// subtrees already behind the closest hit without fetching their node.
+//
+// The loops are warp-lockstep ("while-while" with votes): all lanes of `mask` run the node loop until every lane holds a
+// leaf or is finished, then the lanes that hold a leaf test it together.  Without the votes the leaf code ran with 2 of 32
+// lanes active (profiles/r1d): lanes reached their leaves at different iterations and each paid the leaf code alone.
+//
+// The steps are macros over the per-lane variables (o, d, idir, tmin, hit, stack, sp, cur) because the persistent
+// wavefront kernel in trace.cu runs the same steps around its own ray fetch.
+
+// Slab test of one child: entry distance, or +inf when the ray misses the box within (tmin, hit.t).
 // (plane - o) * idir, not the fused plane*idir - o*idir: no cancellation for grazing rays, so the conservatively
 // inflated boxes (scene.cu addPrim) never cull a primitive the exact test would accept.
 #define OPR_SLAB(LX, HX, LY, HY, LZ, HZ, TOUT)                                                                     \
@@ -125,81 +150,105 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
         const float az = ((LZ) - o.z) * idir.z, bz = ((HZ) - o.z) * idir.z;                                        \
         const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));                   \
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t));                  \
-        TOUT = tn <= tf ? tn : INF;                                                                                \
+        TOUT = tn <= tf ? tn : INF_;                                                                               \
     }
 #define OPR_CSWAP(TA, RA, TB, RB) { if (TB < TA) { const float tt = TA; TA = TB; TB = tt; const int rr = RA; RA = RB; RB = rr; } }
+// pop the next subtree; those that start behind the closest hit so far are dropped unfetched
+#define OPR_POP(ANYHIT)                                                                                            \
+    for (;;) {                                                                                                     \
+        if (sp == 0) { cur = TRAVERSAL_DONE; break; }                                                              \
+        const int2 e_ = stack[--sp];                                                                               \
+        if ((ANYHIT) || __int_as_float(e_.y) < hit.t) { cur = e_.x; break; }                                       \
+    }
+// one node visit of a lane with cur >= 0
+#define OPR_NODE_STEP(ANYHIT)                                                                                      \
+    {                                                                                                              \
+        const float INF_ = __int_as_float(0x7f800000);                                                             \
+        const float4* N_ = sc.nodes + 8 * (size_t)cur;                                                             \
+        const Float8 nx_ = ldg256(N_), ny_ = ldg256(N_ + 2), nz_ = ldg256(N_ + 4), nr_ = ldg256(N_ + 6);            \
+        const float4 lox = nx_.lo, hix = nx_.hi, loy = ny_.lo, hiy = ny_.hi, loz = nz_.lo, hiz = nz_.hi, rf = nr_.lo; \
+        int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w); \
+        float t0, t1, t2, t3;                                                                                      \
+        OPR_SLAB(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, t0)                                                     \
+        OPR_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, t1)                                                     \
+        OPR_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, t2)                                                     \
+        OPR_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, t3)                                                     \
+        OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t2, r2, t3, r3) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t1, r1, t3, r3) OPR_CSWAP(t1, r1, t2, r2) \
+        if (t0 < INF_) {                                                                                           \
+            if (t3 < INF_) stack[sp++] = make_int2(r3, __float_as_int(t3));                                        \
+            if (t2 < INF_) stack[sp++] = make_int2(r2, __float_as_int(t2));                                        \
+            if (t1 < INF_) stack[sp++] = make_int2(r1, __float_as_int(t1));                                        \
+            cur = r0;                                                                                              \
+        } else {                                                                                                   \
+            OPR_POP(ANYHIT)                                                                                        \
+        }                                                                                                          \
+    }
+// one leaf visit of a lane with cur < 0, cur != TRAVERSAL_DONE; FOUND is set when a primitive was accepted
+#define OPR_LEAF_STEP(FOUND)                                                                                       \
+    {                                                                                                              \
+        const unsigned L_ = (unsigned)~cur;                                                                        \
+        const unsigned first_ = L_ >> 4, cnt_ = ((L_ >> 1) & 7u) + 1u;                                             \
+        if (!(L_ & 1u)) {      /* all triangles: one contiguous run of 48-byte records */                          \
+            for (unsigned k_ = 0; k_ < cnt_; k_++) {                                                               \
+                const float4* R_ = sc.leafTri + LEAF_TRI_STRIDE * (size_t)(first_ + k_);                           \
+                const Float8 ab_ = ldg256(R_), cd_ = ldg256(R_ + 2);                                               \
+                const float4 a_ = ab_.lo, b_ = ab_.hi, c_ = cd_.lo;                                                \
+                if (intersect_tri_rec(a_, b_, c_, o, d, tmin, hit.t, hit.t, hit.u, hit.v)) { hit.prim = (int)(first_ + k_); FOUND = true; } \
+            }                                                                                                      \
+        } else {               /* analytic primitives of the built-in scenes (parallelogram.cu, Sphere.cu) mixed in */ \
+            for (unsigned k_ = 0; k_ < cnt_; k_++) {                                                               \
+                const int prim_ = __ldg(&sc.leafPrim[first_ + k_]);                                                \
+                if ((prim_ & 3) == PRIM_TRIANGLE) {                                                                \
+                    const float4* R_ = sc.leafTri + LEAF_TRI_STRIDE * (size_t)(first_ + k_);                       \
+                    const Float8 ab_ = ldg256(R_), cd_ = ldg256(R_ + 2);                                           \
+                    const float4 a_ = ab_.lo, b_ = ab_.hi, c_ = cd_.lo;                                            \
+                    if (intersect_tri_rec(a_, b_, c_, o, d, tmin, hit.t, hit.t, hit.u, hit.v)) { hit.prim = (int)(first_ + k_); FOUND = true; } \
+                } else if (intersect_prim(sc, prim_, o, d, tmin, hit.t, hit)) { hit.prim = (int)(first_ + k_); FOUND = true; } \
+            }                                                                                                      \
+        }                                                                                                          \
+    }
 
-// Stack-based traversal of the 4-wide BVH (bvh.cu).  One node visit = one 128-byte line: six float4 of child boxes and one
-// int4 of child refs.  Hit children are visited front to back (5-comparator sorting network); the far ones are pushed with
-// their entry distance so that a pop can discard subtrees already behind the closest hit without fetching their node.
-// ANY = true returns at the first accepted intersection (shadow rays: ppm/DirectRadianceEstimation.cu:79-83, bound to
-// every material by material/Material.cpp:18-26).  On return hit.prim = (primIndex << 2) | primType, or -1.
+// 1/d with |d| clamped away from zero: keeps every slab product finite-or-inf (never 0 * inf = NaN)
+OPR_DEV float3 safe_inverse_direction(const float3& d)
+{
+    return f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
+              1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
+}
+
+// Closest hit (ANY = false) or first accepted intersection (ANY = true: shadow rays, ppm/DirectRadianceEstimation.cu:79-83,
+// bound to every material by material/Material.cpp:18-26) for the lanes of `mask`, which must all make this call together;
+// lanes with active = false ride along.  On return hit.prim = (primIndex << 2) | primType, or -1.
+template <bool ANY>
+OPR_DEV bool traverse_warp(const SceneView& sc, unsigned mask, bool active, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
+{
+    hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
+    const float3 idir = safe_inverse_direction(d);
+    int2 stack[TRAVERSAL_STACK];
+    int sp = 0;
+    int cur = active ? sc.rootRef : TRAVERSAL_DONE;
+    for (;;) {
+        while (__any_sync(mask, cur >= 0)) {
+            if (cur >= 0) OPR_NODE_STEP(ANY)
+        }
+        if (__all_sync(mask, cur == TRAVERSAL_DONE)) break;
+        if (cur != TRAVERSAL_DONE) {
+            bool found = false;
+            OPR_LEAF_STEP(found)
+            if (ANY && found) { cur = TRAVERSAL_DONE; sp = 0; }
+            else OPR_POP(ANY)
+        }
+    }
+    if (hit.prim < 0) return false;
+    if (!ANY) hit.prim = __ldg(&sc.leafPrim[hit.prim]);     // leaf slot -> (primIndex << 2) | primType
+    return true;
+}
+
+// Call from possibly divergent code: the lanes that arrive together traverse together.
 template <bool ANY>
 OPR_DEV bool traverse(const SceneView& sc, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
 {
-    const float INF = __int_as_float(0x7f800000);
-    hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
-    // 1/d with |d| clamped away from zero: keeps every slab product finite-or-inf (never 0 * inf = NaN)
-    const float3 idir = f3(1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x)), 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y)),
-                           1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
-    int2 stack[TRAVERSAL_STACK];
-    int sp = 0;
-    int cur = sc.rootRef;
-    for (;;) {
-        if (cur >= 0) {
-            const float4* N = sc.nodes + 8 * (size_t)cur;
-            const float4 lox = __ldg(N + 0), hix = __ldg(N + 1), loy = __ldg(N + 2), hiy = __ldg(N + 3), loz = __ldg(N + 4), hiz = __ldg(N + 5);
-            const float4 rf = __ldg(N + 6);
-            int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
-            float t0, t1, t2, t3;
-            OPR_SLAB(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, t0)
-            OPR_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, t1)
-            OPR_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, t2)
-            OPR_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, t3)
-            OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t2, r2, t3, r3) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t1, r1, t3, r3) OPR_CSWAP(t1, r1, t2, r2)
-            if (t0 < INF) {
-                if (t3 < INF) stack[sp++] = make_int2(r3, __float_as_int(t3));
-                if (t2 < INF) stack[sp++] = make_int2(r2, __float_as_int(t2));
-                if (t1 < INF) stack[sp++] = make_int2(r1, __float_as_int(t1));
-                cur = r0;
-                continue;
-            }
-        } else {
-            const unsigned L = (unsigned)~cur;
-            const unsigned first = L >> 4, cnt = ((L >> 1) & 7u) + 1u;
-            bool found = false;
-            if (!(L & 1u)) {      // all triangles: one contiguous run of 48-byte records
-                for (unsigned k = 0; k < cnt; k++) {
-                    const float4* R = sc.leafTri + 3 * (size_t)(first + k);
-                    const float4 a = __ldg(R), b = __ldg(R + 1), c = __ldg(R + 2);
-                    if (intersect_tri_rec(a, b, c, o, d, tmin, hit.t, hit.t, hit.u, hit.v)) { hit.prim = (int)(first + k); found = true; }
-                }
-            } else {              // analytic primitives of the built-in scenes (parallelogram.cu, Sphere.cu) mixed in
-                for (unsigned k = 0; k < cnt; k++) {
-                    const int prim = __ldg(&sc.leafPrim[first + k]);
-                    if ((prim & 3) == PRIM_TRIANGLE) {
-                        const float4* R = sc.leafTri + 3 * (size_t)(first + k);
-                        const float4 a = __ldg(R), b = __ldg(R + 1), c = __ldg(R + 2);
-                        if (intersect_tri_rec(a, b, c, o, d, tmin, hit.t, hit.t, hit.u, hit.v)) { hit.prim = (int)(first + k); found = true; }
-                    } else if (intersect_prim(sc, prim, o, d, tmin, hit.t, hit)) { hit.prim = (int)(first + k); found = true; }
-                }
-            }
-            if (ANY && found) return true;
-        }
-        // pop; subtrees that start behind the closest hit so far are dropped unfetched
-        for (;;) {
-            if (sp == 0) {
-                if (hit.prim < 0) return false;
-                hit.prim = __ldg(&sc.leafPrim[hit.prim]);     // leaf slot -> (primIndex << 2) | primType
-                return true;
-            }
-            const int2 e = stack[--sp];
-            if (ANY || __int_as_float(e.y) < hit.t) { cur = e.x; break; }
-        }
-    }
+    return traverse_warp<ANY>(sc, __activemask(), true, o, d, tmin, tmax, hit);
 }
-#undef OPR_SLAB
-#undef OPR_CSWAP
 
 // Attributes the reference's intersection programs hand to the material programs
 struct Surface { float3 geometricNormal, shadingNormal, tangent, bitangent; float2 uv; int material; };

@@ -5,57 +5,113 @@
 //
 // Algorithmic bytes: closest-hit 48 B/ray (32 B ray in, 16 B hit out) + 4 B queue index; any-hit 36 B/ray.
 #include "renderer.h"
+#include <cstdlib>
 
 namespace opr {
 
 constexpr int TRACE_THREADS = 128;
 
-// Closest hit for the rays [0, *count) of queue `cur`; each hit ray is appended to the queue of its
-// material kind (warp-aggregated: one atomicAdd per distinct kind per warp via __match_any_sync), so the
-// shading kernels run sorted by material.
+// Closest hit for the rays [0, *count) of a queue; each finished ray is appended to the queue of its material kind
+// (warp-aggregated: one atomicAdd per distinct kind per warp via __match_any_sync), so the shading kernels run sorted by
+// material.
+//
+// Persistent warps with dynamic ray fetch: a warp keeps 32 per-lane traversal states; when at least `refillIdle` lanes
+// have finished their ray (or all have), the finished rays are retired (hit record + material queue) and the idle lanes
+// pull fresh rays from the shared cursor, so that warps stay full while ray lengths differ by an order of magnitude
+// (incoherent photon bounces).  The node / leaf steps are the warp-lockstep ones of scene.cuh.
 __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       const unsigned* __restrict__ count, float4* __restrict__ hits,
                                                                       unsigned* __restrict__ matQueue, unsigned* __restrict__ matCount,
-                                                                      unsigned capacity, unsigned* __restrict__ stat)
+                                                                      unsigned capacity, unsigned* __restrict__ stat, unsigned* __restrict__ fetchCursor,
+                                                                      unsigned refillIdle)
 {
+    const unsigned FULL = 0xffffffffu, NONE = 0xffffffffu;
     const unsigned n = *count;
     const unsigned lane = threadIdx.x & 31;
-    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const unsigned i = base + threadIdx.x;
-        const bool active = i < n;
-        int kind = -1;
-        if (active) {
-            const float4 o4 = rayO[i], d4 = rayD[i];
-            HitRec hit;
-            traverse<false>(sc, f3(o4), f3(d4), o4.w, d4.w, hit);
-            hits[i] = make_float4(hit.t, __int_as_float(hit.prim), hit.u, hit.v);
-            kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f);
+    float tmin = 0.f;
+    HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
+    int2 stack[TRAVERSAL_STACK];
+    int sp = 0;
+    int cur = TRAVERSAL_DONE;
+    unsigned ray = NONE;
+    bool exhausted = false;   // warp-uniform
+    for (;;) {
+        const unsigned idleMask = __ballot_sync(FULL, cur == TRAVERSAL_DONE);
+        if (idleMask == FULL || (!exhausted && (unsigned)__popc(idleMask) >= refillIdle)) {
+            // ---- retire finished rays
+            const bool finished = (cur == TRAVERSAL_DONE) && (ray != NONE);
+            int kind = -1;
+            if (finished) {
+                const int prim = hit.prim >= 0 ? __ldg(&sc.leafPrim[hit.prim]) : -1;
+                hits[ray] = make_float4(hit.t, __int_as_float(prim), hit.u, hit.v);
+                kind = prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, prim)].kind;
+            }
+            const unsigned peers = __match_any_sync(FULL, kind);
+            if (finished) {
+                const unsigned leader = __ffs(peers) - 1;
+                unsigned slot = 0;
+                if (lane == leader) slot = atomicAdd(&matCount[kind], __popc(peers));
+                slot = __shfl_sync(peers, slot, leader);
+                matQueue[(size_t)kind * capacity + slot + __popc(peers & ((1u << lane) - 1))] = ray;
+                ray = NONE;
+            }
+            // ---- refill idle lanes
+            if (!exhausted) {
+                const unsigned want = __popc(idleMask);
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(fetchCursor, want);
+                base = __shfl_sync(FULL, base, 0);
+                if (cur == TRAVERSAL_DONE) {
+                    const unsigned idx = base + __popc(idleMask & ((1u << lane) - 1));
+                    if (idx < n) {
+                        const float4 o4 = rayO[idx], d4 = rayD[idx];
+                        o = f3(o4); d = f3(d4); tmin = o4.w;
+                        idir = safe_inverse_direction(d);
+                        hit.t = d4.w; hit.prim = -1; hit.u = hit.v = 0.f;
+                        sp = 0; cur = sc.rootRef; ray = idx;
+                    }
+                }
+                if (base + want >= n) exhausted = true;
+            }
+            if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, kind);
-        if (active) {
-            const unsigned leader = __ffs(peers) - 1;
-            unsigned slot = 0;
-            if (lane == leader) slot = atomicAdd(&matCount[kind], __popc(peers));
-            slot = __shfl_sync(peers, slot, leader);
-            matQueue[(size_t)kind * capacity + slot + __popc(peers & ((1u << lane) - 1))] = i;
+        while (__any_sync(FULL, cur >= 0)) {
+            if (cur >= 0) OPR_NODE_STEP(false)
+        }
+        if (cur != TRAVERSAL_DONE) {
+            bool found = false;
+            OPR_LEAF_STEP(found)
+            (void)found;
+            OPR_POP(false)
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, n);
 }
 
+static unsigned trace_refill_idle()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OPR_TRACE_REFILL"); v = e ? atoi(e) : 16; if (v < 1) v = 1; if (v > 32) v = 32; }
+    return (unsigned)v;
+}
+
+// legacy ping-pong counters ([cur] ray count, [2..9) material counts) used by the VCM passes
 void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc)
 {
-    int blocks = 148 * 16;
-    trace_closest_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + cur, q.hits, q.matQueue,
-                                                              q.counters + 2, q.capacity, q.counters + 16 + STAT_CLOSEST_RAYS);
+    OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_FETCH_LEGACY, 0, sizeof(unsigned), lc.st));
+    trace_closest_kernel<<<148 * 8, TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + cur, q.hits, q.matQueue,
+                                                               q.counters + 2, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
+                                                               q.counters + CTR_FETCH_LEGACY, trace_refill_idle());
     ++*lc.launches;
 }
 
 void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc)
 {
     const int cur = bounce & 1;
-    trace_closest_kernel<<<148 * 16, TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
-                                                                q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS);
+    trace_closest_kernel<<<148 * 8, TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
+                                                               q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
+                                                               q.counters + CTR_FETCH + bounce, trace_refill_idle());
     ++*lc.launches;
 }
 
@@ -63,21 +119,26 @@ void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bo
 __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_raw_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                           unsigned n, float4* __restrict__ hits)
 {
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o4 = rayO[i], d4 = rayD[i];
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = base + threadIdx.x;
+        const bool active = i < n;
+        const float4 o4 = active ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = active ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
         HitRec hit;
-        traverse<false>(sc, f3(o4), f3(d4), o4.w, d4.w, hit);
-        hits[i] = make_float4(hit.t, __int_as_float(hit.prim), hit.u, hit.v);
+        traverse_warp<false>(sc, 0xffffffffu, active, f3(o4), f3(d4), o4.w, d4.w, hit);
+        if (active) hits[i] = make_float4(hit.t, __int_as_float(hit.prim), hit.u, hit.v);
     }
 }
 
 __global__ void __launch_bounds__(TRACE_THREADS) trace_any_raw_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       unsigned n, int* __restrict__ occluded)
 {
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o4 = rayO[i], d4 = rayD[i];
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = base + threadIdx.x;
+        const bool active = i < n;
+        const float4 o4 = active ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = active ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
         HitRec hit;
-        occluded[i] = traverse<true>(sc, f3(o4), f3(d4), o4.w, d4.w, hit) ? 1 : 0;
+        const bool occ = traverse_warp<true>(sc, 0xffffffffu, active, f3(o4), f3(d4), o4.w, d4.w, hit);
+        if (active) occluded[i] = occ ? 1 : 0;
     }
 }
 
