@@ -32,7 +32,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sponza", choices=["sponza", "conference", "cornell"])
+    ap.add_argument("--workload", default="sponza", choices=["sponza", "conference", "cornell", "cornellsmall"])
+    ap.add_argument("--method", default="ppm", choices=["ppm", "bdpt"], help="PROGRESSIVE_PHOTON_MAPPING (headline) or VCM_BIDIRECTIONAL_PATH_TRACING")
+    ap.add_argument("--max-path-length", type=int, default=8, help="BDPT only (BASELINE config 2 names 8; the reference default is 10)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--photons", type=int, default=1024, help="photon launch is photons x photons")
@@ -97,6 +99,9 @@ def build_scene(args):
     if args.workload == "cornell":
         scene = opr.Cornell()
         cam = scene.getDefaultCamera()
+    elif args.workload == "cornellsmall":
+        scene = opr.CornellSmall()
+        cam = scene.getDefaultCamera()
     else:
         from oppositerenderer_b200 import synthetic
         scene = synthetic.make_scene(args.workload, seed=1, detail=args.detail)
@@ -113,9 +118,9 @@ def cpu_reference_run(args, scene, cam, sample, steps, warmup, which):
     wh, pl = sample.split(":")
     w, h = (int(x) for x in wh.split("x"))
     pl = int(pl)
-    o = ol.OracleRenderer(which, (pl, pl), 10, 1645301512)
+    o = ol.OracleRenderer(which, (pl, pl), args.max_path_length if args.method == "bdpt" else 10, 1645301512)
     o.init_scene(scene.getSceneDescription())
-    det = ol.make_details(cam.pod, capi.PROGRESSIVE_PHOTON_MAPPING, w, h)
+    det = ol.make_details(cam.pod, capi.VCM_BIDIRECTIONAL_PATH_TRACING if args.method == "bdpt" else capi.PROGRESSIVE_PHOTON_MAPPING, w, h)
     r0 = scene.getSceneInitialPPMRadiusEstimate()
     radii = ol.ppm_radius_schedule(r0, steps + warmup)
     for i in range(warmup):
@@ -128,7 +133,8 @@ def cpu_reference_run(args, scene, cam, sample, steps, warmup, which):
     c1 = o.ray_counts()
     rays = (c1[0] - c0[0]) + (c1[1] - c0[1])
     cores = ol.load(which).ora_max_threads()
-    desc = "%d PPM iteration(s) of the same scene at %dx%d with a %dx%d photon launch (OpenMP, %d threads)" % (steps, w, h, pl, pl, cores)
+    desc = "%d %s iteration(s) of the same scene at %dx%d%s (OpenMP, %d threads)" % (
+        steps, args.method.upper(), w, h, " with a %dx%d photon launch" % (pl, pl) if args.method == "ppm" else ", max path length %d" % args.max_path_length, cores)
     return rays / dt / 1e6, steps / dt, cores, desc
 
 
@@ -137,12 +143,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload_name = {"sponza": "synthetic ~1M-tri Sponza-scale textured scene, PPM %dx%d, %dx%d photon launch" % (args.width, args.height, args.photons, args.photons),
-                     "conference": "synthetic ~300K-tri Conference-scale scene with glass/mirror caustics, PPM %dx%d, %dx%d photon launch" % (args.width, args.height, args.photons, args.photons),
-                     "cornell": "built-in Cornell box, PPM %dx%d, %dx%d photon launch" % (args.width, args.height, args.photons, args.photons)}[args.workload]
-    config = {"workload": workload_name, "width": args.width, "height": args.height, "photons_per_iteration": args.photons * args.photons,
-              "detail": args.detail, "l2": "per-iteration working set (photon slots 151 MB + hitpoints 133 MB + ray queues) exceeds the 126 MB L2",
+    how = ("PPM %dx%d, %dx%d photon launch" % (args.width, args.height, args.photons, args.photons) if args.method == "ppm"
+           else "BDPT (vertex connection, recursive MIS, max path length %d) %dx%d" % (args.max_path_length, args.width, args.height))
+    workload_name = {"sponza": "synthetic ~1M-tri Sponza-scale textured scene, ", "conference": "synthetic ~300K-tri Conference-scale scene with glass/mirror caustics, ",
+                     "cornell": "built-in Cornell box, ", "cornellsmall": "built-in CornellSmall (LightArea|Blocks), "}[args.workload] + how
+    ws_mb = (args.photons * args.photons * 4 * 36 if args.method == "ppm" else args.width * args.height * 96 * 2) / 1e6 + args.width * args.height * 64 / 1e6
+    config = {"workload": workload_name, "method": args.method, "width": args.width, "height": args.height,
+              "photons_per_iteration": args.photons * args.photons if args.method == "ppm" else None, "detail": args.detail,
+              "l2": ("per-iteration working set (path state + photon/light-vertex records, %.0f MB, plus ray queues) exceeds the 126 MB L2" % ws_mb) if ws_mb > 126
+                    else "working set %.0f MB fits the L2; a 256 MB scratch buffer is overwritten between timed iterations" % ws_mb,
               "parallelism": "iterations partitioned over %d GPU(s), scene replicated, one NCCL reduce of the sum buffer" % world}
+    flush_l2 = ws_mb <= 126
 
     if args.impl == "reference":
         if rank != 0:
@@ -176,23 +187,24 @@ def main():
     t_scene = time.perf_counter() - t0
     W, H = args.width, args.height
     # distinct RNG streams per rank (the reference's servers got this from wall-clock seeds, SpatialHash.cu:322)
-    r = opr.OptixRenderer(photon_launch=(args.photons, args.photons), seed=(1645301512 + rank * 104729) & 0xffffffff)
+    from oppositerenderer_b200 import distributed as D
+    r = opr.OptixRenderer(photon_launch=(args.photons, args.photons), vcm_max_path_length=args.max_path_length if args.method == "bdpt" else 0,
+                          seed=D.rank_seed(1645301512, rank))
     r.initialize(opr.ComputeDevice(local_rank))
     t0 = time.perf_counter()
     r.initScene(scene)
     r.synchronize()
     t_init = time.perf_counter() - t0
-    details = opr.RenderServerRenderRequestDetails(cam, scene.getSceneName(), opr.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, W, H, 2.0 / 3.0)
+    method = opr.RenderMethod.VCM_BIDIRECTIONAL_PATH_TRACING if args.method == "bdpt" else opr.RenderMethod.PROGRESSIVE_PHOTON_MAPPING
+    details = opr.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, W, H, 2.0 / 3.0)
     pod = details.pod()
     r0 = scene.getSceneInitialPPMRadiusEstimate()
     lib = capi.load_library()
-    radius = lambda it: float(lib.opr_ppm_radius_for_iteration(r0, it, 2.0 / 3.0))
-    stream = torch.cuda.ExternalStream(lib.opr_get_stream(r._h), device=torch.device("cuda", local_rank))
-
-    def out_tensor():
-        class _Arr:
-            __cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f4", "data": (r.output_device_ptr(), False), "version": 2}
-        return torch.as_tensor(_Arr(), device=torch.device("cuda", local_rank))
+    part = D.IterationPartition(rank, world, r0)
+    radius = lambda it: D.radius_for_iteration(r0, it)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(lib.opr_get_stream(r._h), device=dev)
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
 
     def barrier():
         if world > 1:
@@ -200,15 +212,16 @@ def main():
         torch.cuda.synchronize()
 
     def run(steps, first_local, readback=None):
-        for k in range(steps):
-            local = first_local + k
-            it = local * world + rank
-            r.renderNextIteration(it, local, radius(it), True, pod)
+        for it, local, rad in part.steps(first_local, steps):
+            if scratch is not None:
+                with torch.cuda.stream(stream):
+                    scratch.fill_(local & 0xff)        # evict the previous iteration's buffers from the 126 MB L2
+            r.renderNextIteration(it, local, rad, True, pod)
             if readback is not None:
                 r.getOutputBuffer(readback)
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.reduce(out_tensor(), dst=0)
+                D.reduce_sum_to_root(D.output_as_tensor(r, dev), dst=0)
 
     # ---- warm-up, then the device-timed region (inputs resident in HBM)
     run(args.warmup, 0)
@@ -264,25 +277,41 @@ def main():
         r.set_timing(False)
         kernel_ms = acc
         stp = r.stats()
-        g = r.debug_buffer("grid", np.uint32, 8)
-        V = int(g[7])
-        ncells = int(g[1]) * int(g[2]) * int(g[3])
         px = W * H
-        N = args.photons * args.photons * 4
         peak, how = peaks()
-        alg = {
-            "ppm.gather": 76.0 * px + 36.0 * V + 8.0 * ncells,
-            "ppm.direct_output": (64 + 12 + 12 + 12 + 24) * px + 36.0 * (stp["any_rays"] - st2["any_rays"]) / nprof,
-            "trace.camera0": 52.0 * px,
-            "trace.photon0": 52.0 * args.photons * args.photons,
-        }
-        cands = [(acc.get(k, 0.0), k) for k in alg if acc.get(k, 0.0) > 0]
+        alg = {}
+        if args.method == "ppm":
+            g = r.debug_buffer("grid", np.uint32, 8)
+            V = int(g[7])
+            ncells = int(g[1]) * int(g[2]) * int(g[3])
+            N = args.photons * args.photons * 4
+            # SURVEY.md §8d per-unit figures x the units one launch processes
+            alg = {
+                "ppm.gather": 76.0 * px + 36.0 * V + 8.0 * ncells,
+                "ppm.direct_output": (64 + 12 + 12 + 12 + 24) * px + 36.0 * (stp["any_rays"] - st2["any_rays"]) / nprof,
+                "trace.camera0": 52.0 * px,
+                "trace.photon0": 52.0 * args.photons * args.photons,
+                "grid.build": 36.0 * N + 132.0 * V + 8.0 * ncells,
+            }
+            acc["grid.build"] = sum(acc.get(k, 0.0) for k in ("grid.bbox", "grid.keys", "grid.sort", "grid.offsets", "grid.reorder"))
+        else:
+            rays_it = ((stp["closest_rays"] + stp["any_rays"]) - (st2["closest_rays"] + st2["any_rays"])) / nprof
+            alg = {"vcm.light": 48.0 * rays_it / 2, "vcm.camera": 48.0 * rays_it / 2}
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")   # dram bytes per launch from the committed `ncu --set full` capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
+        cands = [(acc.get(k, 0.0), k) for k in alg if k != "grid.build" and acc.get(k, 0.0) > 0]
         if cands:
             dur, name = max(cands)
             achieved = alg[name] / (dur * 1e-3) / 1e9
-            roof = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            tr = traffic.get(name, {}) if args.workload == "sponza" and args.method == "ppm" and (W, H) == (1920, 1080) else {}
+            roof = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": tr.get("dram_bytes"), "traffic_source": tr.get("source"),
                     "peak_source": how, "kernel_ms": dur, "algorithmic_bytes": alg[name],
-                    "note": "traversal/gather are L2- and latency-bound by construction (SURVEY.md §8d); see profiles/ for dram/L2 bytes"}
+                    "note": "gather and traversal are issue- / L1- / latency-bound, not HBM-bound (DESIGN.md §4, SURVEY.md §8d); profiles/ holds issue, L1 and L2 utilisation of the same launches",
+                    "others": {k: {"ms": acc[k], "achieved_gbs": alg[k] / (acc[k] * 1e-3) / 1e9, "frac": alg[k] / (acc[k] * 1e-3) / 1e9 / peak}
+                               for k in alg if k != name and acc.get(k, 0.0) > 0}}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -54,7 +54,35 @@ def report(name, path, out):
         out.write("\n")
 
 
+def traffic(path, tag):
+    """profiles/kernel_traffic.json: dram bytes (read + write) per launch of the kernels bench.py reports a roofline for."""
+    import json
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr = rows[0]
+    names = {"ppm_gather_kernel": "ppm.gather", "ppm_direct_output_kernel": "ppm.direct_output"}
+    out, seen_trace = {}, 0
+    for vals in rows[2:]:
+        kn = vals[hdr.index("Kernel Name")].split("(")[0]
+        key = names.get(kn)
+        if kn == "trace_closest_kernel":
+            key = {0: "trace.camera0", 1: "trace.photon0"}.get(seen_trace)
+            seen_trace += 1
+        if not key or key in out:
+            continue
+        rd, wr = float(vals[hdr.index("dram__bytes_read.sum")]), float(vals[hdr.index("dram__bytes_write.sum")])
+        ur, uw = rows[1][hdr.index("dram__bytes_read.sum")], rows[1][hdr.index("dram__bytes_write.sum")]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        out[key] = {"dram_bytes": rd * scale[ur] + wr * scale[uw], "gpu_time_ms_under_ncu": float(vals[hdr.index("gpu__time_duration.sum")]),
+                    "source": "profiles/%s (ncu --set full --clock-control none, one launch)" % tag}
+    json.dump(out, open("profiles/kernel_traffic.json", "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
+        sys.exit(0)
     tag = sys.argv[1]
     with open("profiles/%s_ncu_summary.txt" % tag, "w") as out:
         for a in sys.argv[2:]:
