@@ -544,47 +544,46 @@ void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, cons
 }
 
 // ---- direct lighting + output: DirectRadianceEstimation::kernel (ppm/DirectRadianceEstimation.cu:29-77),
-// getLightContribution (helpers/light.h:29-87), gatherAnyHitOnNonEmitter (:79-83), Output::kernel
-// (ppm/Output.cu:32-37).  One thread per pixel; the four shadow rays are any-hit traversals issued in place
-// (the RNG draws of the four samples are sequential on one state, DirectRadianceEstimation.cu:62,66).
-__global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_output_kernel(SceneView sc, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
-                                                                          const float* __restrict__ indirect, float* __restrict__ direct,
-                                                                          float* __restrict__ output, unsigned localIteration, unsigned* __restrict__ stat)
+// getLightContribution (helpers/light.h:29-87), gatherAnyHitOnNonEmitter (:79-83), Output::kernel (ppm/Output.cu:32-37).
+//
+// Three steps instead of one thread walking four shadow rays: (1) ppm_direct_gen_kernel draws the four light samples of
+// every diffuse pixel in the reference's RNG order (DirectRadianceEstimation.cu:62,66), stores each sample's light index
+// and un-occluded factor and appends the rays that must be cast (factor > 0: 39 % of the 4*W*H slots on the bench scene)
+// to a compacted queue; (2) trace_shadow_queue_kernel (trace.cu) clears the factor of occluded samples; (3)
+// ppm_resolve_output_kernel sums the samples exactly as the reference does and accumulates direct + indirect.
+// The one-thread-per-pixel version kept 61 % of its lanes idle in lockstep and ran the four traversals back to back.
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_gen_kernel(SceneView sc, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
+                                                                       float4* __restrict__ sampleFactor, unsigned* __restrict__ sampleLight,
+                                                                       float4* __restrict__ shadowD, unsigned* __restrict__ shadowIdx,
+                                                                       unsigned* __restrict__ counters)
 {
     const unsigned n = w * h;
-    unsigned shadowRays = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_FETCH_SHADOW] = 0u;     // consumed by the trace kernel that follows
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const unsigned p = base + threadIdx.x;
         const bool inImage = p < n;
         const float4 pos4 = inImage ? hp.pos[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const unsigned flags = __float_as_uint(pos4.w);
-        const bool diffuse = inImage && (flags & PRD_HIT_NON_SPECULAR);
-        float3 directRadiance = f3(0.f);
-        if (inImage && !diffuse) {
-            float3 rad = f3(hp.rad[p]);
-            if ((flags & PRD_HIT_EMITTER) && !(flags & PRD_HIT_SPECULAR)) directRadiance = fmin3(rad, f3(1.f));
-            else directRadiance = rad;
-        }
-        // the warp walks the four shadow samples together; lanes without a diffuse hit (or with a zero light factor) ride along
-        float3 rec_position = f3(pos4), rec_normal = f3(0.f), attenuation = f3(0.f);
+        const bool diffuse = inImage && (__float_as_uint(pos4.w) & PRD_HIT_NON_SPECULAR);
+        float factor[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned lights = 0u;
+        float3 rec_position = f3(pos4), rec_normal = f3(0.f);
         size_t ri = 0;
         Rng rng{};
         if (diffuse) {
-            rec_normal = f3(hp.nrm[p]); attenuation = f3(hp.att[p]);
+            rec_normal = f3(hp.nrm[p]);
             ri = (size_t)(p / w) * rsW + (p % w);
             rng = rng_load(rngBuf, ri);
         }
         const int numLights = sc.numLights;
-        float3 avgLightRadiance = f3(0.f);
-        #pragma unroll 1
+        #pragma unroll
         for (int shadowSample = 0; shadowSample < 4; shadowSample++) {
-            float lightFactor = 0.f, lightDistance = 1.f, scale = 0.f;
-            float3 towardsLight = f3(0.f, 0.f, 1.f), power = f3(0.f);
+            float lightFactor = 0.f, lightDistance = 1.f;
+            float3 towardsLight = f3(0.f, 0.f, 1.f);
             if (diffuse) {
                 float sample = rng_uniform(rng);
                 int randomLightIndex = min(int(sample * numLights), numLights - 1);
                 const opr_light& light = sc.lights[randomLightIndex];
-                scale = (float)numLights;
+                lights |= (unsigned)randomLightIndex << (8 * shadowSample);
                 // getLightContribution
                 lightFactor = 1;
                 float3 pointOnLight = f3(0.f);
@@ -606,44 +605,70 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_output_kernel(SceneV
                 lightFactor *= n_dot_l / (PI_F * lightDistance * lightDistance);
                 if (lightType == OPR_LIGHT_AREA)
                     lightFactor *= maxf_(0, dot(-towardsLight, f3(light.normal[0], light.normal[1], light.normal[2])));
-                power = f3(light.power[0], light.power[1], light.power[2]);
             }
             const bool cast = diffuse && lightFactor > 0.0f;
-            HitRec hit;
-            const bool occluded = traverse_warp<true>(sc, 0xffffffffu, cast, rec_position, towardsLight, 0.0001f, (float)((double)lightDistance - 0.0001), hit);
-            float3 lightContrib = f3(0.f);
+            factor[shadowSample] = cast ? lightFactor : 0.f;
+            const unsigned dst = warp_append(counters + CTR_SHADOW_COUNT, cast);
             if (cast) {
-                shadowRays++;
-                lightFactor *= occluded ? 0.0f : 1.0f;
-                lightContrib = power * lightFactor;
+                shadowD[dst] = make_float4(towardsLight.x, towardsLight.y, towardsLight.z, (float)((double)lightDistance - 0.0001));
+                shadowIdx[dst] = 4u * p + shadowSample;
             }
-            avgLightRadiance += scale * lightContrib;
         }
-        if (diffuse) {
-            rng_store(rngBuf, ri, rng);
-            directRadiance = attenuation * avgLightRadiance / 4.0f;
-        }
-        if (inImage) {
-            const float3 ind = f3(indirect[3 * (size_t)p], indirect[3 * (size_t)p + 1], indirect[3 * (size_t)p + 2]);
-            if (direct) { direct[3 * (size_t)p] = directRadiance.x; direct[3 * (size_t)p + 1] = directRadiance.y; direct[3 * (size_t)p + 2] = directRadiance.z; }
-            const float3 finalRadiance = directRadiance + ind;
-            float3 out = finalRadiance;
-            if (localIteration != 0) out = f3(output[3 * (size_t)p], output[3 * (size_t)p + 1], output[3 * (size_t)p + 2]) + finalRadiance;
-            output[3 * (size_t)p] = out.x; output[3 * (size_t)p + 1] = out.y; output[3 * (size_t)p + 2] = out.z;
-        }
+        if (diffuse) rng_store(rngBuf, ri, rng);
+        if (inImage) { sampleFactor[p] = make_float4(factor[0], factor[1], factor[2], factor[3]); sampleLight[p] = lights; }
     }
-    // shadow-ray count for the Mrays/s metric: warp-reduce, one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) shadowRays += __shfl_xor_sync(0xffffffffu, shadowRays, o);
-    if ((threadIdx.x & 31) == 0 && shadowRays) atomicAdd(stat, shadowRays);
 }
 
-void launch_ppm_direct_output(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
-                              const float* indirect, float* direct, float* output, unsigned localIteration, unsigned* statCounters, LaunchCtx lc)
+__global__ void __launch_bounds__(256) ppm_resolve_output_kernel(SceneView sc, unsigned n, HitpointBuf hp, const float4* __restrict__ sampleFactor,
+                                                                 const unsigned* __restrict__ sampleLight, const float* __restrict__ indirect,
+                                                                 float* __restrict__ direct, float* __restrict__ output, unsigned localIteration)
+{
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const unsigned flags = __float_as_uint(hp.pos[p].w);
+        float3 directRadiance;
+        if (!(flags & PRD_HIT_NON_SPECULAR)) {
+            float3 rad = f3(hp.rad[p]);
+            if ((flags & PRD_HIT_EMITTER) && !(flags & PRD_HIT_SPECULAR)) directRadiance = fmin3(rad, f3(1.f));
+            else directRadiance = rad;
+        } else {
+            const float3 attenuation = f3(hp.att[p]);
+            const float4 f4 = sampleFactor[p];
+            const float factor[4] = {f4.x, f4.y, f4.z, f4.w};
+            const unsigned lights = sampleLight[p];
+            const float scale = (float)sc.numLights;
+            float3 avgLightRadiance = f3(0.f);
+            #pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const opr_light& light = sc.lights[(lights >> (8 * s)) & 0xffu];
+                const float3 lightContrib = f3(light.power[0], light.power[1], light.power[2]) * factor[s];
+                avgLightRadiance += scale * lightContrib;
+            }
+            directRadiance = attenuation * avgLightRadiance / 4.0f;
+        }
+        const float3 ind = f3(indirect[3 * (size_t)p], indirect[3 * (size_t)p + 1], indirect[3 * (size_t)p + 2]);
+        if (direct) { direct[3 * (size_t)p] = directRadiance.x; direct[3 * (size_t)p + 1] = directRadiance.y; direct[3 * (size_t)p + 2] = directRadiance.z; }
+        const float3 finalRadiance = directRadiance + ind;
+        float3 out = finalRadiance;
+        if (localIteration != 0) out = f3(output[3 * (size_t)p], output[3 * (size_t)p + 1], output[3 * (size_t)p + 2]) + finalRadiance;
+        output[3 * (size_t)p] = out.x; output[3 * (size_t)p + 1] = out.y; output[3 * (size_t)p + 2] = out.z;
+    }
+}
+
+void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, float4* sampleFactor,
+                           unsigned* sampleLight, float4* shadowD, unsigned* shadowIdx, unsigned* counters, LaunchCtx lc)
 {
     unsigned n = w * h;
+    OPR_CUDA_CHECK(cudaMemsetAsync(counters + CTR_SHADOW_COUNT, 0, sizeof(unsigned), lc.st));
     int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
-    ppm_direct_output_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, w, h, rsW, rng, hp, indirect, direct, output, localIteration,
-                                                                  statCounters + STAT_ANY_RAYS);
+    ppm_direct_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, w, h, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, counters);
+    ++*lc.launches;
+}
+
+void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const unsigned* sampleLight,
+                               const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc)
+{
+    int blocks = (int)std::min<unsigned>((n + 255) / 256, 148 * 16);
+    ppm_resolve_output_kernel<<<blocks, 256, 0, lc.st>>>(sc, n, hp, sampleFactor, sampleLight, indirect, direct, output, localIteration);
     ++*lc.launches;
 }
 

@@ -28,6 +28,7 @@ Renderer::~Renderer()
     dfree(gridBBox);
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
     scene.release();
+    if (bboxEvent) cudaEventDestroy(bboxEvent);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -46,6 +47,7 @@ void Renderer::initialize(int cudaOrdinal)
     if (const char* e = getenv("OPR_PHOTON_WAVES")) photonWaveBounces = (unsigned)std::max(0, atoi(e));
     OPR_CUDA_CHECK(cudaSetDevice(device));
     OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    OPR_CUDA_CHECK(cudaEventCreateWithFlags(&bboxEvent, cudaEventDisableTiming));
 
     const size_t P = (size_t)photonLaunchWidth * photonLaunchHeight;
     const size_t N = P * MAX_PHOTON_DEPOSITS;
@@ -79,6 +81,7 @@ void Renderer::freeBuffers()
     for (int i = 0; i < 2; i++) { dfree(q.rayO[i]); dfree(q.rayD[i]); dfree(q.rayPath[i]); }
     dfree(q.hits); dfree(q.matQueue); dfree(q.counters);
     dfree(indirect); dfree(direct); dfree(output);
+    dfree(sampleFactor); dfree(sampleLight); dfree(shadowD); dfree(shadowIdx);
     buffersAllocated = false;
 }
 
@@ -96,6 +99,7 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     for (int i = 0; i < 2; i++) { dalloc(q.rayO[i], cap); dalloc(q.rayD[i], cap); dalloc(q.rayPath[i], cap); }
     dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, CTR_TOTAL);
     dalloc(indirect, px * 3); dalloc(direct, px * 3); dalloc(output, px * 3);
+    dalloc(sampleFactor, px); dalloc(sampleLight, px); dalloc(shadowD, px * 4); dalloc(shadowIdx, px * 4);
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, CTR_TOTAL * sizeof(unsigned), stream));
     OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, px * 3 * sizeof(float), stream));
     buffersAllocated = true;
@@ -105,20 +109,26 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     lightVertexCountEstimated = false;      // :847
 }
 
+void Renderer::photonBBoxAsync()
+{   // getPhotonsBoundingBox, OptixRenderer_SpatialHash.cu:123-128.  The result travels to pinned host memory behind an event, so
+    // the direct-lighting kernels queued after it keep the GPU busy while the host computes the grid scalars.
+    LaunchCtx lc{stream, &launches};
+    const unsigned P = photonLaunchWidth * photonLaunchHeight;
+    ScopedTimer t(*this, "grid.bbox");
+    float* h = gridBBoxHost;
+    h[8] = FLT_MAX; h[9] = FLT_MAX; h[10] = FLT_MAX; h[11] = -FLT_MAX; h[12] = -FLT_MAX; h[13] = -FLT_MAX; h[14] = 0.f; h[15] = 0.f;
+    OPR_CUDA_CHECK(cudaMemcpyAsync(gridBBox, h + 8, 7 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    launch_photon_bbox(photons, phState, P, gridBBox, lc);
+    OPR_CUDA_CHECK(cudaMemcpyAsync(h, gridBBox, 7 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    OPR_CUDA_CHECK(cudaEventRecord(bboxEvent, stream));
+}
+
 void Renderer::buildPhotonGrid()
 {   // createUniformGridPhotonMap, OptixRenderer_SpatialHash.cu:209-282
     LaunchCtx lc{stream, &launches};
     const unsigned P = photonLaunchWidth * photonLaunchHeight;
     const unsigned N = P * MAX_PHOTON_DEPOSITS;
-    {
-        ScopedTimer t(*this, "grid.bbox");
-        float* h = gridBBoxHost;
-        h[8] = FLT_MAX; h[9] = FLT_MAX; h[10] = FLT_MAX; h[11] = -FLT_MAX; h[12] = -FLT_MAX; h[13] = -FLT_MAX; h[14] = 0.f; h[15] = 0.f;
-        OPR_CUDA_CHECK(cudaMemcpyAsync(gridBBox, h + 8, 7 * sizeof(float), cudaMemcpyHostToDevice, stream));
-        launch_photon_bbox(photons, phState, P, gridBBox, lc);
-        OPR_CUDA_CHECK(cudaMemcpyAsync(h, gridBBox, 7 * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        OPR_CUDA_CHECK(cudaStreamSynchronize(stream));   // the reference syncs here too (:222)
-    }
+    OPR_CUDA_CHECK(cudaEventSynchronize(bboxEvent));   // the reference syncs here too (:222)
     unsigned numValid; memcpy(&numValid, gridBBoxHost + 6, 4);
     float lo[3] = {gridBBoxHost[0], gridBBoxHost[1], gridBBoxHost[2]}, hi[3] = {gridBBoxHost[3], gridBBoxHost[4], gridBBoxHost[5]};
     if (numValid == 0) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.f; }   // photons[0] is a cleared slot
@@ -184,7 +194,19 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
             launch_ppm_photon_tail(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, waves, lc);
         }
     }
-    // ---- createUniformGridPhotonMap (:628)
+    // ---- photon bounding box (first step of createUniformGridPhotonMap, :628), result in flight to the host
+    photonBBoxAsync();
+    // ---- PPM_DIRECT_RADIANCE_ESTIMATION_PASS (:664) moved before the grid build: it needs hit points and RNG states, not
+    // the photon map, and fills the GPU while the host waits for the bounding box.  The RNG order per state is unchanged
+    // (camera pass -> photon pass -> direct pass).
+    {
+        ScopedTimer t(*this, "ppm.direct");
+        { ScopedTimer t0(*this, "direct.gen"); launch_ppm_direct_gen(sc, width, height, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q.counters, lc); }
+        { ScopedTimer t0(*this, "trace.shadow");
+          launch_trace_shadow_queue(sc, hp.pos, shadowD, shadowIdx, q.counters + CTR_SHADOW_COUNT, (float*)sampleFactor, q.counters + CTR_FETCH_SHADOW,
+                                    q.counters + CTR_STATS + STAT_ANY_RAYS, lc); }
+    }
+    // ---- rest of createUniformGridPhotonMap
     buildPhotonGrid();
     // ---- PPM_INDIRECT_RADIANCE_ESTIMATION_PASS (:657)
     {
@@ -192,11 +214,10 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         launch_gather(hp, width * height, width, height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
                       float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lc);
     }
-    // ---- PPM_DIRECT_RADIANCE_ESTIMATION_PASS + PPM_OUTPUT_PASS (:664, :670)
+    // ---- sum of the light samples + PPM_OUTPUT_PASS (:670)
     {
-        ScopedTimer t(*this, "ppm.direct_output");
-        launch_ppm_direct_output(sc, width, height, rsW, rng, hp, indirect, keepDebugBuffers ? direct : nullptr, output, localIterationNumber,
-                                 q.counters + 16, lc);
+        ScopedTimer t(*this, "ppm.resolve_output");
+        launch_ppm_resolve_output(sc, width * height, hp, sampleFactor, sampleLight, indirect, keepDebugBuffers ? direct : nullptr, output, localIterationNumber, lc);
     }
     (void)iterationNumber;
 }

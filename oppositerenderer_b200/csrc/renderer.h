@@ -17,7 +17,9 @@ constexpr int CTR_STATS = 16;         // StatSlot counters
 constexpr int CTR_RAYCOUNT = 32;      // ray count of bounce b at CTR_RAYCOUNT + b (b < 32)
 constexpr int CTR_MATCOUNT = 64;      // material-queue counts of bounce b at CTR_MATCOUNT + 8 b (b < 24)
 constexpr int CTR_FETCH = 192;        // ray-fetch cursor of the persistent trace kernel, bounce b at CTR_FETCH + b (b < 32)
-constexpr int CTR_FETCH_LEGACY = 10;  // same for the ping-pong (VCM) launcher
+constexpr int CTR_FETCH_LEGACY = 10;
+constexpr int CTR_SHADOW_COUNT = 13;  // shadow-ray queue length of the PPM direct pass
+constexpr int CTR_FETCH_SHADOW = 14;  // its fetch cursor  // same for the ping-pong (VCM) launcher
 constexpr int CTR_TOTAL = 256;
 
 // Wavefront ray queue state (all device pointers)
@@ -83,6 +85,12 @@ struct Renderer {
     unsigned* sortedKeys = nullptr;       // alias of gridKeys[x] after the sort
     GridParams grid{};
     // radiance
+    // direct lighting: per-pixel light samples + compacted shadow-ray queue (4 slots per pixel)
+    float4* sampleFactor = nullptr;       // un-occluded light factor of the four samples; occluded ones are cleared by the trace
+    unsigned* sampleLight = nullptr;      // light index of the four samples, one byte each
+    float4* shadowD = nullptr;            // direction.xyz, tmax
+    unsigned* shadowIdx = nullptr;        // 4 * pixel + sample
+    cudaEvent_t bboxEvent = nullptr;      // photon bbox + count landed in pinned host memory
     float* indirect = nullptr;            // float3 per pixel
     float* direct = nullptr;
     float* output = nullptr;              // running sum, float3 per pixel == reference outputBuffer
@@ -109,6 +117,7 @@ struct Renderer {
                              bool createOutput, const opr_request_details& details);
     void renderPPM(unsigned long long iterationNumber, unsigned localIterationNumber, float PPMRadius, const opr_request_details& details);
     void renderVCM(unsigned long long iterationNumber, unsigned localIterationNumber, float PPMRadius, const opr_request_details& details);
+    void photonBBoxAsync();
     void buildPhotonGrid();
     void getOutputBuffer(void* dst);
 };
@@ -152,8 +161,12 @@ void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, con
                              const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
 void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
-void launch_ppm_direct_output(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
-                              const float* indirect, float* direct, float* output, unsigned localIteration, unsigned* statCounters, LaunchCtx lc);
+void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, float4* sampleFactor,
+                           unsigned* sampleLight, float4* shadowD, unsigned* shadowIdx, unsigned* counters, LaunchCtx lc);
+void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
+                               float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
+void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const unsigned* sampleLight,
+                               const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc);
 
 void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc);
 void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, GridParams g, unsigned* keys, unsigned* hist, LaunchCtx lc);

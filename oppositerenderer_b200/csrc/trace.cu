@@ -115,6 +115,68 @@ void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bo
     ++*lc.launches;
 }
 
+// Any-hit for a compacted queue of shadow rays (ppm/DirectRadianceEstimation.cu:79-83: any intersection in (tmin, tmax)
+// zeroes the sample).  Ray i = (origin = hit point of pixel idx >> 2, direction + tmax = shadowD[i]); an occluded ray
+// clears sampleFactor[idx].  Same persistent / dynamic-fetch / warp-lockstep structure as trace_closest_kernel.
+__global__ void __launch_bounds__(TRACE_THREADS) trace_shadow_queue_kernel(SceneView sc, const float4* __restrict__ hitPos, const float4* __restrict__ shadowD,
+                                                                           const unsigned* __restrict__ shadowIdx, const unsigned* __restrict__ count,
+                                                                           float* __restrict__ sampleFactor, unsigned* __restrict__ fetchCursor,
+                                                                           unsigned* __restrict__ stat, unsigned refillIdle)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned n = *count;
+    const unsigned lane = threadIdx.x & 31;
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f);
+    const float tmin = 0.0001f;
+    HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
+    int2 stack[TRAVERSAL_STACK];
+    int sp = 0;
+    int cur = TRAVERSAL_DONE;
+    unsigned idx = 0;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned idleMask = __ballot_sync(FULL, cur == TRAVERSAL_DONE);
+        if (idleMask == FULL || (!exhausted && (unsigned)__popc(idleMask) >= refillIdle)) {
+            if (!exhausted) {
+                const unsigned want = __popc(idleMask);
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(fetchCursor, want);
+                base = __shfl_sync(FULL, base, 0);
+                if (cur == TRAVERSAL_DONE) {
+                    const unsigned i = base + __popc(idleMask & ((1u << lane) - 1));
+                    if (i < n) {
+                        idx = shadowIdx[i];
+                        const float4 d4 = shadowD[i];
+                        o = f3(hitPos[idx >> 2]); d = f3(d4);
+                        idir = safe_inverse_direction(d);
+                        hit.t = d4.w; hit.prim = -1;
+                        sp = 0; cur = sc.rootRef;
+                    }
+                }
+                if (base + want >= n) exhausted = true;
+            }
+            if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
+        }
+        while (__any_sync(FULL, cur >= 0)) {
+            if (cur >= 0) OPR_NODE_STEP(true)
+        }
+        if (cur != TRAVERSAL_DONE) {
+            bool found = false;
+            OPR_LEAF_STEP(found)
+            if (found) { sampleFactor[idx] = 0.f; cur = TRAVERSAL_DONE; sp = 0; }
+            else OPR_POP(true)
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, n);
+}
+
+void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
+                               float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc)
+{
+    trace_shadow_queue_kernel<<<148 * 8, TRACE_THREADS, 0, lc.st>>>(sc, hitPos, shadowD, shadowIdx, count, sampleFactor, fetchCursor, stat, trace_refill_idle());
+    ++*lc.launches;
+}
+
 // Raw entry points over caller-supplied SoA rays (C-ABI opr_trace_closest / opr_trace_any)
 __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_raw_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                           unsigned n, float4* __restrict__ hits)
