@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -219,6 +219,7 @@ def main():
             r.renderNextIteration(it, local, rad, True, pod)
             if readback is not None:
                 r.getOutputBuffer(readback)
+        r.join()        # the gather / output of the last iteration run on the renderer's second stream: fold them into `stream`
         if world > 1:
             with torch.cuda.stream(stream):
                 D.reduce_sum_to_root(D.output_as_tensor(r, dev), dst=0)

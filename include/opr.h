@@ -47,6 +47,10 @@ uint32_t opr_get_screen_buffer_size_bytes(opr_renderer* r);
  * HBM; the caller reduces it across ranks (NCCL) through this device pointer (W*H*3 floats). */
 void* opr_get_output_device_ptr(opr_renderer* r);
 int opr_synchronize(opr_renderer* r);
+/* The renderer overlaps the photon-grid build / gather / output of iteration i (internal second stream) with the path
+ * passes of iteration i+1.  opr_join_streams orders everything queued so far before later work on opr_get_stream(r);
+ * opr_get_output_buffer, opr_get_output_device_ptr, opr_synchronize and opr_debug_get_buffer join implicitly. */
+int opr_join_streams(opr_renderer* r);
 /* the CUDA stream (cudaStream_t) every kernel of r is launched on — for event timing and for ordering the NCCL reduce */
 void* opr_get_stream(opr_renderer* r);
 /* Closed form of the driver's radius schedule r_{i+1}^2 = r_i^2 (i+alpha)/(i+1)

@@ -117,6 +117,7 @@ def _declare(lib):
         "opr_get_screen_buffer_size_bytes": (u32, [vp]),
         "opr_get_output_device_ptr": (vp, [vp]),
         "opr_synchronize": (i32, [vp]),
+        "opr_join_streams": (i32, [vp]),
         "opr_get_stream": (vp, [vp]),
         "opr_get_stats": (i32, [vp, C.POINTER(C.c_uint64), i32]),
         "opr_get_timings_ms": (i32, [vp, PF, i32]),

@@ -60,9 +60,10 @@ int opr_get_output_buffer(opr_renderer* r, void* dst) { OPR_TRY(r->r.getOutputBu
 uint32_t opr_get_width(opr_renderer* r) { return r->r.width; }
 uint32_t opr_get_height(opr_renderer* r) { return r->r.height; }
 uint32_t opr_get_screen_buffer_size_bytes(opr_renderer* r) { return r->r.width * r->r.height * 3u * (uint32_t)sizeof(float); }
-void* opr_get_output_device_ptr(opr_renderer* r) { return r->r.output; }
+void* opr_get_output_device_ptr(opr_renderer* r) { try { r->r.joinStreams(); } catch (...) {} return r->r.output; }
 void* opr_get_stream(opr_renderer* r) { return (void*)r->r.stream; }
-int opr_synchronize(opr_renderer* r) { OPR_TRY({ OPR_CUDA_CHECK(cudaSetDevice(r->r.device)); OPR_CUDA_CHECK(cudaStreamSynchronize(r->r.stream)); }) }
+int opr_synchronize(opr_renderer* r) { OPR_TRY({ OPR_CUDA_CHECK(cudaSetDevice(r->r.device)); r->r.joinStreams(); OPR_CUDA_CHECK(cudaStreamSynchronize(r->r.stream)); }) }
+int opr_join_streams(opr_renderer* r) { OPR_TRY({ OPR_CUDA_CHECK(cudaSetDevice(r->r.device)); r->r.joinStreams(); }) }
 
 int opr_get_stats(opr_renderer* r, uint64_t* out, int n)
 {
@@ -99,6 +100,7 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
     OPR_TRY({
         Renderer& R = r->r;
         OPR_CUDA_CHECK(cudaSetDevice(R.device));
+        R.joinStreams();
         cudaStream_t st = R.stream;
         const std::string n(name);
         const size_t px = (size_t)R.width * R.height;

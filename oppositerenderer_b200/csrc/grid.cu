@@ -283,10 +283,10 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
 }
 
 void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
-                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc)
+                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc, unsigned blocksPerSM)
 {
     const unsigned numTiles = width ? ((width + 7) / 8) * ((height + 3) / 4) : (numPixels + 31) / 32;
-    int blocks = (int)std::min<unsigned>(numTiles, 148 * 12);
+    int blocks = (int)std::min<unsigned>(numTiles, 148 * std::max(1u, blocksPerSM));
     OPR_CUDA_CHECK(cudaMemsetAsync(tileCounter, 0, sizeof(unsigned), lc.st));
     ppm_gather_kernel<<<blocks, GATHER_THREADS, 0, lc.st>>>(hp, numPixels, width, height, sorted, offsets, g, ppmRadius, ppmRadiusSquared, emittedPhotons, indirect,
                                                             tileCounter);

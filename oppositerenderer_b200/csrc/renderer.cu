@@ -29,6 +29,8 @@ Renderer::~Renderer()
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
     scene.release();
     if (bboxEvent) cudaEventDestroy(bboxEvent);
+    for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin}) if (e) cudaEventDestroy(e);
+    if (streamB) cudaStreamDestroy(streamB);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -48,6 +50,10 @@ void Renderer::initialize(int cudaOrdinal)
     OPR_CUDA_CHECK(cudaSetDevice(device));
     OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     OPR_CUDA_CHECK(cudaEventCreateWithFlags(&bboxEvent, cudaEventDisableTiming));
+    OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&streamB, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin}) OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
+    if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
 
     const size_t P = (size_t)photonLaunchWidth * photonLaunchHeight;
     const size_t N = P * MAX_PHOTON_DEPOSITS;
@@ -74,32 +80,48 @@ void Renderer::initScene(const opr_scene_desc* d)
     sceneLoaded = true;
 }
 
+void Renderer::joinStreams()
+{
+    joinedSinceRender = true;
+    if (!overlap || !workOnB) return;
+    OPR_CUDA_CHECK(cudaEventRecord(evJoin, streamB));
+    OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin, 0));
+    workOnB = false;
+}
+
 void Renderer::freeBuffers()
 {
     dfree(rng.a); dfree(rng.b); dfree(rng.c);
-    dfree(hp.pos); dfree(hp.nrm); dfree(hp.att); dfree(hp.rad);
+    for (int b = 0; b < 2; b++) { dfree(hpBuf[b].pos); dfree(hpBuf[b].nrm); dfree(hpBuf[b].att); dfree(hpBuf[b].rad); dfree(sampleFactorBuf[b]); dfree(sampleLightBuf[b]); }
+    hp = HitpointBuf{}; sampleFactor = nullptr; sampleLight = nullptr;
+    hpFreePending[0] = hpFreePending[1] = gridDonePending = false;
     for (int i = 0; i < 2; i++) { dfree(q.rayO[i]); dfree(q.rayD[i]); dfree(q.rayPath[i]); }
     dfree(q.hits); dfree(q.matQueue); dfree(q.counters);
     dfree(indirect); dfree(direct); dfree(output);
-    dfree(sampleFactor); dfree(sampleLight); dfree(shadowD); dfree(shadowIdx);
+    dfree(shadowD); dfree(shadowIdx);
     buffersAllocated = false;
 }
 
 void Renderer::resizeBuffers(unsigned w, unsigned h)
 {   // OptixRenderer.cpp:828-848
     OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (streamB) OPR_CUDA_CHECK(cudaStreamSynchronize(streamB));
     freeBuffers();
     const size_t px = (size_t)w * h;
     rsW = std::max(photonLaunchWidth, w); rsH = std::max(photonLaunchHeight, h);
     const size_t ns = (size_t)rsW * rsH;
     dalloc(rng.a, ns); dalloc(rng.b, ns); dalloc(rng.c, ns);
-    dalloc(hp.pos, px); dalloc(hp.nrm, px); dalloc(hp.att, px); dalloc(hp.rad, px);
+    for (int b = 0; b < 2; b++) {
+        dalloc(hpBuf[b].pos, px); dalloc(hpBuf[b].nrm, px); dalloc(hpBuf[b].att, px); dalloc(hpBuf[b].rad, px);
+        dalloc(sampleFactorBuf[b], px); dalloc(sampleLightBuf[b], px);
+    }
+    parity = 0; hp = hpBuf[0]; sampleFactor = sampleFactorBuf[0]; sampleLight = sampleLightBuf[0];
     const size_t cap = std::max(px, (size_t)photonLaunchWidth * photonLaunchHeight);
     q.capacity = (unsigned)cap;
     for (int i = 0; i < 2; i++) { dalloc(q.rayO[i], cap); dalloc(q.rayD[i], cap); dalloc(q.rayPath[i], cap); }
     dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, CTR_TOTAL);
     dalloc(indirect, px * 3); dalloc(direct, px * 3); dalloc(output, px * 3);
-    dalloc(sampleFactor, px); dalloc(sampleLight, px); dalloc(shadowD, px * 4); dalloc(shadowIdx, px * 4);
+    dalloc(shadowD, px * 4); dalloc(shadowIdx, px * 4);
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, CTR_TOTAL * sizeof(unsigned), stream));
     OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, px * 3 * sizeof(float), stream));
     buffersAllocated = true;
@@ -125,10 +147,13 @@ void Renderer::photonBBoxAsync()
 
 void Renderer::buildPhotonGrid()
 {   // createUniformGridPhotonMap, OptixRenderer_SpatialHash.cu:209-282
-    LaunchCtx lc{stream, &launches};
+    const cudaStream_t st = sB();
+    LaunchCtx lc{st, &launches};
     const unsigned P = photonLaunchWidth * photonLaunchHeight;
     const unsigned N = P * MAX_PHOTON_DEPOSITS;
     OPR_CUDA_CHECK(cudaEventSynchronize(bboxEvent));   // the reference syncs here too (:222)
+    OPR_CUDA_CHECK(cudaStreamWaitEvent(st, bboxEvent, 0));   // stream B starts once the photon pass of this iteration is complete
+    workOnB = true;
     unsigned numValid; memcpy(&numValid, gridBBoxHost + 6, 4);
     float lo[3] = {gridBBoxHost[0], gridBBoxHost[1], gridBBoxHost[2]}, hi[3] = {gridBBoxHost[3], gridBBoxHost[4], gridBBoxHost[5]};
     if (numValid == 0) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.f; }   // photons[0] is a cleared slot
@@ -137,27 +162,27 @@ void Renderer::buildPhotonGrid()
     grid.numValid = numValid;
     stats[STAT_PHOTONS_STORED] += numValid;
     {
-        ScopedTimer t(*this, "grid.keys");
-        OPR_CUDA_CHECK(cudaMemsetAsync(gridHist, 0, ((size_t)grid.numCells + 2) * sizeof(unsigned), stream));
+        ScopedTimer t(*this, "grid.keys", st);
+        OPR_CUDA_CHECK(cudaMemsetAsync(gridHist, 0, ((size_t)grid.numCells + 2) * sizeof(unsigned), st));
         launch_grid_keys(photons, phState, N, grid, gridKeys[0], gridHist, lc);
     }
     bool flipped;
     {
-        ScopedTimer t(*this, "grid.sort");
+        ScopedTimer t(*this, "grid.sort", st);
         int bits = 1; while ((1ull << bits) <= (unsigned long long)grid.numCells + 1) bits++;
         int nl = 0;
-        flipped = radix_sort_pairs<unsigned>(gridKeys[0], gridVals[0], gridKeys[1], gridVals[1], N, bits, sortTmp, true, stream, &nl);
+        flipped = radix_sort_pairs<unsigned>(gridKeys[0], gridVals[0], gridKeys[1], gridVals[1], N, bits, sortTmp, true, st, &nl);
         launches += nl;
     }
     sortedKeys = flipped ? gridKeys[1] : gridKeys[0];
     const unsigned* sortedSlots = flipped ? gridVals[1] : gridVals[0];
     {
-        ScopedTimer t(*this, "grid.offsets");
-        exclusive_scan_u32(gridHist, gridHist, grid.numCells + 1, scanTmp, stream);
+        ScopedTimer t(*this, "grid.offsets", st);
+        exclusive_scan_u32(gridHist, gridHist, grid.numCells + 1, scanTmp, st);
         launches += 3;
     }
     {
-        ScopedTimer t(*this, "grid.reorder");
+        ScopedTimer t(*this, "grid.reorder", st);
         launch_photon_reorder(photons, sortedSlots, numValid, sorted, lc);
     }
 }
@@ -166,6 +191,18 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
 {
     LaunchCtx lc{stream, &launches};
     const SceneView& sc = scene.view;
+    const cudaStream_t stB = sB();
+    // Two streams.  `stream` (A) runs what consumes the RNG states, in the reference's order: camera pass, photon pass, direct
+    // light samples.  Stream B runs what does not: photon-grid build, gather, sample resolve + output.  B's work for iteration i
+    // overlaps A's work for iteration i+1 (hit points and light samples are double-buffered), so the compute-bound gather fills
+    // the SMs that the latency-bound tail kernels and launch gaps of the path passes leave idle.
+    // A caller that reads the image back after every iteration leaves nothing to overlap with: give the gather the whole GPU then.
+    const unsigned gatherBlocks = (overlap && !joinedSinceRender) ? gatherBlocksPerSM : 12u;
+    joinedSinceRender = false;
+    parity ^= 1u;
+    const unsigned pb = parity;
+    hp = hpBuf[pb]; sampleFactor = sampleFactorBuf[pb]; sampleLight = sampleLightBuf[pb];
+    if (hpFreePending[pb]) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evHpFree[pb], 0)); hpFreePending[pb] = false; }
     // ---- PPM_RAYTRACE_PASS (:576): wavefront bounces, then one per-path tail kernel for the specular continuations
     {
         ScopedTimer t(*this, "ppm.camera");
@@ -181,6 +218,8 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     // ---- PPM_PHOTON_PASS (:612)
     {
         ScopedTimer t(*this, "ppm.photon");
+        // the previous iteration's grid build (stream B) must be done reading the photon slots before they are overwritten
+        if (gridDonePending) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evGridDone, 0)); gridDonePending = false; }
         { ScopedTimer tg(*this, "photon.gen"); launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, lc); }
         const unsigned waves = std::min(photonWaveBounces, MAX_PHOTON_TRACE_DEPTH + 1);
         static const char* tn[] = {"trace.photon0", "trace.photon1", "trace.photon2", "trace.photon3", "trace.photon4+"};
@@ -205,20 +244,25 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         { ScopedTimer t0(*this, "trace.shadow");
           launch_trace_shadow_queue(sc, hp.pos, shadowD, shadowIdx, q.counters + CTR_SHADOW_COUNT, (float*)sampleFactor, q.counters + CTR_FETCH_SHADOW,
                                     q.counters + CTR_STATS + STAT_ANY_RAYS, lc); }
+        OPR_CUDA_CHECK(cudaEventRecord(evDirectDone, stream));
     }
-    // ---- rest of createUniformGridPhotonMap
+    // ---- rest of createUniformGridPhotonMap (stream B; the host waits for the bounding box inside)
     buildPhotonGrid();
+    OPR_CUDA_CHECK(cudaEventRecord(evGridDone, stB)); gridDonePending = true;
+    LaunchCtx lcB{stB, &launches};
     // ---- PPM_INDIRECT_RADIANCE_ESTIMATION_PASS (:657)
     {
-        ScopedTimer t(*this, "ppm.gather");
+        ScopedTimer t(*this, "ppm.gather", stB);
         launch_gather(hp, width * height, width, height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
-                      float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lc);
+                      float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lcB, gatherBlocks);
     }
     // ---- sum of the light samples + PPM_OUTPUT_PASS (:670)
     {
-        ScopedTimer t(*this, "ppm.resolve_output");
-        launch_ppm_resolve_output(sc, width * height, hp, sampleFactor, sampleLight, indirect, keepDebugBuffers ? direct : nullptr, output, localIterationNumber, lc);
+        OPR_CUDA_CHECK(cudaStreamWaitEvent(stB, evDirectDone, 0));
+        ScopedTimer t(*this, "ppm.resolve_output", stB);
+        launch_ppm_resolve_output(sc, width * height, hp, sampleFactor, sampleLight, indirect, keepDebugBuffers ? direct : nullptr, output, localIterationNumber, lcB);
     }
+    OPR_CUDA_CHECK(cudaEventRecord(evHpFree[pb], stB)); hpFreePending[pb] = true;
     (void)iterationNumber;
 }
 
@@ -231,8 +275,11 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber, unsigned 
     if (details.width == 0 || details.height == 0) throw std::runtime_error("zero-sized render request");
     lastTimings.clear();
     if (!buffersAllocated || details.width != width || details.height != height) resizeBuffers(details.width, details.height);   // :534-537
-    if (localIterationNumber == 0)                                                                                               // :540-545
+    if (localIterationNumber == 0) {                                                                                             // :540-545
+        joinStreams();
         OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, (size_t)width * height * 3 * sizeof(float), stream));
+    }
+    if (details.renderMethod != OPR_PROGRESSIVE_PHOTON_MAPPING) joinStreams();   // BDPT accumulates into `output` on `stream`
 
     if (details.renderMethod == OPR_PROGRESSIVE_PHOTON_MAPPING)
         renderPPM(iterationNumber, (unsigned)localIterationNumber, PPMRadius, details);
@@ -247,6 +294,7 @@ void Renderer::getOutputBuffer(void* dst)
 {   // OptixRenderer.cpp:860-865: copies W*H*12 bytes into a caller-owned buffer
     if (!buffersAllocated) throw std::runtime_error("getOutputBuffer before the first iteration");
     OPR_CUDA_CHECK(cudaSetDevice(device));
+    joinStreams();
     OPR_CUDA_CHECK(cudaMemcpyAsync(dst, output, (size_t)width * height * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
     OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
 }

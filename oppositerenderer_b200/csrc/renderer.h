@@ -67,8 +67,22 @@ struct Renderer {
     bool buffersAllocated = false;
     unsigned rsW = 0, rsH = 0;
     RngBuf rng{};
-    HitpointBuf hp{};
+    HitpointBuf hp{};                     // hit points of the latest camera pass (= hpBuf[parity])
+    HitpointBuf hpBuf[2]{};               // double-buffered: the gather of iteration i overlaps the camera/photon passes of i+1
     RayQueues q{};
+    // second stream: photon-grid build, gather and output of iteration i run here while `stream` traces iteration i+1
+    cudaStream_t streamB = nullptr;
+    bool overlap = true;                  // OPR_OVERLAP=0 puts everything on `stream`
+    unsigned gatherBlocksPerSM = 4;       // OPR_GATHER_BLOCKS_PER_SM: gather CTAs per SM while it shares the SMs with the next iteration's path passes
+    bool joinedSinceRender = true;        // the caller consumed the last iteration before asking for the next one (no overlap possible)
+    unsigned parity = 0;
+    cudaEvent_t evHpFree[2] = {nullptr, nullptr};   // stream B finished with hpBuf[b] / sample buffers b
+    cudaEvent_t evGridDone = nullptr;               // stream B finished reading `photons` / phState
+    cudaEvent_t evDirectDone = nullptr;             // stream A finished the light samples of this iteration
+    cudaEvent_t evJoin = nullptr;
+    bool hpFreePending[2] = {false, false}, gridDonePending = false, workOnB = false;
+    cudaStream_t sB() const { return overlap ? streamB : stream; }
+    void joinStreams();                   // later work on `stream` is ordered after everything queued on stream B
     // photon pass
     float4* phPower = nullptr;            // power.xyz, weight   (PhotonPRD.h:11-12)
     unsigned* phState = nullptr;          // depth | numStored << 8
@@ -88,6 +102,8 @@ struct Renderer {
     // direct lighting: per-pixel light samples + compacted shadow-ray queue (4 slots per pixel)
     float4* sampleFactor = nullptr;       // un-occluded light factor of the four samples; occluded ones are cleared by the trace
     unsigned* sampleLight = nullptr;      // light index of the four samples, one byte each
+    float4* sampleFactorBuf[2] = {nullptr, nullptr};
+    unsigned* sampleLightBuf[2] = {nullptr, nullptr};
     float4* shadowD = nullptr;            // direction.xyz, tmax
     unsigned* shadowIdx = nullptr;        // 4 * pixel + sample
     cudaEvent_t bboxEvent = nullptr;      // photon bbox + count landed in pinned host memory
@@ -124,16 +140,17 @@ struct Renderer {
 
 // CUDA-event timer around one pass (enabled by opr_set_timing)
 struct ScopedTimer {
-    Renderer& r; const char* name; cudaEvent_t a = nullptr, b = nullptr;
-    ScopedTimer(Renderer& r_, const char* n) : r(r_), name(n)
+    Renderer& r; const char* name; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    ScopedTimer(Renderer& r_, const char* n, cudaStream_t st_ = nullptr) : r(r_), name(n), st(st_ ? st_ : r_.stream)
     {
         if (!r.timing) return;
-        cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, r.stream);
+        cudaDeviceSynchronize();    // timing mode serialises the two streams: each pass is measured alone
+        cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st);
     }
     ~ScopedTimer()
     {
         if (!r.timing) return;
-        cudaEventRecord(b, r.stream); cudaEventSynchronize(b);
+        cudaEventRecord(b, st); cudaEventSynchronize(b);
         float ms = 0; cudaEventElapsedTime(&ms, a, b);
         r.lastTimings.emplace_back(name, ms);
         cudaEventDestroy(a); cudaEventDestroy(b);
@@ -172,7 +189,7 @@ void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsig
 void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, GridParams g, unsigned* keys, unsigned* hist, LaunchCtx lc);
 void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned numValid, const PhotonBuf& dst, LaunchCtx lc);
 void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
-                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc);
+                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc, unsigned blocksPerSM = 12);
 
 // host-side restatement of createUniformGridPhotonMap's scalar part (OptixRenderer_SpatialHash.cu:209-250)
 bool compute_grid_params(const float lo[3], const float hi[3], GridParams& g);

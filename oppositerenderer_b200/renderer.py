@@ -318,6 +318,10 @@ class OptixRenderer:
     def synchronize(self):
         self._check(self._lib.opr_synchronize(self._h))
 
+    def join(self):
+        """Order all queued work (both internal streams) before later work on the renderer's public stream."""
+        self._check(self._lib.opr_join_streams(self._h))
+
     def stats(self):
         a = (C.c_uint64 * 4)()
         self._check(self._lib.opr_get_stats(self._h, a, 4))
