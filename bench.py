@@ -55,9 +55,16 @@ class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
 
     def __init__(self, index):
-        self.samples, self.reasons, self.maxmhz = [], set(), 0
+        self.samples, self.maxmhz = [], 0      # (monotonic time, sm MHz, reasons)
         self.proc = None
         self.index = index
+        self.windows = []
+
+    def mark(self):
+        return time.monotonic()
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -75,11 +82,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             try:
-                self.samples.append(float(f[0]))
+                rs = [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")]
+                self.samples.append((time.monotonic(), float(f[0]), rs))
                 self.maxmhz = max(self.maxmhz, float(f[1]))
-                for n, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
             except Exception:
                 pass
 
@@ -90,8 +95,11 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxmhz or None, "reasons": sorted(self.reasons), "samples": len(s)}
+        inside = [x for x in self.samples if any(a <= x[0] <= b for a, b in self.windows)]
+        s = sorted(x[1] for x in inside)
+        reasons = sorted({r for x in inside for r in x[2]})
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxmhz or None, "reasons": reasons, "samples": len(s),
+                "window": "device-timed region + end-to-end region (both under load); the sampler runs from before the warm-up"}
 
 
 def build_scene(args):
@@ -225,14 +233,15 @@ def main():
                 D.reduce_sum_to_root(D.output_as_tensor(r, dev), dst=0)
 
     # ---- warm-up, then the device-timed region (inputs resident in HBM)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     run(args.warmup, 0)
     barrier()
     st0 = r.stats()          # counters are cumulative: everything reported below is the difference over the timed region
     launches0 = st0["launches"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = sampler.mark()
     with torch.cuda.stream(stream):
         e0.record()
     run(args.steps, args.warmup)
@@ -240,37 +249,19 @@ def main():
         e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    sampler.window(w0, sampler.mark())
     st = r.stats()
     rays = (st["closest_rays"] + st["any_rays"]) - (st0["closest_rays"] + st0["any_rays"])
-
-    # ---- end to end through the C ABI with host buffers: request struct in, W*H*3 floats out every step
-    host_out = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()
-    barrier()
-    t0 = time.perf_counter()
-    run(args.steps, args.warmup + args.steps, readback=host_out)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    st2 = r.stats()
-    rays_e2e = (st2["closest_rays"] + st2["any_rays"]) - (st["closest_rays"] + st["any_rays"])
-
-    t = torch.tensor([ms, float(rays), e2e_s, float(rays_e2e)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, e2e_s = float(tmax[0]), float(tmax[2])
-        rays, rays_e2e = float(tsum[1]), float(tsum[3])
-    total_steps = args.steps * world
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline of the dominant kernel
     roof = None
     kernel_ms = {}
-    if rank == 0:
+    nprof = 3
+    if True:   # every rank renders the same iterations (keeps the partition aligned); rank 0 reports
         r.set_timing(True)
         acc = {}
-        nprof = 3
         for k in range(nprof):
-            local = args.warmup + 2 * args.steps + k
+            local = args.warmup + args.steps + k
             it = local * world + rank
             r.renderNextIteration(it, local, radius(it), True, pod)
             for name, v in r.timings():
@@ -289,14 +280,14 @@ def main():
             # SURVEY.md §8d per-unit figures x the units one launch processes
             alg = {
                 "ppm.gather": 76.0 * px + 36.0 * V + 8.0 * ncells,
-                "ppm.direct_output": (64 + 12 + 12 + 12 + 24) * px + 36.0 * (stp["any_rays"] - st2["any_rays"]) / nprof,
+                "trace.shadow": 36.0 * (stp["any_rays"] - st["any_rays"]) / nprof,
                 "trace.camera0": 52.0 * px,
                 "trace.photon0": 52.0 * args.photons * args.photons,
                 "grid.build": 36.0 * N + 132.0 * V + 8.0 * ncells,
             }
             acc["grid.build"] = sum(acc.get(k, 0.0) for k in ("grid.bbox", "grid.keys", "grid.sort", "grid.offsets", "grid.reorder"))
         else:
-            rays_it = ((stp["closest_rays"] + stp["any_rays"]) - (st2["closest_rays"] + st2["any_rays"])) / nprof
+            rays_it = ((stp["closest_rays"] + stp["any_rays"]) - (st["closest_rays"] + st["any_rays"])) / nprof
             alg = {"vcm.light": 48.0 * rays_it / 2, "vcm.camera": 48.0 * rays_it / 2}
         traffic = {}
         tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")   # dram bytes per launch from the committed `ncu --set full` capture
@@ -313,6 +304,28 @@ def main():
                     "note": "gather and traversal are issue- / L1- / latency-bound, not HBM-bound (DESIGN.md §4, SURVEY.md §8d); profiles/ holds issue, L1 and L2 utilisation of the same launches",
                     "others": {k: {"ms": acc[k], "achieved_gbs": alg[k] / (acc[k] * 1e-3) / 1e9, "frac": alg[k] / (acc[k] * 1e-3) / 1e9 / peak}
                                for k in alg if k != name and acc.get(k, 0.0) > 0}}
+
+    # ---- end to end through the C ABI with host buffers: request struct in, W*H*3 floats out every step
+    host_out = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()
+    barrier()
+    st1 = r.stats()
+    w1 = sampler.mark()
+    t0 = time.perf_counter()
+    run(args.steps, args.warmup + args.steps + nprof, readback=host_out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.window(w1, sampler.mark())
+    clocks = sampler.stop()
+    st2 = r.stats()
+    rays_e2e = (st2["closest_rays"] + st2["any_rays"]) - (st1["closest_rays"] + st1["any_rays"])
+
+    t = torch.tensor([ms, float(rays), e2e_s, float(rays_e2e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(tmax[0]), float(tmax[2])
+        rays, rays_e2e = float(tsum[1]), float(tsum[3])
+    total_steps = args.steps * world
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -14,7 +14,7 @@
 namespace opr {
 
 constexpr int VCM_THREADS = 128;
-constexpr int VCM_BLOCKS_X = 148 * 2;
+constexpr int VCM_BLOCKS_X = 148 * 6;
 
 struct VcmState {
     float4* thr = nullptr;     // throughput.xyz, depth (uint bits)
