@@ -126,7 +126,8 @@ def cpu_reference_run(args, scene, cam, sample, steps, warmup, which):
     wh, pl = sample.split(":")
     w, h = (int(x) for x in wh.split("x"))
     pl = int(pl)
-    o = ol.OracleRenderer(which, (pl, pl), args.max_path_length if args.method == "bdpt" else 10, 1645301512)
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    o = ol.OracleRenderer(which, (pl, pl), args.max_path_length if args.method == "bdpt" else 10, 1645301512, threads=len(os.sched_getaffinity(0)))
     o.init_scene(scene.getSceneDescription())
     det = ol.make_details(cam.pod, capi.VCM_BIDIRECTIONAL_PATH_TRACING if args.method == "bdpt" else capi.PROGRESSIVE_PHOTON_MAPPING, w, h)
     r0 = scene.getSceneInitialPPMRadiusEstimate()
@@ -140,7 +141,7 @@ def cpu_reference_run(args, scene, cam, sample, steps, warmup, which):
     dt = time.perf_counter() - t0
     c1 = o.ray_counts()
     rays = (c1[0] - c0[0]) + (c1[1] - c0[1])
-    cores = ol.load(which).ora_max_threads()
+    cores = len(os.sched_getaffinity(0))
     desc = "%d %s iteration(s) of the same scene at %dx%d%s (OpenMP, %d threads)" % (
         steps, args.method.upper(), w, h, " with a %dx%d photon launch" % (pl, pl) if args.method == "ppm" else ", max path length %d" % args.max_path_length, cores)
     return rays / dt / 1e6, steps / dt, cores, desc

@@ -283,3 +283,101 @@ def test_gather_matches_oracle(product, oracle, npix, nph, radius, coherent):
     assert olib.ora_gather(*args(out0)) == 0
     assert np.allclose(out, out0, rtol=2e-5, atol=1e-7 * float(out0.max() + 1e-30))
     assert (out[hp["flags"] != ol.PRD_HIT_NON_SPECULAR] == 0).all()
+
+
+@pytest.mark.parametrize("kind,detail,minfrac", [("sponza", 0.08, 0.93), ("conference", 0.12, 0.90)])
+def test_synthetic_scene_ppm_parity(product, oracle, kind, detail, minfrac):
+    """The bench workloads (triangle meshes with shading normals / uvs / tangents, Texture materials with RGBA8 bilinear
+    lookups and normal maps, glass + mirror spheres, area + point lights) at reduced tessellation against the oracle:
+    hit flags, photon count, direct, indirect and the sum buffer on identical paths."""
+    from oppositerenderer_b200 import synthetic
+    scene = synthetic.make_scene(kind, seed=1, detail=detail, texture_size=64)
+    cam = scene.getDefaultCamera()
+    W, H, pl, iters = 96, 54, (96, 96), 2
+    cam.setAspectRatio(W / H)
+    r = product.OptixRenderer(photon_launch=pl, seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    o = oracle.OracleRenderer("oracle", pl, 10, util.SEED)
+    o.init_scene(scene.getSceneDescription())
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, W, H, 2.0 / 3.0)
+    odet = oracle.make_details(cam.pod, capi.PROGRESSIVE_PHOTON_MAPPING, W, H)
+    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), iters)
+    for i in range(iters):
+        r.renderNextIteration(i, i, radii[i], True, det)
+        o.render_next_iteration(i, i, radii[i], odet)
+        hp, hp0 = r.debug_buffer("hitpoints", ol.HITPOINT_DT, W * H), o.hitpoints()
+        assert (hp["flags"] == hp0["flags"]).mean() > minfrac
+        nv, nv0 = int(r.debug_buffer("grid", np.uint32, 8)[7]), o.grid()["numValid"]
+        assert abs(nv - nv0) <= max(8, 0.03 * nv0), (nv, nv0)
+        dr, dr0 = r.debug_buffer("direct", np.float32, W * H * 3).reshape(-1, 3), o.direct().reshape(-1, 3)
+        assert util.rel_close_fraction(dr, dr0, RTOL, ATOL * float(dr0.max() + 1e-20)) > minfrac
+    out, out0 = r.getOutputBuffer(), o.output()
+    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
+    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
+    assert frac > minfrac - 0.05 and rel < 3e-2, (frac, rel)
+
+
+def _render_sum(product, overlap, monkeypatch, scene, cam, W, H, pl, iters, method):
+    monkeypatch.setenv("OPR_OVERLAP", "1" if overlap else "0")
+    r = product.OptixRenderer(photon_launch=pl, vcm_max_path_length=8, seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))      # the knob is read here
+    r.initScene(scene)
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, W, H, 2.0 / 3.0)
+    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), iters)
+    for i in range(iters):
+        r.renderNextIteration(i, i, radii[i], True, det)      # no read-back in between: iterations overlap
+    return r.getOutputBuffer().copy(), r.stats()
+
+
+def test_two_stream_pipeline_is_bit_identical_to_serial(product, monkeypatch):
+    """The iteration pipeline (grid build + gather + output of iteration i on a second stream while iteration i+1 traces) must
+    not change a single bit of the image: same seeds, 6 iterations back to back, overlapped vs everything on one stream."""
+    from oppositerenderer_b200 import synthetic
+    scene = synthetic.make_scene("sponza", seed=1, detail=0.25, texture_size=128)
+    cam = scene.getDefaultCamera()
+    W, H = 480, 270
+    cam.setAspectRatio(W / H)
+    a, sa = _render_sum(product, True, monkeypatch, scene, cam, W, H, (256, 256), 6, product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING)
+    b, sb = _render_sum(product, False, monkeypatch, scene, cam, W, H, (256, 256), 6, product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING)
+    assert sa["closest_rays"] == sb["closest_rays"] and sa["any_rays"] == sb["any_rays"] and sa["photons_stored"] == sb["photons_stored"]
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    assert a.sum() > 0
+
+
+def test_full_size_ppm_properties(product):
+    """BASELINE size (1920x1080, 1024x1024 photons, ~1M triangles): size-independent properties of one PPM iteration —
+    photons stored == valid slots == last offset, every diffuse pixel gathered a finite non-negative radiance, the sum buffer
+    after two iterations dominates the first (running sum), ray accounting adds up."""
+    from oppositerenderer_b200 import synthetic
+    scene = synthetic.make_scene("sponza", seed=1, detail=1.0)
+    cam = scene.getDefaultCamera()
+    W, H = 1920, 1080
+    cam.setAspectRatio(W / H)
+    r = product.OptixRenderer(seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, W, H, 2.0 / 3.0)
+    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), 2)
+    r.renderNextIteration(0, 0, radii[0], True, det)
+    first = r.getOutputBuffer().copy()
+    g = r.debug_buffer("grid", np.uint32, 8)
+    nv = int(g[7])
+    ncell = int(g[1]) * int(g[2]) * int(g[3])
+    assert 0 < ncell <= 1000000
+    off = r.debug_buffer("offsets", np.uint32, ncell + 1)
+    assert off[0] == 0 and off[-1] == nv and (np.diff(off.astype(np.int64)) >= 0).all()
+    keys = r.debug_buffer("photon_keys", np.uint32, 4 * 1024 * 1024)
+    assert (np.diff(keys.astype(np.int64)) >= 0).all() and (keys[:nv] < ncell).all() and (keys[nv:] == ncell + 1).all()
+    ph = r.debug_buffer("photons", ol.PHOTON_DT, 4 * 1024 * 1024)
+    assert (ph["power"].max(axis=1) > 0).sum() == nv
+    hp = r.debug_buffer("hitpoints", ol.HITPOINT_DT, W * H)
+    diffuse = (hp["flags"] & ol.PRD_HIT_NON_SPECULAR) != 0
+    assert diffuse.mean() > 0.8
+    ind = r.debug_buffer("indirect", np.float32, W * H * 3).reshape(-1, 3)
+    assert np.isfinite(ind).all() and (ind >= 0).all() and (ind[~diffuse] == 0).all() and (ind[diffuse].sum(axis=1) > 0).mean() > 0.7
+    st = r.stats()
+    assert st["closest_rays"] >= W * H + 1024 * 1024 and st["any_rays"] <= 4 * W * H and st["photons_stored"] == nv
+    r.renderNextIteration(1, 1, radii[1], True, det)
+    second = r.getOutputBuffer()
+    assert np.isfinite(second).all() and (second >= first - 1e-6 * np.abs(first)).all() and second.sum() > first.sum()
