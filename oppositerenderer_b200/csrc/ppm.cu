@@ -132,8 +132,10 @@ void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsign
 // Mirror.cu:50-63, Glass.cu:90-143, miss RayGeneratorPPM.cu:72-77) for ONE hit of camera path p.  Path state (the
 // RadiancePRD fields) lives in the hitpoint SoA.  Returns true when the program recursed (rtTrace): the continuation
 // ray is (newO, newD) with tmin 1e-4.
+// ptNormal (PATH_TRACING only): receives the world shading normal of a Diffuse / Glossy / Texture hit, from which the
+// programs draw randomNewDirection (Diffuse.cu:82-86, Glossy.cu:85-89, Texture.cu:102-105 — the un-mapped normal).
 OPR_DEV bool shade_camera_hit(const SceneView& sc, int kind, unsigned p, const float3& o, const float3& d, const HitRec& hit, unsigned w, unsigned rsW,
-                              const RngBuf& rngBuf, const HitpointBuf& hp, float3& newO, float3& newD)
+                              const RngBuf& rngBuf, const HitpointBuf& hp, float3& newO, float3& newD, float3* ptNormal = nullptr)
 {
     if (kind == QUEUE_MISS) {
         hp.pos[p].w = __uint_as_float(PRD_MISS);
@@ -150,6 +152,7 @@ OPR_DEV bool shade_camera_hit(const SceneView& sc, int kind, unsigned p, const f
     float3 att = f3(hp.att[p]);
     const float3 worldShadingNormal = normalize(sf.shadingNormal);
     const float3 hitPoint = o + tHit * d;
+    if (ptNormal && (kind == OPR_MAT_DIFFUSE || kind == OPR_MAT_GLOSSY || kind == OPR_MAT_TEXTURE)) *ptNormal = worldShadingNormal;
     if (kind == OPR_MAT_DIFFUSE || kind == OPR_MAT_GLOSSY) {
         flags |= PRD_HIT_NON_SPECULAR;
         att *= m.Kd;
@@ -669,6 +672,165 @@ void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBu
 {
     int blocks = (int)std::min<unsigned>((n + 255) / 256, 148 * 16);
     ppm_resolve_output_kernel<<<blocks, 256, 0, lc.st>>>(sc, n, hp, sampleFactor, sampleLight, indirect, direct, output, localIteration);
+    ++*lc.launches;
+}
+
+// ---- PATH_TRACING: pt/RayGeneratorPT.cu:46-131 (OptixRenderer.cpp:559-567, ptDirectLightSampling = 1) ----------------------
+// One thread per pixel, warp-lockstep traversal.  Up to five path segments; each segment is a closest-hit with the same
+// RADIANCE material programs as the PPM camera pass (specular chains unrolled in place), one light sample with a shadow ray
+// at every diffuse vertex, Russian roulette from the fourth segment.  The reference draws from TWO states that start
+// equal: the payload copy (pixel jitter, Fresnel choice, bounce direction, point on light; written back at the end) and the
+// buffer state itself (light pick, Russian roulette; overwritten by that write-back).  Here the buffer in HBM holds the
+// payload stream and `bufferState` is the register copy of the other one.
+constexpr unsigned PRD_PATH_TRACING = 1u << 26;
+constexpr int PATH_TRACING_RR_START_DEPTH = 3;   // config.h:37
+
+__global__ void __launch_bounds__(SHADE_THREADS) pt_generate_ray_kernel(SceneView sc, opr_camera cam, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf,
+                                                                        HitpointBuf hp, float* __restrict__ output, unsigned localIteration,
+                                                                        unsigned* __restrict__ stats)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned n = w * h;
+    unsigned closestRays = 0, anyRays = 0;
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned p = base + threadIdx.x;
+        const bool inImage = p < n;
+        const unsigned x = inImage ? p % w : 0u, y = inImage ? p / w : 0u;
+        const size_t ri = (size_t)y * rsW + x;
+        float3 rayOrigin = f3(0.f), rayDirection = f3(0.f, 0.f, 1.f);
+        Rng bufferState{};
+        if (inImage) {
+            Rng prdState = rng_load(rngBuf, ri);
+            bufferState = prdState;
+            const float3 eye = f3(cam.eye[0], cam.eye[1], cam.eye[2]);
+            const float3 cu = f3(cam.camera_u[0], cam.camera_u[1], cam.camera_u[2]);
+            const float3 cv = f3(cam.camera_v[0], cam.camera_v[1], cam.camera_v[2]);
+            const float3 lookdir = f3(cam.lookdir[0], cam.lookdir[1], cam.lookdir[2]);
+            float2 sample = rng_uniform2(prdState);
+            float dx = ((float)x + sample.x) / (float)w * 2.0f - 1.0f;
+            float dy = ((float)y + sample.y) / (float)h * 2.0f - 1.0f;
+            rayOrigin = eye;
+            rayDirection = normalize(dx * cu + dy * cv + lookdir);
+            if (cam.aperture > 0) {
+                float3 focalPlaneCenterPoint = eye + lookdir;
+                float3 camLookDir = normalize(lookdir);
+                float focalPlaneT = (dot(camLookDir, focalPlaneCenterPoint) - dot(camLookDir, eye)) / dot(camLookDir, rayDirection);
+                float3 lookAt = rayOrigin + focalPlaneT * rayDirection;
+                float2 dofSample = rng_uniform2(prdState);
+                float2 disc = sampleUnitDisc(dofSample);
+                rayOrigin += disc.x * cu * cam.aperture + disc.y * cv * cam.aperture;
+                rayDirection = normalize(lookAt - rayOrigin);
+            }
+            rng_store(rngBuf, ri, prdState);
+            hp.pos[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+            hp.nrm[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+            hp.att[p] = make_float4(1.f, 1.f, 1.f, 0.f);
+            hp.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float3 finalRadiance = f3(0.f);
+        bool alive = inImage;
+        const int numLights = sc.numLights;
+        for (int i = 0; i < 5 && __any_sync(FULL, alive); i++) {
+            if (alive) hp.pos[p].w = __uint_as_float(PRD_PATH_TRACING);
+            // ---- rtTrace(sceneRootObject, ray, radiancePrd): the chain of recursive closest-hit programs
+            bool chain = alive;
+            float3 o = rayOrigin, d = rayDirection, ptNormal = f3(0.f, 0.f, 1.f);
+            float tmin = 0.001f;     // the Ray object keeps the tmin it was constructed with (:63)
+            bool sampled = false;
+            while (__any_sync(FULL, chain)) {
+                HitRec hit;
+                traverse_warp<false>(sc, FULL, chain, o, d, tmin, RT_DEFAULT_MAX, hit);
+                if (chain) {
+                    closestRays++;
+                    const int kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
+                    float3 newO = f3(0.f), newD = f3(0.f);
+                    chain = shade_camera_hit(sc, kind, p, o, d, hit, w, rsW, rngBuf, hp, newO, newD, &ptNormal);
+                    sampled = (kind == OPR_MAT_DIFFUSE || kind == OPR_MAT_GLOSSY || kind == OPR_MAT_TEXTURE);
+                    o = newO; d = newD; tmin = 0.0001f;
+                }
+            }
+            float lightFactor = 0.f, lightDistance = 1.f;
+            float3 towardsLight = f3(0.f, 0.f, 1.f), power = f3(0.f), position = f3(0.f), attenuation = f3(0.f);
+            bool diffuse = false;
+            if (alive) {
+                const float4 pos4 = hp.pos[p];
+                const unsigned flags = __float_as_uint(pos4.w);
+                if (flags & PRD_HIT_EMITTER) {
+                    if ((flags & PRD_HIT_SPECULAR) || i == 0) finalRadiance = f3(hp.rad[p]);
+                    alive = false;
+                } else if (flags & PRD_HIT_NON_SPECULAR) {
+                    diffuse = true;
+                    position = f3(pos4); attenuation = f3(hp.att[p]);
+                    const float3 normal = f3(hp.nrm[p]);
+                    Rng prdState = rng_load(rngBuf, ri);
+                    if (sampled) {     // randomNewDirection, drawn inside the closest-hit program
+                        float2 s = rng_uniform2(prdState);
+                        rayDirection = sampleUnitHemisphereCos(ptNormal, s);
+                    }
+                    rayOrigin = position;
+                    const int randomLightIndex = int(rng_uniform(bufferState) * numLights);
+                    const opr_light& light = sc.lights[randomLightIndex];
+                    // getLightContribution, helpers/light.h:29-87
+                    lightFactor = 1;
+                    float3 pointOnLight = f3(0.f);
+                    const int lightType = light.lightType;
+                    if (lightType == OPR_LIGHT_AREA) {
+                        float2 s = rng_uniform2(prdState);
+                        pointOnLight = f3(light.position[0], light.position[1], light.position[2]) + s.x * f3(light.v1[0], light.v1[1], light.v1[2]) +
+                                       s.y * f3(light.v2[0], light.v2[1], light.v2[2]);
+                    } else if (lightType == OPR_LIGHT_POINT) {
+                        pointOnLight = f3(light.position[0], light.position[1], light.position[2]);
+                        lightFactor *= 1.f / 4.f;
+                    } else {
+                        lightFactor = 0;
+                    }
+                    rng_store(rngBuf, ri, prdState);
+                    towardsLight = pointOnLight - position;
+                    lightDistance = length(towardsLight);
+                    towardsLight = towardsLight / lightDistance;
+                    float n_dot_l = maxf_(0, dot(normal, towardsLight));
+                    lightFactor *= n_dot_l / (PI_F * lightDistance * lightDistance);
+                    if (lightType == OPR_LIGHT_AREA)
+                        lightFactor *= maxf_(0, dot(-towardsLight, f3(light.normal[0], light.normal[1], light.normal[2])));
+                    power = f3(light.power[0], light.power[1], light.power[2]);
+                } else {
+                    alive = false;
+                }
+            }
+            const bool cast = diffuse && lightFactor > 0.0f;
+            HitRec shadowHit;
+            const bool occluded = traverse_warp<true>(sc, FULL, cast, position, towardsLight, 0.0001f, (float)((double)lightDistance - 0.0001), shadowHit);
+            if (diffuse) {
+                float3 lightContrib = f3(0.f);
+                if (cast) { anyRays++; lightFactor *= occluded ? 0.0f : 1.0f; lightContrib = power * lightFactor; }
+                const float scale = (float)numLights;
+                const float3 accumLightRadiancePreBrdf = f3(0.f) + scale * lightContrib;
+                const float3 directRadiance = attenuation * accumLightRadiancePreBrdf / 1.0f;
+                finalRadiance += directRadiance;
+            }
+            if (alive && i >= PATH_TRACING_RR_START_DEPTH) {
+                const float sample = rng_uniform(bufferState);
+                const float probabilityContinue = fmax3(attenuation);
+                if (sample > probabilityContinue) alive = false;
+                else { attenuation /= probabilityContinue; hp.att[p] = make_float4(attenuation.x, attenuation.y, attenuation.z, 0.f); }
+            }
+        }
+        if (inImage && !(finalRadiance.x != finalRadiance.x || finalRadiance.y != finalRadiance.y || finalRadiance.z != finalRadiance.z)) {
+            float3 out = finalRadiance;
+            if (localIteration != 0) out = f3(output[3 * (size_t)p], output[3 * (size_t)p + 1], output[3 * (size_t)p + 2]) + finalRadiance;
+            output[3 * (size_t)p] = out.x; output[3 * (size_t)p + 1] = out.y; output[3 * (size_t)p + 2] = out.z;
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) { closestRays += __shfl_xor_sync(FULL, closestRays, s); anyRays += __shfl_xor_sync(FULL, anyRays, s); }
+    if ((threadIdx.x & 31) == 0) { if (closestRays) atomicAdd(stats + STAT_CLOSEST_RAYS, closestRays); if (anyRays) atomicAdd(stats + STAT_ANY_RAYS, anyRays); }
+}
+
+void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
+                            float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc)
+{
+    unsigned n = w * h;
+    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
+    pt_generate_ray_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, cam, w, h, rsW, rng, hp, output, localIteration, stats);
     ++*lc.launches;
 }
 

@@ -285,8 +285,13 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber, unsigned 
         renderPPM(iterationNumber, (unsigned)localIterationNumber, PPMRadius, details);
     else if (details.renderMethod == OPR_VCM_BIDIRECTIONAL_PATH_TRACING)
         renderVCM(iterationNumber, (unsigned)localIterationNumber, PPMRadius, details);
-    else
-        throw std::runtime_error("RenderMethod not on the accelerated path (PATH_TRACING is out of scope)");
+    else if (details.renderMethod == OPR_PATH_TRACING) {   // :559-567
+        ScopedTimer t(*this, "pt.generateRay");
+        LaunchCtx lc{stream, &launches};
+        launch_pt_generate_ray(scene.view, details.camera, width, height, rsW, rng, hp, output, (unsigned)localIterationNumber,
+                               q.counters + CTR_STATS, lc);
+    } else
+        throw std::runtime_error("unknown RenderMethod");
     OPR_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -86,6 +86,7 @@ void pass_begin(Renderer&) {}                         // hook used by the oracle
 struct RadiancePRD {   // renderer/RadiancePRD.h:11-29
     float3 attenuation, radiance; uint depth; float3 position, normal; uint flags;
     RandomState randomState; float lastTHit;
+    float3 randomNewDirection;   // written only under PRD_PATH_TRACING
 };
 struct PhotonPRD {     // renderer/ppm/PhotonPRD.h:9-17
     float3 power; float weight; uint pm_index, numStoredPhotons, depth; RandomState randomState;
@@ -130,6 +131,10 @@ static void closestHitRadiance(Renderer& r, const Ray& ray, const Hit& hit, Radi
         prd.position = hitPoint;
         prd.lastTHit = tHit;
         prd.depth++;
+        if (prd.flags & PRD_PATH_TRACING) {   // Diffuse.cu:82-86, Glossy.cu:85-89
+            float2 sample = getRandomUniformFloat2(&prd.randomState);
+            prd.randomNewDirection = sampleUnitHemisphereCos(worldShadingNormal, sample, nullptr, nullptr, false);
+        }
         break;
     }
     case OPR_MAT_TEXTURE: {  // material/Texture.cu:83-110
@@ -146,6 +151,8 @@ static void closestHitRadiance(Renderer& r, const Ray& ray, const Hit& hit, Radi
         prd.normal = normal;
         prd.position = hitPoint;
         prd.lastTHit = tHit;
+        if (prd.flags & PRD_PATH_TRACING)     // Texture.cu:102-105: the un-mapped shading normal
+            prd.randomNewDirection = sampleUnitHemisphereCos(worldShadingNormal, getRandomUniformFloat2(&prd.randomState), nullptr, nullptr, false);
         float4 value = tex2D(r.scene.textures[m.diffuseTexture], hit.textureCoordinate.x, hit.textureCoordinate.y);
         prd.attenuation *= make_float3(value.x, value.y, value.z);
         break;
@@ -518,6 +525,79 @@ void ppm_direct(Renderer& r, uint x, uint y)
         avgLightRadiance += scale * lightContrib;
     }
     r.direct[idx] = rec.attenuation * avgLightRadiance / (float)numShadowSamples;
+}
+
+// pt/RayGeneratorPT.cu:46-131 (RenderMethod::PATH_TRACING, OptixRenderer.cpp:559-567 with ptDirectLightSampling = 1).
+// Two RNG streams, as in the reference: the payload copy (jitter, material samples, point on light) and the buffer state
+// randomStates[launchIndex] itself (light pick, Russian roulette), which the final write-back of the payload copy discards.
+void pt_generateRay(Renderer& r, uint x, uint y)
+{
+    RadiancePRD prd;
+    prd.attenuation = make_float3(1.0f);
+    prd.radiance = make_float3(0.f);
+    prd.depth = 0u;
+    prd.flags = 0;
+    prd.position = prd.normal = prd.randomNewDirection = make_float3(0.f);
+    prd.lastTHit = 0.f;
+    prd.randomState = r.rs(x, y);
+    RandomState& bufferState = r.rs(x, y);
+
+    const Camera& camera = r.camera;
+    float2 screen = make_float2((float)r.width, (float)r.height);
+    float2 sample = getRandomUniformFloat2(&prd.randomState);
+    float2 d = (make_float2((float)x, (float)y) + sample) / screen * 2.0f - 1.0f;
+    float3 rayOrigin = f3(camera.eye);
+    float3 rayDirection = normalize(d.x * f3(camera.camera_u) + d.y * f3(camera.camera_v) + f3(camera.lookdir));
+    if (camera.aperture > 0) {   // modifyRayForDepthOfField, helpers/camera.h:11-27
+        float3 focalPlaneCenterPoint = f3(camera.eye) + f3(camera.lookdir);
+        float3 camLookDir = normalize(f3(camera.lookdir));
+        float focalPlaneT = (dot(camLookDir, focalPlaneCenterPoint) - dot(camLookDir, f3(camera.eye))) / dot(camLookDir, rayDirection);
+        float3 lookAt = rayOrigin + focalPlaneT * rayDirection;
+        float2 dofSample = getRandomUniformFloat2(&prd.randomState);
+        float2 disc = sampleUnitDisc(dofSample);
+        rayOrigin += disc.x * f3(camera.camera_u) * camera.aperture + disc.y * f3(camera.camera_v) * camera.aperture;
+        rayDirection = normalize(lookAt - rayOrigin);
+    }
+    Ray ray{rayOrigin, rayDirection, 0, 0.001f, RT_DEFAULT_MAX_};
+    float3 finalRadiance = make_float3(0.f);
+    const int ptDirectLightSampling = 1;
+    const int numShadowSamples = ptDirectLightSampling ? 1 : 0;
+    const int numPaths = ptDirectLightSampling ? 5 : 10;
+    const std::vector<Light>& lights = r.scene.lights;
+    for (int i = 0; i < numPaths; i++) {
+        prd.flags = PRD_PATH_TRACING;
+        traceRadiance(r, ray, prd);
+        if (prd.flags & PRD_HIT_EMITTER) {
+            if ((prd.flags & PRD_HIT_SPECULAR) || i == 0) finalRadiance = prd.radiance;
+            break;
+        } else if (prd.flags & PRD_HIT_NON_SPECULAR) {
+            int numLights = (int)lights.size();
+            float3 accumLightRadiancePreBrdf = make_float3(0.f);
+            for (int shadowSample = 0; shadowSample < numShadowSamples; shadowSample++) {
+                int randomLightIndex = int(getRandomUniformFloat(&bufferState) * numLights);
+                const Light& light = lights[randomLightIndex];
+                float scale = (float)numLights;
+                float3 lightContrib = scale * getLightContribution(r, light, prd.position, prd.normal, prd.randomState);
+                accumLightRadiancePreBrdf += lightContrib;
+            }
+            float3 directRadiance = prd.attenuation * accumLightRadiancePreBrdf / (float)numShadowSamples;
+            finalRadiance += directRadiance;
+            ray.origin = prd.position;
+            ray.direction = prd.randomNewDirection;
+        } else {
+            break;
+        }
+        if (i >= 3) {   // PATH_TRACING_RR_START_DEPTH, config.h:37
+            float s = getRandomUniformFloat(&bufferState);
+            float probabilityContinue = fmaxf(fmaxf(prd.attenuation.x, prd.attenuation.y), prd.attenuation.z);
+            if (s > probabilityContinue) break;
+            prd.attenuation /= probabilityContinue;
+        }
+    }
+    const size_t idx = (size_t)y * r.width + x;
+    if (!(finalRadiance.x != finalRadiance.x || finalRadiance.y != finalRadiance.y || finalRadiance.z != finalRadiance.z))
+        r.output[idx] = r.localIterationNumber == 0 ? finalRadiance : r.output[idx] + finalRadiance;
+    r.rs(x, y) = prd.randomState;
 }
 
 // ppm/Output.cu:32-37

@@ -115,8 +115,10 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber_, unsigned
         lightVertexBufferIndex.store(0);                                         // :776-778
         launch2D(*this, width, height, vcm_lightPass);                           // :784
         launch2D(*this, width, height, vcm_cameraPass);                          // :793
+    } else if (details.renderMethod == OPR_PATH_TRACING) {
+        launch2D(*this, width, height, pt_generateRay);                          // :559-567
     } else {
-        throw std::runtime_error("render method not on the hot path (PATH_TRACING is out of scope, SURVEY.md §8f)");
+        throw std::runtime_error("unknown render method");
     }
 }
 

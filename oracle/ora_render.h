@@ -76,6 +76,7 @@ void ppm_photonGenerator(Renderer& r, uint x, uint y);   // ppm/PhotonGenerator.
 void ppm_indirect(Renderer& r, uint x, uint y);          // ppm/IndirectRadianceEstimation.cu:69-227
 void ppm_direct(Renderer& r, uint x, uint y);            // ppm/DirectRadianceEstimation.cu:29-77
 void ppm_output(Renderer& r, uint x, uint y);            // ppm/Output.cu:32-37
+void pt_generateRay(Renderer& r, uint x, uint y);        // pt/RayGeneratorPT.cu:46-131
 
 // VCM programs (ora_vcm.cpp)
 void vcm_lightPass(Renderer& r, uint x, uint y);         // vcm/VCMLightPass.cu:60-89

@@ -158,6 +158,8 @@ static void refreshContext(RefCtx& c)
     setVar(c, "vmNormalizationFactor", &r.vmNormalizationFactor, 4);
     setVar(c, "pixelSizeFactor", &r.pixelSizeFactor, 8);
     setVar(c, "vcmUseVC", &r.vcmUseVC, 4); setVar(c, "vcmUseVM", &r.vcmUseVM, 4);
+    static int ptDirectLightSampling = 1;                                   // OptixRenderer.cpp:561
+    setVar(c, "ptDirectLightSampling", &ptDirectLightSampling, 4);
     for (int i = 0; i < 8; i++) c.bufId[i] = i;
     setVar(c, "outputBufferId", &c.bufId[BID_OUTPUT], 4); setVar(c, "lightVertexBufferId", &c.bufId[BID_LIGHT_VERTEX], 4);
     setVar(c, "lightVertexBufferIndexBufferId", &c.bufId[BID_LIGHT_VERTEX_INDEX], 4);
@@ -485,6 +487,7 @@ void ppm_photonGenerator(Renderer& r, uint x, uint y) { launchOne(r, "PhotonGene
 void ppm_indirect(Renderer& r, uint x, uint y) { launchOne(r, "IndirectRadianceEstimation", "kernel", x, y, r.width, r.height); }
 void ppm_direct(Renderer& r, uint x, uint y) { launchOne(r, "DirectRadianceEstimation", "kernel", x, y, r.width, r.height); }
 void ppm_output(Renderer& r, uint x, uint y) { launchOne(r, "Output", "kernel", x, y, r.width, r.height); }
+void pt_generateRay(Renderer& r, uint x, uint y) { launchOne(r, "RayGeneratorPT", "generateRay", x, y, r.width, r.height); }
 void vcm_lightPass(Renderer& r, uint x, uint y) { launchOne(r, "VCMLightPass", "lightPass", x, y, r.width, r.height); }
 void vcm_cameraPass(Renderer& r, uint x, uint y) { launchOne(r, "VCMCameraPass", "cameraPass", x, y, r.width, r.height); }
 void vcm_alloc_vertices(Renderer& r, uint n)

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import oracle_lib as ol  # noqa: E402
 
 SEED = 1645301512
-CASES = [  # name, scene, CornellSmall config, method (2 = PPM, 1 = BDPT), size, photon launch, iterations, max path length, fixed r0
+CASES = [  # name, scene, CornellSmall config, method (2 = PPM, 1 = BDPT, 0 = PT), size, photon launch, iterations, max path length, fixed r0
     ("cornell_ppm_64x64_p64x64_it3", "Cornell", 0, 2, 64, 64, 3, 10, None),
     ("cornellsmall_ppm_48x48_p48x48_it2", "CornellSmall", 0, 2, 48, 48, 2, 10, 0.05),
     ("cornellsmall_mirrorfloor_glass_ppm_48x48_p48x48_it2", "CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 2, 48, 48, 2, 10, 0.05),
@@ -23,6 +23,10 @@ CASES = [  # name, scene, CornellSmall config, method (2 = PPM, 1 = BDPT), size,
     ("cornellsmall_bdpt_48x48_it3_len8", "CornellSmall", 0, 1, 48, 48, 3, 8, None),
     ("cornellsmall_mirrorfloor_glass_bdpt_48x48_it2_len8", "CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 1, 48, 48, 2, 8, None),
     ("cornellsmall_point_glossy_spheres_bdpt_48x48_it2_len10", "CornellSmall", (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 1, 48, 48, 2, 10, None),
+    # method 0 = PATH_TRACING (pt/RayGeneratorPT.cu)
+    ("cornell_pt_64x64_it3", "Cornell", 0, 0, 64, 64, 3, 10, None),
+    ("cornellsmall_mirrorfloor_glass_pt_48x48_it3", "CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 0, 48, 48, 3, 10, None),
+    ("cornellsmall_point_glossy_spheres_pt_48x48_it3", "CornellSmall", (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 0, 48, 48, 3, 10, None),
 ]
 
 

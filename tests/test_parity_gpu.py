@@ -187,7 +187,7 @@ def test_state_rules_gpu(product):
     det2 = product.RenderServerRenderRequestDetails(cam, "Cornell", product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, 40, 40, 2 / 3)
     r.renderNextIteration(0, 0, 7.5, True, det2)                 # resize (:534-537)
     assert r.getOutputBuffer().shape == (40, 40, 3)
-    bad = product.RenderServerRenderRequestDetails(cam, "Cornell", product.RenderMethod.PATH_TRACING, 40, 40, 2 / 3)
+    bad = product.RenderServerRenderRequestDetails(cam, "Cornell", product.RenderMethod.NONE, 40, 40, 2 / 3)
     with pytest.raises(RuntimeError):
         r.renderNextIteration(0, 0, 7.5, True, bad)
 
@@ -381,3 +381,30 @@ def test_full_size_ppm_properties(product):
     r.renderNextIteration(1, 1, radii[1], True, det)
     second = r.getOutputBuffer()
     assert np.isfinite(second).all() and (second >= first - 1e-6 * np.abs(first)).all() and second.sum() > first.sum()
+
+
+@pytest.mark.parametrize("scene_name,config,minfrac", [("Cornell", 0, 0.97), ("CornellSmall", 0, 0.96),
+                                                       ("CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 0.93),
+                                                       ("CornellSmall", (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 0.93)])
+def test_path_tracing_parity(product, oracle, scene_name, config, minfrac):
+    """RenderMethod::PATH_TRACING (pt/RayGeneratorPT.cu) against the oracle on identical paths, including the reference's two
+    RNG streams per pixel (payload copy vs buffer state) and the final states."""
+    size, iters = 48, 3
+    scene, cam, r, o, osc = _renderers(product, oracle, scene_name, config, size, (16, 16))
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.PATH_TRACING, size, size, 2.0 / 3.0)
+    odet = oracle.make_details(osc.camera(1.0), capi.PATH_TRACING, size, size)
+    for i in range(iters):
+        r.renderNextIteration(i, i, 1.0, True, det)
+        o.render_next_iteration(i, i, 1.0, odet)
+    out, out0 = r.getOutputBuffer(), o.output()
+    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
+    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
+    assert frac > minfrac and rel < 3e-2, (frac, rel)
+    st, (c0, a0) = r.stats(), o.ray_counts()
+    assert abs(st["closest_rays"] - c0) <= 0.02 * c0 and abs(st["any_rays"] - a0) <= 0.02 * a0
+    # RNG write-back: the payload stream survives, the buffer-state draws are discarded (RayGeneratorPT.cu:114)
+    rs = r.debug_buffer("random_states", np.uint32, 6 * 1024 * 1024).reshape(-1, 6)
+    n0 = o.lib.ora_num_random_states(o.h)
+    rs0 = np.zeros((n0, 6), np.uint32)
+    o.lib.ora_get_random_states(o.h, rs0.ctypes.data_as(C.c_void_p), 0, n0)
+    assert (rs[:n0] == rs0).all(axis=1).mean() > minfrac
