@@ -152,6 +152,32 @@ public:
     static const char* getCornellSceneName() { return "CornellSmall"; }
 };
 
+// scene/Scene.h — a scene read from a Collada file (Scene::createFromFile, scene/Scene.cpp:73-176)
+class Scene : public IScene {
+    void* m_handle;
+    std::vector<Light> m_sceneLights;
+    explicit Scene(void* h) : m_handle(h)
+    {
+        const opr_scene_desc* d = opr_scene_file_desc(m_handle);
+        for (int i = 0; i < d->numLights; i++) { Light l; *static_cast<opr_light*>(&l) = d->lights[i]; m_sceneLights.push_back(l); }
+    }
+public:
+    static IScene* createFromFile(const char* filename)
+    {
+        void* h = opr_scene_file_load(filename, 0);
+        if (!h) throw std::runtime_error(opr_scene_file_last_error());
+        return new Scene(h);
+    }
+    ~Scene() { opr_scene_file_destroy(m_handle); }
+    const opr_scene_desc& getSceneDescription() { return *opr_scene_file_desc(m_handle); }
+    const std::vector<Light>& getSceneLights() const { return m_sceneLights; }
+    Camera getDefaultCamera() const { opr_camera c; if (opr_scene_file_camera(m_handle, &c)) return Camera(); return Camera(c); }
+    const char* getSceneName() const { return opr_scene_file_desc(m_handle)->name; }
+    AAB getSceneAABB() const { const opr_scene_desc* d = opr_scene_file_desc(m_handle); return AAB(Vector3(d->aabbMin), Vector3(d->aabbMax)); }
+    unsigned int getNumTriangles() const { return opr_scene_file_num_triangles(m_handle); }
+    unsigned int getNumMeshes() const { return opr_scene_file_num_meshes(m_handle); }
+};
+
 // clientserver/RenderServerRenderRequestDetails.h:15-33
 class RenderServerRenderRequestDetails {
     Camera m_camera; std::string m_sceneName; RenderMethod::E m_renderMethod; unsigned m_width, m_height; double m_ppmAlpha;

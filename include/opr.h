@@ -106,6 +106,33 @@ void opr_builtin_scene_destroy(void* scene);
 const opr_scene_desc* opr_builtin_scene_desc(void* scene);
 void opr_builtin_scene_camera(void* scene, opr_camera* out);
 
+/* ---- I/O either side of the path (host only) -------------------------------------------------------------- */
+/* message of the last failure of the functions below on the calling thread */
+const char* opr_io_last_error(void);
+/* display normalisation of the running sum: pow(color / previewedIterations, 1/gamma) * 255 as 8-bit BGR
+ * (fragment shader Gui/gui/RenderWidget.cpp:187-199; per-pixel loop of saveImageAsBMP :297-315) */
+int opr_display_bgr8(const float* sumRGB, uint32_t width, uint32_t height, float previewedIterations, float gamma, uint8_t* outBGR);
+/* RenderWidget::saveImageAsBMP (Gui/gui/RenderWidget.cpp:268-317): 24-bit BMP, rows in buffer order, no row padding */
+int opr_save_bmp(const char* fileName, const float* sumRGB, uint32_t width, uint32_t height, float previewedIterations, float gamma);
+/* Image::Image (RenderEngine/util/Image.cpp:17-140): texel array of a texture file as RGBA8 — uncompressed TGA exactly as the
+ * reference reads it (BGR->RGB, no flip, alpha = 1), 24/32-bit BMP.  Two calls: size, then pixels into caller memory. */
+int opr_image_info(const char* path, int32_t* width, int32_t* height);
+int opr_image_read(const char* path, uint8_t* rgba, uint64_t capacityBytes);
+
+/* Scene::createFromFile (RenderEngine/scene/Scene.cpp:73-176) for COLLADA 1.4 (.dae) files: geometry with node transforms
+ * baked, material classification (Scene.cpp:178-265: emissive -> textured (+normal map) -> refractive index > 1 glass ->
+ * reflective mirror -> diffuse), point / spot lights (:267-285), quad emitters (:287-311), scene AABB (:147-160), default
+ * camera (:469-485).  The handle owns the description and its arrays.  flags bit 0: list every emitter light once (the
+ * reference lists it twice: Scene.cpp:141 and :508).  Returns NULL on failure (message: opr_scene_file_last_error). */
+void* opr_scene_file_load(const char* path, int32_t flags);
+void opr_scene_file_destroy(void* scene);
+const opr_scene_desc* opr_scene_file_desc(void* scene);
+int opr_scene_file_camera(void* scene, opr_camera* out);      /* 0 when the file has a camera */
+uint32_t opr_scene_file_num_triangles(void* scene);
+uint32_t opr_scene_file_num_meshes(void* scene);
+const char* opr_scene_file_warnings(void* scene);
+const char* opr_scene_file_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

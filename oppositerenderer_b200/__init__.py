@@ -6,7 +6,7 @@ used by the tests and the benchmark; there is no CPU fallback.
 """
 from . import capi
 from .renderer import (OptixRenderer, ComputeDevice, RenderServerRenderRequestDetails, RenderMethod, Camera, Light,
-                       Cornell, CornellSmall, SceneDescription, ppm_radius_schedule)
+                       Cornell, CornellSmall, Scene, SceneDescription, ppm_radius_schedule)
 
 __all__ = ["capi", "OptixRenderer", "ComputeDevice", "RenderServerRenderRequestDetails", "RenderMethod", "Camera", "Light",
-           "Cornell", "CornellSmall", "SceneDescription", "ppm_radius_schedule"]
+           "Cornell", "CornellSmall", "Scene", "SceneDescription", "ppm_radius_schedule"]

@@ -140,6 +140,19 @@ def _declare(lib):
         "opr_make_point_light": (None, [C.POINTER(opr_light), PF, PF]),
         "opr_initial_ppm_radius": (f32, [PF, PF]),
         "opr_ppm_radius_for_iteration": (C.c_double, [C.c_double, u64, C.c_double]),
+        "opr_io_last_error": (C.c_char_p, []),
+        "opr_display_bgr8": (i32, [PF, u32, u32, f32, f32, C.POINTER(C.c_uint8)]),
+        "opr_save_bmp": (i32, [C.c_char_p, PF, u32, u32, f32, f32]),
+        "opr_image_info": (i32, [C.c_char_p, PI, PI]),
+        "opr_image_read": (i32, [C.c_char_p, C.POINTER(C.c_uint8), u64]),
+        "opr_scene_file_load": (vp, [C.c_char_p, i32]),
+        "opr_scene_file_destroy": (None, [vp]),
+        "opr_scene_file_desc": (C.POINTER(opr_scene_desc), [vp]),
+        "opr_scene_file_camera": (i32, [vp, C.POINTER(opr_camera)]),
+        "opr_scene_file_num_triangles": (u32, [vp]),
+        "opr_scene_file_num_meshes": (u32, [vp]),
+        "opr_scene_file_warnings": (C.c_char_p, [vp]),
+        "opr_scene_file_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)   # AttributeError here = header/library mismatch: fail loudly

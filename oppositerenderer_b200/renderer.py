@@ -151,6 +151,60 @@ class CornellSmall(_BuiltinScene):
         super().__init__("CornellSmall", self.Default if config is None else config)
 
 
+class Scene:
+    """RenderEngine/scene/Scene.h — a scene read from a Collada file (Scene::createFromFile, scene/Scene.cpp:73-176)."""
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+
+    @staticmethod
+    def createFromFile(filename, single_emitter_lights=False):
+        lib = capi.load_library()
+        h = lib.opr_scene_file_load(str(filename).encode(), 1 if single_emitter_lights else 0)
+        if not h:
+            raise RuntimeError(lib.opr_scene_file_last_error().decode())
+        return Scene(h, lib)
+
+    def __del__(self):
+        try:
+            self._lib.opr_scene_file_destroy(self._h)
+        except Exception:
+            pass
+
+    def getSceneDescription(self):
+        return self._lib.opr_scene_file_desc(self._h)
+
+    def getSceneLights(self):
+        d = self.getSceneDescription().contents
+        return [d.lights[i] for i in range(d.numLights)]
+
+    def getDefaultCamera(self):
+        pod = capi.opr_camera()
+        if self._lib.opr_scene_file_camera(self._h, C.byref(pod)) != 0:
+            return Camera()                     # Scene::m_defaultCamera default-constructed (Scene.h)
+        return Camera(pod=pod)
+
+    def getSceneName(self):
+        return self.getSceneDescription().contents.name.decode()
+
+    def getSceneAABB(self):
+        d = self.getSceneDescription().contents
+        return np.array(list(d.aabbMin), np.float32), np.array(list(d.aabbMax), np.float32)
+
+    def getSceneInitialPPMRadiusEstimate(self):
+        d = self.getSceneDescription().contents
+        return self._lib.opr_initial_ppm_radius(d.aabbMin, d.aabbMax)
+
+    def getNumTriangles(self):
+        return self._lib.opr_scene_file_num_triangles(self._h)
+
+    def getNumMeshes(self):
+        return self._lib.opr_scene_file_num_meshes(self._h)
+
+    def warnings(self):
+        return self._lib.opr_scene_file_warnings(self._h).decode()
+
+
 class SceneDescription:
     """IScene built from numpy arrays (triangle meshes, parallelograms, spheres, materials, textures, lights):
     the neutral replacement of IScene::getSceneRootGroup (SURVEY.md §8b).  Keeps the arrays alive."""

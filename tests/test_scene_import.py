@@ -1,0 +1,134 @@
+"""Collada import: Scene::createFromFile restated for .dae files (host_scene_import.cpp) — node
+transforms, triangulation, generated normals / tangents, the reference's material classification, lights, emitter quads, AABB
+and camera rules (RenderEngine/scene/Scene.cpp:73-311, 469-485), then the imported scene through the renderer."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import collada_fixture as cf
+import oracle_lib as ol
+import util
+from oppositerenderer_b200 import capi
+
+
+def _mesh(d, i):
+    m = d.meshes[i]
+    v = np.ctypeslib.as_array(m.vertices, (m.numVertices, 3)).copy()
+    f = np.ctypeslib.as_array(m.indices, (m.numTriangles, 3)).copy()
+    n = np.ctypeslib.as_array(m.normals, (m.numVertices, 3)).copy() if m.normals else None
+    uv = np.ctypeslib.as_array(m.uvs, (m.numVertices, 2)).copy() if m.uvs else None
+    t = np.ctypeslib.as_array(m.tangents, (m.numVertices, 3)).copy() if m.tangents else None
+    return v, f, n, uv, t, m.material
+
+
+def test_collada_room_import(product, tmp_path):
+    path, tex = cf.write_room(str(tmp_path))
+    scene = product.Scene.createFromFile(path)
+    d = scene.getSceneDescription().contents
+    assert scene.getSceneName() == os.path.realpath(path)
+    # ---- material classification, Scene.cpp:178-265, in <library_materials> order
+    kinds = [d.materials[i].kind for i in range(d.numMaterials)]
+    assert kinds == [capi.MAT_DIFFUSE, capi.MAT_DIFFUSE, capi.MAT_DIFFUSE_EMITTER, capi.MAT_GLASS, capi.MAT_MIRROR, capi.MAT_TEXTURE]
+    assert list(d.materials[1].Kd) == pytest.approx([0.8, 0.1, 0.1]) and d.materials[3].indexOfRefraction == pytest.approx(1.5)
+    assert list(d.materials[3].Kr) == [1, 1, 1] and list(d.materials[4].Kr) == pytest.approx([0.9, 0.9, 0.9])
+    assert d.materials[5].diffuseTexture == 0 and d.materials[5].normalTexture == 1 and d.numTextures == 2
+    t0 = np.ctypeslib.as_array(d.textures[0].rgba, (8, 8, 4))
+    assert (t0[..., 0] == tex[..., 2]).all() and (t0[..., 2] == tex[..., 0]).all() and (t0[..., 3] == 1).all()      # Image.cpp: BGR->RGB, alpha 1
+    # ---- geometry: 9 instances; quads triangulated to 2, the box to 12, the pentagon to 3 triangles
+    assert d.numMeshes == 9 and scene.getNumMeshes() == 9 and scene.getNumTriangles() == 7 * 2 + 12 + 3
+    v, f, n, uv, t, mat = _mesh(d, 0)            # floor: scale (2, 1, 2)
+    assert mat == 5 and sorted(map(tuple, v.tolist())) == sorted([(-2, 0, -2), (2, 0, -2), (2, 0, 2), (-2, 0, 2)])
+    assert np.allclose(n, [0, 1, 0]) and uv is not None and t is not None and np.allclose(np.abs((t * n).sum(1)), 0, atol=1e-6)
+    fn = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    assert (fn[:, 1] > 0).all()                   # winding preserved: faces look up into the room
+    v, f, n, uv, t, mat = _mesh(d, 1)            # ceiling: translate(0,4,0) * rotate(x,180) * scale
+    assert np.allclose(v[:, 1], 4) and np.allclose(n, [0, -1, 0], atol=1e-6)
+    v, f, n, uv, t, mat = _mesh(d, 3)            # left wall through an explicit <matrix>
+    assert mat == 1 and np.allclose(v[:, 0], -2) and np.allclose(n, [1, 0, 0], atol=1e-6) and np.allclose(sorted(v[:, 1]), [0, 0, 4, 4])
+    v, f, n, uv, t, mat = _mesh(d, 6)            # glass box: no normals in the file -> GenSmoothNormals (per position, area weighted)
+    assert mat == 3 and v.shape == (8, 3) and f.shape == (12, 3) and uv is None
+    c = np.array([-0.8, 0.61, 0.3])
+    assert np.allclose(np.linalg.norm(n, axis=1), 1, atol=1e-5) and ((n * (v - c)).sum(1) > 0).all()
+    v, f, n, uv, t, mat = _mesh(d, 8)            # pentagon under two nested nodes, fan-triangulated, generated normals
+    assert f.shape == (3, 3) and np.allclose(v[:, 1], 0.3) and np.allclose(np.abs(n), [0, 1, 0], atol=1e-6)
+    assert np.allclose(v[0], [0.8 + 0.5, 0.3, -0.5], atol=1e-6)
+    # ---- lights: the point light, then the emitter quad twice (Scene.cpp:141 and :508)
+    L = scene.getSceneLights()
+    assert [l.lightType for l in L] == [capi.LIGHT_POINT, capi.LIGHT_AREA, capi.LIGHT_AREA]
+    assert list(L[0].position) == pytest.approx([1.2, 3.0, -1.0]) and list(L[0].power) == pytest.approx([30, 30, 28])
+    assert bytes(memoryview(L[1]).cast("B")) == bytes(memoryview(L[2]).cast("B"))
+    lv, lf, _, _, _, lmat = _mesh(d, 5)
+    assert lmat == 2 and list(L[1].position) == pytest.approx(lv[lf[0, 0]].tolist())
+    assert list(L[1].v1) == pytest.approx((lv[lf[0, 1]] - lv[lf[0, 0]]).tolist()) and list(L[1].v2) == pytest.approx((lv[lf[0, 2]] - lv[lf[0, 0]]).tolist())
+    assert L[1].area_or_angle == pytest.approx(1.0) and d.materials[2].inverseArea == pytest.approx(1.0) and list(L[1].normal) == pytest.approx([0, -1, 0], abs=1e-6)
+    once = product.Scene.createFromFile(path, single_emitter_lights=True)
+    assert len(once.getSceneLights()) == 2
+    # ---- AABB from the FIRST vertex of every face (Scene.cpp:151-153), not the true bounds
+    firsts = np.concatenate([_mesh(d, i)[0][_mesh(d, i)[1][:, 0]] for i in range(d.numMeshes)])
+    mn, mx = scene.getSceneAABB()
+    assert np.allclose(mn, firsts.min(0)) and np.allclose(mx, firsts.max(0))
+    # ---- camera: eye, lookAt = eye + dir, fov = xfov_rad * 365 / (2 pi) (Scene.cpp:469-485), KeepHorizontal
+    cam = scene.getDefaultCamera().pod
+    assert list(cam.eye) == pytest.approx([0, 2, -5.5]) and list(cam.lookat) == pytest.approx([0, 2, -4.5], abs=1e-6)
+    assert cam.hfov == pytest.approx(50.0 * 365.0 / 360.0, rel=1e-6) and cam.aspectRatioMode == 1
+    assert scene.getSceneInitialPPMRadiusEstimate() > 0 and scene.warnings() == ""
+
+
+def test_collada_up_axis_and_errors(product, tmp_path):
+    path, _ = cf.write_room(str(tmp_path / "z"), up_axis="Z_UP")
+    zscene = product.Scene.createFromFile(path)          # the handle owns the arrays: keep it alive
+    d = zscene.getSceneDescription().contents
+    v = _mesh(d, 1)[0]                           # ceiling at y = 4 in file space -> (x, z, -y)
+    assert np.allclose(v[:, 2], -4, atol=1e-6)
+    with pytest.raises(RuntimeError, match=r"The file that was supplied \(.*\) does not exist"):
+        product.Scene.createFromFile(str(tmp_path / "nope.dae"))
+    bad = tmp_path / "bad.dae"
+    bad.write_text("<COLLADA><library_geometries></COLLADA>")
+    with pytest.raises(RuntimeError, match="An error occurred in Assimp during reading of this file"):
+        product.Scene.createFromFile(str(bad))
+    notex = tmp_path / "z" / "floor.tga"
+    os.remove(notex)
+    with pytest.raises(RuntimeError, match="does not exist"):
+        product.Scene.createFromFile(path)
+
+
+def test_oracle_renders_the_imported_scene(product, oracle, tmp_path):
+    """CPU: the imported description is a valid scene for the oracle (all six material kinds but glossy, both light types)."""
+    path, _ = cf.write_room(str(tmp_path))
+    scene = product.Scene.createFromFile(path)
+    o = oracle.OracleRenderer("oracle", (32, 32), 10, util.SEED)
+    o.init_scene(scene.getSceneDescription())
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(1.0)
+    o.render_next_iteration(0, 0, 0.3, oracle.make_details(cam.pod, capi.PROGRESSIVE_PHOTON_MAPPING, 24, 24))
+    out = o.output()
+    assert np.isfinite(out).all() and out.mean() > 0
+    flags = o.hitpoints()["flags"]
+    assert ((flags & ol.PRD_HIT_NON_SPECULAR) != 0).mean() > 0.5 and ((flags & ol.PRD_MISS) != 0).mean() < 0.2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,minfrac", [(2, 0.93), (1, 0.90), (0, 0.93)])
+def test_imported_scene_parity(product, oracle, tmp_path, method, minfrac):
+    """GPU: PPM, BDPT and PT of the imported room against the oracle on identical paths."""
+    path, _ = cf.write_room(str(tmp_path))
+    scene = product.Scene.createFromFile(path)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(1.0)
+    size, pl, iters = 48, (64, 64), 2
+    r = product.OptixRenderer(photon_launch=pl, vcm_max_path_length=8, seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    o = oracle.OracleRenderer("oracle", pl, 8, util.SEED)
+    o.init_scene(scene.getSceneDescription())
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, size, size, 2.0 / 3.0)
+    odet = oracle.make_details(cam.pod, method, size, size)
+    for i in range(iters):
+        r.renderNextIteration(i, i, 0.25, True, det)
+        o.render_next_iteration(i, i, 0.25, odet)
+    out, out0 = r.getOutputBuffer(), o.output()
+    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
+    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
+    assert frac > minfrac - 0.05 and rel < 4e-2, (frac, rel)
