@@ -184,6 +184,8 @@ void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const 
                                float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
 void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                             float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc);
+void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
+                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
 void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const unsigned* sampleLight,
                                const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc);
 

@@ -177,6 +177,73 @@ void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const 
     ++*lc.launches;
 }
 
+// Any-hit for the deferred connections of the BDPT passes (vcm.cu): segment i = (connO[i].xyz, connD[i].xyz) over
+// (EPS_RAY, connO[i].w); when nothing occludes it (isOccluded, vcm/vcm.h:43-59) its contribution connC[i] is added to
+// target[stride * index] (camera-path colour accumulators, or the image for light-tracing splats: vcm.h:159).
+__global__ void __launch_bounds__(TRACE_THREADS) trace_connect_queue_kernel(SceneView sc, const float4* __restrict__ connO, const float4* __restrict__ connD,
+                                                                            const float4* __restrict__ connC, const unsigned* __restrict__ count,
+                                                                            float* __restrict__ target, unsigned stride, unsigned* __restrict__ fetchCursor,
+                                                                            unsigned* __restrict__ stat, unsigned refillIdle)
+{
+    const unsigned FULL = 0xffffffffu, NONE = 0xffffffffu;
+    const unsigned n = *count;
+    const unsigned lane = threadIdx.x & 31;
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f);
+    const float tmin = EPS_RAY;
+    HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
+    int2 stack[TRAVERSAL_STACK];
+    int sp = 0;
+    int cur = TRAVERSAL_DONE;
+    unsigned pending = NONE;      // queue index of a finished, unoccluded segment whose contribution is not added yet
+    bool exhausted = false;
+    for (;;) {
+        const unsigned idleMask = __ballot_sync(FULL, cur == TRAVERSAL_DONE);
+        if (idleMask == FULL || (!exhausted && (unsigned)__popc(idleMask) >= refillIdle)) {
+            if (cur == TRAVERSAL_DONE && pending != NONE) {
+                const float4 c = connC[pending];
+                float* t = target + (size_t)stride * __float_as_uint(connD[pending].w);
+                atomicAdd(t, c.x); atomicAdd(t + 1, c.y); atomicAdd(t + 2, c.z);
+                pending = NONE;
+            }
+            if (!exhausted) {
+                const unsigned want = __popc(idleMask);
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(fetchCursor, want);
+                base = __shfl_sync(FULL, base, 0);
+                if (cur == TRAVERSAL_DONE) {
+                    const unsigned i = base + __popc(idleMask & ((1u << lane) - 1));
+                    if (i < n) {
+                        const float4 o4 = connO[i], d4 = connD[i];
+                        o = f3(o4); d = f3(d4);
+                        idir = safe_inverse_direction(d);
+                        hit.t = o4.w; hit.prim = -1;
+                        sp = 0; cur = sc.rootRef; pending = i;
+                    }
+                }
+                if (base + want >= n) exhausted = true;
+            }
+            if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
+        }
+        while (__any_sync(FULL, cur >= 0)) {
+            if (cur >= 0) OPR_NODE_STEP(true)
+        }
+        if (cur != TRAVERSAL_DONE) {
+            bool found = false;
+            OPR_LEAF_STEP(found)
+            if (found) { pending = NONE; cur = TRAVERSAL_DONE; sp = 0; }
+            else OPR_POP(true)
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, n);
+}
+
+void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
+                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc)
+{
+    trace_connect_queue_kernel<<<148 * 8, TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle());
+    ++*lc.launches;
+}
+
 // Raw entry points over caller-supplied SoA rays (C-ABI opr_trace_closest / opr_trace_any)
 __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_raw_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                           unsigned n, float4* __restrict__ hits)

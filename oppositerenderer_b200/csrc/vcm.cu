@@ -22,6 +22,10 @@ struct VcmState {
     float4* color = nullptr;   // camera-path colour accumulator
     unsigned* lvCount = nullptr;
     float4* lv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // deferred connections of one bounce: shadow segment + the contribution it carries if unoccluded
+    float4* connO = nullptr;   // origin.xyz, tmax
+    float4* connD = nullptr;   // direction.xyz, target index (uint bits)
+    float4* connC = nullptr;   // contribution.xyz
     size_t paths = 0; unsigned maxVerts = 0;
 };
 
@@ -33,13 +37,18 @@ struct VcmParams {
     float2 pixelSizeFactor;
 };
 
-struct VcmBuffers { float4* thr; float4* mis; float4* color; unsigned* lvCount; float4* lv0; float4* lv1; float4* lv2; float4* lv3; float4* lv4; float4* lv5; unsigned paths; };
+struct VcmBuffers { float4* thr; float4* mis; float4* color; unsigned* lvCount; float4* lv0; float4* lv1; float4* lv2; float4* lv3; float4* lv4; float4* lv5; unsigned paths;
+                    float4* connO; float4* connD; float4* connC; unsigned* connCount; };
+constexpr int CTR_CONN_COUNT = 9;     // RayQueues::counters word: length of the connection queue of the current bounce
+constexpr int CTR_CONN_FETCH = 11;    // its fetch cursor
+constexpr int VCM_MAX_CONNECTIONS = 16;   // per camera vertex: one light sample + at most maxPathLength - 1 light vertices
 
 void vcm_free(Renderer& r)
 {
     if (!r.vcm) return;
     VcmState* s = r.vcm;
     cudaFree(s->thr); cudaFree(s->mis); cudaFree(s->color); cudaFree(s->lvCount);
+    cudaFree(s->connO); cudaFree(s->connD); cudaFree(s->connC);
     for (int i = 0; i < 6; i++) cudaFree(s->lv[i]);
     delete s; r.vcm = nullptr;
 }
@@ -55,18 +64,36 @@ static void vcm_alloc(Renderer& r)
     OPR_CUDA_CHECK(cudaMalloc((void**)&s->thr, paths * 16)); OPR_CUDA_CHECK(cudaMalloc((void**)&s->mis, paths * 16));
     OPR_CUDA_CHECK(cudaMalloc((void**)&s->color, paths * 16)); OPR_CUDA_CHECK(cudaMalloc((void**)&s->lvCount, paths * 4));
     for (int i = 0; i < 6; i++) OPR_CUDA_CHECK(cudaMalloc((void**)&s->lv[i], paths * maxVerts * 16));
+    if (maxVerts + 1 > VCM_MAX_CONNECTIONS) throw std::runtime_error("vcmMaxPathLength too large for the connection queue");
+    const size_t cap = paths * (maxVerts + 1);
+    OPR_CUDA_CHECK(cudaMalloc((void**)&s->connO, cap * 16)); OPR_CUDA_CHECK(cudaMalloc((void**)&s->connD, cap * 16));
+    OPR_CUDA_CHECK(cudaMalloc((void**)&s->connC, cap * 16));
 }
 
 // ---- shared device pieces ----------------------------------------------------------------------------------------
 OPR_DEV float pdfWtoA(const float aPdfW, const float aDist, const float aCosThere) { return aPdfW * fabsf(aCosThere) / sqr(aDist); }
 
-// isOccluded, vcm.h:43-59
-OPR_DEV bool vcm_occluded(const SceneView& sc, const float3& p, const float3& d, float tmax, unsigned& shadowRays)
-{
-    if (tmax < 3.f * EPS_RAY) return false;
-    HitRec hit;
-    shadowRays++;
-    return traverse<true>(sc, p, d, EPS_RAY, tmax - 2.f * EPS_RAY, hit);
+// isOccluded (vcm.h:43-59) is deferred: a shading thread records the shadow segment and the contribution it would add, the
+// records of a warp are appended to the connection queue with one atomic, and trace_connect_queue_kernel (persistent any-hit
+// traversal, full warps) adds the contributions of the unoccluded segments.  Testing occlusion inside the shading threads
+// ran the traversal with 5 of 32 lanes (profiles/r1i).  Segments shorter than 3 EPS_RAY are unoccluded by definition (:48).
+struct Connection { float3 dir; float tmax; float3 contrib; };
+OPR_DEV void warp_flush_connections(const VcmBuffers& B, const float3& origin, unsigned target, const Connection* c, unsigned n)
+{   // must be reached by all 32 lanes
+    const unsigned lane = threadIdx.x & 31;
+    unsigned incl = n;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += y; }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    unsigned base = 0;
+    if (lane == 31) base = atomicAdd(B.connCount, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+    for (unsigned k = 0; k < n; k++) {
+        B.connO[base + k] = make_float4(origin.x, origin.y, origin.z, c[k].tmax);
+        B.connD[base + k] = make_float4(c[k].dir.x, c[k].dir.y, c[k].dir.z, __uint_as_float(target));
+        B.connC[base + k] = make_float4(c[k].contrib.x, c[k].contrib.y, c[k].contrib.z, 0.f);
+    }
 }
 
 // updateMisTermsOnHit, mis.h:109-121
@@ -236,12 +263,12 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_shade_kernel(SceneView 
     if (kind == QUEUE_MISS || kind == OPR_MAT_DIFFUSE_EMITTER) return;   // miss / emitter: done (VCMLightPass.cu:95-98, DiffuseEmitter.cu:76-79)
     const unsigned n = matCount[kind];
     const unsigned* queue = matQueue + (size_t)kind * capacity;
-    unsigned shadowRays = 0;
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const unsigned qi = base + threadIdx.x;
         bool push = false;
         float3 newO = f3(0.f), newD = f3(0.f);
         unsigned p = 0;
+        Connection conn; unsigned numConn = 0, connTarget = 0; float3 connOrigin = f3(0.f);
         if (qi < n) {
             const unsigned slot = queue[qi];
             p = rayPath[slot];
@@ -308,10 +335,13 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_shade_kernel(SceneView 
                                         const float misWeight = 1.f / (wLight + 1.f);
                                         const float cameraPdfAConvertedToImagePdfA = 1.f / cameraPdfA;
                                         const float3 contrib = misWeight * throughput * bsdfFactor / (P.lightSubpathCount * cameraPdfAConvertedToImagePdfA);
-                                        if (!vcm_occluded(sc, hitPoint, dirToCamera, distance, shadowRays)) {
+                                        if (distance < 3.f * EPS_RAY) {
                                             // the reference's splat is a plain, racy += (vcm.h:159); atomics here
                                             float* op = output + 3 * ((size_t)py * P.w + px);
                                             atomicAdd(op, contrib.x); atomicAdd(op + 1, contrib.y); atomicAdd(op + 2, contrib.z);
+                                        } else {
+                                            conn.dir = dirToCamera; conn.tmax = distance - 2.f * EPS_RAY; conn.contrib = contrib;
+                                            numConn = 1; connTarget = py * P.w + px; connOrigin = hitPoint;
                                         }
                                     }
                                 }
@@ -331,6 +361,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_shade_kernel(SceneView 
                 B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
             }
         }
+        warp_flush_connections(B, connOrigin, connTarget, &conn, numConn);
         const unsigned dst = warp_append(nextCount, push);
         if (push) {
             nextO[dst] = make_float4(newO.x, newO.y, newO.z, RAY_LEN_MIN);
@@ -338,8 +369,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_shade_kernel(SceneView 
             nextPath[dst] = p;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) shadowRays += __shfl_xor_sync(0xffffffffu, shadowRays, o);
-    if ((threadIdx.x & 31) == 0 && shadowRays) atomicAdd(stat, shadowRays);
+    (void)stat;
 }
 
 // ---- camera pass -----------------------------------------------------------------------------------------------------
@@ -388,12 +418,12 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView
     if (kind == QUEUE_MISS) return;   // VCMCameraPass.cu:87-90
     const unsigned n = matCount[kind];
     const unsigned* queue = matQueue + (size_t)kind * capacity;
-    unsigned shadowRays = 0;
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const unsigned qi = base + threadIdx.x;
         bool push = false;
         float3 newO = f3(0.f), newD = f3(0.f);
         unsigned p = 0;
+        Connection conn[VCM_MAX_CONNECTIONS]; unsigned numConn = 0; float3 connOrigin = f3(0.f);
         if (qi < n) {
             const unsigned slot = queue[qi];
             p = rayPath[slot];
@@ -428,6 +458,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView
                 VcmBSDF bsdf; float3 hitNormal, albedo;
                 if (vcm_build_bsdf(m, kind, sf, d, false, bsdf, hitNormal, albedo)) {
                     const float3 hitPoint = o + hit.t * d;
+                    connOrigin = hitPoint;
                     depth++;
                     const float cosThetaIn = dot(hitNormal, -d);
                     bool done = cosThetaIn < EPS_COSINE;
@@ -485,7 +516,10 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView
                                     const float wCamera = (emissionPdfW * cosToLight / (directPdfW * cosAtLight)) * (P.misVmWeightFactor + dVCM + dVC * bsdfRevPdfW);
                                     const float misWeight = 1.f / (wLight + 1.f + wCamera);
                                     const float3 contrib = (misWeight * cosToLight / (lightPickProb * directPdfW)) * (radiance * bsdfFactor);
-                                    if (!isZero(contrib) && !vcm_occluded(sc, hitPoint, dirToLight, distance, shadowRays)) color += contrib * throughput;
+                                    if (!isZero(contrib)) {
+                                        if (distance < 3.f * EPS_RAY) color += contrib * throughput;
+                                        else { conn[numConn].dir = dirToLight; conn[numConn].tmax = distance - 2.f * EPS_RAY; conn[numConn].contrib = contrib * throughput; numConn++; }
+                                    }
                                 }
                             }
                             // ---- connectVertices with the light path of the same index
@@ -524,8 +558,8 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView
                                 const float misWeight = 1.f / (wLight + 1.f + wCamera);
                                 float3 contrib = geometryTerm * cameraBsdfFactor * lightBsdfFactor * 1.f;
                                 contrib *= misWeight * throughput * f3(a1);
-                                if (vcm_occluded(sc, hitPoint, direction, distance2, shadowRays)) continue;
-                                color += contrib;
+                                if (distance2 < 3.f * EPS_RAY) color += contrib;
+                                else if (numConn < VCM_MAX_CONNECTIONS) { conn[numConn].dir = direction; conn[numConn].tmax = distance2 - 2.f * EPS_RAY; conn[numConn].contrib = contrib; numConn++; }
                             }
                         }
                         if (P.maxPathLen <= depth) done = true;
@@ -541,6 +575,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView
             B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
             B.color[p] = make_float4(color.x, color.y, color.z, 0.f);
         }
+        warp_flush_connections(B, connOrigin, p, conn, numConn);
         const unsigned dst = warp_append(nextCount, push);
         if (push) {
             nextO[dst] = make_float4(newO.x, newO.y, newO.z, RAY_LEN_MIN);
@@ -548,8 +583,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView
             nextPath[dst] = p;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) shadowRays += __shfl_xor_sync(0xffffffffu, shadowRays, o);
-    if ((threadIdx.x & 31) == 0 && shadowRays) atomicAdd(stat, shadowRays);
+    (void)stat;
 }
 
 // cameraPass epilogue: outputBuffer[launchIndex] += cameraPrd.color (VCMCameraPass.cu:75-78)
@@ -577,7 +611,8 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     const SceneView& sc = scene.view;
     vcm_alloc(*this);
     VcmState& S = *vcm;
-    VcmBuffers B{S.thr, S.mis, S.color, S.lvCount, S.lv[0], S.lv[1], S.lv[2], S.lv[3], S.lv[4], S.lv[5], (unsigned)S.paths};
+    VcmBuffers B{S.thr, S.mis, S.color, S.lvCount, S.lv[0], S.lv[1], S.lv[2], S.lv[3], S.lv[4], S.lv[5], (unsigned)S.paths,
+                 S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT};
     const unsigned lightSubPathCount = width * height;
     const float ppmRadiusSquared = PPMRadius * PPMRadius;
     const float etaVCM = (float(lightSubPathCount) / 1u) * PI_F * ppmRadiusSquared;   // nVM / nVC * pi * r^2 (:687)
@@ -601,11 +636,15 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
             launch_trace_closest(sc, q, cur, lc);
+            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_CONN_COUNT, 0, sizeof(unsigned) * 3, stream));   // count, (legacy fetch), connection fetch
             dim3 grid(VCM_BLOCKS_X, NUM_QUEUES);
             vcm_light_shade_kernel<<<grid, VCM_THREADS, 0, stream>>>(sc, P, rng, B, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
                                                                      q.counters + 2, q.capacity, q.rayO[cur ^ 1], q.rayD[cur ^ 1], q.rayPath[cur ^ 1],
                                                                      q.counters + (cur ^ 1), q.counters + 16 + STAT_ANY_RAYS);
             ++launches;
+            if (!P.estimatePass)   // connectCameraT1 splats of the unoccluded segments (vcm.h:159)
+                launch_trace_connect_queue(sc, S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, output, 3, q.counters + CTR_CONN_FETCH,
+                                           q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
             cur ^= 1;
         }
     };
@@ -632,11 +671,15 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
             launch_trace_closest(sc, q, cur, lc);
+            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_CONN_COUNT, 0, sizeof(unsigned) * 3, stream));
             dim3 grid(VCM_BLOCKS_X, NUM_QUEUES);
             vcm_camera_shade_kernel<<<grid, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
                                                                       q.counters + 2, q.capacity, q.rayO[cur ^ 1], q.rayD[cur ^ 1], q.rayPath[cur ^ 1],
                                                                       q.counters + (cur ^ 1), q.counters + 16 + STAT_ANY_RAYS);
             ++launches;
+            // light-source and vertex connections of this bounce: add the unoccluded ones to the paths' colour accumulators
+            launch_trace_connect_queue(sc, S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, (float*)S.color, 4, q.counters + CTR_CONN_FETCH,
+                                       q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
             cur ^= 1;
         }
         vcm_accumulate_kernel<<<blocks, VCM_THREADS, 0, stream>>>(B, width * height, output);
