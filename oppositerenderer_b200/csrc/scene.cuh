@@ -137,17 +137,18 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
 // leaf or is finished, then the lanes that hold a leaf test it together.  Without the votes the leaf code ran with 2 of 32
 // lanes active (profiles/r1d): lanes reached their leaves at different iterations and each paid the leaf code alone.
 //
-// The steps are macros over the per-lane variables (o, d, idir, tmin, hit, stack, sp, cur) because the persistent
+// The steps are macros over the per-lane variables (o, d, idir, ood, tmin, hit, stack, sp, cur) because the persistent
 // wavefront kernel in trace.cu runs the same steps around its own ray fetch.
 
 // Slab test of one child: entry distance, or +inf when the ray misses the box within (tmin, hit.t).
-// (plane - o) * idir, not the fused plane*idir - o*idir: no cancellation for grazing rays, so the conservatively
-// inflated boxes (scene.cu addPrim) never cull a primitive the exact test would accept.
+// Fused form plane * idir + ood with ood = -o * idir (one FFMA per plane instead of FADD + FMUL).  Its rounding error is
+// <= 2^-24 |o| |idir| in t, i.e. 6e-8 * scale in space, against a box inflation of 4e-6 * scale (scene.cu addPrim): the
+// conservatively inflated boxes still never cull a primitive the exact triangle test would accept.
 #define OPR_SLAB(LX, HX, LY, HY, LZ, HZ, TOUT)                                                                     \
     {                                                                                                              \
-        const float ax = ((LX) - o.x) * idir.x, bx = ((HX) - o.x) * idir.x;                                        \
-        const float ay = ((LY) - o.y) * idir.y, by = ((HY) - o.y) * idir.y;                                        \
-        const float az = ((LZ) - o.z) * idir.z, bz = ((HZ) - o.z) * idir.z;                                        \
+        const float ax = fmaf((LX), idir.x, ood.x), bx = fmaf((HX), idir.x, ood.x);                                \
+        const float ay = fmaf((LY), idir.y, ood.y), by = fmaf((HY), idir.y, ood.y);                                \
+        const float az = fmaf((LZ), idir.z, ood.z), bz = fmaf((HZ), idir.z, ood.z);                                \
         const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));                   \
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t));                  \
         TOUT = tn <= tf ? tn : INF_;                                                                               \
@@ -173,14 +174,21 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
         OPR_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, t1)                                                     \
         OPR_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, t2)                                                     \
         OPR_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, t3)                                                     \
-        OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t2, r2, t3, r3) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t1, r1, t3, r3) OPR_CSWAP(t1, r1, t2, r2) \
-        if (t0 < INF_) {                                                                                           \
-            if (t3 < INF_) stack[sp++] = make_int2(r3, __float_as_int(t3));                                        \
-            if (t2 < INF_) stack[sp++] = make_int2(r2, __float_as_int(t2));                                        \
-            if (t1 < INF_) stack[sp++] = make_int2(r1, __float_as_int(t1));                                        \
-            cur = r0;                                                                                              \
+        if (ANYHIT) {          /* any order will do for an occlusion query: skip the sorting network */             \
+            if (t1 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r1, 0); else { t0 = t1; r0 = r1; } }               \
+            if (t2 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r2, 0); else { t0 = t2; r0 = r2; } }               \
+            if (t3 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r3, 0); else { t0 = t3; r0 = r3; } }               \
+            if (t0 < INF_) cur = r0; else OPR_POP(true)                                                            \
         } else {                                                                                                   \
-            OPR_POP(ANYHIT)                                                                                        \
+            OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t2, r2, t3, r3) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t1, r1, t3, r3) OPR_CSWAP(t1, r1, t2, r2) \
+            if (t0 < INF_) {                                                                                       \
+                if (t3 < INF_) stack[sp++] = make_int2(r3, __float_as_int(t3));                                    \
+                if (t2 < INF_) stack[sp++] = make_int2(r2, __float_as_int(t2));                                    \
+                if (t1 < INF_) stack[sp++] = make_int2(r1, __float_as_int(t1));                                    \
+                cur = r0;                                                                                          \
+            } else {                                                                                               \
+                OPR_POP(false)                                                                                     \
+            }                                                                                                      \
         }                                                                                                          \
     }
 // one leaf visit of a lane with cur < 0, cur != TRAVERSAL_DONE; FOUND is set when a primitive was accepted
@@ -223,6 +231,7 @@ OPR_DEV bool traverse_warp(const SceneView& sc, unsigned mask, bool active, cons
 {
     hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
     const float3 idir = safe_inverse_direction(d);
+    const float3 ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
     int2 stack[TRAVERSAL_STACK];
     int sp = 0;
     int cur = active ? sc.rootRef : TRAVERSAL_DONE;

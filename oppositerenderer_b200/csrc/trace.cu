@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView 
     const unsigned FULL = 0xffffffffu, NONE = 0xffffffffu;
     const unsigned n = *count;
     const unsigned lane = threadIdx.x & 31;
-    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f);
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     float tmin = 0.f;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
     int2 stack[TRAVERSAL_STACK];
@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView 
                         const float4 o4 = rayO[idx], d4 = rayD[idx];
                         o = f3(o4); d = f3(d4); tmin = o4.w;
                         idir = safe_inverse_direction(d);
+                        ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
                         hit.t = d4.w; hit.prim = -1; hit.u = hit.v = 0.f;
                         sp = 0; cur = sc.rootRef; ray = idx;
                     }
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_shadow_queue_kernel(Scene
     const unsigned FULL = 0xffffffffu;
     const unsigned n = *count;
     const unsigned lane = threadIdx.x & 31;
-    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f);
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     const float tmin = 0.0001f;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
     int2 stack[TRAVERSAL_STACK];
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_shadow_queue_kernel(Scene
                         const float4 d4 = shadowD[i];
                         o = f3(hitPos[idx >> 2]); d = f3(d4);
                         idir = safe_inverse_direction(d);
+                        ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
                         hit.t = d4.w; hit.prim = -1;
                         sp = 0; cur = sc.rootRef;
                     }
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_connect_queue_kernel(Scen
     const unsigned FULL = 0xffffffffu, NONE = 0xffffffffu;
     const unsigned n = *count;
     const unsigned lane = threadIdx.x & 31;
-    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f);
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     const float tmin = EPS_RAY;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
     int2 stack[TRAVERSAL_STACK];
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_connect_queue_kernel(Scen
                         const float4 o4 = connO[i], d4 = connD[i];
                         o = f3(o4); d = f3(d4);
                         idir = safe_inverse_direction(d);
+                        ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
                         hit.t = o4.w; hit.prim = -1;
                         sp = 0; cur = sc.rootRef; pending = i;
                     }
