@@ -35,7 +35,7 @@ enum opr_aspect_ratio_mode { OPR_KEEP_VERTICAL = 0, OPR_KEEP_HORIZONTAL = 1, OPR
 /* Light::LightType, RenderEngine/renderer/Light.h:17 */
 enum opr_light_type { OPR_LIGHT_AREA = 0, OPR_LIGHT_POINT = 1, OPR_LIGHT_SPOT = 2 };
 
-/* one OptiX Material singleton per class in the reference (material/*.cpp); here a kind id */
+/* one OptiX Material singleton per class in the reference (material/<Kind>.cpp); here a kind id */
 enum opr_material_kind {
     OPR_MAT_DIFFUSE = 0,
     OPR_MAT_DIFFUSE_EMITTER = 1,

@@ -7,6 +7,7 @@
 // kernel either terminates the path or pushes ONE continuation ray into the next queue (warp-aggregated).
 // Shading runs bucketed by material kind: blockIdx.y selects the material queue filled by the trace kernel.
 #include "renderer.h"
+#include <cstdlib>
 
 namespace opr {
 
@@ -62,6 +63,10 @@ OPR_DEV void reset_wave_counters(unsigned* __restrict__ counters, unsigned n)
     if (blockIdx.x == 0)
         for (unsigned i = CTR_RAYCOUNT + threadIdx.x; i < CTR_TOTAL; i += blockDim.x) counters[i] = (i == CTR_RAYCOUNT) ? n : 0u;
 }
+
+// tail-kernel shape (measurement knobs): rays per warp = 32 / spread; freeRun = lanes traverse without votes
+static unsigned tail_spread() { static int v = -1; if (v < 0) { const char* e = getenv("OPR_TAIL_SPREAD"); v = e ? atoi(e) : 1; if (v < 1) v = 1; if (v > 32) v = 32; } return (unsigned)v; }
+static unsigned tail_free() { static int v = -1; if (v < 0) { const char* e = getenv("OPR_TAIL_FREE"); v = e ? atoi(e) : 1; } return (unsigned)v; }
 
 // ---- RNG state init: initRandomStateBuffer (OptixRenderer_SpatialHash.cu:310-317) ---------------------
 __global__ void rng_init_kernel(RngBuf rng, unsigned seed, size_t n)
@@ -256,20 +261,21 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneVi
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_tail_kernel(SceneView sc, unsigned w, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
                                                                         const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                         const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
-                                                                        unsigned* __restrict__ stat)
+                                                                        unsigned* __restrict__ stat, unsigned spread, unsigned freeRun)
 {
     const unsigned n = *count;
     unsigned traced = 0;
-    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const unsigned i = base + threadIdx.x;
-        bool alive = i < n;
+    for (unsigned base = blockIdx.x * blockDim.x; base / spread < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = (base + threadIdx.x) / spread;
+        bool alive = i < n && (threadIdx.x % spread) == 0;
         const float4 o4 = alive ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = alive ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
         const unsigned p = alive ? rayPath[i] : 0u;
         float3 o = f3(o4), d = f3(d4);
         float tmin = o4.w;
         while (__any_sync(0xffffffffu, alive)) {
             HitRec hit;
-            traverse_warp<false>(sc, 0xffffffffu, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+            if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
+            else traverse_warp<false>(sc, 0xffffffffu, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
             if (alive) {
                 traced++;
                 const int kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
@@ -298,8 +304,8 @@ void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const
                             LaunchCtx lc)
 {
     const int cur = bounce & 1;
-    ppm_camera_tail_kernel<<<148 * 4, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
-                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS);
+    ppm_camera_tail_kernel<<<148 * 4 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
+                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
     ++*lc.launches;
 }
 
@@ -495,20 +501,22 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneVi
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_tail_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf, float4* __restrict__ phPower,
                                                                         unsigned* __restrict__ phState, PhotonBuf photons, const float4* __restrict__ rayO,
                                                                         const float4* __restrict__ rayD, const unsigned* __restrict__ rayPath,
-                                                                        const unsigned* __restrict__ count, unsigned* __restrict__ stat)
+                                                                        const unsigned* __restrict__ count, unsigned* __restrict__ stat, unsigned spread,
+                                                                        unsigned freeRun)
 {
     const unsigned n = *count;
     unsigned traced = 0;
-    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const unsigned i = base + threadIdx.x;
-        bool alive = i < n;
+    for (unsigned base = blockIdx.x * blockDim.x; base / spread < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = (base + threadIdx.x) / spread;
+        bool alive = i < n && (threadIdx.x % spread) == 0;
         const float4 o4 = alive ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = alive ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
         const unsigned t = alive ? rayPath[i] : 0u;
         float3 o = f3(o4), d = f3(d4);
         float tmin = o4.w;
         while (__any_sync(0xffffffffu, alive)) {
             HitRec hit;
-            traverse_warp<false>(sc, 0xffffffffu, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+            if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
+            else traverse_warp<false>(sc, 0xffffffffu, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
             if (alive) {
                 traced++;
                 if (hit.prim < 0) alive = false;   // miss: no-op
@@ -541,8 +549,8 @@ void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, cons
                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc)
 {
     const int cur = bounce & 1;
-    ppm_photon_tail_kernel<<<148 * 8, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
-                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS);
+    ppm_photon_tail_kernel<<<148 * 8 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
+                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
     ++*lc.launches;
 }
 

@@ -252,6 +252,29 @@ OPR_DEV bool traverse_warp(const SceneView& sc, unsigned mask, bool active, cons
     return true;
 }
 
+// No votes: every lane runs at its own pace (for latency-bound kernels with a handful of rays per warp).
+template <bool ANY>
+OPR_DEV bool traverse_free(const SceneView& sc, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
+{
+    hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
+    const float3 idir = safe_inverse_direction(d);
+    const float3 ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+    int2 stack[TRAVERSAL_STACK];
+    int sp = 0;
+    int cur = sc.rootRef;
+    for (;;) {
+        while (cur >= 0) OPR_NODE_STEP(ANY)
+        if (cur == TRAVERSAL_DONE) break;
+        bool found = false;
+        OPR_LEAF_STEP(found)
+        if (ANY && found) return true;
+        OPR_POP(ANY)
+    }
+    if (hit.prim < 0) return false;
+    if (!ANY) hit.prim = __ldg(&sc.leafPrim[hit.prim]);
+    return true;
+}
+
 // Call from possibly divergent code: the lanes that arrive together traverse together.
 template <bool ANY>
 OPR_DEV bool traverse(const SceneView& sc, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)

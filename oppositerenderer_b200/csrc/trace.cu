@@ -83,8 +83,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView 
         if (cur != TRAVERSAL_DONE) {
             bool found = false;
             OPR_LEAF_STEP(found)
-            (void)found;
-            OPR_POP(false)
+            if (found || true) OPR_POP(false)
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, n);
