@@ -408,3 +408,79 @@ def test_path_tracing_parity(product, oracle, scene_name, config, minfrac):
     rs0 = np.zeros((n0, 6), np.uint32)
     o.lib.ora_get_random_states(o.h, rs0.ctypes.data_as(C.c_void_p), 0, n0)
     assert (rs[:n0] == rs0).all(axis=1).mean() > minfrac
+
+
+def _quad(p0, e1, e2, material):
+    p0, e1, e2 = (np.array(t, np.float32) for t in (p0, e1, e2))
+    v = np.stack([p0, p0 + e1, p0 + e1 + e2, p0 + e2]).astype(np.float32)
+    n = np.cross(e1, e2)
+    n = (n / np.linalg.norm(n)).astype(np.float32)
+    return dict(vertices=v, normals=np.tile(n, (4, 1)), uvs=None, tangents=None, bitangents=None, indices=np.array([[0, 1, 2], [0, 2, 3]], np.int32), material=material)
+
+
+def _spot_room(product):
+    """A 4x3x4 box of triangle meshes with an area light, a SPOT light (photon emission only: its direct light factor is 0,
+    helpers/light.h:46-50) and a point light; diffuse, glossy and mirror walls."""
+    from oppositerenderer_b200.renderer import make_material, SceneDescription
+    mats = [make_material(capi.MAT_DIFFUSE, Kd=(0.7, 0.7, 0.7)), make_material(capi.MAT_GLOSSY, Kd=(0.4, 0.3, 0.2), Ks=(0.3, 0.3, 0.3), exponent=20.0),
+            make_material(capi.MAT_MIRROR, Kr=(0.8, 0.8, 0.8)), None]
+    area = product.Light((30, 30, 30), (1.5, 2.99, 1.5), (0, 0, 1), (1, 0, 0))
+    mats[3] = make_material(capi.MAT_DIFFUSE_EMITTER, Kd=(1, 1, 1), power=(30, 30, 30), inverseArea=area.pod.inverseArea)
+    spot = product.Light((40, 35, 30), (0.6, 2.6, 0.6))
+    spot.pod.lightType = capi.LIGHT_SPOT
+    d = np.array([0.5, -1.0, 0.6], np.float32)
+    d /= np.linalg.norm(d)
+    spot.pod.normal = (C.c_float * 3)(*d.tolist())
+    spot.pod.area_or_angle = 0.9
+    point = product.Light((20, 22, 25), (3.2, 1.0, 3.0))
+    meshes = [_quad((0, 0, 0), (0, 0, 4), (4, 0, 0), 0), _quad((0, 3, 0), (4, 0, 0), (0, 0, 4), 0), _quad((0, 0, 4), (0, 3, 0), (4, 0, 0), 1),
+              _quad((0, 0, 0), (0, 3, 0), (0, 0, 4), 2), _quad((4, 0, 0), (0, 0, 4), (0, 3, 0), 0), _quad((1.5, 2.99, 1.5), (0, 0, 1), (1, 0, 0), 3)]
+    cam = product.Camera(eye=(2, 1.5, -3.5), lookat=(2, 1.4, 2), up=(0, 1, 0), hfov=50, vfov=50, aperture=0.08, aspectRatioMode=product.Camera.KeepHorizontal)
+    return SceneDescription("spotroom", (0, 0, 0), (4, 3, 4), mats, [area, spot, point], meshes=meshes, default_camera=cam)
+
+
+@pytest.mark.parametrize("method,minfrac", [(2, 0.93), (1, 0.90)])
+def test_spot_light_dof_and_wide_launch_parity(product, oracle, method, minfrac):
+    """Three light types incl. SPOT photon emission (PhotonGenerator.cu:73-77), depth of field (camera.h:11-27), an image wider
+    than the photon launch and a photon launch taller than the image (RNG buffer max(1024,W) x max(1024,H) indexing)."""
+    scene = _spot_room(product)
+    cam = scene.getDefaultCamera()
+    W, H, pl, iters = 80, 20, (32, 48), 2
+    cam.setAspectRatio(W / H)
+    r = product.OptixRenderer(photon_launch=pl, vcm_max_path_length=6, seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    o = oracle.OracleRenderer("oracle", pl, 6, util.SEED)
+    o.init_scene(scene.getSceneDescription())
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, W, H, 2.0 / 3.0)
+    odet = oracle.make_details(cam.pod, method, W, H)
+    for i in range(iters):
+        r.renderNextIteration(i, i, 0.3, True, det)
+        o.render_next_iteration(i, i, 0.3, odet)
+    out, out0 = r.getOutputBuffer(), o.output()
+    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
+    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
+    assert frac > minfrac - 0.05 and rel < 4e-2, (frac, rel)
+    rs = r.debug_buffer("random_states", np.uint32, 6 * 80 * 48).reshape(-1, 6)
+    rs0 = np.zeros((80 * 48, 6), np.uint32)
+    o.lib.ora_get_random_states(o.h, rs0.ctypes.data_as(C.c_void_p), 0, 80 * 48)
+    assert (rs == rs0).all(axis=1).mean() > minfrac - 0.05      # every state was advanced exactly as the reference advances it
+
+
+def test_resize_reseeds_like_a_fresh_renderer(product):
+    """OptixRenderer.cpp:534-537, 828-848: a new width/height re-allocates and re-seeds, so the image equals a fresh renderer's."""
+    scene = product.CornellSmall()
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(1.0)
+
+    def run(sizes):
+        r = product.OptixRenderer(photon_launch=(64, 64), seed=util.SEED)
+        r.initialize(product.ComputeDevice(0))
+        r.initScene(scene)
+        for s in sizes:
+            det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, s, s, 2.0 / 3.0)
+            for i in range(2):
+                r.renderNextIteration(i, i, 0.05, True, det)
+        return r.getOutputBuffer().copy()
+    a, b = run([24, 40]), run([40])
+    assert a.shape == (40, 40, 3) and (a.view(np.uint32) == b.view(np.uint32)).all()
