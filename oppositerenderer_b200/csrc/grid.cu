@@ -251,6 +251,8 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
                     __syncwarp();
                     const unsigned cnt = min(32u, end - base);
                     if (need) {
+                        // One branch per photon (the distance test, which rejects ~45 %); the direction test is a select, so an accepted
+                        // photon is a straight run of loads and FMAs with no nested divergence region.
                         #pragma unroll 4
                         for (unsigned j = 0; j < cnt; j++) {
                             const float4 a = sA[w][j];
@@ -258,10 +260,11 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
                             const float distance2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                             if (distance2 <= radius2) {
                                 const float4 b = sB[w][j];
-                                if (fmaf(sC[w][j], nrm.z, fmaf(b.w, nrm.y, a.w * nrm.x)) <= 0.f) {   // dot(-rayDirection, normal) >= 0
-                                    const float weight = fmaf(w1, exp2f_approx(kexp * distance2), w0);
-                                    acc.x = fmaf(b.x, weight, acc.x); acc.y = fmaf(b.y, weight, acc.y); acc.z = fmaf(b.z, weight, acc.z);
-                                }
+                                const float c = sC[w][j];
+                                const float ndot = fmaf(c, nrm.z, fmaf(b.w, nrm.y, a.w * nrm.x));     // dot(-rayDirection, normal) >= 0  <=>  ndot <= 0
+                                float weight = fmaf(w1, exp2f_approx(kexp * distance2), w0);
+                                weight = ndot <= 0.f ? weight : 0.f;                                   // a rejected photon adds an exact zero
+                                acc.x = fmaf(b.x, weight, acc.x); acc.y = fmaf(b.y, weight, acc.y); acc.z = fmaf(b.z, weight, acc.z);
                             }
                         }
                     }
