@@ -69,14 +69,14 @@ int opr_get_stats(opr_renderer* r, uint64_t* out, int n)
 {
     OPR_TRY({
         Renderer& R = r->r;
-        uint64_t v[4] = {0, 0, 0, 0};
-        if (R.buffersAllocated) {
-            auto c = download(R.q.counters + 16, STAT_NUM, R.stream);
-            v[0] = c[STAT_CLOSEST_RAYS]; v[1] = c[STAT_ANY_RAYS];
+        if (R.stats64) {   // totals live on the device (folded after every iteration); trace_closest / trace_any calls add to the 32-bit words
+            auto t = download(R.stats64, STAT_NUM, R.stream);
+            R.stats[STAT_CLOSEST_RAYS] = t[STAT_CLOSEST_RAYS]; R.stats[STAT_ANY_RAYS] = t[STAT_ANY_RAYS];
+            if (R.buffersAllocated) {
+                auto c = download(R.q.counters + CTR_STATS, STAT_NUM, R.stream);
+                R.stats[STAT_CLOSEST_RAYS] += c[STAT_CLOSEST_RAYS]; R.stats[STAT_ANY_RAYS] += c[STAT_ANY_RAYS];
+            }
         }
-        // device counters are 32-bit and accumulate since the last read; fold them into the 64-bit host totals
-        if (R.buffersAllocated) OPR_CUDA_CHECK(cudaMemsetAsync(R.q.counters + 16, 0, STAT_NUM * sizeof(unsigned), R.stream));
-        R.stats[STAT_CLOSEST_RAYS] += v[0]; R.stats[STAT_ANY_RAYS] += v[1];
         uint64_t all[4] = {R.stats[STAT_CLOSEST_RAYS], R.stats[STAT_ANY_RAYS], R.stats[STAT_PHOTONS_STORED], R.launches};
         for (int i = 0; i < n && i < 4; i++) out[i] = all[i];
     })

@@ -68,6 +68,17 @@ OPR_DEV void reset_wave_counters(unsigned* __restrict__ counters, unsigned n)
 static unsigned tail_spread() { static int v = -1; if (v < 0) { const char* e = getenv("OPR_TAIL_SPREAD"); v = e ? atoi(e) : 1; if (v < 1) v = 1; if (v > 32) v = 32; } return (unsigned)v; }
 static unsigned tail_free() { static int v = -1; if (v < 0) { const char* e = getenv("OPR_TAIL_FREE"); v = e ? atoi(e) : 1; } return (unsigned)v; }
 
+// 32-bit per-iteration ray counters -> 64-bit totals (a long render would wrap 32 bits after a few hundred iterations)
+__global__ void stats_fold_kernel(unsigned* __restrict__ c32, unsigned long long* __restrict__ t64)
+{
+    const unsigned i = threadIdx.x;
+    if (i < STAT_NUM) { t64[i] += c32[i]; c32[i] = 0u; }
+}
+void launch_stats_fold(unsigned* counters32, unsigned long long* totals64, LaunchCtx lc)
+{
+    stats_fold_kernel<<<1, 32, 0, lc.st>>>(counters32, totals64);
+}
+
 // ---- RNG state init: initRandomStateBuffer (OptixRenderer_SpatialHash.cu:310-317) ---------------------
 __global__ void rng_init_kernel(RngBuf rng, unsigned seed, size_t n)
 {

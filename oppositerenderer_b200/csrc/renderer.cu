@@ -25,7 +25,7 @@ Renderer::~Renderer()
     dfree(phPower); dfree(phState); dfree(photons.a); dfree(photons.b); dfree(photons.c);
     dfree(sorted.a); dfree(sorted.b); dfree(sorted.c);
     dfree(gridKeys[0]); dfree(gridKeys[1]); dfree(gridVals[0]); dfree(gridVals[1]); dfree(gridHist); dfree(sortTmp); dfree(scanTmp);
-    dfree(gridBBox);
+    dfree(gridBBox); dfree(stats64);
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
     scene.release();
     if (bboxEvent) cudaEventDestroy(bboxEvent);
@@ -65,6 +65,8 @@ void Renderer::initialize(int cudaOrdinal)
     dalloc(sortTmp, rs_hist_words((unsigned)N));
     dalloc(scanTmp, scan_tmp_words(PHOTON_GRID_MAX_SIZE + 2));
     dalloc(gridBBox, 8);
+    dalloc(stats64, STAT_NUM);
+    OPR_CUDA_CHECK(cudaMemsetAsync(stats64, 0, STAT_NUM * sizeof(unsigned long long), stream));
     OPR_CUDA_CHECK(cudaMallocHost((void**)&gridBBoxHost, 16 * sizeof(float)));
     OPR_CUDA_CHECK(cudaMemsetAsync(phState, 0, P * sizeof(unsigned), stream));
     initialized = true;
@@ -292,6 +294,7 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber, unsigned 
                                q.counters + CTR_STATS, lc);
     } else
         throw std::runtime_error("unknown RenderMethod");
+    { LaunchCtx lc{stream, &launches}; launch_stats_fold(q.counters + CTR_STATS, stats64, lc); }   // every ray kernel of an iteration runs on `stream`
     OPR_CUDA_CHECK(cudaGetLastError());
 }
 

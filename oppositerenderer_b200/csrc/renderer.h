@@ -119,6 +119,7 @@ struct Renderer {
 
     // statistics / timing
     unsigned long long stats[STAT_NUM] = {0};
+    unsigned long long* stats64 = nullptr;   // device: the per-iteration 32-bit counters are folded in here after every iteration
     unsigned long long launches = 0;
     bool timing = false;
     std::vector<std::pair<std::string, float>> lastTimings;
@@ -160,6 +161,7 @@ struct ScopedTimer {
 // ---- kernel launchers (ppm.cu, trace.cu, grid.cu) -------------------------------------------------------
 struct LaunchCtx { cudaStream_t st; unsigned long long* launches; };
 
+void launch_stats_fold(unsigned* counters32, unsigned long long* totals64, LaunchCtx lc);
 void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc);
 void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc);
 void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc);
