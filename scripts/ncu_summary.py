@@ -73,7 +73,14 @@ def traffic(path, tag):
         rd, wr = float(vals[hdr.index("dram__bytes_read.sum")]), float(vals[hdr.index("dram__bytes_write.sum")])
         ur, uw = rows[1][hdr.index("dram__bytes_read.sum")], rows[1][hdr.index("dram__bytes_write.sum")]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        def metric(name):
+            return float(vals[hdr.index(name)]) if name in hdr else None
         out[key] = {"dram_bytes": rd * scale[ur] + wr * scale[uw], "gpu_time_ms_under_ncu": float(vals[hdr.index("gpu__time_duration.sum")]),
+                    "issue_active_pct": metric("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "l1_data_pipe_wavefronts_pct": metric("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                    "l2_throughput_pct": metric("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                    "dram_throughput_pct": metric("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                    "lanes_per_instruction": metric("smsp__thread_inst_executed_per_inst_executed.ratio"),
                     "source": "profiles/%s (ncu --set full --clock-control none, one launch)" % tag}
     json.dump(out, open("profiles/kernel_traffic.json", "w"), indent=1)
     print(json.dumps(out, indent=1))
