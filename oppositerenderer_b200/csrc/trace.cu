@@ -81,9 +81,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView 
             if (cur >= 0) OPR_NODE_STEP(false)
         }
         if (cur != TRAVERSAL_DONE) {
-            bool found = false;
-            OPR_LEAF_STEP(found)
-            if (found || true) OPR_POP(false)
+            [[maybe_unused]] bool found = false;
+            OPR_LEAF_STEP(found)      // a closest-hit query keeps going after an accepted primitive: hit.t only shrinks the search
+            OPR_POP(false)
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, n);
