@@ -259,6 +259,7 @@ def main():
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline of the dominant kernel
     roof = None
     kernel_ms = {}
+    ray_queue = None
     nprof = 3
     if True:   # every rank renders the same iterations (keeps the partition aligned); rank 0 reports
         r.set_timing(True)
@@ -289,6 +290,10 @@ def main():
                 "grid.build": 36.0 * N + 132.0 * V + 8.0 * ncells,
             }
             acc["grid.build"] = sum(acc.get(k, 0.0) for k in ("grid.bbox", "grid.keys", "grid.sort", "grid.offsets", "grid.reorder"))
+            qc = r.debug_buffer("queue_counts", np.uint32, 34)
+            ray_queue = {"capacity": int(qc[0]), "camera_rays_per_bounce": [int(x) for x in qc[2:18] if x], "photon_rays_per_bounce": [int(x) for x in qc[18:34] if x],
+                         "shadow_rays": int(qc[1]), "shadow_capacity": 4 * px,
+                         "note": "wavefront bounces, then the last entry is what the per-path tail kernel starts from; occupancy = rays / capacity"}
         else:
             rays_it = ((stp["closest_rays"] + stp["any_rays"]) - (st["closest_rays"] + st["any_rays"])) / nprof
             alg = {"vcm.light": 48.0 * rays_it / 2, "vcm.camera": 48.0 * rays_it / 2}
@@ -350,7 +355,7 @@ def main():
                 "e2e": {"value": rays_e2e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.opr_request_details),
                         "d2h_bytes_per_step": W * H * 12, "iterations_per_s": total_steps / e2e_s,
                         "how": "opr_render_next_iteration + opr_get_output_buffer into pinned host memory every step, wall clock, max over ranks"},
-                "gpu_launches": int(st["launches"] - launches0), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": int(st["launches"] - launches0), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ray_queue": ray_queue,
                 "kernel_ms": kernel_ms, "scene": {"triangles": scene.getNumTriangles(), "meshes": scene.getNumMeshes(), "generate_s": t_scene, "init_scene_s": t_init}}
         print(json.dumps(line))
     if world > 1:

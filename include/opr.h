@@ -69,7 +69,8 @@ const char* opr_get_timing_name(opr_renderer* r, int index);
  * "hitpoints" (Hitpoint.h, 64 B x W*H), "photons" (Photon.h, 36 B x 4P, as emitted), "sorted_photons"
  * (36 B x numValid), "photon_keys" (u32 x 4P, sorted), "offsets" (u32 x numCells+1), "indirect", "direct"
  * (float3 x W*H), "random_states" ({d,v0..v4} u32 x 6 per state), "grid" (cellSize, gridSize[3], origo[3],
- * numValid as 8 x 4 bytes), "photon_path_lengths" (u32 x P), "light_vertex_counts" (u32 x W*H). */
+ * numValid as 8 x 4 bytes), "photon_path_lengths" (u32 x P), "light_vertex_counts" (u32 x W*H), "queue_counts" (34 x u32: ray-queue
+ * capacity, shadow rays queued, camera-pass and photon-pass ray counts per bounce of the last PPM iteration). */
 int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t bytes);
 
 /* ---- stand-alone kernels of the path (host buffers in, host buffers out) ------------------------------ */

@@ -158,6 +158,14 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
             auto s = download(R.phState, P, st);
             unsigned* o = (unsigned*)dst;
             for (size_t i = 0; i < P; i++) o[i] = s[i] & 0xffu;
+        } else if (n == "queue_counts") {
+            // ray-queue occupancy of the last PPM iteration: [0] capacity, [1] shadow rays queued, [2..18) camera-pass ray counts per
+            // bounce (snapshot taken when the photon pass reset the counters), [18..34) photon-pass ray counts per bounce
+            need(34 * 4);
+            unsigned* o = (unsigned*)dst;
+            auto c = download(R.q.counters, CTR_ALLOC, st);
+            o[0] = R.q.capacity; o[1] = c[CTR_SHADOW_COUNT];
+            for (int i = 0; i < 16; i++) { o[2 + i] = c[CTR_SNAPSHOT + i]; o[18 + i] = c[CTR_RAYCOUNT + i]; }
         } else if (n == "light_vertex_counts") {
             need(px * 4);
             if (R.debugLightVertexCounts((unsigned*)dst)) throw std::runtime_error("no BDPT iteration has run yet");

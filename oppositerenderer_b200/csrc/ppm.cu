@@ -61,7 +61,10 @@ OPR_DEV float3 getNormalMappedNormal(const float3& normal, const float3& tangent
 OPR_DEV void reset_wave_counters(unsigned* __restrict__ counters, unsigned n)
 {
     if (blockIdx.x == 0)
-        for (unsigned i = CTR_RAYCOUNT + threadIdx.x; i < CTR_TOTAL; i += blockDim.x) counters[i] = (i == CTR_RAYCOUNT) ? n : 0u;
+        for (unsigned i = CTR_RAYCOUNT + threadIdx.x; i < CTR_TOTAL; i += blockDim.x) {
+            if (i < CTR_RAYCOUNT + 16) counters[CTR_SNAPSHOT + (i - CTR_RAYCOUNT)] = counters[i];   // keep the previous pass's queue lengths
+            counters[i] = (i == CTR_RAYCOUNT) ? n : 0u;
+        }
 }
 
 // tail-kernel shape (measurement knobs): rays per warp = 32 / spread; freeRun = lanes traverse without votes

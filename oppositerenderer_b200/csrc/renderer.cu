@@ -121,10 +121,10 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     const size_t cap = std::max(px, (size_t)photonLaunchWidth * photonLaunchHeight);
     q.capacity = (unsigned)cap;
     for (int i = 0; i < 2; i++) { dalloc(q.rayO[i], cap); dalloc(q.rayD[i], cap); dalloc(q.rayPath[i], cap); }
-    dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, CTR_TOTAL);
+    dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, CTR_ALLOC);
     dalloc(indirect, px * 3); dalloc(direct, px * 3); dalloc(output, px * 3);
     dalloc(shadowD, px * 4); dalloc(shadowIdx, px * 4);
-    OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, CTR_TOTAL * sizeof(unsigned), stream));
+    OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, CTR_ALLOC * sizeof(unsigned), stream));
     OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, px * 3 * sizeof(float), stream));
     buffersAllocated = true;
     LaunchCtx lc{stream, &launches};

@@ -20,7 +20,9 @@ constexpr int CTR_FETCH = 192;        // ray-fetch cursor of the persistent trac
 constexpr int CTR_FETCH_LEGACY = 10;
 constexpr int CTR_SHADOW_COUNT = 13;  // shadow-ray queue length of the PPM direct pass
 constexpr int CTR_FETCH_SHADOW = 14;  // its fetch cursor  // same for the ping-pong (VCM) launcher
-constexpr int CTR_TOTAL = 256;
+constexpr int CTR_TOTAL = 256;        // [CTR_RAYCOUNT, CTR_TOTAL) is reset by the generation kernel of every pass
+constexpr int CTR_SNAPSHOT = 256;     // 16 words: the ray counts of the pass before the current one (ray-queue occupancy report)
+constexpr int CTR_ALLOC = 288;
 
 // Wavefront ray queue state (all device pointers)
 struct RayQueues {
