@@ -61,10 +61,7 @@ OPR_DEV float3 getNormalMappedNormal(const float3& normal, const float3& tangent
 OPR_DEV void reset_wave_counters(unsigned* __restrict__ counters, unsigned n)
 {
     if (blockIdx.x == 0)
-        for (unsigned i = CTR_RAYCOUNT + threadIdx.x; i < CTR_TOTAL; i += blockDim.x) {
-            if (i < CTR_RAYCOUNT + 16) counters[CTR_SNAPSHOT + (i - CTR_RAYCOUNT)] = counters[i];   // keep the previous pass's queue lengths
-            counters[i] = (i == CTR_RAYCOUNT) ? n : 0u;
-        }
+        for (unsigned i = CTR_RAYCOUNT + threadIdx.x; i < CTR_TOTAL; i += blockDim.x) counters[i] = (i == CTR_RAYCOUNT) ? n : 0u;
 }
 
 // tail-kernel shape (measurement knobs): rays per warp = 32 / spread; freeRun = lanes traverse without votes
@@ -99,11 +96,14 @@ void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc)
 // ---- camera pass: RayGeneratorPPM::generateRay (ppm/RayGeneratorPPM.cu:31-66) + DOF (helpers/camera.h:11-27)
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_gen_kernel(opr_camera cam, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf,
                                                                        HitpointBuf hp, float4* __restrict__ rayO, float4* __restrict__ rayD,
-                                                                       unsigned* __restrict__ rayPath, unsigned* __restrict__ counters)
+                                                                       unsigned* __restrict__ rayPath, unsigned* __restrict__ counters,
+                                                                       unsigned char* __restrict__ camPending)
 {
     const unsigned n = w * h;
     reset_wave_counters(counters, n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[CTR_TAIL_COUNT] = 0u; counters[CTR_DEFERRED_COUNT] = 0u; }
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        camPending[p] = 0;
         const unsigned x = p % w, y = p / w;
         const size_t ri = (size_t)y * rsW + x;
         Rng rng = rng_load(rngBuf, ri);
@@ -143,7 +143,7 @@ void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsign
 {
     unsigned n = w * h;
     int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
-    ppm_camera_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(cam, w, h, rsW, rng, hp, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters);
+    ppm_camera_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(cam, w, h, rsW, rng, hp, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters, q.camPending);
     ++*lc.launches;
 }
 
@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneVi
                                                                          const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
                                                                          const unsigned* __restrict__ matQueue, const unsigned* __restrict__ matCount,
                                                                          unsigned capacity, float4* __restrict__ nextO, float4* __restrict__ nextD,
-                                                                         unsigned* __restrict__ nextPath, unsigned* __restrict__ nextCount)
+                                                                         unsigned* __restrict__ nextPath, unsigned* __restrict__ nextCount,
+                                                                         unsigned char* __restrict__ pending)
 {
     const int kind = blockIdx.y;
     const unsigned n = matCount[kind];
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneVi
             nextO[dst] = make_float4(newO.x, newO.y, newO.z, 0.0001f);
             nextD[dst] = make_float4(newD.x, newD.y, newD.z, RT_DEFAULT_MAX);
             nextPath[dst] = p;
+            if (pending) pending[p] = 1;     // this pixel's path (and its RNG state) is still in flight: see ppm_photon_gen_kernel
         }
     }
 }
@@ -303,88 +305,121 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_tail_kernel(SceneVie
     if ((threadIdx.x & 31) == 0 && traced) atomicAdd(stat, traced);
 }
 
+// lastWave: the continuation rays go to the dedicated tail queue (and their pixels are flagged), so that the tail kernel can run
+// on its own stream while the photon pass re-uses the ping-pong queues.
 void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
-                             const RayQueues& q, int bounce, LaunchCtx lc)
+                             const RayQueues& q, int bounce, bool lastWave, LaunchCtx lc)
 {
     dim3 grid(SHADE_BLOCKS_X, NUM_QUEUES);
     const int cur = bounce & 1, nxt = cur ^ 1;
-    ppm_camera_shade_kernel<<<grid, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
-                                                               q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.rayO[nxt], q.rayD[nxt], q.rayPath[nxt],
-                                                               q.counters + CTR_RAYCOUNT + bounce + 1);
+    if (lastWave)
+        ppm_camera_shade_kernel<<<grid, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
+                                                                   q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.tailO, q.tailD, q.tailPath,
+                                                                   q.counters + CTR_TAIL_COUNT, q.camPending);
+    else
+        ppm_camera_shade_kernel<<<grid, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
+                                                                   q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.rayO[nxt], q.rayD[nxt], q.rayPath[nxt],
+                                                                   q.counters + CTR_RAYCOUNT + bounce + 1, nullptr);
     ++*lc.launches;
 }
 
-void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, int bounce,
-                            LaunchCtx lc)
+void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, LaunchCtx lc)
 {
-    const int cur = bounce & 1;
-    ppm_camera_tail_kernel<<<148 * 4 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
-                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
+    ppm_camera_tail_kernel<<<148 * 4 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.tailO, q.tailD, q.tailPath,
+                                                                 q.counters + CTR_TAIL_COUNT, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
     ++*lc.launches;
 }
 
 // ---- photon pass: PhotonGenerator::generator (ppm/PhotonGenerator.cu:40-128) ----------------------------
+// Emission of photon thread t: draws from its RNG state (1 light pick if several lights, 2 + 2 for an area light), resets
+// the thread's PhotonPRD (phPower / phState) and returns the first ray.
+OPR_DEV void photon_emit(const SceneView& sc, unsigned t, unsigned pw, unsigned rsW, const RngBuf& rngBuf, float4* __restrict__ phPower,
+                         unsigned* __restrict__ phState, float3& origin, float3& direction)
+{
+    const unsigned x = t % pw, y = t / pw;
+    const size_t ri = (size_t)y * rsW + x;
+    Rng rng = rng_load(rngBuf, ri);
+    int lightIndex = 0;
+    if (sc.numLights > 1) {
+        float sample = rng_uniform(rng);
+        lightIndex = min((int)(sample * sc.numLights), sc.numLights - 1);
+    }
+    const opr_light light = sc.lights[lightIndex];
+    float powerScale = (float)sc.numLights;
+    float3 power = f3(light.power[0], light.power[1], light.power[2]) * powerScale;
+    origin = f3(light.position[0], light.position[1], light.position[2]);
+    direction = f3(0.f);
+    float photonPowerFactor = 1.f;
+    float2 sample1 = rng_uniform2(rng);
+    if (light.lightType == OPR_LIGHT_AREA) {
+        float2 sample2 = rng_uniform2(rng);
+        origin += sample1.x * f3(light.v1[0], light.v1[1], light.v1[2]) + sample1.y * f3(light.v2[0], light.v2[1], light.v2[2]);
+        direction = sampleUnitHemisphere(f3(light.normal[0], light.normal[1], light.normal[2]), sample2);
+    } else if (light.lightType == OPR_LIGHT_POINT) {
+        float3 sceneCenterToLight = origin - sc.boundingSphere.center;
+        float lightDistance = length(sceneCenterToLight);
+        sceneCenterToLight /= lightDistance;
+        bool lightWellOutsideSphere = ((double)lightDistance > 1.5 * (double)sc.boundingSphere.radius);
+        if (lightWellOutsideSphere) {
+            float3 pointOnDisc = sampleDisc(sample1, sc.boundingSphere.center, sc.boundingSphere.radius, sceneCenterToLight);
+            direction = normalize(pointOnDisc - origin);
+            float r = sc.boundingSphere.radius;
+            photonPowerFactor = (1 - lightDistance * (1.0f / sqrtf(r * r + lightDistance * lightDistance))) / 2.f;
+        } else {
+            direction = sampleUnitSphere(sample1);
+        }
+    } else {
+        float3 ldir = f3(light.normal[0], light.normal[1], light.normal[2]);
+        float3 pointOnDisc = sampleDisc(sample1, origin + ldir, sinf(light.area_or_angle / 2), ldir);
+        direction = normalize(pointOnDisc - origin);
+    }
+    power *= photonPowerFactor;
+    rng_store(rngBuf, ri, rng);
+    phPower[t] = make_float4(power.x, power.y, power.z, 1.0f);
+    phState[t] = 0u;    // depth 0, numStoredPhotons 0 (also "clears" the 4 slots this thread owns)
+}
+
+// Photon thread (x, y) shares RNG state (x, y) with pixel (x, y) (OptixRenderer.cpp:368-373) and must start from the state the
+// camera pass leaves behind.  The few pixels whose camera path is still bouncing between specular surfaces (camPending, set by
+// the last wavefront shade of the camera pass) are finished by the camera tail kernel on another stream WHILE this pass runs;
+// their photon threads are deferred to ppm_photon_late_kernel, which follows the tail kernel on that stream.  Every other
+// thread emits here; the rays are appended compactly (one atomic per warp).
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_gen_kernel(SceneView sc, unsigned pw, unsigned ph, unsigned rsW, RngBuf rngBuf,
                                                                        float4* __restrict__ phPower, unsigned* __restrict__ phState,
                                                                        float4* __restrict__ rayO, float4* __restrict__ rayD, unsigned* __restrict__ rayPath,
-                                                                       unsigned* __restrict__ counters)
+                                                                       unsigned* __restrict__ counters, const unsigned char* __restrict__ camPending,
+                                                                       unsigned w, unsigned h, unsigned* __restrict__ deferred)
 {
-    const unsigned n = pw * ph;
-    reset_wave_counters(counters, n);
-    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const unsigned x = t % pw, y = t / pw;
-        const size_t ri = (size_t)y * rsW + x;
-        Rng rng = rng_load(rngBuf, ri);
-        int lightIndex = 0;
-        if (sc.numLights > 1) {
-            float sample = rng_uniform(rng);
-            lightIndex = min((int)(sample * sc.numLights), sc.numLights - 1);
+    const unsigned n = pw * ph;     // the per-bounce counters were zeroed by the launcher: this kernel appends to bounce 0
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned t = base + threadIdx.x;
+        const bool valid = t < n;
+        const unsigned x = valid ? t % pw : 0u, y = valid ? t / pw : 0u;
+        const bool deferredThread = valid && x < w && y < h && camPending[(size_t)y * w + x];
+        const bool emit = valid && !deferredThread;
+        float3 origin = f3(0.f), direction = f3(0.f);
+        if (emit) photon_emit(sc, t, pw, rsW, rngBuf, phPower, phState, origin, direction);
+        const unsigned dst = warp_append(counters + CTR_RAYCOUNT, emit);
+        if (emit) {
+            rayO[dst] = make_float4(origin.x, origin.y, origin.z, 0.0001f);
+            rayD[dst] = make_float4(direction.x, direction.y, direction.z, RT_DEFAULT_MAX);
+            rayPath[dst] = t;
         }
-        const opr_light light = sc.lights[lightIndex];
-        float powerScale = (float)sc.numLights;
-        float3 power = f3(light.power[0], light.power[1], light.power[2]) * powerScale;
-        float3 origin = f3(light.position[0], light.position[1], light.position[2]);
-        float3 direction = f3(0.f);
-        float photonPowerFactor = 1.f;
-        float2 sample1 = rng_uniform2(rng);
-        if (light.lightType == OPR_LIGHT_AREA) {
-            float2 sample2 = rng_uniform2(rng);
-            origin += sample1.x * f3(light.v1[0], light.v1[1], light.v1[2]) + sample1.y * f3(light.v2[0], light.v2[1], light.v2[2]);
-            direction = sampleUnitHemisphere(f3(light.normal[0], light.normal[1], light.normal[2]), sample2);
-        } else if (light.lightType == OPR_LIGHT_POINT) {
-            float3 sceneCenterToLight = origin - sc.boundingSphere.center;
-            float lightDistance = length(sceneCenterToLight);
-            sceneCenterToLight /= lightDistance;
-            bool lightWellOutsideSphere = ((double)lightDistance > 1.5 * (double)sc.boundingSphere.radius);
-            if (lightWellOutsideSphere) {
-                float3 pointOnDisc = sampleDisc(sample1, sc.boundingSphere.center, sc.boundingSphere.radius, sceneCenterToLight);
-                direction = normalize(pointOnDisc - origin);
-                float r = sc.boundingSphere.radius;
-                photonPowerFactor = (1 - lightDistance * (1.0f / sqrtf(r * r + lightDistance * lightDistance))) / 2.f;
-            } else {
-                direction = sampleUnitSphere(sample1);
-            }
-        } else {
-            float3 ldir = f3(light.normal[0], light.normal[1], light.normal[2]);
-            float3 pointOnDisc = sampleDisc(sample1, origin + ldir, sinf(light.area_or_angle / 2), ldir);
-            direction = normalize(pointOnDisc - origin);
-        }
-        power *= photonPowerFactor;
-        rng_store(rngBuf, ri, rng);
-        phPower[t] = make_float4(power.x, power.y, power.z, 1.0f);
-        phState[t] = 0u;    // depth 0, numStoredPhotons 0 (also "clears" the 4 slots this thread owns)
-        rayO[t] = make_float4(origin.x, origin.y, origin.z, 0.0001f);
-        rayD[t] = make_float4(direction.x, direction.y, direction.z, RT_DEFAULT_MAX);
-        rayPath[t] = t;
+        const unsigned dd = warp_append(counters + CTR_DEFERRED_COUNT, deferredThread);
+        if (deferredThread) deferred[dd] = t;
     }
 }
 
 void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsigned rsW, const RngBuf& rng, float4* phPower,
-                           unsigned* phState, const RayQueues& q, LaunchCtx lc)
+                           unsigned* phState, const RayQueues& q, unsigned w, unsigned h, LaunchCtx lc)
 {
     unsigned n = pw * ph;
+    // keep the camera pass's queue lengths for the occupancy report, then zero the per-bounce counters of this pass
+    OPR_CUDA_CHECK(cudaMemcpyAsync(q.counters + CTR_SNAPSHOT, q.counters + CTR_RAYCOUNT, 16 * sizeof(unsigned), cudaMemcpyDeviceToDevice, lc.st));
+    OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_RAYCOUNT, 0, (CTR_TOTAL - CTR_RAYCOUNT) * sizeof(unsigned), lc.st));
     int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
-    ppm_photon_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, pw, ph, rsW, rng, phPower, phState, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters);
+    ppm_photon_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, pw, ph, rsW, rng, phPower, phState, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters,
+                                                               q.camPending, w, h, q.deferred);
     ++*lc.launches;
 }
 
@@ -565,6 +600,42 @@ void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, cons
     const int cur = bounce & 1;
     ppm_photon_tail_kernel<<<148 * 8 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
                                                                  q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
+    ++*lc.launches;
+}
+
+// The deferred photon threads (see ppm_photon_gen_kernel): emission and the whole random walk, one thread per photon.
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_late_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf, float4* __restrict__ phPower,
+                                                                        unsigned* __restrict__ phState, PhotonBuf photons, const unsigned* __restrict__ deferred,
+                                                                        const unsigned* __restrict__ count, unsigned* __restrict__ stat)
+{
+    const unsigned n = *count;
+    unsigned traced = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned t = deferred[i];
+        float3 o, d;
+        photon_emit(sc, t, pw, rsW, rngBuf, phPower, phState, o, d);
+        float tmin = 0.0001f;
+        for (;;) {
+            HitRec hit;
+            traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit);
+            traced++;
+            if (hit.prim < 0) break;   // miss: no-op
+            const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+            float3 newO = f3(0.f), newD = f3(0.f);
+            float newTmin;
+            if (!shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin)) break;
+            o = newO; d = newD; tmin = newTmin;
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, s);
+    if ((threadIdx.x & 31) == 0 && traced) atomicAdd(stat, traced);
+}
+
+void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState, const PhotonBuf& photons,
+                            const RayQueues& q, LaunchCtx lc)
+{
+    ppm_photon_late_kernel<<<148 * 4, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.deferred, q.counters + CTR_DEFERRED_COUNT,
+                                                                 q.counters + 16 + STAT_CLOSEST_RAYS);
     ++*lc.launches;
 }
 

@@ -29,8 +29,9 @@ Renderer::~Renderer()
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
     scene.release();
     if (bboxEvent) cudaEventDestroy(bboxEvent);
-    for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone}) if (e) cudaEventDestroy(e);
     if (streamB) cudaStreamDestroy(streamB);
+    if (streamC) cudaStreamDestroy(streamC);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -51,7 +52,9 @@ void Renderer::initialize(int cudaOrdinal)
     OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     OPR_CUDA_CHECK(cudaEventCreateWithFlags(&bboxEvent, cudaEventDisableTiming));
     OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&streamB, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin}) OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&streamC, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone})
+        OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
 
@@ -99,6 +102,7 @@ void Renderer::freeBuffers()
     hpFreePending[0] = hpFreePending[1] = gridDonePending = false;
     for (int i = 0; i < 2; i++) { dfree(q.rayO[i]); dfree(q.rayD[i]); dfree(q.rayPath[i]); }
     dfree(q.hits); dfree(q.matQueue); dfree(q.counters);
+    dfree(q.tailO); dfree(q.tailD); dfree(q.tailPath); dfree(q.camPending); dfree(q.deferred);
     dfree(indirect); dfree(direct); dfree(output);
     dfree(shadowD); dfree(shadowIdx);
     buffersAllocated = false;
@@ -108,6 +112,7 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
 {   // OptixRenderer.cpp:828-848
     OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
     if (streamB) OPR_CUDA_CHECK(cudaStreamSynchronize(streamB));
+    if (streamC) OPR_CUDA_CHECK(cudaStreamSynchronize(streamC));
     freeBuffers();
     const size_t px = (size_t)w * h;
     rsW = std::max(photonLaunchWidth, w); rsH = std::max(photonLaunchHeight, h);
@@ -122,6 +127,8 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     q.capacity = (unsigned)cap;
     for (int i = 0; i < 2; i++) { dalloc(q.rayO[i], cap); dalloc(q.rayD[i], cap); dalloc(q.rayPath[i], cap); }
     dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, CTR_ALLOC);
+    dalloc(q.tailO, px); dalloc(q.tailD, px); dalloc(q.tailPath, px); dalloc(q.camPending, px);
+    dalloc(q.deferred, (size_t)photonLaunchWidth * photonLaunchHeight);
     dalloc(indirect, px * 3); dalloc(direct, px * 3); dalloc(output, px * 3);
     dalloc(shadowD, px * 4); dalloc(shadowIdx, px * 4);
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, CTR_ALLOC * sizeof(unsigned), stream));
@@ -205,16 +212,20 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     const unsigned pb = parity;
     hp = hpBuf[pb]; sampleFactor = sampleFactorBuf[pb]; sampleLight = sampleLightBuf[pb];
     if (hpFreePending[pb]) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evHpFree[pb], 0)); hpFreePending[pb] = false; }
-    // ---- PPM_RAYTRACE_PASS (:576): wavefront bounces, then one per-path tail kernel for the specular continuations
+    // ---- PPM_RAYTRACE_PASS (:576): wavefront bounces on `stream`; the specular continuations go to the tail queue, which a
+    // per-path tail kernel finishes on stream C while the photon wavefronts run (the photon threads whose RNG state those
+    // pixels still hold are deferred behind it: ppm_photon_gen_kernel)
+    const cudaStream_t stC = sC();
+    LaunchCtx lcC{stC, &launches};
     {
         ScopedTimer t(*this, "ppm.camera");
         { ScopedTimer tg(*this, "camera.gen"); launch_ppm_camera_gen(details.camera, width, height, rsW, rng, hp, q, lc); }
-        const unsigned waves = std::min(cameraWaveBounces, MAX_RADIANCE_TRACE_DEPTH + 1);
+        const unsigned waves = std::max(1u, std::min(cameraWaveBounces, MAX_RADIANCE_TRACE_DEPTH + 1));
         for (unsigned bounce = 0; bounce < waves; bounce++) {
             { ScopedTimer t0(*this, bounce == 0 ? "trace.camera0" : "trace.camera1+"); launch_trace_closest_bounce(sc, q, bounce, lc); }
-            { ScopedTimer t0(*this, bounce == 0 ? "shade.camera0" : "shade.camera1+"); launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, bounce, lc); }
+            { ScopedTimer t0(*this, bounce == 0 ? "shade.camera0" : "shade.camera1+"); launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, bounce, bounce + 1 == waves, lc); }
         }
-        if (waves <= MAX_RADIANCE_TRACE_DEPTH) { ScopedTimer t1(*this, "ppm.camera_tail"); launch_ppm_camera_tail(sc, width, rsW, rng, hp, q, waves, lc); }
+        OPR_CUDA_CHECK(cudaEventRecord(evCameraWaves, stream));
     }
     const float ppmRadiusSquared = PPMRadius * PPMRadius;   // :585
     // ---- PPM_PHOTON_PASS (:612)
@@ -222,7 +233,14 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         ScopedTimer t(*this, "ppm.photon");
         // the previous iteration's grid build (stream B) must be done reading the photon slots before they are overwritten
         if (gridDonePending) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evGridDone, 0)); gridDonePending = false; }
-        { ScopedTimer tg(*this, "photon.gen"); launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, lc); }
+        { ScopedTimer tg(*this, "photon.gen"); launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, width, height, lc); }
+        OPR_CUDA_CHECK(cudaEventRecord(evPhotonGen, stream));
+        // stream C: camera tail, then the deferred photon threads
+        OPR_CUDA_CHECK(cudaStreamWaitEvent(stC, evCameraWaves, 0));
+        { ScopedTimer t1(*this, "ppm.camera_tail", stC); launch_ppm_camera_tail(sc, width, rsW, rng, hp, q, lcC); }
+        OPR_CUDA_CHECK(cudaStreamWaitEvent(stC, evPhotonGen, 0));
+        { ScopedTimer t1(*this, "ppm.photon_late", stC); launch_ppm_photon_late(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, lcC); }
+        OPR_CUDA_CHECK(cudaEventRecord(evTailDone, stC));
         const unsigned waves = std::min(photonWaveBounces, MAX_PHOTON_TRACE_DEPTH + 1);
         static const char* tn[] = {"trace.photon0", "trace.photon1", "trace.photon2", "trace.photon3", "trace.photon4+"};
         static const char* sn[] = {"shade.photon0", "shade.photon1", "shade.photon2", "shade.photon3", "shade.photon4+"};
@@ -234,6 +252,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
             ScopedTimer t1(*this, "ppm.photon_tail");
             launch_ppm_photon_tail(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, waves, lc);
         }
+        OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evTailDone, 0));   // hit points, RNG states and photons of the deferred paths are complete
     }
     // ---- photon bounding box (first step of createUniformGridPhotonMap, :628), result in flight to the host
     photonBBoxAsync();

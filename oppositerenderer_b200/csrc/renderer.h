@@ -22,6 +22,8 @@ constexpr int CTR_SHADOW_COUNT = 13;  // shadow-ray queue length of the PPM dire
 constexpr int CTR_FETCH_SHADOW = 14;  // its fetch cursor  // same for the ping-pong (VCM) launcher
 constexpr int CTR_TOTAL = 256;        // [CTR_RAYCOUNT, CTR_TOTAL) is reset by the generation kernel of every pass
 constexpr int CTR_SNAPSHOT = 256;     // 16 words: the ray counts of the pass before the current one (ray-queue occupancy report)
+constexpr int CTR_TAIL_COUNT = 272;    // camera tail queue length (outside the per-pass reset range: the tail runs on its own stream)
+constexpr int CTR_DEFERRED_COUNT = 273; // photon threads deferred behind the camera tail
 constexpr int CTR_ALLOC = 288;
 
 // Wavefront ray queue state (all device pointers)
@@ -31,7 +33,9 @@ struct RayQueues {
     unsigned* rayPath[2];   // owning path (pixel / photon thread / subpath) of each ray slot
     float4* hits;           // HitRec per ray slot of the current queue
     unsigned* matQueue;     // NUM_QUEUES x capacity ray-slot indices, bucketed by material kind
-    unsigned* counters;     // CTR_TOTAL words; VCM passes still use [0],[1] ray counts (ping-pong) + [2..2+NUM_QUEUES) material counts
+    // camera tail (specular continuations after the last wavefront bounce) and the photon threads deferred behind it
+    float4* tailO; float4* tailD; unsigned* tailPath; unsigned char* camPending; unsigned* deferred;
+    unsigned* counters;     // CTR_ALLOC words; VCM passes still use [0],[1] ray counts (ping-pong) + [2..2+NUM_QUEUES) material counts
     unsigned capacity;
 };
 
@@ -82,6 +86,10 @@ struct Renderer {
     cudaEvent_t evGridDone = nullptr;               // stream B finished reading `photons` / phState
     cudaEvent_t evDirectDone = nullptr;             // stream A finished the light samples of this iteration
     cudaEvent_t evJoin = nullptr;
+    // third stream: the camera tail and the photon threads deferred behind it run while `stream` traces the photon wavefronts
+    cudaStream_t streamC = nullptr;
+    cudaEvent_t evCameraWaves = nullptr, evPhotonGen = nullptr, evTailDone = nullptr;
+    cudaStream_t sC() const { return overlap ? streamC : stream; }
     bool hpFreePending[2] = {false, false}, gridDonePending = false, workOnB = false;
     cudaStream_t sB() const { return overlap ? streamB : stream; }
     void joinStreams();                   // later work on `stream` is ordered after everything queued on stream B
@@ -173,11 +181,12 @@ void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4*
 void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                            const RayQueues& q, LaunchCtx lc);
 void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
-                             const RayQueues& q, int bounce, LaunchCtx lc);
-void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, int bounce,
-                            LaunchCtx lc);
+                             const RayQueues& q, int bounce, bool lastWave, LaunchCtx lc);
+void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, LaunchCtx lc);
+void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState, const PhotonBuf& photons,
+                            const RayQueues& q, LaunchCtx lc);
 void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsigned rsW, const RngBuf& rng, float4* phPower,
-                           unsigned* phState, const RayQueues& q, LaunchCtx lc);
+                           unsigned* phState, const RayQueues& q, unsigned w, unsigned h, LaunchCtx lc);
 void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
                              const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
 void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
