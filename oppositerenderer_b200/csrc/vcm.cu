@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_gen_kernel(SceneView sc
 }
 
 // vcmClosestHitLight + lightHit (vcm.h:210-309) + connectCameraT1 (vcm.h:65-161) + sampleScattering
-__global__ void __launch_bounds__(VCM_THREADS) vcm_light_shade_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B, float* __restrict__ output,
+__global__ void __launch_bounds__(VCM_THREADS, 6) vcm_light_shade_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B, float* __restrict__ output,
                                                                       const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
                                                                       const unsigned* __restrict__ matQueue, const unsigned* __restrict__ matCount, unsigned capacity,
