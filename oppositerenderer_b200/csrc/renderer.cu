@@ -48,6 +48,8 @@ void Renderer::initialize(int cudaOrdinal)
     // tuning knobs (measurement only; results do not depend on them)
     if (const char* e = getenv("OPR_CAMERA_WAVES")) cameraWaveBounces = (unsigned)std::max(0, atoi(e));
     if (const char* e = getenv("OPR_PHOTON_WAVES")) photonWaveBounces = (unsigned)std::max(0, atoi(e));
+    if (const char* e = getenv("OPR_VCM_LIGHT_WAVES")) vcmLightWaveBounces = (unsigned)std::max(1, atoi(e));
+    if (const char* e = getenv("OPR_VCM_CAMERA_WAVES")) vcmCameraWaveBounces = (unsigned)std::max(1, atoi(e));
     OPR_CUDA_CHECK(cudaSetDevice(device));
     OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     OPR_CUDA_CHECK(cudaEventCreateWithFlags(&bboxEvent, cudaEventDisableTiming));

@@ -61,7 +61,7 @@ struct Renderer {
     unsigned photonLaunchWidth = 1024, photonLaunchHeight = 1024;
     unsigned vcmMaxPathLength = 10;
     // wavefront bounces before the per-path tail kernels take over (camera: specular chains only; photons: after RR starts)
-    unsigned cameraWaveBounces = 1, photonWaveBounces = 4;
+    unsigned cameraWaveBounces = 1, photonWaveBounces = 4, vcmLightWaveBounces = 4, vcmCameraWaveBounces = 6;
     unsigned seed = 1645301512u;
 
     bool initialized = false, sceneLoaded = false;

@@ -78,6 +78,14 @@ OPR_DEV float pdfWtoA(const float aPdfW, const float aDist, const float aCosTher
 // traversal, full warps) adds the contributions of the unoccluded segments.  Testing occlusion inside the shading threads
 // ran the traversal with 5 of 32 lanes (profiles/r1i).  Segments shorter than 3 EPS_RAY are unoccluded by definition (:48).
 struct Connection { float3 dir; float tmax; float3 contrib; };
+// isOccluded tested in place (tail kernels: a handful of paths, nothing to compact)
+OPR_DEV bool vcm_occluded_inline(const SceneView& sc, const float3& p, const float3& d, float tmax, unsigned& shadowRays)
+{
+    if (tmax < 3.f * EPS_RAY) return false;
+    HitRec hit;
+    shadowRays++;
+    return traverse_free<true>(sc, p, d, EPS_RAY, tmax - 2.f * EPS_RAY, hit);
+}
 OPR_DEV void warp_flush_connections(const VcmBuffers& B, const float3& origin, unsigned target, const Connection* c, unsigned n)
 {   // must be reached by all 32 lanes
     const unsigned lane = threadIdx.x & 31;
@@ -251,7 +259,104 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_gen_kernel(SceneView sc
     }
 }
 
-// vcmClosestHitLight + lightHit (vcm.h:210-309) + connectCameraT1 (vcm.h:65-161) + sampleScattering
+// vcmClosestHitLight + lightHit (vcm.h:210-309) + connectCameraT1 (vcm.h:65-161) + sampleScattering for ONE hit of light path p.
+// DEFER = true (wavefront kernels): the camera connection is recorded in `conn`; false (tail kernel): tested in place.
+// Returns true when a continuation ray (newO, newD) must be traced.
+template <bool DEFER>
+OPR_DEV bool vcm_light_hit(const SceneView& sc, const VcmParams& P, const RngBuf& rngBuf, const VcmBuffers& B, float* __restrict__ output, int kind, unsigned p,
+                           const float3& o, const float3& d, const HitRec& hit, float3& newO, float3& newD, Connection& conn, unsigned& numConn,
+                           unsigned& connTarget, float3& connOrigin, unsigned& shadowRays)
+{
+    bool push = false;
+    const Surface sf = eval_surface(sc, hit, o, d);
+    const DMaterial& m = sc.materials[sf.material];
+    VcmBSDF bsdf; float3 hitNormal, albedo;
+    if (vcm_build_bsdf(m, kind, sf, d, true, bsdf, hitNormal, albedo)) {
+        const float3 hitPoint = o + hit.t * d;
+        float4 t4 = B.thr[p], m4 = B.mis[p];
+        float3 throughput = f3(t4);
+        unsigned depth = __float_as_uint(t4.w);
+        float dVCM = m4.x, dVC = m4.y, dVM = m4.z;
+        depth++;
+        const float cosThetaIn = dot(hitNormal, -d);
+        bool done = false;
+        if (cosThetaIn < EPS_COSINE) done = true;
+        if (!done) {
+            mis_on_hit(dVCM, dVC, dVM, cosThetaIn, hit.t);
+            const bool isBsdfSpecular = bsdf.isSpecular();
+            if (!isBsdfSpecular) {
+                const unsigned k = B.lvCount[p];
+                B.lvCount[p] = k + 1;
+                if (!P.estimatePass) {
+                    const size_t vs = (size_t)k * B.paths + p;
+                    B.lv0[vs] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, dVCM);
+                    B.lv1[vs] = make_float4(throughput.x, throughput.y, throughput.z, dVC);
+                    B.lv2[vs] = make_float4(bsdf.geometricNormal.x, bsdf.geometricNormal.y, bsdf.geometricNormal.z, dVM);
+                    B.lv3[vs] = make_float4(bsdf.localDirFix.x, bsdf.localDirFix.y, bsdf.localDirFix.z, __int_as_float(kind));
+                    B.lv4[vs] = make_float4(albedo.x, albedo.y, albedo.z, m.exponent);
+                    B.lv5[vs] = make_float4(m.Ks.x, m.Ks.y, m.Ks.z, __uint_as_float(depth));
+                    // ---- connectCameraT1
+                    const float3 eye = f3(P.camera.eye[0], P.camera.eye[1], P.camera.eye[2]);
+                    const float3 lookdir = f3(P.camera.lookdir[0], P.camera.lookdir[1], P.camera.lookdir[2]);
+                    float3 dirToCamera = eye - hitPoint;
+                    if (!(dot(lookdir, -dirToCamera) <= 0.f)) {
+                        const float distance = length(dirToCamera);
+                        dirToCamera /= distance;
+                        const float cosAtCamera = dot(normalize(lookdir), -dirToCamera);
+                        const float imagePointToCameraDist = length(lookdir) / cosAtCamera;
+                        const float3 imagePlanePointWorld = eye + (-dirToCamera * imagePointToCameraDist);
+                        const float3 imagePlaneCenterWorld = eye + lookdir;
+                        const float3 c2p = imagePlanePointWorld - imagePlaneCenterWorld;
+                        const float3 unitCameraU = normalize(f3(P.camera.camera_u[0], P.camera.camera_u[1], P.camera.camera_u[2]));
+                        const float3 unitCameraV = normalize(f3(P.camera.camera_v[0], P.camera.camera_v[1], P.camera.camera_v[2]));
+                        const float pu = dot(c2p, unitCameraU), pv = dot(c2p, unitCameraV);
+                        const float ipx = P.camera.imagePlaneSize[0], ipy = P.camera.imagePlaneSize[1];
+                        if (2.f * fabsf(pu) < ipx && 2.f * fabsf(pv) < ipy) {
+                            const float pcx = (pu + 0.5f * ipx) / ipx, pcy = (pv + 0.5f * ipy) / ipy;
+                            unsigned px = (unsigned)(pcx * P.w), py = (unsigned)(pcy * P.h);
+                            px = min(px, P.w - 1); py = min(py, P.h - 1);
+                            float cosToCamera = 0.f, bsdfDirPdfW, bsdfRevPdfW;
+                            const float3 bsdfFactor = bsdf.vcmF(dirToCamera, cosToCamera, &bsdfDirPdfW, &bsdfRevPdfW);
+                            if (!isZero(bsdfFactor)) {
+                                bsdfRevPdfW *= bsdf.contProb;
+                                const float imageToSolidAngleFactor = sqr(imagePointToCameraDist) / cosAtCamera;
+                                const float pixelArea = P.pixelSizeFactor.x * ipx * P.pixelSizeFactor.x * ipy;   // sic: .x twice (vcm.h:126)
+                                const float imageSamplePdfA = 1.f / pixelArea;
+                                const float cameraPdfW = imageSamplePdfA * imageToSolidAngleFactor;
+                                const float cameraPdfA = cameraPdfW * fabsf(cosToCamera) / sqr(distance);
+                                const float wLight = (cameraPdfA / P.lightSubpathCount) * (P.misVmWeightFactor + dVCM + dVC * bsdfRevPdfW);
+                                const float misWeight = 1.f / (wLight + 1.f);
+                                const float cameraPdfAConvertedToImagePdfA = 1.f / cameraPdfA;
+                                const float3 contrib = misWeight * throughput * bsdfFactor / (P.lightSubpathCount * cameraPdfAConvertedToImagePdfA);
+                                if (distance < 3.f * EPS_RAY || (!DEFER && !vcm_occluded_inline(sc, hitPoint, dirToCamera, distance, shadowRays))) {
+                                    // the reference's splat is a plain, racy += (vcm.h:159); atomics here
+                                    float* op = output + 3 * ((size_t)py * P.w + px);
+                                    atomicAdd(op, contrib.x); atomicAdd(op + 1, contrib.y); atomicAdd(op + 2, contrib.z);
+                                } else if (DEFER) {
+                                    conn.dir = dirToCamera; conn.tmax = distance - 2.f * EPS_RAY; conn.contrib = contrib;
+                                    numConn = 1; connTarget = py * P.w + px; connOrigin = hitPoint;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (P.maxPathLen < depth + 2) done = true;
+            if (!done) {
+                const size_t ri = (size_t)(p / P.w) * P.rsW + (p % P.w);
+                Rng rng = rng_load(rngBuf, ri);
+                newO = o; newD = d;
+                push = vcm_sample_scattering(bsdf, rng, P, throughput, dVCM, dVC, dVM, hitPoint, newO, newD);
+                rng_store(rngBuf, ri, rng);
+            }
+        }
+        B.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(depth));
+        B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
+    }
+    return push;
+}
+
+// wavefront shading of one light-pass bounce, one material kind per blockIdx.y
 __global__ void __launch_bounds__(VCM_THREADS, 6) vcm_light_shade_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B, float* __restrict__ output,
                                                                       const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
@@ -268,98 +373,14 @@ __global__ void __launch_bounds__(VCM_THREADS, 6) vcm_light_shade_kernel(SceneVi
         bool push = false;
         float3 newO = f3(0.f), newD = f3(0.f);
         unsigned p = 0;
-        Connection conn; unsigned numConn = 0, connTarget = 0; float3 connOrigin = f3(0.f);
+        Connection conn; unsigned numConn = 0, connTarget = 0, shadowRays = 0; float3 connOrigin = f3(0.f);
         if (qi < n) {
             const unsigned slot = queue[qi];
             p = rayPath[slot];
             const float4 o4 = rayO[slot], d4 = rayD[slot], h4 = hits[slot];
             const float3 o = f3(o4), d = f3(d4);
             HitRec hit; hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
-            const Surface sf = eval_surface(sc, hit, o, d);
-            const DMaterial& m = sc.materials[sf.material];
-            VcmBSDF bsdf; float3 hitNormal, albedo;
-            if (vcm_build_bsdf(m, kind, sf, d, true, bsdf, hitNormal, albedo)) {
-                const float3 hitPoint = o + hit.t * d;
-                float4 t4 = B.thr[p], m4 = B.mis[p];
-                float3 throughput = f3(t4);
-                unsigned depth = __float_as_uint(t4.w);
-                float dVCM = m4.x, dVC = m4.y, dVM = m4.z;
-                depth++;
-                const float cosThetaIn = dot(hitNormal, -d);
-                bool done = false;
-                if (cosThetaIn < EPS_COSINE) done = true;
-                if (!done) {
-                    mis_on_hit(dVCM, dVC, dVM, cosThetaIn, hit.t);
-                    const bool isBsdfSpecular = bsdf.isSpecular();
-                    if (!isBsdfSpecular) {
-                        const unsigned k = B.lvCount[p];
-                        B.lvCount[p] = k + 1;
-                        if (!P.estimatePass) {
-                            const size_t vs = (size_t)k * B.paths + p;
-                            B.lv0[vs] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, dVCM);
-                            B.lv1[vs] = make_float4(throughput.x, throughput.y, throughput.z, dVC);
-                            B.lv2[vs] = make_float4(bsdf.geometricNormal.x, bsdf.geometricNormal.y, bsdf.geometricNormal.z, dVM);
-                            B.lv3[vs] = make_float4(bsdf.localDirFix.x, bsdf.localDirFix.y, bsdf.localDirFix.z, __int_as_float(kind));
-                            B.lv4[vs] = make_float4(albedo.x, albedo.y, albedo.z, m.exponent);
-                            B.lv5[vs] = make_float4(m.Ks.x, m.Ks.y, m.Ks.z, __uint_as_float(depth));
-                            // ---- connectCameraT1
-                            const float3 eye = f3(P.camera.eye[0], P.camera.eye[1], P.camera.eye[2]);
-                            const float3 lookdir = f3(P.camera.lookdir[0], P.camera.lookdir[1], P.camera.lookdir[2]);
-                            float3 dirToCamera = eye - hitPoint;
-                            if (!(dot(lookdir, -dirToCamera) <= 0.f)) {
-                                const float distance = length(dirToCamera);
-                                dirToCamera /= distance;
-                                const float cosAtCamera = dot(normalize(lookdir), -dirToCamera);
-                                const float imagePointToCameraDist = length(lookdir) / cosAtCamera;
-                                const float3 imagePlanePointWorld = eye + (-dirToCamera * imagePointToCameraDist);
-                                const float3 imagePlaneCenterWorld = eye + lookdir;
-                                const float3 c2p = imagePlanePointWorld - imagePlaneCenterWorld;
-                                const float3 unitCameraU = normalize(f3(P.camera.camera_u[0], P.camera.camera_u[1], P.camera.camera_u[2]));
-                                const float3 unitCameraV = normalize(f3(P.camera.camera_v[0], P.camera.camera_v[1], P.camera.camera_v[2]));
-                                const float pu = dot(c2p, unitCameraU), pv = dot(c2p, unitCameraV);
-                                const float ipx = P.camera.imagePlaneSize[0], ipy = P.camera.imagePlaneSize[1];
-                                if (2.f * fabsf(pu) < ipx && 2.f * fabsf(pv) < ipy) {
-                                    const float pcx = (pu + 0.5f * ipx) / ipx, pcy = (pv + 0.5f * ipy) / ipy;
-                                    unsigned px = (unsigned)(pcx * P.w), py = (unsigned)(pcy * P.h);
-                                    px = min(px, P.w - 1); py = min(py, P.h - 1);
-                                    float cosToCamera = 0.f, bsdfDirPdfW, bsdfRevPdfW;
-                                    const float3 bsdfFactor = bsdf.vcmF(dirToCamera, cosToCamera, &bsdfDirPdfW, &bsdfRevPdfW);
-                                    if (!isZero(bsdfFactor)) {
-                                        bsdfRevPdfW *= bsdf.contProb;
-                                        const float imageToSolidAngleFactor = sqr(imagePointToCameraDist) / cosAtCamera;
-                                        const float pixelArea = P.pixelSizeFactor.x * ipx * P.pixelSizeFactor.x * ipy;   // sic: .x twice (vcm.h:126)
-                                        const float imageSamplePdfA = 1.f / pixelArea;
-                                        const float cameraPdfW = imageSamplePdfA * imageToSolidAngleFactor;
-                                        const float cameraPdfA = cameraPdfW * fabsf(cosToCamera) / sqr(distance);
-                                        const float wLight = (cameraPdfA / P.lightSubpathCount) * (P.misVmWeightFactor + dVCM + dVC * bsdfRevPdfW);
-                                        const float misWeight = 1.f / (wLight + 1.f);
-                                        const float cameraPdfAConvertedToImagePdfA = 1.f / cameraPdfA;
-                                        const float3 contrib = misWeight * throughput * bsdfFactor / (P.lightSubpathCount * cameraPdfAConvertedToImagePdfA);
-                                        if (distance < 3.f * EPS_RAY) {
-                                            // the reference's splat is a plain, racy += (vcm.h:159); atomics here
-                                            float* op = output + 3 * ((size_t)py * P.w + px);
-                                            atomicAdd(op, contrib.x); atomicAdd(op + 1, contrib.y); atomicAdd(op + 2, contrib.z);
-                                        } else {
-                                            conn.dir = dirToCamera; conn.tmax = distance - 2.f * EPS_RAY; conn.contrib = contrib;
-                                            numConn = 1; connTarget = py * P.w + px; connOrigin = hitPoint;
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (P.maxPathLen < depth + 2) done = true;
-                    if (!done) {
-                        const size_t ri = (size_t)(p / P.w) * P.rsW + (p % P.w);
-                        Rng rng = rng_load(rngBuf, ri);
-                        newO = o; newD = d;
-                        push = vcm_sample_scattering(bsdf, rng, P, throughput, dVCM, dVC, dVM, hitPoint, newO, newD);
-                        rng_store(rngBuf, ri, rng);
-                    }
-                }
-                B.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(depth));
-                B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
-            }
+            push = vcm_light_hit<true>(sc, P, rngBuf, B, output, kind, p, o, d, hit, newO, newD, conn, numConn, connTarget, connOrigin, shadowRays);
         }
         warp_flush_connections(B, connOrigin, connTarget, &conn, numConn);
         const unsigned dst = warp_append(nextCount, push);
@@ -407,6 +428,161 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_gen_kernel(VcmParams P
 // vcmClosestHitCamera + cameraHit (vcm.h:527-628): connectLightSourceS1 (:406-488, lightIlluminate helpers/light.h:147-213),
 // connectVertices against the same-index light path (:315-400, :607-615), connectLightSourceS0 on emitters
 // (:493-522, DiffuseEmitter.cu:95-120), sampleScattering.
+// for ONE hit of camera path p.  DEFER as in vcm_light_hit.  Returns true when a continuation ray must be traced.
+template <bool DEFER>
+OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBuf& rngBuf, const VcmBuffers& B, int kind, unsigned p, const float3& o,
+                            const float3& d, const HitRec& hit, float3& newO, float3& newD, Connection* conn, unsigned& numConn, float3& connOrigin,
+                            unsigned& shadowRays)
+{
+    bool push = false;
+    const Surface sf = eval_surface(sc, hit, o, d);
+    const DMaterial& m = sc.materials[sf.material];
+    float4 t4 = B.thr[p], m4 = B.mis[p];
+    float3 throughput = f3(t4);
+    unsigned depth = __float_as_uint(t4.w);
+    float dVCM = m4.x, dVC = m4.y, dVM = m4.z;
+    float3 color = f3(B.color[p]);
+    if (kind == OPR_MAT_DIFFUSE_EMITTER) {
+        depth++;
+        if (!isZero(m.Lemit)) {
+            const float3 worldGeometricNormal = normalize(sf.geometricNormal);
+            if (!(dot(worldGeometricNormal, -d) < 0.f)) {
+                const float lightPickProb = 1.f / sc.numLights;
+                float directPdfA = m.inverseArea;
+                float emissionPdfW = maxf_(0.f, dot(worldGeometricNormal, -d)) * INV_PI_F * m.inverseArea;
+                if (depth == 1) color += throughput * m.Lemit;
+                else {
+                    directPdfA *= lightPickProb; emissionPdfW *= lightPickProb;
+                    const float wCamera = directPdfA * dVCM + emissionPdfW * dVC;
+                    const float misWeight = 1.f / (1.f + wCamera);
+                    color += throughput * misWeight * m.Lemit;
+                }
+            }
+        }
+    } else {
+        VcmBSDF bsdf; float3 hitNormal, albedo;
+        if (vcm_build_bsdf(m, kind, sf, d, false, bsdf, hitNormal, albedo)) {
+            const float3 hitPoint = o + hit.t * d;
+            connOrigin = hitPoint;
+            depth++;
+            const float cosThetaIn = dot(hitNormal, -d);
+            bool done = cosThetaIn < EPS_COSINE;
+            if (!done) {
+                mis_on_hit(dVCM, dVC, dVM, cosThetaIn, hit.t);
+                const bool isBsdfSpecular = bsdf.isSpecular();
+                const size_t ri = (size_t)(p / P.w) * P.rsW + (p % P.w);
+                Rng rng = rng_load(rngBuf, ri);
+                if (!isBsdfSpecular) {
+                    // ---- connectLightSourceS1
+                    int lightIndex = 0;
+                    if (1 < sc.numLights) {
+                        float sample = rng_uniform(rng);
+                        lightIndex = min((int)(sample * sc.numLights), sc.numLights - 1);
+                    }
+                    const opr_light light = sc.lights[lightIndex];
+                    const float lightPickProb = 1.f / sc.numLights;
+                    float emissionPdfW = 0.f, directPdfW = 0.f, cosAtLight = 0.f, distance = 0.f;
+                    float3 dirToLight = f3(0.f), radiance = f3(0.f);
+                    const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
+                    if (light.lightType == OPR_LIGHT_AREA) {
+                        const float2 posRnd = rng_uniform2(rng);
+                        const float3 pointOnLight = lpos + posRnd.x * f3(light.v1[0], light.v1[1], light.v1[2]) + posRnd.y * f3(light.v2[0], light.v2[1], light.v2[2]);
+                        dirToLight = pointOnLight - hitPoint;
+                        distance = length(dirToLight);
+                        dirToLight /= distance;
+                        const float cosThetaLight = dot(f3(light.normal[0], light.normal[1], light.normal[2]), -dirToLight);
+                        if (!(cosThetaLight < EPS_COSINE)) {
+                            directPdfW = light.inverseArea * sqr(distance) / cosThetaLight;
+                            cosAtLight = cosThetaLight;
+                            emissionPdfW = light.inverseArea * cosThetaLight * INV_PI_F;
+                            radiance = f3(light.Lemit[0], light.Lemit[1], light.Lemit[2]);
+                        }
+                    } else if (light.lightType == OPR_LIGHT_POINT) {
+                        dirToLight = lpos - hitPoint;
+                        distance = length(dirToLight);
+                        dirToLight /= distance;
+                        const float lightSceneCenterDistance = length(sc.boundingSphere.center - lpos);
+                        if (sc.boundingSphere.radius < lightSceneCenterDistance) {
+                            const float theta = asinf(sc.boundingSphere.radius / lightSceneCenterDistance);
+                            emissionPdfW = 1.f / (2.f * PI_F * (1.f - cosf(theta)));
+                        } else emissionPdfW = 0.25f * INV_PI_F;
+                        directPdfW = sqr(distance);
+                        cosAtLight = 1.f;
+                        radiance = f3(light.Lemit[0], light.Lemit[1], light.Lemit[2]);
+                    }
+                    if (!isZero(radiance)) {
+                        float bsdfDirPdfW, bsdfRevPdfW, cosToLight = 0.f;
+                        const float3 bsdfFactor = bsdf.vcmF(dirToLight, cosToLight, &bsdfDirPdfW, &bsdfRevPdfW);
+                        if (!isZero(bsdfFactor)) {
+                            const float contiueProb = bsdf.contProb;
+                            bsdfDirPdfW *= light.isDelta ? 0.f : contiueProb;
+                            bsdfRevPdfW *= contiueProb;
+                            const float wLight = bsdfDirPdfW / (lightPickProb * directPdfW);
+                            const float wCamera = (emissionPdfW * cosToLight / (directPdfW * cosAtLight)) * (P.misVmWeightFactor + dVCM + dVC * bsdfRevPdfW);
+                            const float misWeight = 1.f / (wLight + 1.f + wCamera);
+                            const float3 contrib = (misWeight * cosToLight / (lightPickProb * directPdfW)) * (radiance * bsdfFactor);
+                            if (!isZero(contrib)) {
+                                if (distance < 3.f * EPS_RAY || (!DEFER && !vcm_occluded_inline(sc, hitPoint, dirToLight, distance, shadowRays))) color += contrib * throughput;
+                                else if (DEFER) { conn[numConn].dir = dirToLight; conn[numConn].tmax = distance - 2.f * EPS_RAY; conn[numConn].contrib = contrib * throughput; numConn++; }
+                            }
+                        }
+                    }
+                    // ---- connectVertices with the light path of the same index
+                    const unsigned pathIndex = p % P.lightSubpathCount;
+                    const unsigned lightSubpathVertexCount = B.lvCount[pathIndex];
+                    for (unsigned i = 0; i < lightSubpathVertexCount; ++i) {
+                        const size_t vs = (size_t)i * B.paths + pathIndex;
+                        const float4 a0 = B.lv0[vs], a1 = B.lv1[vs];
+                        float3 direction = f3(a0) - hitPoint;
+                        const float dist2 = dot(direction, direction);
+                        const float distance2 = sqrtf(dist2);
+                        direction /= distance2;
+                        float cameraCosTheta = 0.f, cameraBsdfDirPdfW, cameraBsdfRevPdfW;
+                        const float3 cameraBsdfFactor = bsdf.vcmF(direction, cameraCosTheta, &cameraBsdfDirPdfW, &cameraBsdfRevPdfW);
+                        if (isZero(cameraBsdfFactor)) continue;
+                        const float cameraCont = bsdf.contProb;
+                        cameraBsdfDirPdfW *= cameraCont; cameraBsdfRevPdfW *= cameraCont;
+                        // rebuild the light vertex' BSDF from its 96-byte record
+                        const float4 a2 = B.lv2[vs], a3 = B.lv3[vs], a4 = B.lv4[vs], a5 = B.lv5[vs];
+                        VcmBSDF lb;
+                        lb.initLocal(f3(a2), f3(a3), true);
+                        const int lkind = __float_as_int(a3.w);
+                        lb.add(bx_lambertian(f3(a4)));
+                        if (lkind == OPR_MAT_GLOSSY) lb.add(bx_phong(f3(a5), a4.w));
+                        float lightCosTheta = 0.f, lightBsdfDirPdfW, lightBsdfRevPdfW;
+                        const float3 lightBsdfFactor = lb.vcmF(-direction, lightCosTheta, &lightBsdfDirPdfW, &lightBsdfRevPdfW);
+                        if (isZero(lightBsdfFactor)) continue;
+                        const float lightCont = lb.contProb;
+                        lightBsdfDirPdfW *= lightCont; lightBsdfRevPdfW *= lightCont;
+                        const float geometryTerm = lightCosTheta * cameraCosTheta / dist2;
+                        if (geometryTerm < 0.f) continue;
+                        const float cameraBsdfDirPdfA = pdfWtoA(cameraBsdfDirPdfW, distance2, cameraCosTheta);
+                        const float lightBsdfDirPdfA = pdfWtoA(lightBsdfDirPdfW, distance2, lightCosTheta);
+                        const float wLight = cameraBsdfDirPdfA * (P.misVmWeightFactor * 1.f + a0.w + a1.w * lightBsdfRevPdfW);
+                        const float wCamera = lightBsdfDirPdfA * (P.misVmWeightFactor * 1.f + dVCM + dVC * cameraBsdfRevPdfW);
+                        const float misWeight = 1.f / (wLight + 1.f + wCamera);
+                        float3 contrib = geometryTerm * cameraBsdfFactor * lightBsdfFactor * 1.f;
+                        contrib *= misWeight * throughput * f3(a1);
+                        if (distance2 < 3.f * EPS_RAY || (!DEFER && !vcm_occluded_inline(sc, hitPoint, direction, distance2, shadowRays))) color += contrib;
+                        else if (DEFER && numConn < VCM_MAX_CONNECTIONS) { conn[numConn].dir = direction; conn[numConn].tmax = distance2 - 2.f * EPS_RAY; conn[numConn].contrib = contrib; numConn++; }
+                    }
+                }
+                if (P.maxPathLen <= depth) done = true;
+                if (!done) {
+                    newO = o; newD = d;
+                    push = vcm_sample_scattering(bsdf, rng, P, throughput, dVCM, dVC, dVM, hitPoint, newO, newD);
+                }
+                rng_store(rngBuf, ri, rng);
+            }
+        }
+    }
+    B.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(depth));
+    B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
+    B.color[p] = make_float4(color.x, color.y, color.z, 0.f);
+    return push;
+}
+
+// wavefront shading of one camera-pass bounce, one material kind per blockIdx.y
 __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B,
                                                                        const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                        const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
@@ -423,157 +599,14 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView
         bool push = false;
         float3 newO = f3(0.f), newD = f3(0.f);
         unsigned p = 0;
-        Connection conn[VCM_MAX_CONNECTIONS]; unsigned numConn = 0; float3 connOrigin = f3(0.f);
+        Connection conn[VCM_MAX_CONNECTIONS]; unsigned numConn = 0, shadowRays = 0; float3 connOrigin = f3(0.f);
         if (qi < n) {
             const unsigned slot = queue[qi];
             p = rayPath[slot];
             const float4 o4 = rayO[slot], d4 = rayD[slot], h4 = hits[slot];
             const float3 o = f3(o4), d = f3(d4);
             HitRec hit; hit.t = h4.x; hit.prim = __float_as_int(h4.y); hit.u = h4.z; hit.v = h4.w;
-            const Surface sf = eval_surface(sc, hit, o, d);
-            const DMaterial& m = sc.materials[sf.material];
-            float4 t4 = B.thr[p], m4 = B.mis[p];
-            float3 throughput = f3(t4);
-            unsigned depth = __float_as_uint(t4.w);
-            float dVCM = m4.x, dVC = m4.y, dVM = m4.z;
-            float3 color = f3(B.color[p]);
-            if (kind == OPR_MAT_DIFFUSE_EMITTER) {
-                depth++;
-                if (!isZero(m.Lemit)) {
-                    const float3 worldGeometricNormal = normalize(sf.geometricNormal);
-                    if (!(dot(worldGeometricNormal, -d) < 0.f)) {
-                        const float lightPickProb = 1.f / sc.numLights;
-                        float directPdfA = m.inverseArea;
-                        float emissionPdfW = maxf_(0.f, dot(worldGeometricNormal, -d)) * INV_PI_F * m.inverseArea;
-                        if (depth == 1) color += throughput * m.Lemit;
-                        else {
-                            directPdfA *= lightPickProb; emissionPdfW *= lightPickProb;
-                            const float wCamera = directPdfA * dVCM + emissionPdfW * dVC;
-                            const float misWeight = 1.f / (1.f + wCamera);
-                            color += throughput * misWeight * m.Lemit;
-                        }
-                    }
-                }
-            } else {
-                VcmBSDF bsdf; float3 hitNormal, albedo;
-                if (vcm_build_bsdf(m, kind, sf, d, false, bsdf, hitNormal, albedo)) {
-                    const float3 hitPoint = o + hit.t * d;
-                    connOrigin = hitPoint;
-                    depth++;
-                    const float cosThetaIn = dot(hitNormal, -d);
-                    bool done = cosThetaIn < EPS_COSINE;
-                    if (!done) {
-                        mis_on_hit(dVCM, dVC, dVM, cosThetaIn, hit.t);
-                        const bool isBsdfSpecular = bsdf.isSpecular();
-                        const size_t ri = (size_t)(p / P.w) * P.rsW + (p % P.w);
-                        Rng rng = rng_load(rngBuf, ri);
-                        if (!isBsdfSpecular) {
-                            // ---- connectLightSourceS1
-                            int lightIndex = 0;
-                            if (1 < sc.numLights) {
-                                float sample = rng_uniform(rng);
-                                lightIndex = min((int)(sample * sc.numLights), sc.numLights - 1);
-                            }
-                            const opr_light light = sc.lights[lightIndex];
-                            const float lightPickProb = 1.f / sc.numLights;
-                            float emissionPdfW = 0.f, directPdfW = 0.f, cosAtLight = 0.f, distance = 0.f;
-                            float3 dirToLight = f3(0.f), radiance = f3(0.f);
-                            const float3 lpos = f3(light.position[0], light.position[1], light.position[2]);
-                            if (light.lightType == OPR_LIGHT_AREA) {
-                                const float2 posRnd = rng_uniform2(rng);
-                                const float3 pointOnLight = lpos + posRnd.x * f3(light.v1[0], light.v1[1], light.v1[2]) + posRnd.y * f3(light.v2[0], light.v2[1], light.v2[2]);
-                                dirToLight = pointOnLight - hitPoint;
-                                distance = length(dirToLight);
-                                dirToLight /= distance;
-                                const float cosThetaLight = dot(f3(light.normal[0], light.normal[1], light.normal[2]), -dirToLight);
-                                if (!(cosThetaLight < EPS_COSINE)) {
-                                    directPdfW = light.inverseArea * sqr(distance) / cosThetaLight;
-                                    cosAtLight = cosThetaLight;
-                                    emissionPdfW = light.inverseArea * cosThetaLight * INV_PI_F;
-                                    radiance = f3(light.Lemit[0], light.Lemit[1], light.Lemit[2]);
-                                }
-                            } else if (light.lightType == OPR_LIGHT_POINT) {
-                                dirToLight = lpos - hitPoint;
-                                distance = length(dirToLight);
-                                dirToLight /= distance;
-                                const float lightSceneCenterDistance = length(sc.boundingSphere.center - lpos);
-                                if (sc.boundingSphere.radius < lightSceneCenterDistance) {
-                                    const float theta = asinf(sc.boundingSphere.radius / lightSceneCenterDistance);
-                                    emissionPdfW = 1.f / (2.f * PI_F * (1.f - cosf(theta)));
-                                } else emissionPdfW = 0.25f * INV_PI_F;
-                                directPdfW = sqr(distance);
-                                cosAtLight = 1.f;
-                                radiance = f3(light.Lemit[0], light.Lemit[1], light.Lemit[2]);
-                            }
-                            if (!isZero(radiance)) {
-                                float bsdfDirPdfW, bsdfRevPdfW, cosToLight = 0.f;
-                                const float3 bsdfFactor = bsdf.vcmF(dirToLight, cosToLight, &bsdfDirPdfW, &bsdfRevPdfW);
-                                if (!isZero(bsdfFactor)) {
-                                    const float contiueProb = bsdf.contProb;
-                                    bsdfDirPdfW *= light.isDelta ? 0.f : contiueProb;
-                                    bsdfRevPdfW *= contiueProb;
-                                    const float wLight = bsdfDirPdfW / (lightPickProb * directPdfW);
-                                    const float wCamera = (emissionPdfW * cosToLight / (directPdfW * cosAtLight)) * (P.misVmWeightFactor + dVCM + dVC * bsdfRevPdfW);
-                                    const float misWeight = 1.f / (wLight + 1.f + wCamera);
-                                    const float3 contrib = (misWeight * cosToLight / (lightPickProb * directPdfW)) * (radiance * bsdfFactor);
-                                    if (!isZero(contrib)) {
-                                        if (distance < 3.f * EPS_RAY) color += contrib * throughput;
-                                        else { conn[numConn].dir = dirToLight; conn[numConn].tmax = distance - 2.f * EPS_RAY; conn[numConn].contrib = contrib * throughput; numConn++; }
-                                    }
-                                }
-                            }
-                            // ---- connectVertices with the light path of the same index
-                            const unsigned pathIndex = p % P.lightSubpathCount;
-                            const unsigned lightSubpathVertexCount = B.lvCount[pathIndex];
-                            for (unsigned i = 0; i < lightSubpathVertexCount; ++i) {
-                                const size_t vs = (size_t)i * B.paths + pathIndex;
-                                const float4 a0 = B.lv0[vs], a1 = B.lv1[vs];
-                                float3 direction = f3(a0) - hitPoint;
-                                const float dist2 = dot(direction, direction);
-                                const float distance2 = sqrtf(dist2);
-                                direction /= distance2;
-                                float cameraCosTheta = 0.f, cameraBsdfDirPdfW, cameraBsdfRevPdfW;
-                                const float3 cameraBsdfFactor = bsdf.vcmF(direction, cameraCosTheta, &cameraBsdfDirPdfW, &cameraBsdfRevPdfW);
-                                if (isZero(cameraBsdfFactor)) continue;
-                                const float cameraCont = bsdf.contProb;
-                                cameraBsdfDirPdfW *= cameraCont; cameraBsdfRevPdfW *= cameraCont;
-                                // rebuild the light vertex' BSDF from its 96-byte record
-                                const float4 a2 = B.lv2[vs], a3 = B.lv3[vs], a4 = B.lv4[vs], a5 = B.lv5[vs];
-                                VcmBSDF lb;
-                                lb.initLocal(f3(a2), f3(a3), true);
-                                const int lkind = __float_as_int(a3.w);
-                                lb.add(bx_lambertian(f3(a4)));
-                                if (lkind == OPR_MAT_GLOSSY) lb.add(bx_phong(f3(a5), a4.w));
-                                float lightCosTheta = 0.f, lightBsdfDirPdfW, lightBsdfRevPdfW;
-                                const float3 lightBsdfFactor = lb.vcmF(-direction, lightCosTheta, &lightBsdfDirPdfW, &lightBsdfRevPdfW);
-                                if (isZero(lightBsdfFactor)) continue;
-                                const float lightCont = lb.contProb;
-                                lightBsdfDirPdfW *= lightCont; lightBsdfRevPdfW *= lightCont;
-                                const float geometryTerm = lightCosTheta * cameraCosTheta / dist2;
-                                if (geometryTerm < 0.f) continue;
-                                const float cameraBsdfDirPdfA = pdfWtoA(cameraBsdfDirPdfW, distance2, cameraCosTheta);
-                                const float lightBsdfDirPdfA = pdfWtoA(lightBsdfDirPdfW, distance2, lightCosTheta);
-                                const float wLight = cameraBsdfDirPdfA * (P.misVmWeightFactor * 1.f + a0.w + a1.w * lightBsdfRevPdfW);
-                                const float wCamera = lightBsdfDirPdfA * (P.misVmWeightFactor * 1.f + dVCM + dVC * cameraBsdfRevPdfW);
-                                const float misWeight = 1.f / (wLight + 1.f + wCamera);
-                                float3 contrib = geometryTerm * cameraBsdfFactor * lightBsdfFactor * 1.f;
-                                contrib *= misWeight * throughput * f3(a1);
-                                if (distance2 < 3.f * EPS_RAY) color += contrib;
-                                else if (numConn < VCM_MAX_CONNECTIONS) { conn[numConn].dir = direction; conn[numConn].tmax = distance2 - 2.f * EPS_RAY; conn[numConn].contrib = contrib; numConn++; }
-                            }
-                        }
-                        if (P.maxPathLen <= depth) done = true;
-                        if (!done) {
-                            newO = o; newD = d;
-                            push = vcm_sample_scattering(bsdf, rng, P, throughput, dVCM, dVC, dVM, hitPoint, newO, newD);
-                        }
-                        rng_store(rngBuf, ri, rng);
-                    }
-                }
-            }
-            B.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(depth));
-            B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
-            B.color[p] = make_float4(color.x, color.y, color.z, 0.f);
+            push = vcm_camera_hit<true>(sc, P, rngBuf, B, kind, p, o, d, hit, newO, newD, conn, numConn, connOrigin, shadowRays);
         }
         warp_flush_connections(B, connOrigin, p, conn, numConn);
         const unsigned dst = warp_append(nextCount, push);
@@ -584,6 +617,62 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView
         }
     }
     (void)stat;
+}
+
+// ---- tails of the two passes: the paths still alive after the wavefront bounces are finished one thread per path (trace ->
+// material program -> connections tested in place), as in the PPM passes (ppm_camera_tail_kernel): late bounces hold a few per
+// cent of the paths, and a wavefront bounce over them costs three launches whose duration is one ray's dependent-load latency.
+__global__ void __launch_bounds__(VCM_THREADS) vcm_light_tail_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B, float* __restrict__ output,
+                                                                     const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+                                                                     const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
+                                                                     unsigned* __restrict__ stats)
+{
+    const unsigned n = *count;
+    unsigned closest = 0, any = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = rayO[i], d4 = rayD[i];
+        const unsigned p = rayPath[i];
+        float3 o = f3(o4), d = f3(d4);
+        for (;;) {
+            HitRec hit;
+            traverse_free<false>(sc, o, d, RAY_LEN_MIN, RT_DEFAULT_MAX, hit);
+            closest++;
+            if (hit.prim < 0) break;                                              // VCMLightPass.cu:95-98
+            const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+            if (kind == OPR_MAT_DIFFUSE_EMITTER) break;                           // DiffuseEmitter.cu:76-79
+            Connection conn; unsigned numConn = 0, connTarget = 0; float3 connOrigin = f3(0.f), newO = f3(0.f), newD = f3(0.f);
+            if (!vcm_light_hit<false>(sc, P, rngBuf, B, output, kind, p, o, d, hit, newO, newD, conn, numConn, connTarget, connOrigin, any)) break;
+            o = newO; d = newD;
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) { closest += __shfl_xor_sync(0xffffffffu, closest, s); any += __shfl_xor_sync(0xffffffffu, any, s); }
+    if ((threadIdx.x & 31) == 0) { if (closest) atomicAdd(stats + STAT_CLOSEST_RAYS, closest); if (any) atomicAdd(stats + STAT_ANY_RAYS, any); }
+}
+
+__global__ void __launch_bounds__(VCM_THREADS) vcm_camera_tail_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B,
+                                                                      const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+                                                                      const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
+                                                                      unsigned* __restrict__ stats)
+{
+    const unsigned n = *count;
+    unsigned closest = 0, any = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = rayO[i], d4 = rayD[i];
+        const unsigned p = rayPath[i];
+        float3 o = f3(o4), d = f3(d4);
+        for (;;) {
+            HitRec hit;
+            traverse_free<false>(sc, o, d, RAY_LEN_MIN, RT_DEFAULT_MAX, hit);
+            closest++;
+            if (hit.prim < 0) break;                                              // VCMCameraPass.cu:87-90
+            const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+            unsigned numConn = 0; float3 connOrigin = f3(0.f), newO = f3(0.f), newD = f3(0.f);
+            if (!vcm_camera_hit<false>(sc, P, rngBuf, B, kind, p, o, d, hit, newO, newD, nullptr, numConn, connOrigin, any)) break;
+            o = newO; d = newD;
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) { closest += __shfl_xor_sync(0xffffffffu, closest, s); any += __shfl_xor_sync(0xffffffffu, any, s); }
+    if ((threadIdx.x & 31) == 0) { if (closest) atomicAdd(stats + STAT_CLOSEST_RAYS, closest); if (any) atomicAdd(stats + STAT_ANY_RAYS, any); }
 }
 
 // cameraPass epilogue: outputBuffer[launchIndex] += cameraPrd.color (VCMCameraPass.cu:75-78)
@@ -632,7 +721,8 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         vcm_light_gen_kernel<<<blocks, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[0], q.rayD[0], q.rayPath[0]);
         ++launches;
         int cur = 0;
-        for (unsigned bounce = 0; bounce <= P.maxPathLen; bounce++) {
+        const unsigned waves = std::min(vcmLightWaveBounces, P.maxPathLen + 1);
+        for (unsigned bounce = 0; bounce < waves; bounce++) {
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
             launch_trace_closest(sc, q, cur, lc);
@@ -646,6 +736,11 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
                 launch_trace_connect_queue(sc, S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, output, 3, q.counters + CTR_CONN_FETCH,
                                            q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
             cur ^= 1;
+        }
+        if (waves <= P.maxPathLen) {
+            vcm_light_tail_kernel<<<148 * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur,
+                                                                       q.counters + CTR_STATS);
+            ++launches;
         }
     };
 
@@ -667,7 +762,8 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         vcm_camera_gen_kernel<<<blocks, VCM_THREADS, 0, stream>>>(P, rng, B, q.rayO[0], q.rayD[0], q.rayPath[0]);
         ++launches;
         int cur = 0;
-        for (unsigned bounce = 0; bounce <= P.maxPathLen; bounce++) {
+        const unsigned waves = std::min(vcmCameraWaveBounces, P.maxPathLen + 1);
+        for (unsigned bounce = 0; bounce < waves; bounce++) {
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
             launch_trace_closest(sc, q, cur, lc);
@@ -681,6 +777,10 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             launch_trace_connect_queue(sc, S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, (float*)S.color, 4, q.counters + CTR_CONN_FETCH,
                                        q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
             cur ^= 1;
+        }
+        if (waves <= P.maxPathLen) {
+            vcm_camera_tail_kernel<<<148 * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur, q.counters + CTR_STATS);
+            ++launches;
         }
         vcm_accumulate_kernel<<<blocks, VCM_THREADS, 0, stream>>>(B, width * height, output);
         ++launches;
