@@ -484,3 +484,50 @@ def test_resize_reseeds_like_a_fresh_renderer(product):
         return r.getOutputBuffer().copy()
     a, b = run([24, 40]), run([40])
     assert a.shape == (40, 40, 3) and (a.view(np.uint32) == b.view(np.uint32)).all()
+
+
+def _rel_mse(a, b, mask):
+    """relMSE of image a against reference b over the masked pixels (squared error over squared reference, epsilon-regularised)."""
+    ref2 = (b ** 2).sum(-1)
+    return float(np.mean((((a - b) ** 2).sum(-1) / (ref2 + 1e-3 * float(ref2[mask].mean())))[mask]))
+
+
+@pytest.mark.parametrize("method,scene_name,config", [(2, "Cornell", 0), (1, "CornellSmall", 0), (0, "CornellSmall", (1 << 1) | (1 << 9) | (1 << 13))])
+def test_converged_render_within_monte_carlo_noise(product, oracle, method, scene_name, config):
+    """Independent seeds: the distance of a GPU render from oracle renders must be the Monte Carlo noise floor, i.e. the distance
+    between independent oracle renders of the same length (north_star: 'converged relMSE bound below the noise floor').  Three
+    oracle seeds give the floor (largest pairwise relMSE); the GPU render (a fourth seed) must be within 1.5 x of it from every
+    oracle render, and its mean within the oracle means' spread + 2 %.  Pixels that see the emitter directly are left out: the
+    anti-aliased emitter edge has a per-pixel variance hundreds of times that of the rest of the image."""
+    size, pl, iters = 40, (64, 64), 24
+    scene = product.Cornell() if scene_name == "Cornell" else product.CornellSmall(config or None)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(1.0)
+    osc = oracle.BuiltinScene(scene_name, config or 0)
+    r0 = scene.getSceneInitialPPMRadiusEstimate() if scene_name == "Cornell" else 0.05
+    radii = product.ppm_radius_schedule(r0, iters)
+
+    def run_oracle(seed):
+        o = oracle.OracleRenderer("oracle", pl, 8, seed)
+        o.init_scene(osc.desc)
+        det = oracle.make_details(osc.camera(1.0), method, size, size)
+        for i in range(iters):
+            o.render_next_iteration(i, i, radii[i], det)
+        return o.output() / iters
+
+    refs = [run_oracle(s) for s in (1001, 2002, 4004)]
+    r = product.OptixRenderer(photon_launch=pl, vcm_max_path_length=8, seed=3003)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, size, size, 2.0 / 3.0)
+    for i in range(iters):
+        r.renderNextIteration(i, i, radii[i], True, det)
+    g = r.getOutputBuffer() / iters
+    bright = np.max([x.max(-1) for x in refs + [g]], axis=0)
+    mask = bright < 4.0 * float(np.median(bright))
+    assert mask.mean() > 0.9
+    floor = max(_rel_mse(refs[i], refs[j], mask) for i in range(3) for j in range(3) if i != j)
+    ours = max(_rel_mse(g, x, mask) for x in refs)
+    assert ours <= 1.5 * floor + 1e-4, (ours, floor)
+    means = [float(x[mask].mean()) for x in refs]
+    assert min(means) * 0.98 <= float(g[mask].mean()) <= max(means) * 1.02, (float(g[mask].mean()), means)
