@@ -649,7 +649,7 @@ void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, cons
 // ppm_resolve_output_kernel sums the samples exactly as the reference does and accumulates direct + indirect.
 // The one-thread-per-pixel version kept 61 % of its lanes idle in lockstep and ran the four traversals back to back.
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_gen_kernel(SceneView sc, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
-                                                                       float4* __restrict__ sampleFactor, unsigned* __restrict__ sampleLight,
+                                                                       float4* __restrict__ sampleFactor, uint2* __restrict__ sampleLight,
                                                                        float4* __restrict__ shadowD, unsigned* __restrict__ shadowIdx,
                                                                        unsigned* __restrict__ counters)
 {
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_gen_kernel(SceneView
         const float4 pos4 = inImage ? hp.pos[p] : make_float4(0.f, 0.f, 0.f, 0.f);
         const bool diffuse = inImage && (__float_as_uint(pos4.w) & PRD_HIT_NON_SPECULAR);
         float factor[4] = {0.f, 0.f, 0.f, 0.f};
-        unsigned lights = 0u;
+        unsigned lights01 = 0u, lights23 = 0u;      // 16 bits per sample
         float3 rec_position = f3(pos4), rec_normal = f3(0.f);
         size_t ri = 0;
         Rng rng{};
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_gen_kernel(SceneView
                 float sample = rng_uniform(rng);
                 int randomLightIndex = min(int(sample * numLights), numLights - 1);
                 const opr_light& light = sc.lights[randomLightIndex];
-                lights |= (unsigned)randomLightIndex << (8 * shadowSample);
+                if (shadowSample < 2) lights01 |= (unsigned)randomLightIndex << (16 * shadowSample); else lights23 |= (unsigned)randomLightIndex << (16 * (shadowSample - 2));
                 // getLightContribution
                 lightFactor = 1;
                 float3 pointOnLight = f3(0.f);
@@ -711,12 +711,12 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_gen_kernel(SceneView
             }
         }
         if (diffuse) rng_store(rngBuf, ri, rng);
-        if (inImage) { sampleFactor[p] = make_float4(factor[0], factor[1], factor[2], factor[3]); sampleLight[p] = lights; }
+        if (inImage) { sampleFactor[p] = make_float4(factor[0], factor[1], factor[2], factor[3]); sampleLight[p] = make_uint2(lights01, lights23); }
     }
 }
 
 __global__ void __launch_bounds__(256) ppm_resolve_output_kernel(SceneView sc, unsigned n, HitpointBuf hp, const float4* __restrict__ sampleFactor,
-                                                                 const unsigned* __restrict__ sampleLight, const float* __restrict__ indirect,
+                                                                 const uint2* __restrict__ sampleLight, const float* __restrict__ indirect,
                                                                  float* __restrict__ direct, float* __restrict__ output, unsigned localIteration)
 {
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
@@ -730,12 +730,12 @@ __global__ void __launch_bounds__(256) ppm_resolve_output_kernel(SceneView sc, u
             const float3 attenuation = f3(hp.att[p]);
             const float4 f4 = sampleFactor[p];
             const float factor[4] = {f4.x, f4.y, f4.z, f4.w};
-            const unsigned lights = sampleLight[p];
+            const uint2 lights = sampleLight[p];
             const float scale = (float)sc.numLights;
             float3 avgLightRadiance = f3(0.f);
             #pragma unroll
             for (int s = 0; s < 4; s++) {
-                const opr_light& light = sc.lights[(lights >> (8 * s)) & 0xffu];
+                const opr_light& light = sc.lights[((s < 2 ? lights.x : lights.y) >> (16 * (s & 1))) & 0xffffu];
                 const float3 lightContrib = f3(light.power[0], light.power[1], light.power[2]) * factor[s];
                 avgLightRadiance += scale * lightContrib;
             }
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(256) ppm_resolve_output_kernel(SceneView sc, u
 }
 
 void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, float4* sampleFactor,
-                           unsigned* sampleLight, float4* shadowD, unsigned* shadowIdx, unsigned* counters, LaunchCtx lc)
+                           uint2* sampleLight, float4* shadowD, unsigned* shadowIdx, unsigned* counters, LaunchCtx lc)
 {
     unsigned n = w * h;
     OPR_CUDA_CHECK(cudaMemsetAsync(counters + CTR_SHADOW_COUNT, 0, sizeof(unsigned), lc.st));
@@ -760,7 +760,7 @@ void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned
     ++*lc.launches;
 }
 
-void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const unsigned* sampleLight,
+void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const uint2* sampleLight,
                                const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc)
 {
     int blocks = (int)std::min<unsigned>((n + 255) / 256, 148 * 16);

@@ -111,9 +111,9 @@ struct Renderer {
     // radiance
     // direct lighting: per-pixel light samples + compacted shadow-ray queue (4 slots per pixel)
     float4* sampleFactor = nullptr;       // un-occluded light factor of the four samples; occluded ones are cleared by the trace
-    unsigned* sampleLight = nullptr;      // light index of the four samples, one byte each
+    uint2* sampleLight = nullptr;         // light index of the four samples, 16 bits each
     float4* sampleFactorBuf[2] = {nullptr, nullptr};
-    unsigned* sampleLightBuf[2] = {nullptr, nullptr};
+    uint2* sampleLightBuf[2] = {nullptr, nullptr};
     float4* shadowD = nullptr;            // direction.xyz, tmax
     unsigned* shadowIdx = nullptr;        // 4 * pixel + sample
     cudaEvent_t bboxEvent = nullptr;      // photon bbox + count landed in pinned host memory
@@ -192,14 +192,14 @@ void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, con
 void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
 void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, float4* sampleFactor,
-                           unsigned* sampleLight, float4* shadowD, unsigned* shadowIdx, unsigned* counters, LaunchCtx lc);
+                           uint2* sampleLight, float4* shadowD, unsigned* shadowIdx, unsigned* counters, LaunchCtx lc);
 void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
                                float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
 void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                             float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc);
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
                                 unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
-void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const unsigned* sampleLight,
+void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const uint2* sampleLight,
                                const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc);
 
 void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc);

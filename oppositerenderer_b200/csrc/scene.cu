@@ -40,6 +40,7 @@ void DeviceScene::load(const opr_scene_desc* d, cudaStream_t st)
 {
     release();
     if (d->numLights <= 0) throw std::runtime_error("No lights exists in this scene.");   // OptixRenderer.cpp:443-447
+    if (d->numLights > 65535) throw std::runtime_error("more than 65535 lights: the direct-light sample records hold 16-bit light indices");
 
     // ---- textures (material/Texture.cpp:109-130): RGBA8, wrap repeat, bilinear, normalised float reads
     std::vector<cudaTextureObject_t> tex(d->numTextures);
