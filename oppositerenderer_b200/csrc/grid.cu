@@ -250,10 +250,15 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
                 const unsigned rx_lo = __reduce_min_sync(0xffffffffu, need ? lx_lo : 0xffffffffu), rx_hi = __reduce_max_sync(0xffffffffu, need ? lx_hi : 0u);
                 const unsigned from = rx_lo + y * gx + z * gxy;
                 const unsigned begin = __ldg(offsets + from), end = __ldg(offsets + from + (rx_hi - rx_lo) + 1);
+                // software pipeline: the next 32 photons of the row are in flight (registers) while the current 32 are tested from
+                // shared memory
+                float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra; float rc = 0.f;
+                if (begin + lane < end) { ra = __ldg(sorted.a + begin + lane); rb = __ldg(sorted.b + begin + lane); rc = __ldg(sorted.c + begin + lane); }
                 for (unsigned base = begin; base < end; base += 32) {
-                    const unsigned i = base + lane;
-                    if (i < end) { sA[w][lane] = __ldg(sorted.a + i); sB[w][lane] = __ldg(sorted.b + i); sC[w][lane] = __ldg(sorted.c + i); }
+                    sA[w][lane] = ra; sB[w][lane] = rb; sC[w][lane] = rc;
                     __syncwarp();
+                    const unsigned nxt = base + 32 + lane;
+                    if (nxt < end) { ra = __ldg(sorted.a + nxt); rb = __ldg(sorted.b + nxt); rc = __ldg(sorted.c + nxt); }
                     const unsigned cnt = min(32u, end - base);
                     if (need) {
                         // One branch per photon (the distance test, which rejects ~45 %); the direction test is a select, so an accepted
