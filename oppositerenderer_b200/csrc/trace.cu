@@ -89,6 +89,13 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView 
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, n);
 }
 
+static unsigned trace_blocks_per_sm()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OPR_TRACE_BLOCKS_PER_SM"); v = e ? atoi(e) : 9; if (v < 1) v = 1; if (v > 16) v = 16; }
+    return (unsigned)v;
+}
+
 static unsigned trace_refill_idle()
 {
     static int v = -1;
@@ -100,7 +107,7 @@ static unsigned trace_refill_idle()
 void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc)
 {
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_FETCH_LEGACY, 0, sizeof(unsigned), lc.st));
-    trace_closest_kernel<<<148 * 8, TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + cur, q.hits, q.matQueue,
+    trace_closest_kernel<<<148 * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + cur, q.hits, q.matQueue,
                                                                q.counters + 2, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
                                                                q.counters + CTR_FETCH_LEGACY, trace_refill_idle());
     ++*lc.launches;
@@ -109,7 +116,7 @@ void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, Laun
 void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc)
 {
     const int cur = bounce & 1;
-    trace_closest_kernel<<<148 * 8, TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
+    trace_closest_kernel<<<148 * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
                                                                q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
                                                                q.counters + CTR_FETCH + bounce, trace_refill_idle());
     ++*lc.launches;
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_shadow_queue_kernel(Scene
 void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
                                float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc)
 {
-    trace_shadow_queue_kernel<<<148 * 8, TRACE_THREADS, 0, lc.st>>>(sc, hitPos, shadowD, shadowIdx, count, sampleFactor, fetchCursor, stat, trace_refill_idle());
+    trace_shadow_queue_kernel<<<148 * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, hitPos, shadowD, shadowIdx, count, sampleFactor, fetchCursor, stat, trace_refill_idle());
     ++*lc.launches;
 }
 
@@ -242,7 +249,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_connect_queue_kernel(Scen
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
                                 unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc)
 {
-    trace_connect_queue_kernel<<<148 * 8, TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle());
+    trace_connect_queue_kernel<<<148 * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle());
     ++*lc.launches;
 }
 
