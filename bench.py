@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--photons", type=int, default=1024, help="photon launch is photons x photons")
     ap.add_argument("--detail", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--relmse-target", type=float, default=0.0,
+                    help="extra leg (BASELINE config 5): device time until the relMSE of the running mean against a longer reference render drops below this")
+    ap.add_argument("--relmse-reference-iterations", type=int, default=256)
     ap.add_argument("--cpu-sample", default="480x270:256", help="--impl reference: WxH:photonLaunch of one step of the bounded CPU sample")
     ap.add_argument("--cpu-baseline-sample", default="960x540:512", help="cpu_baseline leg of the default arm (3 timed iterations + 1 warm-up)")
     return ap.parse_args()
@@ -337,6 +340,48 @@ def main():
         rays, rays_e2e = float(tsum[1]), float(tsum[3])
     total_steps = args.steps * world
 
+    # ---- optional: time to a target relMSE (BASELINE config 5), iteration-partitioned like everything else
+    ttt = None
+    if args.relmse_target > 0:
+        nref = args.relmse_reference_iterations
+        ref_r = opr.OptixRenderer(photon_launch=(args.photons, args.photons), vcm_max_path_length=args.max_path_length if args.method == "bdpt" else 0,
+                                  seed=D.rank_seed(987654321, rank))
+        ref_r.initialize(opr.ComputeDevice(local_rank))
+        ref_r.initScene(scene)
+        for k in range(nref):                                   # every rank renders the same reference (independent seed set)
+            ref_r.renderNextIteration(k, k, radius(k), True, pod)
+        ref = D.output_as_tensor(ref_r, dev).clone() / nref
+        ref2 = (ref ** 2).sum(-1)
+        eps = 1e-3 * float(ref2.mean())
+        ref_r.close()
+        barrier()
+        check_every, max_local = 4, 4096
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            t0e.record()
+        reached, done_local, err = None, 0, None
+        while done_local < max_local and reached is None:
+            for it, local, rad in part.steps(done_local, check_every):
+                r.renderNextIteration(it, local, rad, True, pod)
+            done_local += check_every
+            r.join()
+            with torch.cuda.stream(stream):
+                total = D.output_as_tensor(r, dev).clone()
+                if world > 1:
+                    dist.all_reduce(total)
+                mean = total / (done_local * world)
+                err = float((((mean - ref) ** 2).sum(-1) / (ref2 + eps)).mean())
+            if err <= args.relmse_target:
+                reached = done_local * world
+        with torch.cuda.stream(stream):
+            t1e.record()
+        barrier()
+        tsec = torch.tensor([t0e.elapsed_time(t1e) * 1e-3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+        ttt = {"target_relmse": args.relmse_target, "reached": reached is not None, "iterations": reached, "seconds": float(tsec[0]), "final_relmse": err,
+               "reference_iterations": nref, "note": "relMSE of the running mean of all ranks against an independent %d-iteration render; includes a check (clone + all-reduce) every %d local iterations" % (nref, check_every)}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
@@ -355,7 +400,7 @@ def main():
                 "e2e": {"value": rays_e2e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.opr_request_details),
                         "d2h_bytes_per_step": W * H * 12, "iterations_per_s": total_steps / e2e_s,
                         "how": "opr_render_next_iteration + opr_get_output_buffer into pinned host memory every step, wall clock, max over ranks"},
-                "gpu_launches": int(st["launches"] - launches0), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ray_queue": ray_queue,
+                "gpu_launches": int(st["launches"] - launches0), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ray_queue": ray_queue, "time_to_relmse": ttt,
                 "kernel_ms": kernel_ms, "scene": {"triangles": scene.getNumTriangles(), "meshes": scene.getNumMeshes(), "generate_s": t_scene, "init_scene_s": t_init}}
         print(json.dumps(line))
     if world > 1:
