@@ -73,6 +73,14 @@ const char* opr_get_timing_name(opr_renderer* r, int index);
  * capacity, shadow rays queued, camera-pass and photon-pass ray counts per bounce of the last PPM iteration). */
 int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t bytes);
 
+/* Out-of-bounds write detection without a sanitizer: after opr_debug_set_guards(1) every device allocation of the library
+ * carries a 4 KiB band of a known byte pattern on both sides; opr_debug_check_guards synchronises the device, reads every band
+ * back and returns the number of allocations whose band was modified — live ones, plus those freed since the guards were switched
+ * on, which are checked as they die (-1: nothing guarded has been checked, -2: CUDA error).  *checkedBlocks (may be NULL)
+ * receives the number of allocations that count covers. */
+void opr_debug_set_guards(int enabled);
+int opr_debug_check_guards(int* checkedBlocks);
+
 /* ---- stand-alone kernels of the path (host buffers in, host buffers out) ------------------------------ */
 /* initRandomStateBuffer (OptixRenderer_SpatialHash.cu:310-317): states6[6*i..] = XORWOW state of seed+first+i */
 int opr_rng_init(uint32_t* states6, uint32_t seed, uint32_t first, uint32_t count);

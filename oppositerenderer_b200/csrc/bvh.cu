@@ -249,8 +249,8 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
     float3 cinv = f3(ext.x > 0 ? 1.0f / ext.x : 0.f, ext.y > 0 ? 1.0f / ext.y : 0.f, ext.z > 0 ? 1.0f / ext.z : 0.f);
 
     std::vector<void*> tmp;
-    auto dalloc = [&](size_t bytes) { void* p; OPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); tmp.push_back(p); return p; };
-    struct Cleanup { std::vector<void*>& v; ~Cleanup() { for (void* p : v) cudaFree(p); } } cleanup{tmp};
+    auto dalloc = [&](size_t bytes) { void* p; devAlloc(&p, bytes); tmp.push_back(p); return p; };
+    struct Cleanup { std::vector<void*>& v; ~Cleanup() { for (void* p : v) devFree(p); } } cleanup{tmp};
 
     float4* dLo = (float4*)dalloc(sizeof(float4) * n);
     float4* dHi = (float4*)dalloc(sizeof(float4) * n);
@@ -305,7 +305,7 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
     float4* wideTmp = (float4*)dalloc(128 * (size_t)std::max(n, 1));
     int2* queue[2] = {(int2*)dalloc(8 * (size_t)std::max(n, 1)), (int2*)dalloc(8 * (size_t)std::max(n, 1))};
     int* leafPrim = nullptr;
-    OPR_CUDA_CHECK(cudaMalloc(&leafPrim, 4 * (size_t)n)); owned.push_back(leafPrim);
+    devAlloc((void**)&leafPrim, 4 * (size_t)n); owned.push_back(leafPrim);
     {
         int h[4] = {1, 0, 0, 0};
         OPR_CUDA_CHECK(cudaMemcpyAsync(counters, h, sizeof h, cudaMemcpyHostToDevice, st));
@@ -326,10 +326,10 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
     if (h[2] != n) throw std::runtime_error("BVH build: leaf slots do not cover the primitives");
     if (3 * levels + 4 > TRAVERSAL_STACK) throw std::runtime_error("BVH build: tree deeper than the traversal stack");
     float4* nodes = nullptr;
-    OPR_CUDA_CHECK(cudaMalloc(&nodes, 128 * (size_t)numWide)); owned.push_back(nodes);
+    devAlloc((void**)&nodes, 128 * (size_t)numWide); owned.push_back(nodes);
     OPR_CUDA_CHECK(cudaMemcpyAsync(nodes, wideTmp, 128 * (size_t)numWide, cudaMemcpyDeviceToDevice, st));
     float4* leafTri = nullptr;
-    OPR_CUDA_CHECK(cudaMalloc(&leafTri, sizeof(float4) * LEAF_TRI_STRIDE * (size_t)n)); owned.push_back(leafTri);
+    devAlloc((void**)&leafTri, sizeof(float4) * LEAF_TRI_STRIDE * (size_t)n); owned.push_back(leafTri);
     bvh_leaf_tri_kernel<<<B256, 256, 0, st>>>(leafPrim, n, view.triRec, leafTri);
     OPR_CUDA_CHECK(cudaStreamSynchronize(st));
     OPR_CUDA_CHECK(cudaGetLastError());

@@ -15,8 +15,8 @@ static thread_local std::string g_lastError;
 namespace {
 struct DevBuf {
     void* p = nullptr;
-    explicit DevBuf(size_t bytes) { OPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); }
-    ~DevBuf() { if (p) cudaFree(p); }
+    explicit DevBuf(size_t bytes) { opr::devAlloc(&p, bytes); }
+    ~DevBuf() { opr::devFree(p); }
     template <class T> T* as() { return (T*)p; }
 };
 void requireDevice()
@@ -174,6 +174,13 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
             throw std::runtime_error("opr_debug_get_buffer: unknown buffer " + n);
         }
     })
+}
+
+void opr_debug_set_guards(int enabled) { opr::devSetGuards(enabled != 0); }
+int opr_debug_check_guards(int* liveBlocks)
+{
+    try { return opr::devCheckGuards(liveBlocks); }
+    catch (const std::exception& e) { g_lastError = e.what(); return -2; }
 }
 
 // ---- stand-alone kernels ------------------------------------------------------------------------------------

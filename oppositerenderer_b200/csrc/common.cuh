@@ -226,4 +226,12 @@ OPR_DEV unsigned warp_append(unsigned* counter, bool push)
 
 } // namespace opr
 
+namespace opr {
+// devmem.cu: cudaMalloc / cudaFree with optional guard bands (opr_debug_set_guards)
+void devAlloc(void** out, size_t bytes);
+void devFree(void* p);
+void devSetGuards(bool on);
+int devCheckGuards(int* liveBlocks);
+}
+
 #define OPR_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)

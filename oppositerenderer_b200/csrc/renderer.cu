@@ -13,9 +13,9 @@ void vcm_free(Renderer& r);   // vcm.cu
 
 template <class T> static void dalloc(T*& p, size_t count)
 {
-    OPR_CUDA_CHECK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+    devAlloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
 }
-template <class T> static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+template <class T> static void dfree(T*& p) { devFree(p); p = nullptr; }
 
 Renderer::~Renderer()
 {

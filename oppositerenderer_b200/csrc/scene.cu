@@ -15,7 +15,7 @@ template <class T> static T* upload(const std::vector<T>& v, std::vector<void*>&
 {
     T* d = nullptr;
     size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-    OPR_CUDA_CHECK(cudaMalloc(&d, bytes));
+    devAlloc((void**)&d, bytes);
     if (!v.empty()) OPR_CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     owned.push_back(d);
     return d;
@@ -27,7 +27,7 @@ DeviceScene::~DeviceScene() { release(); }
 
 void DeviceScene::release()
 {
-    for (void* p : owned) cudaFree(p);
+    for (void* p : owned) devFree(p);
     owned.clear();
     for (auto t : texObjects) cudaDestroyTextureObject(t);
     texObjects.clear();

@@ -47,9 +47,9 @@ void vcm_free(Renderer& r)
 {
     if (!r.vcm) return;
     VcmState* s = r.vcm;
-    cudaFree(s->thr); cudaFree(s->mis); cudaFree(s->color); cudaFree(s->lvCount);
-    cudaFree(s->connO); cudaFree(s->connD); cudaFree(s->connC);
-    for (int i = 0; i < 6; i++) cudaFree(s->lv[i]);
+    devFree(s->thr); devFree(s->mis); devFree(s->color); devFree(s->lvCount);
+    devFree(s->connO); devFree(s->connD); devFree(s->connC);
+    for (int i = 0; i < 6; i++) devFree(s->lv[i]);
     delete s; r.vcm = nullptr;
 }
 
@@ -61,13 +61,13 @@ static void vcm_alloc(Renderer& r)
     vcm_free(r);
     VcmState* s = new VcmState(); r.vcm = s;
     s->paths = paths; s->maxVerts = maxVerts;
-    OPR_CUDA_CHECK(cudaMalloc((void**)&s->thr, paths * 16)); OPR_CUDA_CHECK(cudaMalloc((void**)&s->mis, paths * 16));
-    OPR_CUDA_CHECK(cudaMalloc((void**)&s->color, paths * 16)); OPR_CUDA_CHECK(cudaMalloc((void**)&s->lvCount, paths * 4));
-    for (int i = 0; i < 6; i++) OPR_CUDA_CHECK(cudaMalloc((void**)&s->lv[i], paths * maxVerts * 16));
+    devAlloc((void**)&s->thr, paths * 16); devAlloc((void**)&s->mis, paths * 16);
+    devAlloc((void**)&s->color, paths * 16); devAlloc((void**)&s->lvCount, paths * 4);
+    for (int i = 0; i < 6; i++) devAlloc((void**)&s->lv[i], paths * maxVerts * 16);
     if (maxVerts + 1 > VCM_MAX_CONNECTIONS) throw std::runtime_error("vcmMaxPathLength too large for the connection queue");
     const size_t cap = paths * (maxVerts + 1);
-    OPR_CUDA_CHECK(cudaMalloc((void**)&s->connO, cap * 16)); OPR_CUDA_CHECK(cudaMalloc((void**)&s->connD, cap * 16));
-    OPR_CUDA_CHECK(cudaMalloc((void**)&s->connC, cap * 16));
+    devAlloc((void**)&s->connO, cap * 16); devAlloc((void**)&s->connD, cap * 16);
+    devAlloc((void**)&s->connC, cap * 16);
 }
 
 // ---- shared device pieces ----------------------------------------------------------------------------------------

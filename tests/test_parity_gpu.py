@@ -4,6 +4,7 @@ bit-exact; float images must match per pixel within rel 1e-3 + abs 1e-5 on ident
 stated fraction of pixels (the remainder are paths that diverged at a discrete decision — Russian roulette,
 Fresnel choice, cell boundary — because sinf/cosf/expf differ by ulps between CUDA and glibc)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -15,6 +16,7 @@ from oppositerenderer_b200 import capi
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL = 1e-3, 1e-5
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_rng_bit_exact(product, oracle):
@@ -531,3 +533,17 @@ def test_converged_render_within_monte_carlo_noise(product, oracle, method, scen
     assert ours <= 1.5 * floor + 1e-4, (ours, floor)
     means = [float(x[mask].mean()) for x in refs]
     assert min(means) * 0.98 <= float(g[mask].mean()) <= max(means) * 1.02, (float(g[mask].mean()), means)
+
+
+def test_no_kernel_writes_outside_its_buffers(product):
+    """Every device allocation framed by 4 KiB guard bands (opr_debug_set_guards); all three methods, both BVH paths, odd
+    image sizes and the stand-alone grid / gather entry points must leave every band untouched."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("guard_check", os.path.join(ROOT, "scripts", "guard_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    results = mod.main(guards=True, verbose=False)
+    assert len(results) >= 8
+    for what, bad, checked in results:
+        assert checked > 10, (what, checked)
+        assert bad == 0, "%s: %d of %d allocations have a damaged guard band" % (what, bad, checked)
