@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liboppositerenderer_b200.so")
+# OPR_LIBRARY: another build of the same library (scripts/build_variant.sh), for A/B timing
+LIB_PATH = os.environ.get("OPR_LIBRARY") or os.path.join(_HERE, "csrc", "liboppositerenderer_b200.so")
 
 F3 = C.c_float * 3
 F2 = C.c_float * 2

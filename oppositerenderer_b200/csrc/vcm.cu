@@ -583,7 +583,10 @@ OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBu
 }
 
 // wavefront shading of one camera-pass bounce, one material kind per blockIdx.y
-__global__ void __launch_bounds__(VCM_THREADS) vcm_camera_shade_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B,
+#ifndef OPR_VCM_CAMERA_MINBLOCKS
+#define OPR_VCM_CAMERA_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(VCM_THREADS, OPR_VCM_CAMERA_MINBLOCKS) vcm_camera_shade_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B,
                                                                        const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                        const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
                                                                        const unsigned* __restrict__ matQueue, const unsigned* __restrict__ matCount, unsigned capacity,
