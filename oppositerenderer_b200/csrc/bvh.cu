@@ -228,6 +228,39 @@ __global__ void bvh_leaf_tri_kernel(const int* __restrict__ leafPrim, int n, con
     dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// ---- quantised copy of the wide nodes (built only with -DOPR_QBVH=1; measured slower overall) ------------
+// 64 bytes = 16 words: [0,1] lo.x of children 0..3 as 16-bit values, [2,3] hi.x, [4,5] lo.y, [6,7] hi.y, [8,9] lo.z,
+// [10,11] hi.z, [12..15] child refs.  A value is 0x8000 | q with q in [0, 32767] on the grid origin + q * extent / 32768;
+// lo is rounded down and hi up, each by one further cell, which covers the fp32 error of the decode (2^-23 of the extent).
+__device__ __forceinline__ unsigned quant_lo(float v, float origin, float invCell)
+{
+    const float q = floorf((v - origin) * invCell) - 1.0f;
+    return 0x8000u | (unsigned)fminf(fmaxf(q, 0.0f), 32767.0f);
+}
+__device__ __forceinline__ unsigned quant_hi(float v, float origin, float invCell)
+{
+    const float q = ceilf((v - origin) * invCell) + 1.0f;
+    return 0x8000u | (unsigned)fminf(fmaxf(q, 0.0f), 32767.0f);
+}
+__global__ void bvh_quantize_kernel(const float4* __restrict__ wide, int numWide, float3 origin, float3 invCell, uint4* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numWide) return;
+    const float4* N = wide + 8 * (size_t)i;
+    const float4 lox = N[0], hix = N[1], loy = N[2], hiy = N[3], loz = N[4], hiz = N[5], rf = N[6];
+    const float INF = __int_as_float(0x7f800000);
+    auto lo2 = [&](float a, float b, float o, float ic) { return (a < INF ? quant_lo(a, o, ic) : 0x8000u) | ((b < INF ? quant_lo(b, o, ic) : 0x8000u) << 16); };
+    auto hi2 = [&](float a, float b, float o, float ic) { return (a < INF ? quant_hi(a, o, ic) : 0x8000u) | ((b < INF ? quant_hi(b, o, ic) : 0x8000u) << 16); };
+    uint4* Q = out + 4 * (size_t)i;
+    Q[0] = make_uint4(lo2(lox.x, lox.y, origin.x, invCell.x), lo2(lox.z, lox.w, origin.x, invCell.x),
+                      hi2(hix.x, hix.y, origin.x, invCell.x), hi2(hix.z, hix.w, origin.x, invCell.x));
+    Q[1] = make_uint4(lo2(loy.x, loy.y, origin.y, invCell.y), lo2(loy.z, loy.w, origin.y, invCell.y),
+                      hi2(hiy.x, hiy.y, origin.y, invCell.y), hi2(hiy.z, hiy.w, origin.y, invCell.y));
+    Q[2] = make_uint4(lo2(loz.x, loz.y, origin.z, invCell.z), lo2(loz.z, loz.w, origin.z, invCell.z),
+                      hi2(hiz.x, hiz.y, origin.z, invCell.z), hi2(hiz.z, hiz.w, origin.z, invCell.z));
+    Q[3] = make_uint4(__float_as_uint(rf.x), __float_as_uint(rf.y), __float_as_uint(rf.z), __float_as_uint(rf.w));
+}
+
 // ---- host driver -----------------------------------------------------------------------------------------------------
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static float env_float(const char* name, float dflt) { const char* e = getenv(name); return e ? (float)atof(e) : dflt; }
@@ -341,6 +374,25 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
     const float rootA = (rhi.x - rlo.x) * (rhi.y - rlo.y) + (rhi.y - rlo.y) * (rhi.z - rlo.z) + (rhi.z - rlo.z) * (rhi.x - rlo.x);
     sahCost = rootA > 0.f ? rootCost / rootA : 0.f;
     view.nodes = nodes; view.rootRef = 0; view.leafPrim = leafPrim; view.leafTri = leafTri;
+#if OPR_QBVH
+    {   // quantised copy on a grid that frames the root box with a margin of a few cells
+        const float3 ext = f3(rhi.x - rlo.x, rhi.y - rlo.y, rhi.z - rlo.z);
+        const float big = std::max(std::max(ext.x, ext.y), std::max(ext.z, 1e-20f));
+        auto axis = [&](float lo, float e, float& origin, float& extent) {
+            const float e2 = std::max(e, big * 1e-4f);           // flat scenes: keep the cell size finite
+            extent = e2 * (1.0f + 16.0f / 32768.0f);
+            origin = lo - 8.0f * extent / 32768.0f;
+        };
+        float3 qo, qe;
+        axis(rlo.x, ext.x, qo.x, qe.x); axis(rlo.y, ext.y, qo.y, qe.y); axis(rlo.z, ext.z, qo.z, qe.z);
+        uint4* qnodes = nullptr;
+        devAlloc((void**)&qnodes, 64 * (size_t)numWide); owned.push_back(qnodes);
+        bvh_quantize_kernel<<<(numWide + 255) / 256, 256, 0, st>>>(nodes, numWide, qo, f3(32768.0f / qe.x, 32768.0f / qe.y, 32768.0f / qe.z), qnodes);
+        OPR_CUDA_CHECK(cudaStreamSynchronize(st));
+        OPR_CUDA_CHECK(cudaGetLastError());
+        view.qnodes = (const float4*)qnodes; view.qOrigin = qo; view.qExtent = qe;
+    }
+#endif
     numNodes = numWide; bvhLevels = levels; plocRounds = rounds;
     if (getenv("OPR_BVH_VERBOSE"))
         fprintf(stderr, "[opr] BVH: %d prims, PLOC R=%d %d rounds, %d wide nodes (%.1f MB), %d levels, SAH %.2f\n", n, R, rounds, numWide, numWide * 128.0 / 1e6,

@@ -34,8 +34,14 @@ struct DMaterial {
 
 struct DSphere { float3 center; float radius; };
 
+// 1: traverse the 64-byte quantised nodes (two 256-bit loads per node visit instead of four); 0: the 128-byte fp32 nodes
+#ifndef OPR_QBVH
+#define OPR_QBVH 0
+#endif
+
 struct SceneView {
     const float4* nodes; int rootRef;                 // 4-wide BVH (bvh.cu), 8 float4 per node
+    const float4* qnodes; float3 qOrigin, qExtent;   // the same tree with child boxes on a 15-bit scene grid, 4 float4 (64 B) per node
     const float4* leafTri; const int* leafPrim;       // leaf-slot order: 3 float4 per slot; (primIndex << 2) | primType per slot
     const float4* triRec; const int4* triShade;
     const float4* pgramRec; const int* pgramMat;
@@ -161,19 +167,42 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
         const int2 e_ = stack[--sp];                                                                               \
         if ((ANYHIT) || __int_as_float(e_.y) < hit.t) { cur = e_.x; break; }                                       \
     }
+// the four child boxes (lox .. hiz) and child refs (r0 .. r3) of node `cur`
+#if OPR_QBVH
+#define OPR_QLO(W) __uint_as_float(__byte_perm(__float_as_uint(W), 0x3F800000u, 0x7104u))
+#define OPR_QHI(W) __uint_as_float(__byte_perm(__float_as_uint(W), 0x3F800000u, 0x7324u))
+#define OPR_Q4(A, B) make_float4(OPR_QLO(A), OPR_QHI(A), OPR_QLO(B), OPR_QHI(B))
+#define OPR_NODE_LOAD                                                                                              \
+        const float4* N_ = sc.qnodes + 4 * (size_t)cur;                                                            \
+        const Float8 na_ = ldg256(N_), nb_ = ldg256(N_ + 2);                                                       \
+        const float4 lox = OPR_Q4(na_.lo.x, na_.lo.y), hix = OPR_Q4(na_.lo.z, na_.lo.w);                          \
+        const float4 loy = OPR_Q4(na_.hi.x, na_.hi.y), hiy = OPR_Q4(na_.hi.z, na_.hi.w);                          \
+        const float4 loz = OPR_Q4(nb_.lo.x, nb_.lo.y), hiz = OPR_Q4(nb_.lo.z, nb_.lo.w), rf = nb_.hi;             \
+        int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
+// an absent child has no box on the grid that every ray misses: recognise it by its ref (child 0 always exists)
+#define OPR_NODE_EMPTY                                                                                             \
+        if (r1 == 0x7fffffff) t1 = INF_;                                                                           \
+        if (r2 == 0x7fffffff) t2 = INF_;                                                                           \
+        if (r3 == 0x7fffffff) t3 = INF_;
+#else
+#define OPR_NODE_LOAD                                                                                              \
+        const float4* N_ = sc.nodes + 8 * (size_t)cur;                                                             \
+        const Float8 nx_ = ldg256(N_), ny_ = ldg256(N_ + 2), nz_ = ldg256(N_ + 4), nr_ = ldg256(N_ + 6);            \
+        const float4 lox = nx_.lo, hix = nx_.hi, loy = ny_.lo, hiy = ny_.hi, loz = nz_.lo, hiz = nz_.hi, rf = nr_.lo; \
+        int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
+#define OPR_NODE_EMPTY
+#endif
 // one node visit of a lane with cur >= 0
 #define OPR_NODE_STEP(ANYHIT)                                                                                      \
     {                                                                                                              \
         const float INF_ = __int_as_float(0x7f800000);                                                             \
-        const float4* N_ = sc.nodes + 8 * (size_t)cur;                                                             \
-        const Float8 nx_ = ldg256(N_), ny_ = ldg256(N_ + 2), nz_ = ldg256(N_ + 4), nr_ = ldg256(N_ + 6);            \
-        const float4 lox = nx_.lo, hix = nx_.hi, loy = ny_.lo, hiy = ny_.hi, loz = nz_.lo, hiz = nz_.hi, rf = nr_.lo; \
-        int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w); \
+        OPR_NODE_LOAD                                                                                              \
         float t0, t1, t2, t3;                                                                                      \
         OPR_SLAB(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, t0)                                                     \
         OPR_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, t1)                                                     \
         OPR_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, t2)                                                     \
         OPR_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, t3)                                                     \
+        OPR_NODE_EMPTY                                                                                             \
         if (ANYHIT) {          /* any order will do for an occlusion query: skip the sorting network */             \
             if (t1 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r1, 0); else { t0 = t1; r0 = r1; } }               \
             if (t2 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r2, 0); else { t0 = t2; r0 = r2; } }               \
@@ -223,6 +252,22 @@ OPR_DEV float3 safe_inverse_direction(const float3& d)
               1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
 }
 
+// Per-ray constants of the slab test.  Full-precision nodes: t = plane * idir + ood.  Quantised nodes (OPR_QBVH): a plane is
+// stored as q in [0, 32767] on the scene grid, decoded by ONE byte permute into the float v = 1 + q / 32768 (the stored
+// half-word carries the exponent's low bit), and world = qOrigin + (v - 1) * qExtent, so t = v * (qExtent * idir) +
+// (qOrigin - qExtent - o) * idir: the same single FFMA per plane with different per-ray constants.
+OPR_DEV void ray_slab_setup(const SceneView& sc, const float3& o, const float3& d, float3& idir, float3& ood)
+{
+    const float3 inv = safe_inverse_direction(d);
+#if OPR_QBVH
+    idir = f3(sc.qExtent.x * inv.x, sc.qExtent.y * inv.y, sc.qExtent.z * inv.z);
+    ood = f3((sc.qOrigin.x - sc.qExtent.x - o.x) * inv.x, (sc.qOrigin.y - sc.qExtent.y - o.y) * inv.y, (sc.qOrigin.z - sc.qExtent.z - o.z) * inv.z);
+#else
+    idir = inv;
+    ood = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+#endif
+}
+
 // Closest hit (ANY = false) or first accepted intersection (ANY = true: shadow rays, ppm/DirectRadianceEstimation.cu:79-83,
 // bound to every material by material/Material.cpp:18-26) for the lanes of `mask`, which must all make this call together;
 // lanes with active = false ride along.  On return hit.prim = (primIndex << 2) | primType, or -1.
@@ -230,8 +275,8 @@ template <bool ANY>
 OPR_DEV bool traverse_warp(const SceneView& sc, unsigned mask, bool active, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
 {
     hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
-    const float3 idir = safe_inverse_direction(d);
-    const float3 ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+    float3 idir, ood;
+    ray_slab_setup(sc, o, d, idir, ood);
     int2 stack[TRAVERSAL_STACK];
     int sp = 0;
     int cur = active ? sc.rootRef : TRAVERSAL_DONE;
@@ -257,8 +302,8 @@ template <bool ANY>
 OPR_DEV bool traverse_free(const SceneView& sc, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
 {
     hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
-    const float3 idir = safe_inverse_direction(d);
-    const float3 ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+    float3 idir, ood;
+    ray_slab_setup(sc, o, d, idir, ood);
     int2 stack[TRAVERSAL_STACK];
     int sp = 0;
     int cur = sc.rootRef;

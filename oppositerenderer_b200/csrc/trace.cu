@@ -67,8 +67,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView 
                     if (idx < n) {
                         const float4 o4 = rayO[idx], d4 = rayD[idx];
                         o = f3(o4); d = f3(d4); tmin = o4.w;
-                        idir = safe_inverse_direction(d);
-                        ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+                        ray_slab_setup(sc, o, d, idir, ood);
                         hit.t = d4.w; hit.prim = -1; hit.u = hit.v = 0.f;
                         sp = 0; cur = sc.rootRef; ray = idx;
                     }
@@ -155,8 +154,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_shadow_queue_kernel(Scene
                         idx = shadowIdx[i];
                         const float4 d4 = shadowD[i];
                         o = f3(hitPos[idx >> 2]); d = f3(d4);
-                        idir = safe_inverse_direction(d);
-                        ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+                        ray_slab_setup(sc, o, d, idir, ood);
                         hit.t = d4.w; hit.prim = -1;
                         sp = 0; cur = sc.rootRef;
                     }
@@ -223,8 +221,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_connect_queue_kernel(Scen
                     if (i < n) {
                         const float4 o4 = connO[i], d4 = connD[i];
                         o = f3(o4); d = f3(d4);
-                        idir = safe_inverse_direction(d);
-                        ood = f3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+                        ray_slab_setup(sc, o, d, idir, ood);
                         hit.t = o4.w; hit.prim = -1;
                         sp = 0; cur = sc.rootRef; pending = i;
                     }
