@@ -29,7 +29,7 @@ Renderer::~Renderer()
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
     scene.release();
     if (bboxEvent) cudaEventDestroy(bboxEvent);
-    for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone, evVcmShade, evVcmConn[0], evVcmConn[1]}) if (e) cudaEventDestroy(e);
     if (streamB) cudaStreamDestroy(streamB);
     if (streamC) cudaStreamDestroy(streamC);
     if (stream) cudaStreamDestroy(stream);
@@ -55,7 +55,7 @@ void Renderer::initialize(int cudaOrdinal)
     OPR_CUDA_CHECK(cudaEventCreateWithFlags(&bboxEvent, cudaEventDisableTiming));
     OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&streamB, cudaStreamNonBlocking));
     OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&streamC, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone})
+    for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone, &evVcmShade, &evVcmConn[0], &evVcmConn[1]})
         OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));

@@ -24,6 +24,8 @@ constexpr int CTR_TOTAL = 256;        // [CTR_RAYCOUNT, CTR_TOTAL) is reset by t
 constexpr int CTR_SNAPSHOT = 256;     // 16 words: the ray counts of the pass before the current one (ray-queue occupancy report)
 constexpr int CTR_TAIL_COUNT = 272;    // camera tail queue length (outside the per-pass reset range: the tail runs on its own stream)
 constexpr int CTR_DEFERRED_COUNT = 273; // photon threads deferred behind the camera tail
+constexpr int CTR_CONN2_COUNT = 274; // second BDPT connection queue (vcm.cu): length, -, fetch cursor at 274..276
+constexpr int CTR_CONN2_FETCH = 276;
 constexpr int CTR_ALLOC = 288;
 
 // Wavefront ray queue state (all device pointers)
@@ -90,6 +92,8 @@ struct Renderer {
     cudaStream_t streamC = nullptr;
     cudaEvent_t evCameraWaves = nullptr, evPhotonGen = nullptr, evTailDone = nullptr;
     cudaStream_t sC() const { return overlap ? streamC : stream; }
+    // BDPT: the occlusion tests of bounce b's connections (stream B) run while `stream` traces and shades bounce b+1
+    cudaEvent_t evVcmShade = nullptr, evVcmConn[2] = {nullptr, nullptr};
     bool hpFreePending[2] = {false, false}, gridDonePending = false, workOnB = false;
     cudaStream_t sB() const { return overlap ? streamB : stream; }
     void joinStreams();                   // later work on `stream` is ordered after everything queued on stream B

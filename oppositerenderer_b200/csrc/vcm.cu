@@ -26,6 +26,7 @@ struct VcmState {
     float4* connO = nullptr;   // origin.xyz, tmax
     float4* connD = nullptr;   // direction.xyz, target index (uint bits)
     float4* connC = nullptr;   // contribution.xyz
+    float4* conn2[3] = {nullptr, nullptr, nullptr};   // second set: bounce b+1 fills it while stream B still tests the segments of bounce b
     size_t paths = 0; unsigned maxVerts = 0;
 };
 
@@ -49,6 +50,7 @@ void vcm_free(Renderer& r)
     VcmState* s = r.vcm;
     devFree(s->thr); devFree(s->mis); devFree(s->color); devFree(s->lvCount);
     devFree(s->connO); devFree(s->connD); devFree(s->connC);
+    for (int i = 0; i < 3; i++) devFree(s->conn2[i]);
     for (int i = 0; i < 6; i++) devFree(s->lv[i]);
     delete s; r.vcm = nullptr;
 }
@@ -68,6 +70,7 @@ static void vcm_alloc(Renderer& r)
     const size_t cap = paths * (maxVerts + 1);
     devAlloc((void**)&s->connO, cap * 16); devAlloc((void**)&s->connD, cap * 16);
     devAlloc((void**)&s->connC, cap * 16);
+    if (r.overlap) for (int i = 0; i < 3; i++) devAlloc((void**)&s->conn2[i], cap * 16);
 }
 
 // ---- shared device pieces ----------------------------------------------------------------------------------------
@@ -715,6 +718,38 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     P.misVcWeightFactor = 1.f / etaVCM;         // m_vcmUseVC = true
     P.pixelSizeFactor = make_float2(1.0f / width, 1.0f / height);   // resizeBuffers :846
 
+    // Connection queues: with the stream pipeline on, bounce b's shadow segments are tested on stream B while `stream` traces and
+    // shades bounce b+1 into the other queue.  The camera pass then adds the unoccluded contributions to the output image (float
+    // atomics, like the light pass' splats) instead of the per-path colour that the next bounce's shading reads and rewrites.
+    const bool ov = overlap && !timing && S.conn2[0] != nullptr;
+    VcmBuffers Bq[2] = {B, B};
+    Bq[1].connO = S.conn2[0]; Bq[1].connD = S.conn2[1]; Bq[1].connC = S.conn2[2]; Bq[1].connCount = q.counters + CTR_CONN2_COUNT;
+    unsigned* const connFetch[2] = {q.counters + CTR_CONN_FETCH, q.counters + CTR_CONN2_FETCH};
+    int connSet = 0;
+    bool connBusy[2] = {false, false};
+    if (ov) joinStreams();
+    auto beginConnections = [&]() -> const VcmBuffers& {      // before the shading kernel that fills the queue
+        if (ov) { connSet ^= 1; if (connBusy[connSet]) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evVcmConn[connSet], 0)); connBusy[connSet] = false; } }
+        OPR_CUDA_CHECK(cudaMemsetAsync(Bq[connSet].connCount, 0, sizeof(unsigned) * 3, stream));   // count, (legacy fetch), connection fetch
+        return Bq[connSet];
+    };
+    auto traceConnections = [&](float* target, unsigned stride) {
+        const VcmBuffers& b = Bq[connSet];
+        if (!ov) {
+            launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
+            return;
+        }
+        OPR_CUDA_CHECK(cudaEventRecord(evVcmShade, stream));
+        OPR_CUDA_CHECK(cudaStreamWaitEvent(streamB, evVcmShade, 0));
+        launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS,
+                                   LaunchCtx{streamB, &launches});
+        OPR_CUDA_CHECK(cudaEventRecord(evVcmConn[connSet], streamB));
+        connBusy[connSet] = true;
+    };
+    auto joinConnections = [&]() {
+        for (int s = 0; s < 2; s++) if (connBusy[s]) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evVcmConn[s], 0)); connBusy[s] = false; }
+    };
+
     auto lightPass = [&](const char* name) {
         ScopedTimer t(*this, name);
         unsigned c[2 + NUM_QUEUES] = {0};
@@ -729,15 +764,14 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
             launch_trace_closest(sc, q, cur, lc);
-            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_CONN_COUNT, 0, sizeof(unsigned) * 3, stream));   // count, (legacy fetch), connection fetch
+            const VcmBuffers& Bc = beginConnections();
             dim3 grid(VCM_BLOCKS_X, NUM_QUEUES);
-            vcm_light_shade_kernel<<<grid, VCM_THREADS, 0, stream>>>(sc, P, rng, B, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
+            vcm_light_shade_kernel<<<grid, VCM_THREADS, 0, stream>>>(sc, P, rng, Bc, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
                                                                      q.counters + 2, q.capacity, q.rayO[cur ^ 1], q.rayD[cur ^ 1], q.rayPath[cur ^ 1],
                                                                      q.counters + (cur ^ 1), q.counters + 16 + STAT_ANY_RAYS);
             ++launches;
             if (!P.estimatePass)   // connectCameraT1 splats of the unoccluded segments (vcm.h:159)
-                launch_trace_connect_queue(sc, S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, output, 3, q.counters + CTR_CONN_FETCH,
-                                           q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
+                traceConnections(output, 3);
             cur ^= 1;
         }
         if (waves <= P.maxPathLen) {
@@ -770,21 +804,21 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
             launch_trace_closest(sc, q, cur, lc);
-            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_CONN_COUNT, 0, sizeof(unsigned) * 3, stream));
+            const VcmBuffers& Bc = beginConnections();
             dim3 grid(VCM_BLOCKS_X, NUM_QUEUES);
-            vcm_camera_shade_kernel<<<grid, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
+            vcm_camera_shade_kernel<<<grid, VCM_THREADS, 0, stream>>>(sc, P, rng, Bc, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
                                                                       q.counters + 2, q.capacity, q.rayO[cur ^ 1], q.rayD[cur ^ 1], q.rayPath[cur ^ 1],
                                                                       q.counters + (cur ^ 1), q.counters + 16 + STAT_ANY_RAYS);
             ++launches;
             // light-source and vertex connections of this bounce: add the unoccluded ones to the paths' colour accumulators
-            launch_trace_connect_queue(sc, S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, (float*)S.color, 4, q.counters + CTR_CONN_FETCH,
-                                       q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
+            if (ov) traceConnections(output, 3); else traceConnections((float*)S.color, 4);
             cur ^= 1;
         }
         if (waves <= P.maxPathLen) {
             vcm_camera_tail_kernel<<<148 * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur, q.counters + CTR_STATS);
             ++launches;
         }
+        joinConnections();
         vcm_accumulate_kernel<<<blocks, VCM_THREADS, 0, stream>>>(B, width * height, output);
         ++launches;
     }
