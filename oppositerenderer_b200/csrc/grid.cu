@@ -164,7 +164,7 @@ constexpr int GATHER_WARPS = GATHER_THREADS / 32;
 
 __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf hp, unsigned numPixels, unsigned width, unsigned height, PhotonBuf sorted,
                                                                     const unsigned* __restrict__ offsets, GridParams g, float ppmRadius, float ppmRadiusSquared,
-                                                                    float emittedPhotons, float* __restrict__ indirect, unsigned* __restrict__ tileCounter)
+                                                                    float emittedPhotons, float* __restrict__ indirect, unsigned* __restrict__ tileCounter, unsigned tilesPerBlock)
 {
     __shared__ float4 sA[GATHER_WARPS][32];
     __shared__ float4 sB[GATHER_WARPS][32];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
     // cull radius: a relative margin (plus the fp32 error of cell coordinates ~ extent * 2^-22) keeps the cull conservative
     const float cullRadius = radius * 1.0001f + 1e-6f * g.cellSize * (float)max(max(g.gridSize.x, g.gridSize.y), g.gridSize.z);
     const float cullRadius2 = cullRadius * cullRadius;
-    for (;;) {
+    for (unsigned done = 0; tilesPerBlock == 0 || done < tilesPerBlock; done++) {
         __syncthreads();
         if (threadIdx.x == 0) sTile = atomicAdd(tileCounter, 1u);
         __syncthreads();
@@ -296,13 +296,15 @@ __global__ void __launch_bounds__(GATHER_THREADS) ppm_gather_kernel(HitpointBuf 
 }
 
 void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
-                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc, unsigned blocksPerSM)
+                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc, unsigned blocksPerSM,
+                   unsigned tilesPerBlock)
 {
     const unsigned numTiles = width ? ((width + 7) / 8) * ((height + 3) / 4) : (numPixels + 31) / 32;
     int blocks = (int)std::min<unsigned>(numTiles, 148 * std::max(1u, blocksPerSM));
+    if (tilesPerBlock) blocks = (int)((numTiles + tilesPerBlock - 1) / tilesPerBlock);   // short-lived CTAs: as many resident as fit
     OPR_CUDA_CHECK(cudaMemsetAsync(tileCounter, 0, sizeof(unsigned), lc.st));
     ppm_gather_kernel<<<blocks, GATHER_THREADS, 0, lc.st>>>(hp, numPixels, width, height, sorted, offsets, g, ppmRadius, ppmRadiusSquared, emittedPhotons, indirect,
-                                                            tileCounter);
+                                                            tileCounter, tilesPerBlock);
     ++*lc.launches;
 }
 

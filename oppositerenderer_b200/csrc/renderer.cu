@@ -51,14 +51,24 @@ void Renderer::initialize(int cudaOrdinal)
     if (const char* e = getenv("OPR_VCM_LIGHT_WAVES")) vcmLightWaveBounces = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("OPR_VCM_CAMERA_WAVES")) vcmCameraWaveBounces = (unsigned)std::max(1, atoi(e));
     OPR_CUDA_CHECK(cudaSetDevice(device));
-    OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // Stream priorities: the RNG-ordered path passes (`stream`, and their tails on stream C) are the critical path of an
+    // iteration; the gather / connection work on stream B only has to finish before it is needed again.
+    int prLeast = 0, prGreatest = 0;
+    OPR_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+    if (const char* e = getenv("OPR_STREAM_PRIORITY")) streamPriorities = atoi(e) != 0;
+    if (!streamPriorities) prLeast = prGreatest = 0;
+    OPR_CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prGreatest));
     OPR_CUDA_CHECK(cudaEventCreateWithFlags(&bboxEvent, cudaEventDisableTiming));
-    OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&streamB, cudaStreamNonBlocking));
-    OPR_CUDA_CHECK(cudaStreamCreateWithFlags(&streamC, cudaStreamNonBlocking));
+    OPR_CUDA_CHECK(cudaStreamCreateWithPriority(&streamB, cudaStreamNonBlocking, prLeast));
+    int prC = prGreatest;
+    if (const char* e = getenv("OPR_STREAM_PRIORITY_C")) prC = std::min(prLeast, std::max(prGreatest, prGreatest + atoi(e)));
+    OPR_CUDA_CHECK(cudaStreamCreateWithPriority(&streamC, cudaStreamNonBlocking, prC));
     for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone, &evVcmShade, &evVcmConn[0], &evVcmConn[1]})
         OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
+    if (const char* e = getenv("OPR_VCM_CONNECT_BLOCKS_PER_SM")) vcmConnectBlocksPerSM = (unsigned)std::max(0, atoi(e));
+    if (const char* e = getenv("OPR_GATHER_TILES_PER_BLOCK")) gatherTilesPerBlock = (unsigned)std::max(0, atoi(e));
 
     const size_t P = (size_t)photonLaunchWidth * photonLaunchHeight;
     const size_t N = P * MAX_PHOTON_DEPOSITS;
@@ -277,7 +287,8 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     {
         ScopedTimer t(*this, "ppm.gather", stB);
         launch_gather(hp, width * height, width, height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
-                      float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lcB, gatherBlocks);
+                      float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lcB, gatherBlocks,
+                      (overlap && gatherBlocks == gatherBlocksPerSM) ? gatherTilesPerBlock : 0u);
     }
     // ---- sum of the light samples + PPM_OUTPUT_PASS (:670)
     {

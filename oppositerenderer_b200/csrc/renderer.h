@@ -82,6 +82,9 @@ struct Renderer {
     cudaStream_t streamB = nullptr;
     bool overlap = true;                  // OPR_OVERLAP=0 puts everything on `stream`
     unsigned gatherBlocksPerSM = 4;       // OPR_GATHER_BLOCKS_PER_SM: gather CTAs per SM while it shares the SMs with the next iteration's path passes
+    unsigned gatherTilesPerBlock = 5;     // OPR_GATHER_TILES_PER_BLOCK: > 0 = short-lived gather CTAs (that many tiles each) that the block scheduler can interleave with higher-priority work
+    bool streamPriorities = true;         // OPR_STREAM_PRIORITY=0: all streams at the default priority
+    unsigned vcmConnectBlocksPerSM = 3;   // OPR_VCM_CONNECT_BLOCKS_PER_SM: CTAs per SM of the connection kernel while it shares the SMs with the next bounce (0 = as the other trace kernels)
     bool joinedSinceRender = true;        // the caller consumed the last iteration before asking for the next one (no overlap possible)
     unsigned parity = 0;
     cudaEvent_t evHpFree[2] = {nullptr, nullptr};   // stream B finished with hpBuf[b] / sample buffers b
@@ -202,7 +205,7 @@ void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const 
 void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                             float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc);
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
-                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
+                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM = 0);
 void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const uint2* sampleLight,
                                const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc);
 
@@ -210,7 +213,7 @@ void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsig
 void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, GridParams g, unsigned* keys, unsigned* hist, LaunchCtx lc);
 void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned numValid, const PhotonBuf& dst, LaunchCtx lc);
 void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
-                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc, unsigned blocksPerSM = 12);
+                   float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc, unsigned blocksPerSM = 12, unsigned tilesPerBlock = 0);
 
 // host-side restatement of createUniformGridPhotonMap's scalar part (OptixRenderer_SpatialHash.cu:209-250)
 bool compute_grid_params(const float lo[3], const float hi[3], GridParams& g);

@@ -244,9 +244,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_connect_queue_kernel(Scen
 }
 
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
-                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc)
+                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM)
 {
-    trace_connect_queue_kernel<<<148 * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle());
+    const unsigned blocks = 148 * (blocksPerSM ? blocksPerSM : trace_blocks_per_sm());
+    trace_connect_queue_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle());
     ++*lc.launches;
 }
 

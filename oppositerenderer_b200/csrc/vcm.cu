@@ -742,7 +742,7 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         OPR_CUDA_CHECK(cudaEventRecord(evVcmShade, stream));
         OPR_CUDA_CHECK(cudaStreamWaitEvent(streamB, evVcmShade, 0));
         launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS,
-                                   LaunchCtx{streamB, &launches});
+                                   LaunchCtx{streamB, &launches}, vcmConnectBlocksPerSM);
         OPR_CUDA_CHECK(cudaEventRecord(evVcmConn[connSet], streamB));
         connBusy[connSet] = true;
     };
