@@ -91,14 +91,14 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView 
 static unsigned trace_blocks_per_sm()
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("OPR_TRACE_BLOCKS_PER_SM"); v = e ? atoi(e) : 9; if (v < 1) v = 1; if (v > 16) v = 16; }
+    if (v < 0) { const char* e = getenv("OPR_TRACE_BLOCKS_PER_SM"); v = e ? atoi(e) : 8; if (v < 1) v = 1; if (v > 16) v = 16; }
     return (unsigned)v;
 }
 
 static unsigned trace_refill_idle()
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("OPR_TRACE_REFILL"); v = e ? atoi(e) : 16; if (v < 1) v = 1; if (v > 32) v = 32; }
+    if (v < 0) { const char* e = getenv("OPR_TRACE_REFILL"); v = e ? atoi(e) : 24; if (v < 1) v = 1; if (v > 32) v = 32; }
     return (unsigned)v;
 }
 
