@@ -76,10 +76,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView 
             }
             if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
         }
-        while (__any_sync(FULL, cur >= 0)) {
-            if (cur >= 0) OPR_NODE_STEP(false)
-        }
-        if (cur != TRAVERSAL_DONE) {
+        OPR_NODE_PHASE(FULL, false)
+        if (cur < 0 && cur != TRAVERSAL_DONE) {
             [[maybe_unused]] bool found = false;
             OPR_LEAF_STEP(found)      // a closest-hit query keeps going after an accepted primitive: hit.t only shrinks the search
             OPR_POP(false)
@@ -163,10 +161,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_shadow_queue_kernel(Scene
             }
             if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
         }
-        while (__any_sync(FULL, cur >= 0)) {
-            if (cur >= 0) OPR_NODE_STEP(true)
-        }
-        if (cur != TRAVERSAL_DONE) {
+        OPR_NODE_PHASE(FULL, true)
+        if (cur < 0 && cur != TRAVERSAL_DONE) {
             bool found = false;
             OPR_LEAF_STEP(found)
             if (found) { sampleFactor[idx] = 0.f; cur = TRAVERSAL_DONE; sp = 0; }
@@ -230,10 +226,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_connect_queue_kernel(Scen
             }
             if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
         }
-        while (__any_sync(FULL, cur >= 0)) {
-            if (cur >= 0) OPR_NODE_STEP(true)
-        }
-        if (cur != TRAVERSAL_DONE) {
+        OPR_NODE_PHASE(FULL, true)
+        if (cur < 0 && cur != TRAVERSAL_DONE) {
             bool found = false;
             OPR_LEAF_STEP(found)
             if (found) { pending = NONE; cur = TRAVERSAL_DONE; sp = 0; }
