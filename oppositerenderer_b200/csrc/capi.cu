@@ -164,7 +164,7 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
             need(34 * 4);
             unsigned* o = (unsigned*)dst;
             auto c = download(R.q.counters, CTR_ALLOC, st);
-            o[0] = R.q.capacity; o[1] = c[CTR_SHADOW_COUNT];
+            o[0] = R.q.capacity; o[1] = c[CTR_SHADOW_COUNT] + c[CTR_SHADOW2_COUNT];
             for (int i = 0; i < 16; i++) { o[2 + i] = c[CTR_SNAPSHOT + i]; o[18 + i] = c[CTR_RAYCOUNT + i]; }
             for (int i = 1; i < 16; i++) if (o[2 + i] == 0) { o[2 + i] = c[CTR_TAIL_COUNT]; break; }   // what the camera tail kernel started from
         } else if (n == "light_vertex_counts") {

@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_gen_kernel(SceneView
                                                                        float4* __restrict__ phPower, unsigned* __restrict__ phState,
                                                                        float4* __restrict__ rayO, float4* __restrict__ rayD, unsigned* __restrict__ rayPath,
                                                                        unsigned* __restrict__ counters, const unsigned char* __restrict__ camPending,
-                                                                       unsigned w, unsigned h, unsigned* __restrict__ deferred)
+                                                                       unsigned w, unsigned h, unsigned* __restrict__ deferred,
+                                                                       unsigned char* __restrict__ photonPending, unsigned char pendingValue)
 {
     const unsigned n = pw * ph;     // the per-bounce counters were zeroed by the launcher: this kernel appends to bounce 0
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -399,6 +400,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_gen_kernel(SceneView
         const bool emit = valid && !deferredThread;
         float3 origin = f3(0.f), direction = f3(0.f);
         if (emit) photon_emit(sc, t, pw, rsW, rngBuf, phPower, phState, origin, direction);
+        if (valid) photonPending[t] = emit ? pendingValue : (unsigned char)0;   // (a deferred thread is covered by its pixel's camPending)
         const unsigned dst = warp_append(counters + CTR_RAYCOUNT, emit);
         if (emit) {
             rayO[dst] = make_float4(origin.x, origin.y, origin.z, 0.0001f);
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_gen_kernel(SceneView
 }
 
 void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsigned rsW, const RngBuf& rng, float4* phPower,
-                           unsigned* phState, const RayQueues& q, unsigned w, unsigned h, LaunchCtx lc)
+                           unsigned* phState, const RayQueues& q, unsigned w, unsigned h, LaunchCtx lc, bool feedsTail)
 {
     unsigned n = pw * ph;
     // keep the camera pass's queue lengths for the occupancy report, then zero the per-bounce counters of this pass
@@ -419,7 +421,7 @@ void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsign
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_RAYCOUNT, 0, (CTR_TOTAL - CTR_RAYCOUNT) * sizeof(unsigned), lc.st));
     int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
     ppm_photon_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, pw, ph, rsW, rng, phPower, phState, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters,
-                                                               q.camPending, w, h, q.deferred);
+                                                               q.camPending, w, h, q.deferred, q.photonPending, feedsTail ? 1 : 0);
     ++*lc.launches;
 }
 
@@ -511,7 +513,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneVi
                                                                          const unsigned* __restrict__ rayPath, const float4* __restrict__ hits,
                                                                          const unsigned* __restrict__ matQueue, const unsigned* __restrict__ matCount,
                                                                          unsigned capacity, float4* __restrict__ nextO, float4* __restrict__ nextD,
-                                                                         unsigned* __restrict__ nextPath, unsigned* __restrict__ nextCount)
+                                                                         unsigned* __restrict__ nextPath, unsigned* __restrict__ nextCount,
+                                                                         unsigned char* __restrict__ pendingOut /* last wavefront bounce only */)
 {
     const int kind = blockIdx.y;
     if (kind == QUEUE_MISS) return;
@@ -541,6 +544,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneVi
             nextO[dst] = make_float4(newO.x, newO.y, newO.z, newTmin);
             nextD[dst] = make_float4(newD.x, newD.y, newD.z, RT_DEFAULT_MAX);
             nextPath[dst] = t;
+            if (pendingOut) pendingOut[t] = 1;      // this photon goes on in the tail kernel: its RNG state is not final yet
         }
     }
 }
@@ -584,13 +588,13 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_tail_kernel(SceneVie
 }
 
 void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
-                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc)
+                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc, bool lastWave)
 {
     dim3 grid(SHADE_BLOCKS_X, NUM_QUEUES);
     const int cur = bounce & 1, nxt = cur ^ 1;
     ppm_photon_shade_kernel<<<grid, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
                                                                q.hits, q.matQueue, q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.rayO[nxt], q.rayD[nxt],
-                                                               q.rayPath[nxt], q.counters + CTR_RAYCOUNT + bounce + 1);
+                                                               q.rayPath[nxt], q.counters + CTR_RAYCOUNT + bounce + 1, lastWave ? q.photonPending : nullptr);
     ++*lc.launches;
 }
 
@@ -648,70 +652,106 @@ void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, cons
 // to a compacted queue; (2) trace_shadow_queue_kernel (trace.cu) clears the factor of occluded samples; (3)
 // ppm_resolve_output_kernel sums the samples exactly as the reference does and accumulates direct + indirect.
 // The one-thread-per-pixel version kept 61 % of its lanes idle in lockstep and ran the four traversals back to back.
+// The four light samples of pixel p (all lanes of the warp call this together; lanes with inImage = false ride along).
+OPR_DEV void direct_samples(const SceneView& sc, unsigned p, bool inImage, unsigned w, unsigned rsW, const RngBuf& rngBuf, const HitpointBuf& hp,
+                            float4* __restrict__ sampleFactor, uint2* __restrict__ sampleLight, float4* __restrict__ shadowD,
+                            unsigned* __restrict__ shadowIdx, unsigned* __restrict__ shadowCount)
+{
+    const float4 pos4 = inImage ? hp.pos[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool diffuse = inImage && (__float_as_uint(pos4.w) & PRD_HIT_NON_SPECULAR);
+    float factor[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned lights01 = 0u, lights23 = 0u;      // 16 bits per sample
+    float3 rec_position = f3(pos4), rec_normal = f3(0.f);
+    size_t ri = 0;
+    Rng rng{};
+    if (diffuse) {
+        rec_normal = f3(hp.nrm[p]);
+        ri = (size_t)(p / w) * rsW + (p % w);
+        rng = rng_load(rngBuf, ri);
+    }
+    const int numLights = sc.numLights;
+    #pragma unroll
+    for (int shadowSample = 0; shadowSample < 4; shadowSample++) {
+        float lightFactor = 0.f, lightDistance = 1.f;
+        float3 towardsLight = f3(0.f, 0.f, 1.f);
+        if (diffuse) {
+            float sample = rng_uniform(rng);
+            int randomLightIndex = min(int(sample * numLights), numLights - 1);
+            const opr_light& light = sc.lights[randomLightIndex];
+            if (shadowSample < 2) lights01 |= (unsigned)randomLightIndex << (16 * shadowSample); else lights23 |= (unsigned)randomLightIndex << (16 * (shadowSample - 2));
+            // getLightContribution
+            lightFactor = 1;
+            float3 pointOnLight = f3(0.f);
+            const int lightType = light.lightType;
+            if (lightType == OPR_LIGHT_AREA) {
+                float2 s = rng_uniform2(rng);
+                pointOnLight = f3(light.position[0], light.position[1], light.position[2]) + s.x * f3(light.v1[0], light.v1[1], light.v1[2]) +
+                               s.y * f3(light.v2[0], light.v2[1], light.v2[2]);
+            } else if (lightType == OPR_LIGHT_POINT) {
+                pointOnLight = f3(light.position[0], light.position[1], light.position[2]);
+                lightFactor *= 1.f / 4.f;
+            } else {
+                lightFactor = 0;
+            }
+            towardsLight = pointOnLight - rec_position;
+            lightDistance = length(towardsLight);
+            towardsLight = towardsLight / lightDistance;
+            float n_dot_l = maxf_(0, dot(rec_normal, towardsLight));
+            lightFactor *= n_dot_l / (PI_F * lightDistance * lightDistance);
+            if (lightType == OPR_LIGHT_AREA)
+                lightFactor *= maxf_(0, dot(-towardsLight, f3(light.normal[0], light.normal[1], light.normal[2])));
+        }
+        const bool cast = diffuse && lightFactor > 0.0f;
+        factor[shadowSample] = cast ? lightFactor : 0.f;
+        const unsigned dst = warp_append(shadowCount, cast);
+        if (cast) {
+            shadowD[dst] = make_float4(towardsLight.x, towardsLight.y, towardsLight.z, (float)((double)lightDistance - 0.0001));
+            shadowIdx[dst] = 4u * p + shadowSample;
+        }
+    }
+    if (diffuse) rng_store(rngBuf, ri, rng);
+    if (inImage) { sampleFactor[p] = make_float4(factor[0], factor[1], factor[2], factor[3]); sampleLight[p] = make_uint2(lights01, lights23); }
+}
+
+// Early part: every pixel whose hit point and RNG state are final once the photon wavefronts are done.  A pixel waits (is
+// appended to `deferred`) when its camera path is still in the camera tail (camPending) or when the photon thread that shares
+// its RNG state is still walking (photonPending): the tails run on another stream meanwhile.
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_gen_kernel(SceneView sc, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
                                                                        float4* __restrict__ sampleFactor, uint2* __restrict__ sampleLight,
                                                                        float4* __restrict__ shadowD, unsigned* __restrict__ shadowIdx,
-                                                                       unsigned* __restrict__ counters)
+                                                                       unsigned* __restrict__ counters, const unsigned char* __restrict__ camPending,
+                                                                       const unsigned char* __restrict__ photonPending, unsigned pw, unsigned ph,
+                                                                       unsigned* __restrict__ deferred)
 {
     const unsigned n = w * h;
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_FETCH_SHADOW] = 0u;     // consumed by the trace kernel that follows
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const unsigned p = base + threadIdx.x;
-        const bool inImage = p < n;
-        const float4 pos4 = inImage ? hp.pos[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool diffuse = inImage && (__float_as_uint(pos4.w) & PRD_HIT_NON_SPECULAR);
-        float factor[4] = {0.f, 0.f, 0.f, 0.f};
-        unsigned lights01 = 0u, lights23 = 0u;      // 16 bits per sample
-        float3 rec_position = f3(pos4), rec_normal = f3(0.f);
-        size_t ri = 0;
-        Rng rng{};
-        if (diffuse) {
-            rec_normal = f3(hp.nrm[p]);
-            ri = (size_t)(p / w) * rsW + (p % w);
-            rng = rng_load(rngBuf, ri);
+        bool inImage = p < n;
+        bool wait = false;
+        if (inImage) {
+            const unsigned x = p % w, y = p / w;
+            wait = camPending && (camPending[p] || (x < pw && y < ph && photonPending[(size_t)y * pw + x]));   // null: nothing is pending
         }
-        const int numLights = sc.numLights;
-        #pragma unroll
-        for (int shadowSample = 0; shadowSample < 4; shadowSample++) {
-            float lightFactor = 0.f, lightDistance = 1.f;
-            float3 towardsLight = f3(0.f, 0.f, 1.f);
-            if (diffuse) {
-                float sample = rng_uniform(rng);
-                int randomLightIndex = min(int(sample * numLights), numLights - 1);
-                const opr_light& light = sc.lights[randomLightIndex];
-                if (shadowSample < 2) lights01 |= (unsigned)randomLightIndex << (16 * shadowSample); else lights23 |= (unsigned)randomLightIndex << (16 * (shadowSample - 2));
-                // getLightContribution
-                lightFactor = 1;
-                float3 pointOnLight = f3(0.f);
-                const int lightType = light.lightType;
-                if (lightType == OPR_LIGHT_AREA) {
-                    float2 s = rng_uniform2(rng);
-                    pointOnLight = f3(light.position[0], light.position[1], light.position[2]) + s.x * f3(light.v1[0], light.v1[1], light.v1[2]) +
-                                   s.y * f3(light.v2[0], light.v2[1], light.v2[2]);
-                } else if (lightType == OPR_LIGHT_POINT) {
-                    pointOnLight = f3(light.position[0], light.position[1], light.position[2]);
-                    lightFactor *= 1.f / 4.f;
-                } else {
-                    lightFactor = 0;
-                }
-                towardsLight = pointOnLight - rec_position;
-                lightDistance = length(towardsLight);
-                towardsLight = towardsLight / lightDistance;
-                float n_dot_l = maxf_(0, dot(rec_normal, towardsLight));
-                lightFactor *= n_dot_l / (PI_F * lightDistance * lightDistance);
-                if (lightType == OPR_LIGHT_AREA)
-                    lightFactor *= maxf_(0, dot(-towardsLight, f3(light.normal[0], light.normal[1], light.normal[2])));
-            }
-            const bool cast = diffuse && lightFactor > 0.0f;
-            factor[shadowSample] = cast ? lightFactor : 0.f;
-            const unsigned dst = warp_append(counters + CTR_SHADOW_COUNT, cast);
-            if (cast) {
-                shadowD[dst] = make_float4(towardsLight.x, towardsLight.y, towardsLight.z, (float)((double)lightDistance - 0.0001));
-                shadowIdx[dst] = 4u * p + shadowSample;
-            }
-        }
-        if (diffuse) rng_store(rngBuf, ri, rng);
-        if (inImage) { sampleFactor[p] = make_float4(factor[0], factor[1], factor[2], factor[3]); sampleLight[p] = make_uint2(lights01, lights23); }
+        const unsigned dd = warp_append(counters + CTR_DIRECT_DEFERRED, wait);
+        if (wait) { deferred[dd] = p; inImage = false; }
+        direct_samples(sc, p, inImage, w, rsW, rngBuf, hp, sampleFactor, sampleLight, shadowD, shadowIdx, counters + CTR_SHADOW_COUNT);
+    }
+}
+
+// Late part: the pixels that waited, after the tail kernels.
+__global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_late_kernel(SceneView sc, unsigned w, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
+                                                                        float4* __restrict__ sampleFactor, uint2* __restrict__ sampleLight,
+                                                                        float4* __restrict__ shadowD, unsigned* __restrict__ shadowIdx,
+                                                                        unsigned* __restrict__ counters, const unsigned* __restrict__ deferred)
+{
+    const unsigned n = counters[CTR_DIRECT_DEFERRED];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_FETCH_SHADOW2] = 0u;
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = base + threadIdx.x;
+        const bool valid = i < n;
+        const unsigned p = valid ? deferred[i] : 0u;
+        direct_samples(sc, p, valid, w, rsW, rngBuf, hp, sampleFactor, sampleLight, shadowD, shadowIdx, counters + CTR_SHADOW2_COUNT);
     }
 }
 
@@ -751,12 +791,19 @@ __global__ void __launch_bounds__(256) ppm_resolve_output_kernel(SceneView sc, u
 }
 
 void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, float4* sampleFactor,
-                           uint2* sampleLight, float4* shadowD, unsigned* shadowIdx, unsigned* counters, LaunchCtx lc)
-{
+                           uint2* sampleLight, float4* shadowD, unsigned* shadowIdx, const RayQueues& q, unsigned pw, unsigned ph, int part, LaunchCtx lc)
+{   // part 0: every pixel (nothing pending); 1: early part, pixels behind the tails are deferred; 2: the deferred pixels
     unsigned n = w * h;
-    OPR_CUDA_CHECK(cudaMemsetAsync(counters + CTR_SHADOW_COUNT, 0, sizeof(unsigned), lc.st));
-    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
-    ppm_direct_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, w, h, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, counters);
+    const bool late = part == 2;
+    if (!late) {
+        OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_SHADOW_COUNT, 0, sizeof(unsigned), lc.st));
+        OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_SHADOW2_COUNT, 0, 3 * sizeof(unsigned), lc.st));   // late queue length, cursor, deferred pixels
+        int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
+        ppm_direct_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, w, h, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q.counters,
+                                                                   part == 1 ? q.camPending : nullptr, q.photonPending, pw, ph, q.directDeferred);
+    } else {
+        ppm_direct_late_kernel<<<148 * 4, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q.counters, q.directDeferred);
+    }
     ++*lc.launches;
 }
 

@@ -29,7 +29,7 @@ Renderer::~Renderer()
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
     scene.release();
     if (bboxEvent) cudaEventDestroy(bboxEvent);
-    for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone, evVcmShade, evVcmConn[0], evVcmConn[1]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone, evPhotonWaves, evVcmShade, evVcmConn[0], evVcmConn[1]}) if (e) cudaEventDestroy(e);
     if (streamB) cudaStreamDestroy(streamB);
     if (streamC) cudaStreamDestroy(streamC);
     if (stream) cudaStreamDestroy(stream);
@@ -63,11 +63,12 @@ void Renderer::initialize(int cudaOrdinal)
     int prC = prGreatest;
     if (const char* e = getenv("OPR_STREAM_PRIORITY_C")) prC = std::min(prLeast, std::max(prGreatest, prGreatest + atoi(e)));
     OPR_CUDA_CHECK(cudaStreamCreateWithPriority(&streamC, cudaStreamNonBlocking, prC));
-    for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone, &evVcmShade, &evVcmConn[0], &evVcmConn[1]})
+    for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone, &evPhotonWaves, &evVcmShade, &evVcmConn[0], &evVcmConn[1]})
         OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("OPR_VCM_CONNECT_BLOCKS_PER_SM")) vcmConnectBlocksPerSM = (unsigned)std::max(0, atoi(e));
+    if (const char* e = getenv("OPR_EARLY_DIRECT")) earlyDirect = atoi(e);
     if (const char* e = getenv("OPR_GATHER_TILES_PER_BLOCK")) gatherTilesPerBlock = (unsigned)std::max(0, atoi(e));
 
     const size_t P = (size_t)photonLaunchWidth * photonLaunchHeight;
@@ -114,9 +115,9 @@ void Renderer::freeBuffers()
     hpFreePending[0] = hpFreePending[1] = gridDonePending = false;
     for (int i = 0; i < 2; i++) { dfree(q.rayO[i]); dfree(q.rayD[i]); dfree(q.rayPath[i]); }
     dfree(q.hits); dfree(q.matQueue); dfree(q.counters);
-    dfree(q.tailO); dfree(q.tailD); dfree(q.tailPath); dfree(q.camPending); dfree(q.deferred);
+    dfree(q.tailO); dfree(q.tailD); dfree(q.tailPath); dfree(q.camPending); dfree(q.deferred); dfree(q.photonPending); dfree(q.directDeferred);
     dfree(indirect); dfree(direct); dfree(output);
-    dfree(shadowD); dfree(shadowIdx);
+    dfree(shadowD); dfree(shadowIdx); dfree(shadowD2); dfree(shadowIdx2);
     buffersAllocated = false;
 }
 
@@ -141,8 +142,9 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     dalloc(q.hits, cap); dalloc(q.matQueue, cap * NUM_QUEUES); dalloc(q.counters, CTR_ALLOC);
     dalloc(q.tailO, px); dalloc(q.tailD, px); dalloc(q.tailPath, px); dalloc(q.camPending, px);
     dalloc(q.deferred, (size_t)photonLaunchWidth * photonLaunchHeight);
+    dalloc(q.photonPending, (size_t)photonLaunchWidth * photonLaunchHeight); dalloc(q.directDeferred, px);
     dalloc(indirect, px * 3); dalloc(direct, px * 3); dalloc(output, px * 3);
-    dalloc(shadowD, px * 4); dalloc(shadowIdx, px * 4);
+    dalloc(shadowD, px * 4); dalloc(shadowIdx, px * 4); dalloc(shadowD2, px * 4); dalloc(shadowIdx2, px * 4);
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters, 0, CTR_ALLOC * sizeof(unsigned), stream));
     OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, px * 3 * sizeof(float), stream));
     buffersAllocated = true;
@@ -152,18 +154,18 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     lightVertexCountEstimated = false;      // :847
 }
 
-void Renderer::photonBBoxAsync()
+void Renderer::photonBBoxAsync(cudaStream_t st)
 {   // getPhotonsBoundingBox, OptixRenderer_SpatialHash.cu:123-128.  The result travels to pinned host memory behind an event, so
     // the direct-lighting kernels queued after it keep the GPU busy while the host computes the grid scalars.
-    LaunchCtx lc{stream, &launches};
+    LaunchCtx lc{st, &launches};
     const unsigned P = photonLaunchWidth * photonLaunchHeight;
-    ScopedTimer t(*this, "grid.bbox");
+    ScopedTimer t(*this, "grid.bbox", st);
     float* h = gridBBoxHost;
     h[8] = FLT_MAX; h[9] = FLT_MAX; h[10] = FLT_MAX; h[11] = -FLT_MAX; h[12] = -FLT_MAX; h[13] = -FLT_MAX; h[14] = 0.f; h[15] = 0.f;
-    OPR_CUDA_CHECK(cudaMemcpyAsync(gridBBox, h + 8, 7 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    OPR_CUDA_CHECK(cudaMemcpyAsync(gridBBox, h + 8, 7 * sizeof(float), cudaMemcpyHostToDevice, st));
     launch_photon_bbox(photons, phState, P, gridBBox, lc);
-    OPR_CUDA_CHECK(cudaMemcpyAsync(h, gridBBox, 7 * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    OPR_CUDA_CHECK(cudaEventRecord(bboxEvent, stream));
+    OPR_CUDA_CHECK(cudaMemcpyAsync(h, gridBBox, 7 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    OPR_CUDA_CHECK(cudaEventRecord(bboxEvent, st));
 }
 
 void Renderer::buildPhotonGrid()
@@ -219,6 +221,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     // the SMs that the latency-bound tail kernels and launch gaps of the path passes leave idle.
     // A caller that reads the image back after every iteration leaves nothing to overlap with: give the gather the whole GPU then.
     const unsigned gatherBlocks = (overlap && !joinedSinceRender) ? gatherBlocksPerSM : 12u;
+    const bool early = overlap && (earlyDirect > 0 || (earlyDirect < 0 && joinedSinceRender));
     joinedSinceRender = false;
     parity ^= 1u;
     const unsigned pb = parity;
@@ -245,38 +248,59 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         ScopedTimer t(*this, "ppm.photon");
         // the previous iteration's grid build (stream B) must be done reading the photon slots before they are overwritten
         if (gridDonePending) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evGridDone, 0)); gridDonePending = false; }
-        { ScopedTimer tg(*this, "photon.gen"); launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, width, height, lc); }
+        const unsigned waves = std::min(photonWaveBounces, MAX_PHOTON_TRACE_DEPTH + 1);
+        { ScopedTimer tg(*this, "photon.gen");
+          launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, width, height, lc, waves == 0); }
         OPR_CUDA_CHECK(cudaEventRecord(evPhotonGen, stream));
         // stream C: camera tail, then the deferred photon threads
         OPR_CUDA_CHECK(cudaStreamWaitEvent(stC, evCameraWaves, 0));
         { ScopedTimer t1(*this, "ppm.camera_tail", stC); launch_ppm_camera_tail(sc, width, rsW, rng, hp, q, lcC); }
         OPR_CUDA_CHECK(cudaStreamWaitEvent(stC, evPhotonGen, 0));
         { ScopedTimer t1(*this, "ppm.photon_late", stC); launch_ppm_photon_late(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, lcC); }
-        OPR_CUDA_CHECK(cudaEventRecord(evTailDone, stC));
-        const unsigned waves = std::min(photonWaveBounces, MAX_PHOTON_TRACE_DEPTH + 1);
         static const char* tn[] = {"trace.photon0", "trace.photon1", "trace.photon2", "trace.photon3", "trace.photon4+"};
         static const char* sn[] = {"shade.photon0", "shade.photon1", "shade.photon2", "shade.photon3", "shade.photon4+"};
         for (unsigned bounce = 0; bounce < waves; bounce++) {
             { ScopedTimer t0(*this, tn[std::min(bounce, 4u)]); launch_trace_closest_bounce(sc, q, bounce, lc); }
-            { ScopedTimer t0(*this, sn[std::min(bounce, 4u)]); launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, bounce, lc); }
+            { ScopedTimer t0(*this, sn[std::min(bounce, 4u)]);
+              launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, bounce, lc, bounce + 1 == waves); }
+        }
+        if (early) {
+            // stream C again: the photons still alive finish their walk there, then the photon bounding box (first step of
+            // createUniformGridPhotonMap, :628) goes to the host, while `stream` already draws the light samples of every pixel
+            // whose RNG state and hit point are final (all but the pixels behind the two tails)
+            OPR_CUDA_CHECK(cudaEventRecord(evPhotonWaves, stream));
+            OPR_CUDA_CHECK(cudaStreamWaitEvent(stC, evPhotonWaves, 0));
         }
         if (waves <= MAX_PHOTON_TRACE_DEPTH) {
-            ScopedTimer t1(*this, "ppm.photon_tail");
-            launch_ppm_photon_tail(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, waves, lc);
+            ScopedTimer t1(*this, "ppm.photon_tail", early ? stC : stream);
+            launch_ppm_photon_tail(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, waves, early ? lcC : lc);
         }
-        OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evTailDone, 0));   // hit points, RNG states and photons of the deferred paths are complete
+        if (early) photonBBoxAsync(stC);
+        OPR_CUDA_CHECK(cudaEventRecord(evTailDone, stC));
+        if (!early) {
+            OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evTailDone, 0));   // hit points, RNG states and photons of the deferred paths are complete
+            photonBBoxAsync(stream);
+        }
     }
-    // ---- photon bounding box (first step of createUniformGridPhotonMap, :628), result in flight to the host
-    photonBBoxAsync();
-    // ---- PPM_DIRECT_RADIANCE_ESTIMATION_PASS (:664) moved before the grid build: it needs hit points and RNG states, not
-    // the photon map, and fills the GPU while the host waits for the bounding box.  The RNG order per state is unchanged
-    // (camera pass -> photon pass -> direct pass).
+    // ---- PPM_DIRECT_RADIANCE_ESTIMATION_PASS (:664) moved before the grid build: it needs hit points and RNG states, not the
+    // photon map, and fills the GPU while the host waits for the bounding box.  The RNG order per state is unchanged (camera pass
+    // -> photon pass -> direct pass): with `early`, a pixel's samples are drawn in the first launch only if nothing before them in
+    // that order is still running, else in the late one.
     {
         ScopedTimer t(*this, "ppm.direct");
-        { ScopedTimer t0(*this, "direct.gen"); launch_ppm_direct_gen(sc, width, height, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q.counters, lc); }
+        { ScopedTimer t0(*this, "direct.gen");
+          launch_ppm_direct_gen(sc, width, height, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q, photonLaunchWidth, photonLaunchHeight,
+                                early ? 1 : 0, lc); }
         { ScopedTimer t0(*this, "trace.shadow");
           launch_trace_shadow_queue(sc, hp.pos, shadowD, shadowIdx, q.counters + CTR_SHADOW_COUNT, (float*)sampleFactor, q.counters + CTR_FETCH_SHADOW,
                                     q.counters + CTR_STATS + STAT_ANY_RAYS, lc); }
+        if (early) {
+            OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evTailDone, 0));   // hit points, RNG states and photons of the tail paths are complete
+            ScopedTimer t0(*this, "direct.late");
+            launch_ppm_direct_gen(sc, width, height, rsW, rng, hp, sampleFactor, sampleLight, shadowD2, shadowIdx2, q, photonLaunchWidth, photonLaunchHeight, 2, lc);
+            launch_trace_shadow_queue(sc, hp.pos, shadowD2, shadowIdx2, q.counters + CTR_SHADOW2_COUNT, (float*)sampleFactor, q.counters + CTR_FETCH_SHADOW2,
+                                      q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
+        }
         OPR_CUDA_CHECK(cudaEventRecord(evDirectDone, stream));
     }
     // ---- rest of createUniformGridPhotonMap (stream B; the host waits for the bounding box inside)

@@ -24,6 +24,9 @@ constexpr int CTR_TOTAL = 256;        // [CTR_RAYCOUNT, CTR_TOTAL) is reset by t
 constexpr int CTR_SNAPSHOT = 256;     // 16 words: the ray counts of the pass before the current one (ray-queue occupancy report)
 constexpr int CTR_TAIL_COUNT = 272;    // camera tail queue length (outside the per-pass reset range: the tail runs on its own stream)
 constexpr int CTR_DEFERRED_COUNT = 273; // photon threads deferred behind the camera tail
+constexpr int CTR_SHADOW2_COUNT = 277; // shadow-ray queue of the late direct samples (pixels deferred behind the tails): length, fetch cursor
+constexpr int CTR_FETCH_SHADOW2 = 278;
+constexpr int CTR_DIRECT_DEFERRED = 279; // pixels whose direct samples wait for a tail kernel
 constexpr int CTR_CONN2_COUNT = 274; // second BDPT connection queue (vcm.cu): length, -, fetch cursor at 274..276
 constexpr int CTR_CONN2_FETCH = 276;
 constexpr int CTR_ALLOC = 288;
@@ -37,6 +40,9 @@ struct RayQueues {
     unsigned* matQueue;     // NUM_QUEUES x capacity ray-slot indices, bucketed by material kind
     // camera tail (specular continuations after the last wavefront bounce) and the photon threads deferred behind it
     float4* tailO; float4* tailD; unsigned* tailPath; unsigned char* camPending; unsigned* deferred;
+    // photon threads still walking after the last wavefront bounce (their RNG state is not final), and the pixels whose direct
+    // light samples therefore wait for the tail kernels
+    unsigned char* photonPending; unsigned* directDeferred;
     unsigned* counters;     // CTR_ALLOC words; VCM passes still use [0],[1] ray counts (ping-pong) + [2..2+NUM_QUEUES) material counts
     unsigned capacity;
 };
@@ -83,6 +89,8 @@ struct Renderer {
     bool overlap = true;                  // OPR_OVERLAP=0 puts everything on `stream`
     unsigned gatherBlocksPerSM = 4;       // OPR_GATHER_BLOCKS_PER_SM: gather CTAs per SM while it shares the SMs with the next iteration's path passes
     unsigned gatherTilesPerBlock = 5;     // OPR_GATHER_TILES_PER_BLOCK: > 0 = short-lived gather CTAs (that many tiles each) that the block scheduler can interleave with higher-priority work
+    int earlyDirect = -1;                 // OPR_EARLY_DIRECT: 1 = light samples of the pixels not behind a tail are drawn while the tails run (shorter critical path,
+                                          // two more launches); -1 = only for a caller that reads every iteration back (nothing else fills the GPU then); 0 = never
     bool streamPriorities = true;         // OPR_STREAM_PRIORITY=0: all streams at the default priority
     unsigned vcmConnectBlocksPerSM = 3;   // OPR_VCM_CONNECT_BLOCKS_PER_SM: CTAs per SM of the connection kernel while it shares the SMs with the next bounce (0 = as the other trace kernels)
     bool joinedSinceRender = true;        // the caller consumed the last iteration before asking for the next one (no overlap possible)
@@ -93,7 +101,7 @@ struct Renderer {
     cudaEvent_t evJoin = nullptr;
     // third stream: the camera tail and the photon threads deferred behind it run while `stream` traces the photon wavefronts
     cudaStream_t streamC = nullptr;
-    cudaEvent_t evCameraWaves = nullptr, evPhotonGen = nullptr, evTailDone = nullptr;
+    cudaEvent_t evCameraWaves = nullptr, evPhotonGen = nullptr, evTailDone = nullptr, evPhotonWaves = nullptr;
     cudaStream_t sC() const { return overlap ? streamC : stream; }
     // BDPT: the occlusion tests of bounce b's connections (stream B) run while `stream` traces and shades bounce b+1
     cudaEvent_t evVcmShade = nullptr, evVcmConn[2] = {nullptr, nullptr};
@@ -123,6 +131,7 @@ struct Renderer {
     uint2* sampleLightBuf[2] = {nullptr, nullptr};
     float4* shadowD = nullptr;            // direction.xyz, tmax
     unsigned* shadowIdx = nullptr;        // 4 * pixel + sample
+    float4* shadowD2 = nullptr; unsigned* shadowIdx2 = nullptr;   // the same for the late direct samples
     cudaEvent_t bboxEvent = nullptr;      // photon bbox + count landed in pinned host memory
     float* indirect = nullptr;            // float3 per pixel
     float* direct = nullptr;
@@ -151,7 +160,7 @@ struct Renderer {
                              bool createOutput, const opr_request_details& details);
     void renderPPM(unsigned long long iterationNumber, unsigned localIterationNumber, float PPMRadius, const opr_request_details& details);
     void renderVCM(unsigned long long iterationNumber, unsigned localIterationNumber, float PPMRadius, const opr_request_details& details);
-    void photonBBoxAsync();
+    void photonBBoxAsync(cudaStream_t st);
     void buildPhotonGrid();
     void getOutputBuffer(void* dst);
 };
@@ -193,13 +202,13 @@ void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const
 void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState, const PhotonBuf& photons,
                             const RayQueues& q, LaunchCtx lc);
 void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsigned rsW, const RngBuf& rng, float4* phPower,
-                           unsigned* phState, const RayQueues& q, unsigned w, unsigned h, LaunchCtx lc);
+                           unsigned* phState, const RayQueues& q, unsigned w, unsigned h, LaunchCtx lc, bool feedsTail = false);
 void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
-                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
+                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc, bool lastWave = false);
 void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
 void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, float4* sampleFactor,
-                           uint2* sampleLight, float4* shadowD, unsigned* shadowIdx, unsigned* counters, LaunchCtx lc);
+                           uint2* sampleLight, float4* shadowD, unsigned* shadowIdx, const RayQueues& q, unsigned pw, unsigned ph, int part, LaunchCtx lc);
 void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
                                float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
 void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
