@@ -68,6 +68,7 @@ void Renderer::initialize(int cudaOrdinal)
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("OPR_VCM_CONNECT_BLOCKS_PER_SM")) vcmConnectBlocksPerSM = (unsigned)std::max(0, atoi(e));
+    if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM_ALONE")) gatherBlocksPerSMAlone = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("OPR_EARLY_DIRECT")) earlyDirect = atoi(e);
     if (const char* e = getenv("OPR_GATHER_TILES_PER_BLOCK")) gatherTilesPerBlock = (unsigned)std::max(0, atoi(e));
 
@@ -220,7 +221,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     // overlaps A's work for iteration i+1 (hit points and light samples are double-buffered), so the compute-bound gather fills
     // the SMs that the latency-bound tail kernels and launch gaps of the path passes leave idle.
     // A caller that reads the image back after every iteration leaves nothing to overlap with: give the gather the whole GPU then.
-    const unsigned gatherBlocks = (overlap && !joinedSinceRender) ? gatherBlocksPerSM : 12u;
+    const unsigned gatherBlocks = (overlap && !joinedSinceRender) ? gatherBlocksPerSM : gatherBlocksPerSMAlone;
     const bool early = overlap && (earlyDirect > 0 || (earlyDirect < 0 && joinedSinceRender));
     joinedSinceRender = false;
     parity ^= 1u;

@@ -88,6 +88,7 @@ struct Renderer {
     cudaStream_t streamB = nullptr;
     bool overlap = true;                  // OPR_OVERLAP=0 puts everything on `stream`
     unsigned gatherBlocksPerSM = 4;       // OPR_GATHER_BLOCKS_PER_SM: gather CTAs per SM while it shares the SMs with the next iteration's path passes
+    unsigned gatherBlocksPerSMAlone = 12; // OPR_GATHER_BLOCKS_PER_SM_ALONE: persistent gather CTAs per SM when nothing overlaps (read-back pattern)
     unsigned gatherTilesPerBlock = 5;     // OPR_GATHER_TILES_PER_BLOCK: > 0 = short-lived gather CTAs (that many tiles each) that the block scheduler can interleave with higher-priority work
     int earlyDirect = -1;                 // OPR_EARLY_DIRECT: 1 = light samples of the pixels not behind a tail are drawn while the tails run (shorter critical path,
                                           // two more launches); -1 = only for a caller that reads every iteration back (nothing else fills the GPU then); 0 = never

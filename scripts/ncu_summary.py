@@ -54,14 +54,24 @@ def report(name, path, out):
         out.write("\n")
 
 
-def traffic(path, tag):
+def traffic(paths, tag):
     """profiles/kernel_traffic.json: dram bytes (read + write) per launch of the kernels bench.py reports a roofline for."""
     import json
+    out = {}
+    for path in paths:
+        traffic_one(path, tag, out)
+    json.dump(out, open("profiles/kernel_traffic.json", "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+def traffic_one(path, tag, out):
     txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr = rows[0]
     names = {"ppm_gather_kernel": "ppm.gather", "ppm_direct_output_kernel": "ppm.direct_output"}
-    out, seen_trace = {}, 0
+    seen_trace = 0
+    tunit = rows[1][hdr.index("gpu__time_duration.sum")]
+    tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(tunit, 1.0)
     for vals in rows[2:]:
         kn = vals[hdr.index("Kernel Name")].split("(")[0]
         key = names.get(kn)
@@ -75,20 +85,18 @@ def traffic(path, tag):
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         def metric(name):
             return float(vals[hdr.index(name)]) if name in hdr else None
-        out[key] = {"dram_bytes": rd * scale[ur] + wr * scale[uw], "gpu_time_ms_under_ncu": float(vals[hdr.index("gpu__time_duration.sum")]),
+        out[key] = {"dram_bytes": rd * scale[ur] + wr * scale[uw], "gpu_time_ms_under_ncu": float(vals[hdr.index("gpu__time_duration.sum")]) * tscale,
                     "issue_active_pct": metric("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                     "l1_data_pipe_wavefronts_pct": metric("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
                     "l2_throughput_pct": metric("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
                     "dram_throughput_pct": metric("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                     "lanes_per_instruction": metric("smsp__thread_inst_executed_per_inst_executed.ratio"),
                     "source": "profiles/%s (ncu --set full --clock-control none, one launch)" % tag}
-    json.dump(out, open("profiles/kernel_traffic.json", "w"), indent=1)
-    print(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "traffic":
-        traffic(sys.argv[2], sys.argv[3])
+        traffic(sys.argv[3:], sys.argv[2])     # traffic <summary file name> report.ncu-rep [...]
         sys.exit(0)
     tag = sys.argv[1]
     with open("profiles/%s_ncu_summary.txt" % tag, "w") as out:
