@@ -19,7 +19,10 @@ constexpr int TRACE_THREADS = 128;
 // have finished their ray (or all have), the finished rays are retired (hit record + material queue) and the idle lanes
 // pull fresh rays from the shared cursor, so that warps stay full while ray lengths differ by an order of magnitude
 // (incoherent photon bounces).  The node / leaf steps are the warp-lockstep ones of scene.cuh.
-__global__ void __launch_bounds__(TRACE_THREADS) trace_closest_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+#ifndef OPR_TRACE_MINBLOCKS
+#define OPR_TRACE_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_closest_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       const unsigned* __restrict__ count, float4* __restrict__ hits,
                                                                       unsigned* __restrict__ matQueue, unsigned* __restrict__ matCount,
                                                                       unsigned capacity, unsigned* __restrict__ stat, unsigned* __restrict__ fetchCursor,
@@ -122,7 +125,7 @@ void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bo
 // Any-hit for a compacted queue of shadow rays (ppm/DirectRadianceEstimation.cu:79-83: any intersection in (tmin, tmax)
 // zeroes the sample).  Ray i = (origin = hit point of pixel idx >> 2, direction + tmax = shadowD[i]); an occluded ray
 // clears sampleFactor[idx].  Same persistent / dynamic-fetch / warp-lockstep structure as trace_closest_kernel.
-__global__ void __launch_bounds__(TRACE_THREADS) trace_shadow_queue_kernel(SceneView sc, const float4* __restrict__ hitPos, const float4* __restrict__ shadowD,
+__global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shadow_queue_kernel(SceneView sc, const float4* __restrict__ hitPos, const float4* __restrict__ shadowD,
                                                                            const unsigned* __restrict__ shadowIdx, const unsigned* __restrict__ count,
                                                                            float* __restrict__ sampleFactor, unsigned* __restrict__ fetchCursor,
                                                                            unsigned* __restrict__ stat, unsigned refillIdle)
@@ -182,7 +185,7 @@ void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const 
 // Any-hit for the deferred connections of the BDPT passes (vcm.cu): segment i = (connO[i].xyz, connD[i].xyz) over
 // (EPS_RAY, connO[i].w); when nothing occludes it (isOccluded, vcm/vcm.h:43-59) its contribution connC[i] is added to
 // target[stride * index] (camera-path colour accumulators, or the image for light-tracing splats: vcm.h:159).
-__global__ void __launch_bounds__(TRACE_THREADS) trace_connect_queue_kernel(SceneView sc, const float4* __restrict__ connO, const float4* __restrict__ connD,
+__global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_connect_queue_kernel(SceneView sc, const float4* __restrict__ connO, const float4* __restrict__ connD,
                                                                             const float4* __restrict__ connC, const unsigned* __restrict__ count,
                                                                             float* __restrict__ target, unsigned stride, unsigned* __restrict__ fetchCursor,
                                                                             unsigned* __restrict__ stat, unsigned refillIdle)
