@@ -83,7 +83,7 @@ void DeviceScene::load(const opr_scene_desc* d, cudaStream_t st)
 
     // ---- primitives.  Degenerate ones are dropped exactly as the bounds programs invalidate them
     // (TriangleMesh.cu:105-117, parallelogram.cu:89-97).
-    std::vector<float4> triRec, pgramRec, sphereRec, vN, vT, vB;
+    std::vector<float4> triRec, triAttr, pgramRec, sphereRec, vN, vT, vB;
     std::vector<int4> triShade;
     std::vector<float2> vUV;
     std::vector<int> pgramMat, sphereMat;
@@ -125,6 +125,14 @@ void DeviceScene::load(const opr_scene_desc* d, cudaStream_t st)
             triRec.push_back(make_float4(e0.y, e0.z, e1.x, e1.y));
             triRec.push_back(make_float4(e1.z, n.x, n.y, n.z));
             triShade.push_back(make_int4((int)vbase + i0, (int)vbase + i1, (int)vbase + i2, me.material | (flags << 24)));
+            {   // per-triangle copy of the vertex normals and texture coordinates (eval_surface)
+                const float4 n0 = vN[vbase + i0], n1 = vN[vbase + i1], n2 = vN[vbase + i2];
+                const float2 u0 = vUV[vbase + i0], u1 = vUV[vbase + i1], u2 = vUV[vbase + i2];
+                triAttr.push_back(make_float4(n0.x, n0.y, n0.z, u0.x));
+                triAttr.push_back(make_float4(n1.x, n1.y, n1.z, u0.y));
+                triAttr.push_back(make_float4(n2.x, n2.y, n2.z, u1.x));
+                triAttr.push_back(make_float4(u1.y, u2.x, u2.y, __builtin_bit_cast(float, me.material | (flags << 24))));
+            }
             addPrim(fmin3(fmin3(p0, p1), p2), fmax3(fmax3(p0, p1), p2), (idx << 2) | PRIM_TRIANGLE);
         }
         vbase += me.numVertices;
@@ -160,7 +168,7 @@ void DeviceScene::load(const opr_scene_desc* d, cudaStream_t st)
     numPrims = (unsigned)primLo.size();
     if (numPrims == 0) throw std::runtime_error("scene has no intersectable geometry");
 
-    view.triRec = upload(triRec, owned); view.triShade = upload(triShade, owned);
+    view.triRec = upload(triRec, owned); view.triShade = upload(triShade, owned); view.triAttr = upload(triAttr, owned);
     view.pgramRec = upload(pgramRec, owned); view.pgramMat = upload(pgramMat, owned);
     view.sphereRec = upload(sphereRec, owned); view.sphereMat = upload(sphereMat, owned);
     view.vNormal = upload(vN, owned); view.vUV = upload(vUV, owned); view.vTangent = upload(vT, owned); view.vBitangent = upload(vB, owned);
