@@ -313,6 +313,7 @@ def main():
                     "traffic": tr.get("dram_bytes"), "traffic_source": tr.get("source"),
                     "actual_limiter": {k: tr.get(k) for k in ("issue_active_pct", "l1_data_pipe_wavefronts_pct", "l2_throughput_pct", "dram_throughput_pct",
                                                               "lanes_per_instruction")} if tr else None,
+                    "issue_frac": (tr["issue_active_pct"] / 100.0 if tr and tr.get("issue_active_pct") else None),   # share of the SM issue slots in use: the roofline that does bound this kernel
                     "peak_source": how, "kernel_ms": dur, "algorithmic_bytes": alg[name],
                     "note": "gather and traversal are issue- / L1- / latency-bound, not HBM-bound (DESIGN.md §4, SURVEY.md §8d); profiles/ holds issue, L1 and L2 utilisation of the same launches",
                     "others": {k: {"ms": acc[k], "achieved_gbs": alg[k] / (acc[k] * 1e-3) / 1e9, "frac": alg[k] / (acc[k] * 1e-3) / 1e9 / peak}
