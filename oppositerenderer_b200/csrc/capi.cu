@@ -145,9 +145,9 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
         } else if (n == "random_states") {
             const size_t ns = (size_t)R.rsW * R.rsH;
             need(ns * 24);
-            auto a = download(R.rng.a, ns, st); auto b = download(R.rng.b, ns, st); auto c = download(R.rng.c, ns, st);
+            auto a = download(R.rng.s, 2 * ns, st);
             unsigned* o = (unsigned*)dst;
-            for (size_t i = 0; i < ns; i++, o += 6) { o[0] = a[i].x; o[1] = a[i].y; o[2] = b[i].x; o[3] = b[i].y; o[4] = c[i].x; o[5] = c[i].y; }
+            for (size_t i = 0; i < ns; i++, o += 6) { o[0] = a[2 * i].x; o[1] = a[2 * i].y; o[2] = a[2 * i].z; o[3] = a[2 * i].w; o[4] = a[2 * i + 1].x; o[5] = a[2 * i + 1].y; }
         } else if (n == "grid") {
             need(32);
             float* o = (float*)dst; unsigned* u = (unsigned*)dst;

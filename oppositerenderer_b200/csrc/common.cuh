@@ -135,15 +135,21 @@ OPR_HD float rng_uniform(Rng& s)
 OPR_HD float2 rng_uniform2(Rng& s) { float2 r; r.x = rng_uniform(s); r.y = rng_uniform(s); return r; }
 OPR_HD float3 rng_uniform3(Rng& s) { float3 r; r.x = rng_uniform(s); r.y = rng_uniform(s); r.z = rng_uniform(s); return r; }
 
-struct RngBuf { uint2* a; uint2* b; uint2* c; };   // a=(d,v0) b=(v1,v2) c=(v3,v4)
+// One 32-byte record per state, (d, v0, v1, v2) (v3, v4, -, -), read and written with one 256-bit access: the shading kernels
+// reach the states through path indices in queue order, where three separate arrays cost three sectors per read and three per
+// write; the generation kernels walk the states in order and stay fully coalesced.
+struct RngBuf { uint4* s; };
 OPR_DEV Rng rng_load(const RngBuf& buf, size_t i)
 {
-    uint2 a = buf.a[i], b = buf.b[i], c = buf.c[i];
-    Rng s; s.d = a.x; s.v0 = a.y; s.v1 = b.x; s.v2 = b.y; s.v3 = c.x; s.v4 = c.y; return s;
+    Rng s; [[maybe_unused]] unsigned p0, p1;
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(s.d), "=r"(s.v0), "=r"(s.v1), "=r"(s.v2), "=r"(s.v3), "=r"(s.v4), "=r"(p0), "=r"(p1) : "l"(buf.s + 2 * i) : "memory");
+    return s;
 }
 OPR_DEV void rng_store(const RngBuf& buf, size_t i, const Rng& s)
 {
-    buf.a[i] = make_uint2(s.d, s.v0); buf.b[i] = make_uint2(s.v1, s.v2); buf.c[i] = make_uint2(s.v3, s.v4);
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(buf.s + 2 * i), "r"(s.d), "r"(s.v0), "r"(s.v1), "r"(s.v2), "r"(s.v3), "r"(s.v4), "r"(0u), "r"(0u) : "memory");
 }
 
 // ---- samplers (helpers/samplers.h:21-95) ----------------------------------------------------------------

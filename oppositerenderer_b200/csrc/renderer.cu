@@ -110,7 +110,7 @@ void Renderer::joinStreams()
 
 void Renderer::freeBuffers()
 {
-    dfree(rng.a); dfree(rng.b); dfree(rng.c);
+    dfree(rng.s);
     for (int b = 0; b < 2; b++) { dfree(hpBuf[b].pos); dfree(hpBuf[b].nrm); dfree(hpBuf[b].att); dfree(hpBuf[b].rad); dfree(sampleFactorBuf[b]); dfree(sampleLightBuf[b]); }
     hp = HitpointBuf{}; sampleFactor = nullptr; sampleLight = nullptr;
     hpFreePending[0] = hpFreePending[1] = gridDonePending = false;
@@ -131,7 +131,7 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     const size_t px = (size_t)w * h;
     rsW = std::max(photonLaunchWidth, w); rsH = std::max(photonLaunchHeight, h);
     const size_t ns = (size_t)rsW * rsH;
-    dalloc(rng.a, ns); dalloc(rng.b, ns); dalloc(rng.c, ns);
+    dalloc(rng.s, 2 * ns);
     for (int b = 0; b < 2; b++) {
         dalloc(hpBuf[b].pos, px); dalloc(hpBuf[b].nrm, px); dalloc(hpBuf[b].att, px); dalloc(hpBuf[b].rad, px);
         dalloc(sampleFactorBuf[b], px); dalloc(sampleLightBuf[b], px);
