@@ -21,7 +21,7 @@ struct VcmState {
     float4* mis = nullptr;     // dVCM, dVC, dVM, -
     float4* color = nullptr;   // camera-path colour accumulator
     unsigned* lvCount = nullptr;
-    float4* lv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float4* lv = nullptr;      // stored light vertices, six float4 (96 B, contiguous) per slot
     // deferred connections of one bounce: shadow segment + the contribution it carries if unoccluded
     float4* connO = nullptr;   // origin.xyz, tmax
     float4* connD = nullptr;   // direction.xyz, target index (uint bits)
@@ -38,7 +38,7 @@ struct VcmParams {
     float2 pixelSizeFactor;
 };
 
-struct VcmBuffers { float4* thr; float4* mis; float4* color; unsigned* lvCount; float4* lv0; float4* lv1; float4* lv2; float4* lv3; float4* lv4; float4* lv5; unsigned paths;
+struct VcmBuffers { float4* thr; float4* mis; float4* color; unsigned* lvCount; float4* lv; unsigned paths;
                     float4* connO; float4* connD; float4* connC; unsigned* connCount; };
 constexpr int CTR_CONN_COUNT = 9;     // RayQueues::counters word: length of the connection queue of the current bounce
 constexpr int CTR_CONN_FETCH = 11;    // its fetch cursor
@@ -51,7 +51,7 @@ void vcm_free(Renderer& r)
     devFree(s->thr); devFree(s->mis); devFree(s->color); devFree(s->lvCount);
     devFree(s->connO); devFree(s->connD); devFree(s->connC);
     for (int i = 0; i < 3; i++) devFree(s->conn2[i]);
-    for (int i = 0; i < 6; i++) devFree(s->lv[i]);
+    devFree(s->lv);
     delete s; r.vcm = nullptr;
 }
 
@@ -65,7 +65,7 @@ static void vcm_alloc(Renderer& r)
     s->paths = paths; s->maxVerts = maxVerts;
     devAlloc((void**)&s->thr, paths * 16); devAlloc((void**)&s->mis, paths * 16);
     devAlloc((void**)&s->color, paths * 16); devAlloc((void**)&s->lvCount, paths * 4);
-    for (int i = 0; i < 6; i++) devAlloc((void**)&s->lv[i], paths * maxVerts * 16);
+    devAlloc((void**)&s->lv, paths * maxVerts * 96);
     if (maxVerts + 1 > VCM_MAX_CONNECTIONS) throw std::runtime_error("vcmMaxPathLength too large for the connection queue");
     const size_t cap = paths * (maxVerts + 1);
     devAlloc((void**)&s->connO, cap * 16); devAlloc((void**)&s->connD, cap * 16);
@@ -292,12 +292,13 @@ OPR_DEV bool vcm_light_hit(const SceneView& sc, const VcmParams& P, const RngBuf
                 B.lvCount[p] = k + 1;
                 if (!P.estimatePass) {
                     const size_t vs = (size_t)k * B.paths + p;
-                    B.lv0[vs] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, dVCM);
-                    B.lv1[vs] = make_float4(throughput.x, throughput.y, throughput.z, dVC);
-                    B.lv2[vs] = make_float4(bsdf.geometricNormal.x, bsdf.geometricNormal.y, bsdf.geometricNormal.z, dVM);
-                    B.lv3[vs] = make_float4(bsdf.localDirFix.x, bsdf.localDirFix.y, bsdf.localDirFix.z, __int_as_float(kind));
-                    B.lv4[vs] = make_float4(albedo.x, albedo.y, albedo.z, m.exponent);
-                    B.lv5[vs] = make_float4(m.Ks.x, m.Ks.y, m.Ks.z, __uint_as_float(depth));
+                    float4* V = B.lv + 6 * vs;      // one contiguous 96-byte record: three sectors for the camera pass instead of six
+                    V[0] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, dVCM);
+                    V[1] = make_float4(throughput.x, throughput.y, throughput.z, dVC);
+                    V[2] = make_float4(bsdf.geometricNormal.x, bsdf.geometricNormal.y, bsdf.geometricNormal.z, dVM);
+                    V[3] = make_float4(bsdf.localDirFix.x, bsdf.localDirFix.y, bsdf.localDirFix.z, __int_as_float(kind));
+                    V[4] = make_float4(albedo.x, albedo.y, albedo.z, m.exponent);
+                    V[5] = make_float4(m.Ks.x, m.Ks.y, m.Ks.z, __uint_as_float(depth));
                     // ---- connectCameraT1
                     const float3 eye = f3(P.camera.eye[0], P.camera.eye[1], P.camera.eye[2]);
                     const float3 lookdir = f3(P.camera.lookdir[0], P.camera.lookdir[1], P.camera.lookdir[2]);
@@ -535,7 +536,9 @@ OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBu
                     const unsigned lightSubpathVertexCount = B.lvCount[pathIndex];
                     for (unsigned i = 0; i < lightSubpathVertexCount; ++i) {
                         const size_t vs = (size_t)i * B.paths + pathIndex;
-                        const float4 a0 = B.lv0[vs], a1 = B.lv1[vs];
+                        const float4* V = B.lv + 6 * vs;
+                        const Float8 v01 = ldg256(V);
+                        const float4 a0 = v01.lo, a1 = v01.hi;
                         float3 direction = f3(a0) - hitPoint;
                         const float dist2 = dot(direction, direction);
                         const float distance2 = sqrtf(dist2);
@@ -546,7 +549,8 @@ OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBu
                         const float cameraCont = bsdf.contProb;
                         cameraBsdfDirPdfW *= cameraCont; cameraBsdfRevPdfW *= cameraCont;
                         // rebuild the light vertex' BSDF from its 96-byte record
-                        const float4 a2 = B.lv2[vs], a3 = B.lv3[vs], a4 = B.lv4[vs], a5 = B.lv5[vs];
+                        const Float8 v23 = ldg256(V + 2), v45 = ldg256(V + 4);
+                        const float4 a2 = v23.lo, a3 = v23.hi, a4 = v45.lo, a5 = v45.hi;
                         VcmBSDF lb;
                         lb.initLocal(f3(a2), f3(a3), true);
                         const int lkind = __float_as_int(a3.w);
@@ -706,7 +710,7 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     const SceneView& sc = scene.view;
     vcm_alloc(*this);
     VcmState& S = *vcm;
-    VcmBuffers B{S.thr, S.mis, S.color, S.lvCount, S.lv[0], S.lv[1], S.lv[2], S.lv[3], S.lv[4], S.lv[5], (unsigned)S.paths,
+    VcmBuffers B{S.thr, S.mis, S.color, S.lvCount, S.lv, (unsigned)S.paths,
                  S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT};
     const unsigned lightSubPathCount = width * height;
     const float ppmRadiusSquared = PPMRadius * PPMRadius;
