@@ -17,8 +17,7 @@ constexpr int VCM_THREADS = 128;
 constexpr int VCM_BLOCKS_X = 148 * 6;
 
 struct VcmState {
-    float4* thr = nullptr;     // throughput.xyz, depth (uint bits)
-    float4* mis = nullptr;     // dVCM, dVC, dVM, -
+    float4* state = nullptr;   // per path, one 32-byte record: throughput.xyz, depth (uint bits) | dVCM, dVC, dVM, -
     float4* color = nullptr;   // camera-path colour accumulator
     unsigned* lvCount = nullptr;
     float4* lv = nullptr;      // stored light vertices, six float4 (96 B, contiguous) per slot
@@ -38,8 +37,19 @@ struct VcmParams {
     float2 pixelSizeFactor;
 };
 
-struct VcmBuffers { float4* thr; float4* mis; float4* color; unsigned* lvCount; float4* lv; unsigned paths;
+struct VcmBuffers { float4* state; float4* color; unsigned* lvCount; float4* lv; unsigned paths;
                     float4* connO; float4* connD; float4* connC; unsigned* connCount; };
+// path state record: one 256-bit load / store (the shading kernels reach paths in queue order: one sector instead of two each way)
+OPR_DEV void path_load(const VcmBuffers& B, unsigned p, float4& t4, float4& m4)
+{
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w), "=f"(m4.x), "=f"(m4.y), "=f"(m4.z), "=f"(m4.w) : "l"(B.state + 2 * (size_t)p) : "memory");
+}
+OPR_DEV void path_store(const VcmBuffers& B, unsigned p, const float4& t4, const float4& m4)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(B.state + 2 * (size_t)p), "f"(t4.x), "f"(t4.y), "f"(t4.z), "f"(t4.w), "f"(m4.x), "f"(m4.y), "f"(m4.z), "f"(m4.w) : "memory");
+}
 constexpr int CTR_CONN_COUNT = 9;     // RayQueues::counters word: length of the connection queue of the current bounce
 constexpr int CTR_CONN_FETCH = 11;    // its fetch cursor
 constexpr int VCM_MAX_CONNECTIONS = 16;   // per camera vertex: one light sample + at most maxPathLength - 1 light vertices
@@ -48,7 +58,7 @@ void vcm_free(Renderer& r)
 {
     if (!r.vcm) return;
     VcmState* s = r.vcm;
-    devFree(s->thr); devFree(s->mis); devFree(s->color); devFree(s->lvCount);
+    devFree(s->state); devFree(s->color); devFree(s->lvCount);
     devFree(s->connO); devFree(s->connD); devFree(s->connC);
     for (int i = 0; i < 3; i++) devFree(s->conn2[i]);
     devFree(s->lv);
@@ -63,7 +73,7 @@ static void vcm_alloc(Renderer& r)
     vcm_free(r);
     VcmState* s = new VcmState(); r.vcm = s;
     s->paths = paths; s->maxVerts = maxVerts;
-    devAlloc((void**)&s->thr, paths * 16); devAlloc((void**)&s->mis, paths * 16);
+    devAlloc((void**)&s->state, paths * 32);
     devAlloc((void**)&s->color, paths * 16); devAlloc((void**)&s->lvCount, paths * 4);
     devAlloc((void**)&s->lv, paths * maxVerts * 96);
     if (maxVerts + 1 > VCM_MAX_CONNECTIONS) throw std::runtime_error("vcmMaxPathLength too large for the connection queue");
@@ -254,8 +264,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_gen_kernel(SceneView sc
         if (!light.isDelta) { const float usedCosLight = light.isFinite ? cosAtLight : 1.f; dVC = usedCosLight / emissionPdfW; }
         const float dVM = dVC * P.misVcWeightFactor;
         rng_store(rngBuf, ri, rng);
-        B.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(0u));
-        B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
+        path_store(B, p, make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(0u)), make_float4(dVCM, dVC, dVM, 0.f));
         rayO[p] = make_float4(origin.x, origin.y, origin.z, RAY_LEN_MIN);
         rayD[p] = make_float4(direction.x, direction.y, direction.z, RT_DEFAULT_MAX);
         rayPath[p] = p;
@@ -276,7 +285,8 @@ OPR_DEV bool vcm_light_hit(const SceneView& sc, const VcmParams& P, const RngBuf
     VcmBSDF bsdf; float3 hitNormal, albedo;
     if (vcm_build_bsdf(m, kind, sf, d, true, bsdf, hitNormal, albedo)) {
         const float3 hitPoint = o + hit.t * d;
-        float4 t4 = B.thr[p], m4 = B.mis[p];
+        float4 t4, m4;
+        path_load(B, p, t4, m4);
         float3 throughput = f3(t4);
         unsigned depth = __float_as_uint(t4.w);
         float dVCM = m4.x, dVC = m4.y, dVM = m4.z;
@@ -354,8 +364,7 @@ OPR_DEV bool vcm_light_hit(const SceneView& sc, const VcmParams& P, const RngBuf
                 rng_store(rngBuf, ri, rng);
             }
         }
-        B.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(depth));
-        B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
+        path_store(B, p, make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(depth)), make_float4(dVCM, dVC, dVM, 0.f));
     }
     return push;
 }
@@ -420,8 +429,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_gen_kernel(VcmParams P
         const float imageToSolidAngleFactor = sqr(imagePointToCameraDist) / cosAtCamera;
         const float pixelArea = P.pixelSizeFactor.x * P.camera.imagePlaneSize[0] * P.pixelSizeFactor.x * P.camera.imagePlaneSize[1];   // sic (:138)
         const float cameraPdfW = (1.f / pixelArea) * imageToSolidAngleFactor;
-        B.thr[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
-        B.mis[p] = make_float4(P.lightSubpathCount / cameraPdfW, 0.f, 0.f, 0.f);
+        path_store(B, p, make_float4(1.f, 1.f, 1.f, __uint_as_float(0u)), make_float4(P.lightSubpathCount / cameraPdfW, 0.f, 0.f, 0.f));
         B.color[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         rayO[p] = make_float4(eye.x, eye.y, eye.z, RAY_LEN_MIN);
         rayD[p] = make_float4(dir.x, dir.y, dir.z, RT_DEFAULT_MAX);
@@ -441,7 +449,8 @@ OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBu
     bool push = false;
     const Surface sf = eval_surface(sc, hit, o, d);
     const DMaterial& m = sc.materials[sf.material];
-    float4 t4 = B.thr[p], m4 = B.mis[p];
+    float4 t4, m4;
+    path_load(B, p, t4, m4);
     float3 throughput = f3(t4);
     unsigned depth = __float_as_uint(t4.w);
     float dVCM = m4.x, dVC = m4.y, dVM = m4.z;
@@ -583,8 +592,7 @@ OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBu
             }
         }
     }
-    B.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(depth));
-    B.mis[p] = make_float4(dVCM, dVC, dVM, 0.f);
+    path_store(B, p, make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(depth)), make_float4(dVCM, dVC, dVM, 0.f));
     B.color[p] = make_float4(color.x, color.y, color.z, 0.f);
     return push;
 }
@@ -710,7 +718,7 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     const SceneView& sc = scene.view;
     vcm_alloc(*this);
     VcmState& S = *vcm;
-    VcmBuffers B{S.thr, S.mis, S.color, S.lvCount, S.lv, (unsigned)S.paths,
+    VcmBuffers B{S.state, S.color, S.lvCount, S.lv, (unsigned)S.paths,
                  S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT};
     const unsigned lightSubPathCount = width * height;
     const float ppmRadiusSquared = PPMRadius * PPMRadius;
