@@ -193,6 +193,17 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
         int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
 #define OPR_NODE_EMPTY
 #endif
+// Order of the hit children.  Full: 5-comparator network, visit and pop strictly front to back.  OPR_SORT_NEAREST: only the
+// nearest child is found (3 comparators); the others are pushed as they come, each with its entry distance, so a pop still
+// drops the ones behind the closest hit.
+#ifndef OPR_SORT_NEAREST
+#define OPR_SORT_NEAREST 0
+#endif
+#if OPR_SORT_NEAREST
+#define OPR_SORT_CHILDREN OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t0, r0, t3, r3)
+#else
+#define OPR_SORT_CHILDREN OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t2, r2, t3, r3) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t1, r1, t3, r3) OPR_CSWAP(t1, r1, t2, r2)
+#endif
 // one node visit of a lane with cur >= 0
 #define OPR_NODE_STEP(ANYHIT)                                                                                      \
     {                                                                                                              \
@@ -210,7 +221,7 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
             if (t3 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r3, 0); else { t0 = t3; r0 = r3; } }               \
             if (t0 < INF_) cur = r0; else OPR_POP(true)                                                            \
         } else {                                                                                                   \
-            OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t2, r2, t3, r3) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t1, r1, t3, r3) OPR_CSWAP(t1, r1, t2, r2) \
+            OPR_SORT_CHILDREN                                                                                      \
             if (t0 < INF_) {                                                                                       \
                 if (t3 < INF_) stack[sp++] = make_int2(r3, __float_as_int(t3));                                    \
                 if (t2 < INF_) stack[sp++] = make_int2(r2, __float_as_int(t2));                                    \
