@@ -47,7 +47,7 @@ uint32_t opr_get_screen_buffer_size_bytes(opr_renderer* r);
  * HBM; the caller reduces it across ranks (NCCL) through this device pointer (W*H*3 floats). */
 void* opr_get_output_device_ptr(opr_renderer* r);
 int opr_synchronize(opr_renderer* r);
-/* The renderer overlaps the photon-grid build / gather / output of iteration i (internal second stream) with the path
+/* The renderer overlaps the photon-grid build / gather / output of iteration i (internal low-priority stream; BDPT: the connection occlusion tests of a bounce) with the path
  * passes of iteration i+1.  opr_join_streams orders everything queued so far before later work on opr_get_stream(r);
  * opr_get_output_buffer, opr_get_output_device_ptr, opr_synchronize and opr_debug_get_buffer join implicitly. */
 int opr_join_streams(opr_renderer* r);

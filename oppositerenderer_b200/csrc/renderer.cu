@@ -216,7 +216,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     LaunchCtx lc{stream, &launches};
     const SceneView& sc = scene.view;
     const cudaStream_t stB = sB();
-    // Two streams.  `stream` (A) runs what consumes the RNG states, in the reference's order: camera pass, photon pass, direct
+    // Streams.  `stream` (A, greatest priority) runs what consumes the RNG states, in the reference's order: camera pass, photon pass, direct
     // light samples.  Stream B runs what does not: photon-grid build, gather, sample resolve + output.  B's work for iteration i
     // overlaps A's work for iteration i+1 (hit points and light samples are double-buffered), so the compute-bound gather fills
     // the SMs that the latency-bound tail kernels and launch gaps of the path passes leave idle.
