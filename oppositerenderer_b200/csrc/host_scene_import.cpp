@@ -280,9 +280,10 @@ struct Importer {
             std::vector<Input> inputs; int stride = 0;
             for (const Xml* in : prim->children("input")) {
                 Input i{in->attrs_or("semantic"), frag(in->attrs_or("source")), atoi(in->attrs_or("offset", "0").c_str())};
+                if (i.offset < 0 || i.offset > 255) continue;        // malformed file: an index tuple has no such slot
+                stride = std::max(stride, i.offset + 1);             // the slot exists in the index stream even if the input is not used
                 const std::string set = in->attrs_or("set", "0");
                 if (i.semantic == "TEXCOORD" && set != "0" && set != "1") continue;
-                stride = std::max(stride, i.offset + 1);
                 if (i.semantic == "VERTEX") { for (Input vi : vertexInputs[i.source]) { vi.offset = i.offset; inputs.push_back(vi); } }
                 else inputs.push_back(i);
             }
@@ -307,8 +308,9 @@ struct Importer {
                 size_t cur = 0;
                 const size_t npoly = plist ? vc.size() : idx.size() / (3 * (size_t)stride);
                 for (size_t k = 0; k < npoly; k++) {
+                    if (plist && vc[k] < 0) break;                    // malformed vcount
                     const size_t nv = plist ? (size_t)vc[k] : 3;
-                    if (cur + nv * stride > idx.size()) break;
+                    if (nv > (idx.size() - cur) / (size_t)stride) break;   // (no overflow: the remaining indices cannot hold this polygon)
                     polygons.emplace_back(idx.begin() + cur, idx.begin() + cur + nv * stride);
                     cur += nv * stride;
                 }

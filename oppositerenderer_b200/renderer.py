@@ -162,7 +162,7 @@ class Scene:
         lib = capi.load_library()
         h = lib.opr_scene_file_load(str(filename).encode(), 1 if single_emitter_lights else 0)
         if not h:
-            raise RuntimeError(lib.opr_scene_file_last_error().decode())
+            raise RuntimeError(lib.opr_scene_file_last_error().decode(errors="replace"))
         return Scene(h, lib)
 
     def __del__(self):
@@ -185,7 +185,7 @@ class Scene:
         return Camera(pod=pod)
 
     def getSceneName(self):
-        return self.getSceneDescription().contents.name.decode()
+        return self.getSceneDescription().contents.name.decode(errors="replace")
 
     def getSceneAABB(self):
         d = self.getSceneDescription().contents
@@ -202,7 +202,7 @@ class Scene:
         return self._lib.opr_scene_file_num_meshes(self._h)
 
     def warnings(self):
-        return self._lib.opr_scene_file_warnings(self._h).decode()
+        return self._lib.opr_scene_file_warnings(self._h).decode(errors="replace")
 
 
 class SceneDescription:
@@ -325,7 +325,7 @@ class OptixRenderer:
 
     def _check(self, rc):
         if rc != 0:
-            raise RuntimeError(self._lib.opr_last_error().decode())
+            raise RuntimeError(self._lib.opr_last_error().decode(errors="replace"))
 
     def close(self):
         if getattr(self, "_h", None):

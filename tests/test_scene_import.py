@@ -94,6 +94,45 @@ def test_collada_up_axis_and_errors(product, tmp_path):
         product.Scene.createFromFile(path)
 
 
+def test_malformed_collada_never_reads_out_of_bounds(product, tmp_path):
+    """Regression for two fuzz findings (AddressSanitizer on host_scene_import.cpp): a negative <input offset> indexed in front of
+    the index tuple, and a negative <vcount> entry wrapped the bounds check of the polygon split.  Every mutation must either load
+    (with the damaged primitive dropped or clamped) or fail with a message — and the arrays it returns must be self-consistent."""
+    import random
+    import re
+    path, _ = cf.write_room(str(tmp_path / "m"))
+    src = open(path).read()
+    rng = random.Random(7)
+    cases = [re.sub(r'offset="1"', 'offset="-1"', src, count=1), re.sub(r'offset="0"', 'offset="-7"', src, count=2),
+             re.sub(r'offset="1"', 'offset="100000"', src, count=1),
+             re.sub(r"<vcount>(\d+) ", lambda m: "<vcount>-3 ", src, count=1), re.sub(r"<vcount>(\d+) ", lambda m: "<vcount>4611686018427387904 ", src, count=1)]
+    for _ in range(40):                                  # numbers replaced by hostile values anywhere in the file
+        t = src
+        for _ in range(rng.randrange(1, 4)):
+            ms = list(re.finditer(r"-?\d+", t))
+            m = rng.choice(ms)
+            t = t[:m.start()] + str(rng.choice([-1, 99999999, 0, 2 ** 31, 7, -5, 1000])) + t[m.end():]
+        cases.append(t)
+    loaded = 0
+    for i, text in enumerate(cases):
+        f = tmp_path / "m" / ("case%d.dae" % i)
+        f.write_text(text)
+        try:
+            scene = product.Scene.createFromFile(str(f))
+        except RuntimeError as e:
+            assert str(e)
+            continue
+        loaded += 1
+        d = scene.getSceneDescription().contents
+        for k in range(d.numMeshes):
+            if d.meshes[k].numTriangles == 0:
+                continue
+            v, f = _mesh(d, k)[:2]
+            assert f.min() >= 0 and f.max() < len(v)
+            assert np.isfinite(v).all()
+    assert loaded >= 10
+
+
 def test_oracle_renders_the_imported_scene(product, oracle, tmp_path):
     """CPU: the imported description is a valid scene for the oracle (all six material kinds but glossy, both light types)."""
     path, _ = cf.write_room(str(tmp_path))
