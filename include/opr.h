@@ -108,6 +108,10 @@ void opr_make_area_light(opr_light* out, const float* power3, const float* posit
 void opr_make_point_light(opr_light* out, const float* power3, const float* position3);
 /* IScene::getSceneInitialPPMRadiusEstimate (scene/IScene.cpp:23-31) */
 float opr_initial_ppm_radius(const float* aabbMin3, const float* aabbMax3);
+/* Checks every count, pointer and index of a scene description that the renderer will follow (material kinds, material /
+ * texture / vertex indices, light types).  0 = sound; 1 = not, with the reason in msg.  opr_init_scene runs it first and fails
+ * with the same text. */
+int opr_scene_desc_check(const opr_scene_desc* scene, char* msg, int capacity);
 /* Built-in scenes: "Cornell" (scene/Cornell.cpp) and "CornellSmall" (scene/CornellSmall.cpp; config = Config bits,
  * 0 = Default).  The returned handle owns the description. */
 void* opr_builtin_scene_create(const char* name, uint32_t config);

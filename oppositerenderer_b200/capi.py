@@ -133,6 +133,7 @@ def _declare(lib):
         "opr_gather": (i32, [u32, PF, u32, PF, PU, f32, PU, PF, f32, f32, PF]),
         "opr_trace_closest": (i32, [vp, PF, u32, PF, PI, PF]),
         "opr_trace_any": (i32, [vp, PF, u32, PI]),
+        "opr_scene_desc_check": (i32, [C.POINTER(opr_scene_desc), C.c_char_p, i32]),
         "opr_builtin_scene_create": (vp, [C.c_char_p, u32]),
         "opr_builtin_scene_destroy": (None, [vp]),
         "opr_builtin_scene_desc": (C.POINTER(opr_scene_desc), [vp]),

@@ -1,6 +1,7 @@
 // host_api.cpp — host-only pieces of the drop-in surface: Camera::setup / setAspectRatio, the Light
 // constructors, the initial-radius estimate, the PPM radius schedule and the built-in Cornell /
 // CornellSmall scene tables.  No CUDA here; these run on a machine without a GPU.
+#include <cstdio>
 #include "../../include/opr.h"
 #include <cmath>
 #include <cstring>
@@ -308,3 +309,44 @@ const opr_scene_desc* opr_builtin_scene_desc(void* scene) { return &static_cast<
 void opr_builtin_scene_camera(void* scene, opr_camera* out) { *out = static_cast<SceneTable*>(scene)->cam; }
 
 }  // extern "C"
+
+// ---- opr_scene_desc sanity (called by initScene before anything is uploaded) ---------------------------------------------
+// The reference trusts its own Scene / Cornell classes; a C ABI cannot: every index the device code will follow is checked here.
+extern "C" int opr_scene_desc_check(const opr_scene_desc* d, char* msg, int capacity)
+{
+    auto fail = [&](const char* fmt, int a, int b) { if (msg && capacity > 0) snprintf(msg, (size_t)capacity, fmt, a, b); return 1; };
+    if (!d) return fail("scene description is NULL", 0, 0);
+    if (d->numMeshes < 0 || d->numParallelograms < 0 || d->numSpheres < 0 || d->numMaterials < 0 || d->numTextures < 0 || d->numLights < 0)
+        return fail("scene description with a negative count", 0, 0);
+    if ((d->numMeshes && !d->meshes) || (d->numParallelograms && !d->parallelograms) || (d->numSpheres && !d->spheres) ||
+        (d->numMaterials && !d->materials) || (d->numTextures && !d->textures) || (d->numLights && !d->lights))
+        return fail("scene description with a count but no array", 0, 0);
+    for (int i = 0; i < d->numTextures; i++) {
+        const opr_texture& t = d->textures[i];
+        if (t.width <= 0 || t.height <= 0 || !t.rgba) return fail("texture %d has no texels", i, 0);
+    }
+    for (int i = 0; i < d->numMaterials; i++) {
+        const opr_material& m = d->materials[i];
+        if (m.kind < 0 || m.kind >= OPR_MAT_NUM_KINDS) return fail("material %d has unknown kind %d", i, m.kind);
+        if (m.kind == OPR_MAT_TEXTURE) {
+            if (m.diffuseTexture < 0 || m.diffuseTexture >= d->numTextures) return fail("Texture material %d without a diffuse texture", i, 0);
+            if (m.normalTexture >= d->numTextures) return fail("Texture material %d: normal map %d does not exist", i, m.normalTexture);
+        }
+    }
+    auto badMaterial = [&](int m) { return m < 0 || m >= d->numMaterials; };
+    for (int i = 0; i < d->numMeshes; i++) {
+        const opr_mesh& me = d->meshes[i];
+        if (me.numVertices < 0 || me.numTriangles < 0) return fail("mesh %d with a negative count", i, 0);
+        if (badMaterial(me.material)) return fail("mesh %d: material %d does not exist", i, me.material);
+        if (me.numTriangles && (!me.indices || !me.vertices)) return fail("mesh %d has triangles but no index / vertex array", i, 0);
+        for (long long k = 0; k < 3LL * me.numTriangles; k++)
+            if (me.indices[k] < 0 || me.indices[k] >= me.numVertices) return fail("mesh %d: vertex index %d out of range", i, me.indices[k]);
+    }
+    for (int i = 0; i < d->numParallelograms; i++)
+        if (badMaterial(d->parallelograms[i].material)) return fail("parallelogram %d: material %d does not exist", i, d->parallelograms[i].material);
+    for (int i = 0; i < d->numSpheres; i++)
+        if (badMaterial(d->spheres[i].material)) return fail("sphere %d: material %d does not exist", i, d->spheres[i].material);
+    for (int i = 0; i < d->numLights; i++)
+        if (d->lights[i].lightType < OPR_LIGHT_AREA || d->lights[i].lightType > OPR_LIGHT_SPOT) return fail("light %d has unknown type %d", i, d->lights[i].lightType);
+    return 0;
+}

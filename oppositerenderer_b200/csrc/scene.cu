@@ -2,6 +2,7 @@
 // (the values the reference hands to OptiX in scene/Scene.cpp:361-467, scene/Cornell.cpp:46-197, material/*.cpp).
 // The acceleration structure is built in bvh.cu.
 #include "device_scene.h"
+#include "../../include/opr.h"
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -39,6 +40,7 @@ void DeviceScene::release()
 void DeviceScene::load(const opr_scene_desc* d, cudaStream_t st)
 {
     release();
+    { char msg[160]; if (opr_scene_desc_check(d, msg, (int)sizeof msg)) throw std::runtime_error(msg); }
     if (d->numLights <= 0) throw std::runtime_error("No lights exists in this scene.");   // OptixRenderer.cpp:443-447
     if (d->numLights > 65535) throw std::runtime_error("more than 65535 lights: the direct-light sample records hold 16-bit light indices");
 

@@ -111,3 +111,39 @@ def test_light_constructors(product, oracle):
     a = product.Light((30, 30, 30), (1.25, 2.25, 1.25)).pod
     olib.ora_make_point_light(C.byref(b), f3(30, 30, 30), f3(1.25, 2.25, 1.25))
     assert _bytes(a) == _bytes(b)
+
+
+def test_scene_description_check_rejects_what_the_device_would_follow(product):
+    """opr_scene_desc_check (run by opr_init_scene before anything is uploaded): material kinds, material / texture / vertex indices
+    and light types of a caller-built description — the reference trusts its own scene classes, a C ABI cannot."""
+    from oppositerenderer_b200.renderer import make_material, SceneDescription
+    lib = capi.load_library()
+    msg = C.create_string_buffer(200)
+
+    def check(scene):
+        rc = lib.opr_scene_desc_check(scene.getSceneDescription(), msg, 200)
+        return rc, msg.value.decode()
+
+    verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    light = product.Light((1, 1, 1), (0, 5, 0))
+
+    def scene(indices=(0, 1, 2), material=0, kind=capi.MAT_DIFFUSE, n_mats=1):
+        mats = [make_material(kind, Kd=(0.5, 0.5, 0.5)) for _ in range(n_mats)]
+        return SceneDescription("t", (0, 0, 0), (1, 1, 1), mats, [light], meshes=[dict(vertices=verts, indices=np.array([indices], np.int32), material=material)])
+
+    assert check(scene())[0] == 0
+    rc, text = check(scene(indices=(0, 1, 3)))
+    assert rc == 1 and "vertex index 3 out of range" in text
+    rc, text = check(scene(indices=(0, -1, 2)))
+    assert rc == 1 and "out of range" in text
+    rc, text = check(scene(material=1))
+    assert rc == 1 and "material 1 does not exist" in text
+    rc, text = check(scene(kind=17))
+    assert rc == 1 and "unknown kind 17" in text
+    rc, text = check(scene(kind=capi.MAT_TEXTURE))
+    assert rc == 1 and "without a diffuse texture" in text
+    assert lib.opr_scene_desc_check(None, msg, 200) == 1
+    for name in ("Cornell", "CornellSmall"):                 # the built-in tables are sound
+        h = lib.opr_builtin_scene_create(name.encode(), 0)
+        assert lib.opr_scene_desc_check(lib.opr_builtin_scene_desc(h), msg, 200) == 0, msg.value
+        lib.opr_builtin_scene_destroy(h)

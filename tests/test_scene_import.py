@@ -28,6 +28,7 @@ def test_collada_room_import(product, tmp_path):
     scene = product.Scene.createFromFile(path)
     d = scene.getSceneDescription().contents
     assert scene.getSceneName() == os.path.realpath(path)
+    assert capi.load_library().opr_scene_desc_check(scene.getSceneDescription(), None, 0) == 0     # what initScene checks first
     # ---- material classification, Scene.cpp:178-265, in <library_materials> order
     kinds = [d.materials[i].kind for i in range(d.numMaterials)]
     assert kinds == [capi.MAT_DIFFUSE, capi.MAT_DIFFUSE, capi.MAT_DIFFUSE_EMITTER, capi.MAT_GLASS, capi.MAT_MIRROR, capi.MAT_TEXTURE]
