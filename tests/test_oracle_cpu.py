@@ -68,3 +68,36 @@ def test_grid_build_properties(oracle):
     ph = util.synthetic_photons(256, 5, invalid_fraction=1.1)
     g = util.oracle_grid(ph)
     assert g["numValid"] == 0 and g["gridSize"] == (1, 1, 1)
+
+
+def test_xorwow_matches_nvidia_curand_host_generator(oracle):
+    """Known-answer pin of row a1 against NVIDIA's own library: cuRAND's HOST generator (no GPU needed) with
+    CURAND_RNG_PSEUDO_XORWOW and the default ordering emits, at output positions 0, 4096, 8192, ..., the successive draws of
+    subsequence 0 of the seed — exactly the stream curand_init(seed, 0, 0) + curand_uniform gives a device thread
+    (OptixRenderer_SpatialHash.cu:310-317, helpers/random.h:65-69: getRandomUniformFloat = max(curand_uniform - FLT_EPSILON, 0))."""
+    import ctypes as C
+    import ctypes.util
+    path = next((p for p in ("/usr/local/cuda/lib64/libcurand.so", ctypes.util.find_library("curand")) if p and (os.path.exists(p) or "/" not in p)), None)
+    if not path:
+        pytest.skip("libcurand not found")
+    try:
+        cr = C.CDLL(path)
+    except OSError:
+        pytest.skip("libcurand cannot be loaded")
+    gen = C.c_void_p()
+    if cr.curandCreateGeneratorHost(C.byref(gen), 101) != 0:          # CURAND_RNG_PSEUDO_XORWOW
+        pytest.skip("cuRAND host generator unavailable")
+    lib = oracle.load("oracle")
+    draws = 8
+    for seed in (0, 1, 1645301512, 1645301512 + 1919, 0xffffffff):
+        assert cr.curandSetPseudoRandomGeneratorSeed(gen, C.c_ulonglong(seed)) == 0
+        assert cr.curandSetGeneratorOffset(gen, C.c_ulonglong(0)) == 0
+        out = np.zeros(4096 * (draws - 1) + 1, np.float32)
+        assert cr.curandGenerateUniform(gen, out.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(out.size)) == 0
+        expect = np.maximum(out[::4096] - np.float32(np.finfo(np.float32).eps), 0).astype(np.float32)
+        st = np.zeros(6, np.uint32)
+        lib.ora_rng_init(st.ctypes.data_as(C.POINTER(C.c_uint32)), seed, 0, 1)
+        u = np.zeros(draws, np.float32)
+        lib.ora_rng_uniform(st.ctypes.data_as(C.POINTER(C.c_uint32)), u.ctypes.data_as(C.POINTER(C.c_float)), draws)
+        assert np.array_equal(expect, u), (seed, expect, u)
+    cr.curandDestroyGenerator(gen)
