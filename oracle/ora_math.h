@@ -1,5 +1,8 @@
 // ORACLE — test infrastructure only. Nothing under oracle/ is part of the product; only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may build or call it.
+// PARITY PINNED: against oracle/_ref — the reference's own device programs host-compiled from /root/reference by oracle/refshim
+// (tests/test_oracle_vs_ref.py; the same outputs are committed as tests/golden/*.npz) — and, for the XORWOW generator, against
+// NVIDIA's cuRAND host generator (tests/test_oracle_cpu.py).
 //
 // ora_math.h — vector types plus the OptiX SDK 3.5/3.6 `optixu_math_namespace.h` functions the hot
 // path uses.  The OptiX SDK is NOT vendored in /root/reference (SDKs.props:16-17), so these restate
