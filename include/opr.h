@@ -70,8 +70,14 @@ const char* opr_get_timing_name(opr_renderer* r, int index);
  * (36 B x numValid), "photon_keys" (u32 x 4P, sorted), "offsets" (u32 x numCells+1), "indirect", "direct"
  * (float3 x W*H), "random_states" ({d,v0..v4} u32 x 6 per state), "grid" (cellSize, gridSize[3], origo[3],
  * numValid as 8 x 4 bytes), "photon_path_lengths" (u32 x P), "light_vertex_counts" (u32 x W*H), "queue_counts" (34 x u32: ray-queue
- * capacity, shadow rays queued, camera-pass and photon-pass ray counts per bounce of the last PPM iteration). */
+ * capacity, shadow rays queued, camera-pass and photon-pass ray counts per bounce of the last PPM iteration).
+ * Parity diagnostics (they let a test tell WHICH discrete decision made a pixel differ from the oracle):
+ * "direct_sample_mask" (u8 x W*H: bit s = shadow sample s of DirectRadianceEstimation.cu:54-70 was unoccluded and non-zero),
+ * "light_vertex_positions" (u32 count + 12 B pad, then {u32 path, float3 hitPoint} per stored light vertex of the last light
+ * pass), "connection_counts" (u32 x W*H: contributions that passed isOccluded, vcm.h:43-59, per target pixel, last BDPT
+ * iteration; needs opr_debug_set_connection_counts(r, 1) before the iteration). */
 int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t bytes);
+int opr_debug_set_connection_counts(opr_renderer* r, int enabled);
 
 /* Out-of-bounds write detection without a sanitizer: after opr_debug_set_guards(1) every device allocation of the library
  * carries a 4 KiB band of a known byte pattern on both sides; opr_debug_check_guards synchronises the device, reads every band

@@ -170,12 +170,28 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
         } else if (n == "light_vertex_counts") {
             need(px * 4);
             if (R.debugLightVertexCounts((unsigned*)dst)) throw std::runtime_error("no BDPT iteration has run yet");
+        } else if (n == "connection_counts") {
+            need(px * 4);
+            if (R.debugConnectionCountsGet((unsigned*)dst)) throw std::runtime_error("connection counts are off (opr_debug_set_connection_counts) or no BDPT iteration has run");
+        } else if (n == "direct_sample_mask") {
+            // bit s of byte p: shadow sample s of pixel p was cast, unoccluded and non-zero (last PPM iteration)
+            need(px);
+            auto f = download(R.sampleFactor, px, st);
+            unsigned char* o = (unsigned char*)dst;
+            for (size_t i = 0; i < px; i++) o[i] = (unsigned char)((f[i].x > 0.f) | ((f[i].y > 0.f) << 1) | ((f[i].z > 0.f) << 2) | ((f[i].w > 0.f) << 3));
+        } else if (n == "light_vertex_positions") {
+            // [0] = number of stored light vertices, then (path, x, y, z) 16-byte records, path-major
+            need(16);
+            const long long cnt = R.debugLightVertexPositions((float*)dst + 4, (size_t)(bytes / 16) - 1);
+            if (cnt < 0) throw std::runtime_error("no BDPT iteration has run yet");
+            memset(dst, 0, 16); const unsigned c32 = (unsigned)cnt; memcpy(dst, &c32, 4);
         } else {
             throw std::runtime_error("opr_debug_get_buffer: unknown buffer " + n);
         }
     })
 }
 
+int opr_debug_set_connection_counts(opr_renderer* r, int enabled) { r->r.debugConnectionCounts = enabled != 0; return 0; }
 void opr_debug_set_guards(int enabled) { opr::devSetGuards(enabled != 0); }
 int opr_debug_check_guards(int* liveBlocks)
 {

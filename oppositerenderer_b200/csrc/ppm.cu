@@ -181,7 +181,11 @@ OPR_DEV bool shade_camera_hit(const SceneView& sc, int kind, unsigned p, const f
         hp.att[p] = make_float4(att.x, att.y, att.z, 0.f);
     } else if (kind == OPR_MAT_TEXTURE) {
         float3 normal = worldShadingNormal;
-        if (m.hasNormalTex) {
+        // A normal map on a mesh without tangents / bitangents: the reference reads OptiX attributes its intersection program
+        // never wrote (TriangleMesh.cu:61-72 vs Texture.cu:89-95, undefined); here the map is ignored and the interpolated
+        // shading normal is used.  assimp's CalcTangentSpace (scene/Scene.cpp:96) gives every imported mesh
+        // with normals and uvs a tangent frame, so reference scenes never get here.
+        if (m.hasNormalTex && sf.hasTangents) {
             float3 worldTangent = normalize(sf.tangent), worldBitangent = normalize(sf.bitangent);
             normal = getNormalMappedNormal(worldShadingNormal, worldTangent, worldBitangent, tex2D<float4>(m.normalTex, sf.uv.x, sf.uv.y));
         }

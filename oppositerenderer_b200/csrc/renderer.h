@@ -142,6 +142,9 @@ struct Renderer {
     // VCM state lives in vcm.cu
     struct VcmState* vcm = nullptr;
     int debugLightVertexCounts(unsigned* dstHost);
+    bool debugConnectionCounts = false;   // opr_debug_set_connection_counts
+    int debugConnectionCountsGet(unsigned* dstHost);
+    long long debugLightVertexPositions(float* dstHost, size_t capacityVerts);
     bool lightVertexCountEstimated = false;
 
     // statistics / timing
@@ -215,7 +218,7 @@ void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const 
 void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                             float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc);
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
-                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM = 0);
+                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM = 0, unsigned* dbgCount = nullptr);
 void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const uint2* sampleLight,
                                const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc);
 

@@ -360,12 +360,12 @@ OPR_DEV bool traverse(const SceneView& sc, const float3& o, const float3& d, flo
 }
 
 // Attributes the reference's intersection programs hand to the material programs
-struct Surface { float3 geometricNormal, shadingNormal, tangent, bitangent; float2 uv; int material; };
+struct Surface { float3 geometricNormal, shadingNormal, tangent, bitangent; float2 uv; int material; bool hasTangents; };
 
 OPR_DEV Surface eval_surface(const SceneView& sc, const HitRec& hit, const float3& o, const float3& d)
 {
     Surface s;
-    s.tangent = s.bitangent = f3(0.f); s.uv = make_float2(0.f, 0.f);
+    s.tangent = s.bitangent = f3(0.f); s.uv = make_float2(0.f, 0.f); s.hasTangents = false;
     const int type = hit.prim & 3, idx = hit.prim >> 2;
     if (type == PRIM_TRIANGLE) {                       // TriangleMesh.cu:48-88
         const float4 c = __ldg(&sc.triRec[3 * idx + 2]);
@@ -382,6 +382,7 @@ OPR_DEV Surface eval_surface(const SceneView& sc, const HitRec& hit, const float
             const float3 n0 = f3(a01.lo), n1 = f3(a01.hi), n2 = f3(a23.lo);
             s.shadingNormal = normalize(n1 * beta + n2 * gamma + n0 * (1.0f - beta - gamma));
             if (flags & TRI_HAS_TANGENTS) {
+                s.hasTangents = true;
                 const int4 sh = __ldg(&sc.triShade[idx]);
                 const float3 t0 = f3(__ldg(&sc.vTangent[sh.x])), t1 = f3(__ldg(&sc.vTangent[sh.y])), t2 = f3(__ldg(&sc.vTangent[sh.z]));
                 s.tangent = normalize(t1 * beta + t2 * gamma + t0 * (1.0f - beta - gamma));

@@ -188,7 +188,7 @@ void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const 
 __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_connect_queue_kernel(SceneView sc, const float4* __restrict__ connO, const float4* __restrict__ connD,
                                                                             const float4* __restrict__ connC, const unsigned* __restrict__ count,
                                                                             float* __restrict__ target, unsigned stride, unsigned* __restrict__ fetchCursor,
-                                                                            unsigned* __restrict__ stat, unsigned refillIdle)
+                                                                            unsigned* __restrict__ stat, unsigned refillIdle, unsigned* __restrict__ dbgCount)
 {
     const unsigned FULL = 0xffffffffu, NONE = 0xffffffffu;
     const unsigned n = *count;
@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
         if (idleMask == FULL || (!exhausted && (unsigned)__popc(idleMask) >= refillIdle)) {
             if (cur == TRAVERSAL_DONE && pending != NONE) {
                 const float4 c = connC[pending];
-                float* t = target + (size_t)stride * __float_as_uint(connD[pending].w);
+                const unsigned ti = __float_as_uint(connD[pending].w);
+                float* t = target + (size_t)stride * ti;
+                if (dbgCount) atomicAdd(dbgCount + ti, 1u);     // parity diagnostics only (null otherwise)
                 atomicAdd(t, c.x); atomicAdd(t + 1, c.y); atomicAdd(t + 2, c.z);
                 pending = NONE;
             }
@@ -241,10 +243,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
 }
 
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
-                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM)
+                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM, unsigned* dbgCount)
 {
     const unsigned blocks = 148 * (blocksPerSM ? blocksPerSM : trace_blocks_per_sm());
-    trace_connect_queue_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle());
+    trace_connect_queue_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle(), dbgCount);
     ++*lc.launches;
 }
 

@@ -26,6 +26,7 @@ struct VcmState {
     float4* connD = nullptr;   // direction.xyz, target index (uint bits)
     float4* connC = nullptr;   // contribution.xyz
     float4* conn2[3] = {nullptr, nullptr, nullptr};   // second set: bounce b+1 fills it while stream B still tests the segments of bounce b
+    unsigned* dbgConn = nullptr;   // parity diagnostics (opr_debug_set_connection_counts): contributions that passed isOccluded, per target pixel
     size_t paths = 0; unsigned maxVerts = 0;
 };
 
@@ -38,7 +39,7 @@ struct VcmParams {
 };
 
 struct VcmBuffers { float4* state; float4* color; unsigned* lvCount; float4* lv; unsigned paths;
-                    float4* connO; float4* connD; float4* connC; unsigned* connCount; };
+                    float4* connO; float4* connD; float4* connC; unsigned* connCount; unsigned* dbgConn; };
 // path state record: one 256-bit load / store (the shading kernels reach paths in queue order: one sector instead of two each way)
 OPR_DEV void path_load(const VcmBuffers& B, unsigned p, float4& t4, float4& m4)
 {
@@ -61,7 +62,7 @@ void vcm_free(Renderer& r)
     devFree(s->state); devFree(s->color); devFree(s->lvCount);
     devFree(s->connO); devFree(s->connD); devFree(s->connC);
     for (int i = 0; i < 3; i++) devFree(s->conn2[i]);
-    devFree(s->lv);
+    devFree(s->lv); devFree(s->dbgConn);
     delete s; r.vcm = nullptr;
 }
 
@@ -345,6 +346,7 @@ OPR_DEV bool vcm_light_hit(const SceneView& sc, const VcmParams& P, const RngBuf
                                 if (distance < 3.f * EPS_RAY || (!DEFER && !vcm_occluded_inline(sc, hitPoint, dirToCamera, distance, shadowRays))) {
                                     // the reference's splat is a plain, racy += (vcm.h:159); atomics here
                                     float* op = output + 3 * ((size_t)py * P.w + px);
+                                    if (B.dbgConn) atomicAdd(B.dbgConn + ((size_t)py * P.w + px), 1u);
                                     atomicAdd(op, contrib.x); atomicAdd(op + 1, contrib.y); atomicAdd(op + 2, contrib.z);
                                 } else if (DEFER) {
                                     conn.dir = dirToCamera; conn.tmax = distance - 2.f * EPS_RAY; conn.contrib = contrib;
@@ -535,7 +537,7 @@ OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBu
                             const float misWeight = 1.f / (wLight + 1.f + wCamera);
                             const float3 contrib = (misWeight * cosToLight / (lightPickProb * directPdfW)) * (radiance * bsdfFactor);
                             if (!isZero(contrib)) {
-                                if (distance < 3.f * EPS_RAY || (!DEFER && !vcm_occluded_inline(sc, hitPoint, dirToLight, distance, shadowRays))) color += contrib * throughput;
+                                if (distance < 3.f * EPS_RAY || (!DEFER && !vcm_occluded_inline(sc, hitPoint, dirToLight, distance, shadowRays))) { color += contrib * throughput; if (B.dbgConn) atomicAdd(B.dbgConn + p, 1u); }
                                 else if (DEFER) { conn[numConn].dir = dirToLight; conn[numConn].tmax = distance - 2.f * EPS_RAY; conn[numConn].contrib = contrib * throughput; numConn++; }
                             }
                         }
@@ -579,7 +581,7 @@ OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBu
                         const float misWeight = 1.f / (wLight + 1.f + wCamera);
                         float3 contrib = geometryTerm * cameraBsdfFactor * lightBsdfFactor * 1.f;
                         contrib *= misWeight * throughput * f3(a1);
-                        if (distance2 < 3.f * EPS_RAY || (!DEFER && !vcm_occluded_inline(sc, hitPoint, direction, distance2, shadowRays))) color += contrib;
+                        if (distance2 < 3.f * EPS_RAY || (!DEFER && !vcm_occluded_inline(sc, hitPoint, direction, distance2, shadowRays))) { color += contrib; if (B.dbgConn) atomicAdd(B.dbgConn + p, 1u); }
                         else if (DEFER && numConn < VCM_MAX_CONNECTIONS) { conn[numConn].dir = direction; conn[numConn].tmax = distance2 - 2.f * EPS_RAY; conn[numConn].contrib = contrib; numConn++; }
                     }
                 }
@@ -703,12 +705,43 @@ __global__ void vcm_accumulate_kernel(VcmBuffers B, unsigned n, float* __restric
     }
 }
 
+int Renderer::debugConnectionCountsGet(unsigned* dstHost)
+{
+    if (!vcm || !vcm->dbgConn) return 1;
+    OPR_CUDA_CHECK(cudaMemcpyAsync(dstHost, vcm->dbgConn, vcm->paths * 4, cudaMemcpyDeviceToHost, stream));
+    OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
 int Renderer::debugLightVertexCounts(unsigned* dstHost)
 {
     if (!vcm) return 1;
     OPR_CUDA_CHECK(cudaMemcpyAsync(dstHost, vcm->lvCount, vcm->paths * 4, cudaMemcpyDeviceToHost, stream));
     OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
     return 0;
+}
+
+// Parity diagnostics: (owning path, hit point) of every stored light vertex of the last light pass, 16 bytes each, path-major.
+// Returns the number of vertices (<= capacityVerts are written).
+long long Renderer::debugLightVertexPositions(float* dstHost, size_t capacityVerts)
+{
+    if (!vcm) return -1;
+    const size_t paths = vcm->paths;
+    std::vector<unsigned> cnt(paths);
+    OPR_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), vcm->lvCount, paths * 4, cudaMemcpyDeviceToHost, stream));
+    OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    std::vector<float4> lv((size_t)paths * vcm->maxVerts * 6);
+    OPR_CUDA_CHECK(cudaMemcpy(lv.data(), vcm->lv, lv.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+    size_t n = 0;
+    for (size_t p = 0; p < paths; p++)
+        for (unsigned k = 0; k < cnt[p] && k < vcm->maxVerts; k++, n++) {
+            if (n >= capacityVerts) continue;
+            const float4 v = lv[6 * ((size_t)k * paths + p)];
+            const unsigned path = (unsigned)p;
+            memcpy(dstHost + 4 * n, &path, 4);
+            dstHost[4 * n + 1] = v.x; dstHost[4 * n + 2] = v.y; dstHost[4 * n + 3] = v.z;
+        }
+    return (long long)n;
 }
 
 // ---- host orchestration: OptixRenderer.cpp:675-797 ---------------------------------------------------------------------
@@ -718,8 +751,9 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     const SceneView& sc = scene.view;
     vcm_alloc(*this);
     VcmState& S = *vcm;
+    if (debugConnectionCounts && !S.dbgConn) devAlloc((void**)&S.dbgConn, S.paths * 4);
     VcmBuffers B{S.state, S.color, S.lvCount, S.lv, (unsigned)S.paths,
-                 S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT};
+                 S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, debugConnectionCounts ? S.dbgConn : nullptr};
     const unsigned lightSubPathCount = width * height;
     const float ppmRadiusSquared = PPMRadius * PPMRadius;
     const float etaVCM = (float(lightSubPathCount) / 1u) * PI_F * ppmRadiusSquared;   // nVM / nVC * pi * r^2 (:687)
@@ -748,13 +782,13 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     auto traceConnections = [&](float* target, unsigned stride) {
         const VcmBuffers& b = Bq[connSet];
         if (!ov) {
-            launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
+            launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS, lc, 0, b.dbgConn);
             return;
         }
         OPR_CUDA_CHECK(cudaEventRecord(evVcmShade, stream));
         OPR_CUDA_CHECK(cudaStreamWaitEvent(streamB, evVcmShade, 0));
         launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS,
-                                   LaunchCtx{streamB, &launches}, vcmConnectBlocksPerSM);
+                                   LaunchCtx{streamB, &launches}, vcmConnectBlocksPerSM, b.dbgConn);
         OPR_CUDA_CHECK(cudaEventRecord(evVcmConn[connSet], streamB));
         connBusy[connSet] = true;
     };
@@ -801,6 +835,7 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         P.estimatePass = 0;
         lightVertexCountEstimated = true;
     }
+    if (B.dbgConn) OPR_CUDA_CHECK(cudaMemsetAsync(B.dbgConn, 0, S.paths * 4, stream));
     lightPass("vcm.light");
     {
         ScopedTimer t(*this, "vcm.camera");

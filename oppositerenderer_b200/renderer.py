@@ -394,6 +394,16 @@ class OptixRenderer:
         self._check(self._lib.opr_debug_get_buffer(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.nbytes))
         return a
 
+    def set_connection_counts(self, on):
+        self._check(self._lib.opr_debug_set_connection_counts(self._h, 1 if on else 0))
+
+    def light_vertex_positions(self):
+        cap = self.getWidth() * self.getHeight() * 16 + 1
+        a = self.debug_buffer("light_vertex_positions", np.float32, cap * 4).reshape(-1, 4)
+        n = int(a[0, 0:1].view(np.uint32)[0])
+        a = a[1:1 + min(n, cap - 1)]
+        return a[:, 0].copy().view(np.uint32), a[:, 1:4].copy()
+
     def trace_closest(self, rays8):
         rays8 = np.ascontiguousarray(rays8, np.float32)
         n = rays8.shape[0]

@@ -87,6 +87,7 @@ def make_scene(kind="sponza", seed=1, detail=1.0, texture_size=1024, textured=Tr
     s = float(detail)
     q = lambda n: max(2, int(round(n * s)))
     meshes, materials, textures = [], [], []
+    normal_mapped = set()      # materials with a normal map: their meshes must carry tangents / bitangents (Texture.cu:92-97)
 
     def tex_material(tint, normal=False):
         if not textured:
@@ -99,10 +100,14 @@ def make_scene(kind="sponza", seed=1, detail=1.0, texture_size=1024, textured=Tr
             textures.append(_normal_texture(rng, texture_size))
             nidx = len(textures) - 1
         materials.append(make_material(capi.MAT_TEXTURE, diffuseTexture=d, normalTexture=nidx))
+        if normal:
+            normal_mapped.add(len(materials) - 1)
         return len(materials) - 1
 
     def add(mesh, mat, keep_tangents=False):
-        if not keep_tangents:
+        # assimp's CalcTangentSpace (scene/Scene.cpp:96) gives every mesh with normals and uvs a tangent frame; here only the
+        # normal-mapped meshes keep theirs (nothing else reads them)
+        if not keep_tangents and mat not in normal_mapped:
             mesh["tangents"] = mesh["bitangents"] = None
         mesh["material"] = mat
         meshes.append(mesh)

@@ -69,6 +69,7 @@ struct Hit {
     float3 geometricNormal, shadingNormal, tangent, bitangent;
     float2 textureCoordinate;
     int material;
+    bool hasTangents;   // TriangleMesh.cu:61 hasTangentsAndBitangents of the mesh that was hit
 };
 
 struct BvhNode { Aabb box; int left, right; int first, count; };   // leaf if count > 0

@@ -141,7 +141,8 @@ static void closestHitRadiance(Renderer& r, const Ray& ray, const Hit& hit, Radi
         float3 worldShadingNormal = normalize(hit.shadingNormal);
         float3 hitPoint = ray.origin + tHit * ray.direction;
         float3 normal = worldShadingNormal;
-        if (m.normalTexture >= 0) {
+        // without tangents the reference reads unwritten attributes (undefined): the map is ignored here, as in the product
+        if (m.normalTexture >= 0 && hit.hasTangents) {
             float3 worldTangent = normalize(hit.tangent);
             float3 worldBitangent = normalize(hit.bitangent);
             normal = getNormalMappedNormal(worldShadingNormal, worldTangent, worldBitangent,
@@ -515,6 +516,7 @@ void ppm_direct(Renderer& r, uint x, uint y)
     int numLights = (int)lights.size();
     const int numShadowSamples = 4;
     float3 avgLightRadiance = make_float3(0.f);
+    unsigned sampleMask = 0;
     RandomState& st = r.rs(x, y);
     for (int shadowSample = 0; shadowSample < numShadowSamples; shadowSample++) {
         float sample = getRandomUniformFloat(&st);
@@ -523,7 +525,9 @@ void ppm_direct(Renderer& r, uint x, uint y)
         float scale = (float)numLights;
         float3 lightContrib = getLightContribution(r, light, rec.position, rec.normal, st);
         avgLightRadiance += scale * lightContrib;
+        if (fmaxf(fmaxf(lightContrib.x, lightContrib.y), lightContrib.z) > 0.f) sampleMask |= 1u << shadowSample;
     }
+    if (idx < r.directSampleMask.size()) r.directSampleMask[idx] = (unsigned char)sampleMask;
     r.direct[idx] = rec.attenuation * avgLightRadiance / (float)numShadowSamples;
 }
 

@@ -81,9 +81,11 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber_, unsigned
         ppmRadius = PPMRadius;
         ppmRadiusSquared = PPMRadius * PPMRadius;                               // :585
         launch2D(*this, photonLaunchWidth, photonLaunchHeight, ppm_photonGenerator);   // :612
+        photonsAsEmitted = photons;
         if (!build_photon_grid(photons.data(), (uint)photons.size(), photonKeys, offsets, grid))   // :628
             throw std::runtime_error("Too many cells in SpatialHash.cu, over defined PHOTON_GRID_MAX_SIZE.");
         launch2D(*this, width, height, ppm_indirect);                            // :657
+        directSampleMask.assign((size_t)width * height, 0);
         launch2D(*this, width, height, ppm_direct);                              // :664
         launch2D(*this, width, height, ppm_output);                              // :670
     } else if (details.renderMethod == OPR_VCM_BIDIRECTIONAL_PATH_TRACING) {
@@ -113,6 +115,7 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber_, unsigned
             lightVertexCountEstimatePass = 0u;
         }
         lightVertexBufferIndex.store(0);                                         // :776-778
+        connectionCount.assign((size_t)width * height, 0u);
         launch2D(*this, width, height, vcm_lightPass);                           // :784
         launch2D(*this, width, height, vcm_cameraPass);                          // :793
     } else if (details.renderMethod == OPR_PATH_TRACING) {
@@ -159,6 +162,7 @@ unsigned ora_get_height(void* h) { return ((Renderer*)h)->height; }
 // intermediate buffers (reference layouts) for stage-by-stage parity
 int ora_get_hitpoints(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->hitpoints.data(), sizeof(Hitpoint) * r->hitpoints.size()); return 0; }
 int ora_get_photons(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->photons.data(), sizeof(Photon) * r->photons.size()); return 0; }
+int ora_get_photons_as_emitted(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->photonsAsEmitted.data(), sizeof(Photon) * r->photonsAsEmitted.size()); return 0; }
 int ora_get_photon_keys(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->photonKeys.data(), 4 * r->photonKeys.size()); return 0; }
 int ora_get_offsets(void* h, void* dst, unsigned n) { Renderer* r = (Renderer*)h; memcpy(dst, r->offsets.data(), 4 * std::min<size_t>(n, r->offsets.size())); return 0; }
 int ora_get_grid(void* h, float* cellSize, unsigned* gridSize3, float* origo3, unsigned* numValid)
@@ -172,6 +176,8 @@ unsigned long long ora_num_random_states(void* h) { return ((Renderer*)h)->rando
 int ora_get_ray_counts(void* h, unsigned long long* closest, unsigned long long* any)
 { Renderer* r = (Renderer*)h; *closest = r->stats.closest.load(); *any = r->stats.any.load(); return 0; }
 int ora_get_photon_path_lengths(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->photonPathLength.data(), 4 * r->photonPathLength.size()); return 0; }
+int ora_get_direct_sample_mask(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->directSampleMask.data(), r->directSampleMask.size()); return 0; }
+int ora_get_connection_counts(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->connectionCount.data(), 4 * r->connectionCount.size()); return 0; }
 int ora_get_light_vertex_counts(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->lightSubpathVertexCount.data(), 4 * r->lightSubpathVertexCount.size()); return 0; }
 
 // stand-alone pieces -----------------------------------------------------------------------------------

@@ -25,11 +25,13 @@ struct Renderer {
     std::vector<RandomState> randomStates;
     std::vector<Hitpoint> hitpoints;        // raytracePassOutputBuffer
     std::vector<Photon> photons;            // NUM_PHOTONS = emitted * 4
+    std::vector<Photon> photonsAsEmitted;   // copy taken before the grid build sorts `photons` in place (slot = 4 * thread + k): parity diagnostics
     std::vector<uint> photonKeys;           // m_photonsHashCells
     std::vector<uint> offsets;              // hashmapOffsetTable
     PhotonGrid grid{};
     std::vector<float3> indirect, direct, output;
     std::vector<uint> photonPathLength;     // debugPhotonPathLengthBuffer
+    std::vector<unsigned char> directSampleMask;   // parity diagnostics: bit s = shadow sample s of the pixel was unoccluded and non-zero
 
     // per-iteration context scalars (OptixRenderer.cpp:555-557, 583-589, 616-617)
     Camera camera{};
@@ -50,6 +52,7 @@ struct Renderer {
     std::vector<uint> lightSubpathVertexCount;
     std::vector<uint> lightSubpathVertexIndex;   // [path][vcmMaxPathLength-1]
     uint lightVertexBufferSize = 0;
+    std::vector<uint> connectionCount;           // parity diagnostics: contributions that passed isOccluded, per target pixel, last iteration
     int vcmUseVC = 1, vcmUseVM = 0;
     int numThreads = 0;                     // 0 = OpenMP default
 

@@ -327,13 +327,14 @@ bool Scene::intersectPrim(int pi, const Ray& ray, float tmax, Hit& hit) const
         Ray r = ray; r.tmax = tmax;
         if (!intersect_triangle(r, p0, p1, p2, n, t, beta, gamma)) return false;
         hit.t = t; hit.prim = pi; hit.material = m.material;
-        hit.tangent = hit.bitangent = make_float3(0.f);
+        hit.tangent = hit.bitangent = make_float3(0.f); hit.hasTangents = false;
         if (m.normals.empty()) {
             hit.shadingNormal = normalize(n);
         } else {
             const float3 n0 = m.normals[index.x], n1 = m.normals[index.y], n2 = m.normals[index.z];
             hit.shadingNormal = normalize(n1 * beta + n2 * gamma + n0 * (1.0f - beta - gamma));
             if (!m.tangents.empty()) {
+                hit.hasTangents = true;
                 const float3 t0 = m.tangents[index.x], t1 = m.tangents[index.y], t2 = m.tangents[index.z];
                 hit.tangent = normalize(t1 * beta + t2 * gamma + t0 * (1.0f - beta - gamma));
                 const float3 b0 = m.bitangents[index.x], b1 = m.bitangents[index.y], b2 = m.bitangents[index.z];
@@ -364,7 +365,7 @@ bool Scene::intersectPrim(int pi, const Ray& ray, float tmax, Hit& hit) const
                 if (a2 >= 0 && a2 <= 1) {
                     hit.t = t; hit.prim = pi; hit.material = g.material;
                     hit.shadingNormal = hit.geometricNormal = n;
-                    hit.tangent = hit.bitangent = make_float3(0.f);
+                    hit.tangent = hit.bitangent = make_float3(0.f); hit.hasTangents = false;
                     hit.textureCoordinate = make_float2(0.f, 0.f);   // `texcoord` attribute is not `textureCoordinate`
                     return true;
                 }
@@ -384,14 +385,14 @@ bool Scene::intersectPrim(int pi, const Ray& ray, float tmax, Hit& hit) const
         if (root1 > ray.tmin && root1 < tmax) {
             hit.t = root1; hit.prim = pi; hit.material = s.material;
             hit.shadingNormal = hit.geometricNormal = (O + root1 * ray.direction) / s.radius;
-            hit.tangent = hit.bitangent = make_float3(0.f); hit.textureCoordinate = make_float2(0.f, 0.f);
+            hit.tangent = hit.bitangent = make_float3(0.f); hit.hasTangents = false; hit.textureCoordinate = make_float2(0.f, 0.f);
             return true;
         }
         float root2 = (-b + sdisc);
         if (root2 > ray.tmin && root2 < tmax) {
             hit.t = root2; hit.prim = pi; hit.material = s.material;
             hit.shadingNormal = hit.geometricNormal = (O + root2 * ray.direction) / s.radius;
-            hit.tangent = hit.bitangent = make_float3(0.f); hit.textureCoordinate = make_float2(0.f, 0.f);
+            hit.tangent = hit.bitangent = make_float3(0.f); hit.hasTangents = false; hit.textureCoordinate = make_float2(0.f, 0.f);
             return true;
         }
     }

@@ -354,6 +354,19 @@ void vcm_alloc_vertices(Renderer& r, uint n)
 }
 void vcm_free(Renderer& r) { delete r.lightVertexBuffer; r.lightVertexBuffer = nullptr; }
 
+// parity diagnostics: (owning path, hit point) of every light vertex stored by the last light pass, 16 bytes each
+unsigned vcm_light_vertex_positions(Renderer& r, float* dst4, unsigned capacity)
+{
+    const uint n = std::min<uint>(r.lightVertexBufferIndex.load(), r.lightVertexBufferSize);
+    for (uint i = 0; i < n && i < capacity; i++) {
+        const LightVertex& v = (*r.lightVertexBuffer)[i];
+        const uint path = v.launchIndex.y * r.width + v.launchIndex.x;
+        memcpy(dst4 + 4 * (size_t)i, &path, 4);
+        dst4[4 * (size_t)i + 1] = v.hitPoint.x; dst4[4 * (size_t)i + 2] = v.hitPoint.y; dst4[4 * (size_t)i + 3] = v.hitPoint.z;
+    }
+    return n;
+}
+
 // ---- vcm.h:43-59 -----------------------------------------------------------------------------------------
 static int isOccluded(Renderer& r, const float3& aPoint, const float3& aDirection, const float aTMax)
 {
@@ -418,6 +431,7 @@ static void connectCameraT1(Renderer& r, SubpathPRD& aLightPrd, const VcmBSDF& a
     const float cameraPdfAConvertedToImagePdfA = 1.f / cameraPdfA;
     float3 contrib = misWeight * aLightPrd.throughput * bsdfFactor / (r.lightSubpathCount * cameraPdfAConvertedToImagePdfA);
     if (!isOccluded(r, aLightHitpoint, dirToCamera, distance)) {
+        __atomic_fetch_add(&r.connectionCount[(size_t)pixelIndex.y * r.width + pixelIndex.x], 1u, __ATOMIC_RELAXED);
         float* o = &r.output[(size_t)pixelIndex.y * r.width + pixelIndex.x].x;
         atomicAddFloat(o, contrib.x); atomicAddFloat(o + 1, contrib.y); atomicAddFloat(o + 2, contrib.z);
     }
@@ -522,6 +536,7 @@ static void connectVertices(Renderer& r, const LightVertex& aLightVertex, Subpat
     float3 contrib = geometryTerm * cameraBsdfFactor * lightBsdfFactor * invVertPickPdf;
     contrib *= misWeight * aCameraPrd.throughput * aLightVertex.throughput;
     if (isOccluded(r, aCameraHitpoint, direction, distance)) return;
+    __atomic_fetch_add(&r.connectionCount[aCameraPrd.launchIndex1D], 1u, __ATOMIC_RELAXED);
     aCameraPrd.color += contrib;
 }
 
@@ -620,6 +635,7 @@ static void connectLightSourceS1(Renderer& r, SubpathPRD& aCameraPrd, const VcmB
     float3 contrib = (misWeight * cosToLight / (lightPickProb * directPdfW)) * (radiance * bsdfFactor);
     if (isZero(contrib)) return;
     if (isOccluded(r, aCameraHitpoint, dirToLight, distance)) return;
+    __atomic_fetch_add(&r.connectionCount[aCameraPrd.launchIndex1D], 1u, __ATOMIC_RELAXED);
     aCameraPrd.color += contrib * aCameraPrd.throughput;
 }
 
@@ -824,3 +840,7 @@ void vcm_cameraPass(Renderer& r, uint x, uint y)
 }
 
 } // namespace ora
+
+// parity diagnostics (restatement only; the oracle/_ref build has no such entry)
+extern "C" unsigned ora_get_light_vertex_positions(void* h, float* dst4, unsigned capacity)
+{ return ora::vcm_light_vertex_positions(*(ora::Renderer*)h, dst4, capacity); }

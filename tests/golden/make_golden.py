@@ -30,6 +30,45 @@ CASES = [  # name, scene, CornellSmall config, method (2 = PPM, 1 = BDPT, 0 = PT
 ]
 
 
+# The bench workloads (BASELINE configs 3/4/5) at reduced tessellation: triangle meshes with shading normals / uvs / tangent
+# frames, Texture materials with RGBA8 bilinear lookups and normal maps, tessellated glass + mirror spheres, area + point
+# lights (TriangleMesh.cu:35-96, Texture.cu:83-110,116-175,210-286).
+# name, kind, detail, texture size, method, width, height, photon launch, iterations, max path length
+SYNTH_CASES = [
+    ("synthetic_sponza_ppm_96x54_p96x96_it2", "sponza", 0.08, 64, 2, 96, 54, 96, 2, 10),
+    ("synthetic_sponza_bdpt_96x54_it2_len8", "sponza", 0.08, 64, 1, 96, 54, 16, 2, 8),
+    ("synthetic_sponza_pt_96x54_it2", "sponza", 0.08, 64, 0, 96, 54, 16, 2, 10),
+    ("synthetic_conference_ppm_96x54_p96x96_it2", "conference", 0.12, 64, 2, 96, 54, 96, 2, 10),
+    ("synthetic_conference_bdpt_96x54_it2_len8", "conference", 0.12, 64, 1, 96, 54, 16, 2, 8),
+    ("synthetic_conference_pt_96x54_it2", "conference", 0.12, 64, 0, 96, 54, 16, 2, 10),
+]
+
+# BASELINE config 1 exactly: built-in Cornell, PPM, 256x256, 100 K photons per iteration (316 x 316 launch), 16 iterations
+CONFIG1 = ("cornell_ppm_256x256_p316x316_it16", "Cornell", 0, 2, 256, 316, 16, 10, None)
+
+
+def render_synthetic(which, kind, detail, texsize, method, W, H, pl, iters, maxlen):
+    """One of the synthetic bench scenes through the oracle ('oracle') or the host-compiled reference programs ('ref')."""
+    from oppositerenderer_b200 import synthetic
+    scene = synthetic.make_scene(kind, seed=1, detail=detail, texture_size=texsize)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(W / H)
+    r = ol.OracleRenderer(which, (pl, pl), maxlen, SEED, threads=1 if (which == "ref" and method == 1) else 0)
+    r.init_scene(scene.getSceneDescription())
+    det = ol.make_details(cam.pod, method, W, H)
+    radii = ol.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), iters)
+    for i in range(iters):
+        r.render_next_iteration(i, i, radii[i], det)
+    out = dict(output=r.output(), rays=np.array(r.ray_counts(), np.uint64))
+    if method == 2:
+        hp = r.hitpoints()
+        out["photon_keys"] = r.photon_keys()
+        out["offsets"] = r.offsets()
+        out["hitpoint_flags"] = hp["flags"]
+        out["hitpoint_normals"] = hp["normal"]
+    return out
+
+
 def render(which, scene, cfg, method, size, pl, iters, maxlen, r0):
     sc = ol.BuiltinScene(scene, cfg, which)
     # the reference's light-tracing splat is a plain `+=` (vcm.h:159): run its programs on one thread so that no update is lost
@@ -49,7 +88,11 @@ def render(which, scene, cfg, method, size, pl, iters, maxlen, r0):
 
 if __name__ == "__main__":
     assert ol.have_ref(), "build oracle/_ref first: make -C oracle/refshim"
-    for case in CASES:
+    for case in SYNTH_CASES:
+        data = render_synthetic("ref", *case[1:])
+        np.savez_compressed(os.path.join(HERE, case[0] + ".npz"), **data)
+        print(case[0], "rays", data["rays"], "mean", data["output"].mean())
+    for case in CASES + [CONFIG1]:
         data = render("ref", *case[1:])
         np.savez_compressed(os.path.join(HERE, case[0] + ".npz"), **data)
         print(case[0], "rays", data["rays"], "mean", data["output"].mean())

@@ -48,6 +48,9 @@ def _declare(lib):
         "ora_get_ray_counts": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "ora_get_photon_path_lengths": (i32, [vp, vp]),
         "ora_get_light_vertex_counts": (i32, [vp, vp]),
+        "ora_get_photons_as_emitted": (i32, [vp, vp]),
+        "ora_get_direct_sample_mask": (i32, [vp, vp]),
+        "ora_get_connection_counts": (i32, [vp, vp]),
         "ora_rng_init": (None, [PU, u32, u32, u32]),
         "ora_rng_uniform": (None, [PU, PF, u32]),
         "ora_build_photon_grid": (i32, [PF, u32, PU, PU, PF, PU, PF, PU]),
@@ -161,6 +164,38 @@ class OracleRenderer:
         a = np.empty(self.photon_launch[0] * self.photon_launch[1] * 4, PHOTON_DT)
         self.lib.ora_get_photons(self.h, a.ctypes.data_as(C.c_void_p))
         return a
+
+    def photons_as_emitted(self):
+        """Photon slots before the grid build sorted them (slot = 4 * thread + k), like the product's "photons" buffer."""
+        a = np.empty(self.photon_launch[0] * self.photon_launch[1] * 4, PHOTON_DT)
+        self.lib.ora_get_photons_as_emitted(self.h, a.ctypes.data_as(C.c_void_p))
+        return a
+
+    def direct_sample_mask(self):
+        a = np.empty(self.width * self.height, np.uint8)
+        self.lib.ora_get_direct_sample_mask(self.h, a.ctypes.data_as(C.c_void_p))
+        return a
+
+    def connection_counts(self):
+        a = np.empty(self.width * self.height, np.uint32)
+        self.lib.ora_get_connection_counts(self.h, a.ctypes.data_as(C.c_void_p))
+        return a
+
+    def random_states(self):
+        n = self.lib.ora_num_random_states(self.h)
+        a = np.zeros((n, 6), np.uint32)
+        self.lib.ora_get_random_states(self.h, a.ctypes.data_as(C.c_void_p), 0, n)
+        return a
+
+    def light_vertex_positions(self):
+        """(path u32, hit point float3) of every light vertex stored by the last light pass (restatement only)."""
+        fn = self.lib.ora_get_light_vertex_positions
+        fn.restype, fn.argtypes = C.c_uint32, [C.c_void_p, C.POINTER(C.c_float), C.c_uint32]
+        cap = self.width * self.height * 16
+        a = np.zeros((cap, 4), np.float32)
+        n = fn(self.h, fptr(a), cap)
+        a = a[:min(n, cap)]
+        return a[:, 0].copy().view(np.uint32), a[:, 1:4].copy()
 
     def photon_keys(self):
         a = np.empty(self.photon_launch[0] * self.photon_launch[1] * 4, np.uint32)

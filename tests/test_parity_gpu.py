@@ -116,6 +116,43 @@ def test_traversal_matches_oracle(product, oracle, scene_name, config):
     assert (occ == occ0).mean() > 0.9995
 
 
+def test_traversal_full_size_matches_oracle(product, oracle):
+    """The 1.1 M-triangle bench scene (PLOC build, 4-wide collapse, SAH leaves, 17 levels): closest hit and any hit against the
+    oracle's CPU BVH ray by ray — 57.6 K camera rays, 100 K random rays, 100 K shadow segments."""
+    from oppositerenderer_b200 import synthetic
+    scene = synthetic.make_scene("sponza", seed=1, detail=1.0, texture_size=64)
+    assert scene.num_triangles > 1000000
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(16 / 9)
+    r = product.OptixRenderer(photon_launch=(16, 16), seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    o = oracle.OracleRenderer("oracle", (16, 16), 10, util.SEED)
+    o.init_scene(scene.getSceneDescription())
+    rng = np.random.default_rng(5)
+    mn, mx = scene.getSceneAABB()
+    rays = np.concatenate([util.camera_rays(cam.pod, 320, 180, rng), util.random_rays_in_box(100000, mn, mx, rng)])
+    t, mat, ng = r.trace_closest(rays)
+    t0, mat0, ng0 = o.trace_closest(rays)
+    hit, hit0 = t >= 0, t0 >= 0
+    both = hit & hit0
+    same_t = np.isclose(t, t0, rtol=1e-5, atol=1e-4) & both
+    exact = float((t.view(np.uint32) == t0.view(np.uint32)).mean())
+    print("full-size closest hit: %d rays, hit/miss agrees %.6f, t within 1e-5 %.6f, t bit-identical %.6f"
+          % (rays.shape[0], (hit == hit0).mean(), same_t[both].mean(), exact))
+    assert (hit == hit0).mean() > 0.99995 and same_t[both].mean() > 0.99995
+    assert (mat[same_t] == mat0[same_t]).mean() > 0.9999                     # same scene description: material ids are comparable
+    assert np.isclose(ng[same_t], ng0[same_t], atol=1e-4).all(axis=1).mean() > 0.9995   # (a ray through a shared edge may name either triangle)
+    a = (rng.random((100000, 3)) * (mx - mn) + mn).astype(np.float32)
+    b = (rng.random((100000, 3)) * (mx - mn) + mn).astype(np.float32)
+    dist = np.linalg.norm(b - a, axis=1).astype(np.float32)
+    sh = np.zeros((100000, 8), np.float32)
+    sh[:, 0:3], sh[:, 3], sh[:, 4:7], sh[:, 7] = a, 1e-4, (b - a) / dist[:, None], dist - 1e-4
+    occ, occ0 = r.trace_any(sh), o.trace_any(sh)
+    print("full-size any hit: agreement %.6f, occluded %.3f" % ((occ == occ0).mean(), occ0.mean()))
+    assert (occ == occ0).mean() > 0.9999
+
+
 @pytest.mark.parametrize("scene_name,config,size,pl,iters,minfrac", [
     ("Cornell", 0, 64, (64, 64), 3, 0.98),
     ("CornellSmall", 0, 48, (64, 64), 2, 0.97),
@@ -230,27 +267,37 @@ def test_cuda_matches_reference_golden(product):
     import os
     from golden.make_golden import CASES, SEED
     gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    for name, scene_name, cfg, method, size, pl, iters, maxlen, r0 in CASES:
+    from golden.make_golden import SYNTH_CASES
+    from oppositerenderer_b200 import synthetic
+    cases = [(name, scene_name, cfg, method, size, size, pl, iters, maxlen, r0) for name, scene_name, cfg, method, size, pl, iters, maxlen, r0 in CASES]
+    cases += [(name, "synthetic:" + kind, (detail, tex), method, W, H, pl, iters, maxlen, None) for name, kind, detail, tex, method, W, H, pl, iters, maxlen in SYNTH_CASES]
+    for name, scene_name, cfg, method, size, sizeH, pl, iters, maxlen, r0 in cases:
         gold = np.load(os.path.join(gdir, name + ".npz"))
-        scene = product.Cornell() if scene_name == "Cornell" else product.CornellSmall(cfg or None)
+        if scene_name.startswith("synthetic:"):
+            scene = synthetic.make_scene(scene_name.split(":")[1], seed=1, detail=cfg[0], texture_size=cfg[1])
+        else:
+            scene = product.Cornell() if scene_name == "Cornell" else product.CornellSmall(cfg or None)
         cam = scene.getDefaultCamera()
-        cam.setAspectRatio(1.0)
+        cam.setAspectRatio(size / sizeH)
         r = product.OptixRenderer(photon_launch=(pl, pl), vcm_max_path_length=maxlen, seed=SEED)
         r.initialize(product.ComputeDevice(0))
         r.initScene(scene)
-        det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, size, size, 2.0 / 3.0)
+        det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, size, sizeH, 2.0 / 3.0)
         radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate() if r0 is None else r0, iters)
         for i in range(iters):
             r.renderNextIteration(i, i, radii[i], True, det)
         out = r.getOutputBuffer()
         frac = util.rel_close_fraction(out.reshape(-1, 3), gold["output"].reshape(-1, 3), 5e-3, 2e-5 * float(gold["output"].max()))
         rel = np.abs(out - gold["output"]).sum() / np.abs(gold["output"]).sum()
+        print("%s: pixels within rel 5e-3 of the reference golden %.4f, relative L1 %.2e" % (name, frac, rel))
+        # no oracle runs here, so the divergent paths cannot be named: the per-pixel rule is tests/test_parity_rule_gpu.py;
+        # this test bounds the whole-image error against the reference's own output and the share of untouched pixels
         assert frac > 0.85 and rel < 3e-2, (name, frac, rel)
         st = r.stats()
         rays = st["closest_rays"] + st["any_rays"]
         assert abs(rays - int(gold["rays"].sum())) <= 0.02 * int(gold["rays"].sum()), (name, rays, gold["rays"])
         if method == 2:
-            flags = r.debug_buffer("hitpoints", ol.HITPOINT_DT, size * size)["flags"]
+            flags = r.debug_buffer("hitpoints", ol.HITPOINT_DT, size * sizeH)["flags"]
             assert (flags == gold["hitpoint_flags"]).mean() > 0.97
 
 
@@ -376,8 +423,10 @@ def test_full_size_ppm_properties(product):
     hp = r.debug_buffer("hitpoints", ol.HITPOINT_DT, W * H)
     diffuse = (hp["flags"] & ol.PRD_HIT_NON_SPECULAR) != 0
     assert diffuse.mean() > 0.8
+    assert not np.isnan(hp["normal"]).any() and not np.isnan(hp["position"]).any()     # round 1: normal maps on tangent-less meshes gave NaN
+    assert np.isclose(np.linalg.norm(hp["normal"][diffuse], axis=1), 1.0, atol=1e-3).all()
     ind = r.debug_buffer("indirect", np.float32, W * H * 3).reshape(-1, 3)
-    assert np.isfinite(ind).all() and (ind >= 0).all() and (ind[~diffuse] == 0).all() and (ind[diffuse].sum(axis=1) > 0).mean() > 0.7
+    assert np.isfinite(ind).all() and (ind >= 0).all() and (ind[~diffuse] == 0).all() and (ind[diffuse].sum(axis=1) > 0).mean() > 0.95
     st = r.stats()
     assert st["closest_rays"] >= W * H + 1024 * 1024 and st["any_rays"] <= 4 * W * H and st["photons_stored"] == nv
     r.renderNextIteration(1, 1, radii[1], True, det)
