@@ -5,8 +5,16 @@
 A "step" is one PPM iteration (camera pass, photon pass, photon-grid build, gather, direct + output) of the
 synthetic ~1M-triangle textured scene at 1920x1080 with a 1024x1024 photon launch, through the C ABI
 (opr_render_next_iteration).  With N > 1 ranks (torchrun, one process per GPU) rank g renders the global
-iterations g, g+N, ... with the closed-form radius schedule and the per-GPU running sums are combined with one
-NCCL reduce inside the timed region; value = rays of all ranks / max-over-ranks device time.
+iterations B+g, B+g+N, ... with the closed-form radius schedule and the per-GPU running sums are combined with one
+NCCL reduce — issued by the C++ library itself, opr_reduce_output — inside the timed region (SURVEY.md §8e);
+value = rays of all ranks / max-over-ranks device time.
+
+Window.  The PPM radius shrinks as r_i ~ i^(-1/6), and the gather costs ~ r^2: a rank of an 8-GPU job walks the
+schedule eight times faster than a single GPU, so windows that start at iteration 0 give every N different work
+per step (round 1's curve showed 1.04-1.09 "efficiency" for that reason).  All arms and all N therefore time the
+steady state of a progressive render: the window starts at global iteration B = --first-iteration (default 1024),
+where r^2 changes by < 1.5 % over the 8 x (W + 5 K) iterations of the largest job.  The first iterations of a
+render (large radius, gather-heavy) are measured separately at N = 1 and reported under "early_iterations".
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sponza|conference|cornell]
 """
@@ -44,8 +52,10 @@ def parse():
     ap.add_argument("--relmse-target", type=float, default=0.0,
                     help="extra leg (BASELINE config 5): device time until the relMSE of the running mean against a longer reference render drops below this")
     ap.add_argument("--relmse-reference-iterations", type=int, default=256)
-    ap.add_argument("--cpu-sample", default="480x270:256", help="--impl reference: WxH:photonLaunch of one step of the bounded CPU sample")
-    ap.add_argument("--cpu-baseline-sample", default="960x540:512", help="cpu_baseline leg of the default arm (3 timed iterations + 1 warm-up)")
+    ap.add_argument("--first-iteration", type=int, default=1024, help="global iteration the timed window starts at (see the module docstring)")
+    ap.add_argument("--repeats", type=int, default=5, help="the K-step window is timed this many times back to back; ms_per_step is the median window")
+    ap.add_argument("--cpu-sample", default="full", help="--impl reference: WxH:photonLaunch of one step, or 'full' = the configuration itself")
+    ap.add_argument("--cpu-baseline-sample", default="full", help="cpu_baseline leg of the default arm (3 timed iterations + 1 warm-up)")
     return ap.parse_args()
 
 
@@ -128,27 +138,34 @@ def cpu_reference_run(args, scene, cam, sample, steps, warmup, which):
     sample of the same workload, all host threads.  Returns (Mrays/s, it/s, cores, description)."""
     import oracle_lib as ol
     from oppositerenderer_b200 import capi
-    wh, pl = sample.split(":")
-    w, h = (int(x) for x in wh.split("x"))
-    pl = int(pl)
+    if sample == "full":
+        w, h, pl = args.width, args.height, args.photons
+    else:
+        wh, pl = sample.split(":")
+        w, h = (int(x) for x in wh.split("x"))
+        pl = int(pl)
     # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
     o = ol.OracleRenderer(which, (pl, pl), args.max_path_length if args.method == "bdpt" else 10, 1645301512, threads=len(os.sched_getaffinity(0)))
     o.init_scene(scene.getSceneDescription())
     det = ol.make_details(cam.pod, capi.VCM_BIDIRECTIONAL_PATH_TRACING if args.method == "bdpt" else capi.PROGRESSIVE_PHOTON_MAPPING, w, h)
     r0 = scene.getSceneInitialPPMRadiusEstimate()
-    radii = ol.ppm_radius_schedule(r0, steps + warmup)
+    B = args.first_iteration
+    lib = capi.load_library()
+    radius = lambda i: float(lib.opr_ppm_radius_for_iteration(float(r0), int(B + i), 2.0 / 3.0))   # same window as the GPU arm
     for i in range(warmup):
-        o.render_next_iteration(i, i, radii[i], det)
+        o.render_next_iteration(B + i, i, radius(i), det)
     c0 = o.ray_counts()
     t0 = time.perf_counter()
     for i in range(warmup, warmup + steps):
-        o.render_next_iteration(i, i, radii[i], det)
+        o.render_next_iteration(B + i, i, radius(i), det)
     dt = time.perf_counter() - t0
     c1 = o.ray_counts()
     rays = (c1[0] - c0[0]) + (c1[1] - c0[1])
     cores = len(os.sched_getaffinity(0))
-    desc = "%d %s iteration(s) of the same scene at %dx%d%s (OpenMP, %d threads)" % (
-        steps, args.method.upper(), w, h, " with a %dx%d photon launch" % (pl, pl) if args.method == "ppm" else ", max path length %d" % args.max_path_length, cores)
+    desc = "%d %s iteration(s) (global iterations %d..%d) of the same scene at %dx%d%s (%s; OpenMP, %d threads)" % (
+        steps, args.method.upper(), B + warmup, B + warmup + steps - 1, w, h,
+        " with a %dx%d photon launch" % (pl, pl) if args.method == "ppm" else ", max path length %d" % args.max_path_length,
+        "the full configuration" if (w, h, pl) == (args.width, args.height, args.photons) else "a REDUCED sample of the configuration", cores)
     return rays / dt / 1e6, steps / dt, cores, desc
 
 
@@ -166,7 +183,9 @@ def main():
               "photons_per_iteration": args.photons * args.photons if args.method == "ppm" else None, "detail": args.detail,
               "l2": ("per-iteration working set (path state + photon/light-vertex records, %.0f MB, plus ray queues) exceeds the 126 MB L2" % ws_mb) if ws_mb > 126
                     else "working set %.0f MB fits the L2; a 256 MB scratch buffer is overwritten between timed iterations" % ws_mb,
-              "parallelism": "iterations partitioned over %d GPU(s), scene replicated, one NCCL reduce of the sum buffer" % world}
+              "first_iteration": args.first_iteration,
+              "window": "steady state of a progressive render: global iterations from %d on (radius schedule flat: the same work per step for every N)" % args.first_iteration,
+              "parallelism": "iterations partitioned over %d GPU(s), scene replicated, one NCCL reduce of the sum buffer (opr_reduce_output, C++)" % world}
     flush_l2 = ws_mb <= 126
 
     if args.impl == "reference":
@@ -177,6 +196,12 @@ def main():
         which = "ref" if ol.have_ref() else "oracle"
         steps = max(1, args.steps)      # K steps and W warm-up steps as asked; each step is one iteration of the bounded sample
         v, its, cores, desc = cpu_reference_run(args, scene, cam, args.cpu_sample, steps, max(0, args.warmup), which)
+        if args.cpu_sample != "full":     # the line must describe what ran
+            wh, pls = args.cpu_sample.split(":")
+            config["width"], config["height"] = (int(x) for x in wh.split("x"))
+            config["photons_per_iteration"] = int(pls) ** 2 if args.method == "ppm" else None
+            config["workload"] += " — REDUCED to %s for this CPU run" % args.cpu_sample
+        config["parallelism"] = "host CPU, OpenMP over launch indices, %d threads; loads liboppositerenderer_b200.so only for scene generation and host helpers" % cores
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(0, args.warmup),
                 "ms_per_step": 1000.0 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "iterations_per_s": its,
@@ -214,50 +239,73 @@ def main():
     pod = details.pod()
     r0 = scene.getSceneInitialPPMRadiusEstimate()
     lib = capi.load_library()
-    part = D.IterationPartition(rank, world, r0)
+    D.check_state_count(max(args.photons, W) * max(args.photons, H))     # per-rank seed ranges stay disjoint over the whole state buffer
+    B = args.first_iteration
     radius = lambda it: D.radius_for_iteration(r0, it)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(lib.opr_get_stream(r._h), device=dev)
     scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
+    if world > 1:
+        # the collective of the data path is the product's own (C++ -> NCCL, opr_reduce_output); torch.distributed only carries the 128-byte id
+        ids = [opr.renderer.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        r.comm_init_rank(ids[0], rank, world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(steps, first_local, readback=None):
-        for it, local, rad in part.steps(first_local, steps):
+    cursor = [0]     # next local iteration of this rank; global iteration = B + local * world + rank (SURVEY.md §8e partition, offset by B)
+
+    def run(steps, readback=None, first_iteration=None):
+        base = B if first_iteration is None else first_iteration
+        for _ in range(steps):
+            local = cursor[0]
+            cursor[0] += 1
+            it = base + local * world + rank
             if scratch is not None:
                 with torch.cuda.stream(stream):
                     scratch.fill_(local & 0xff)        # evict the previous iteration's buffers from the 126 MB L2
-            r.renderNextIteration(it, local, rad, True, pod)
-            if readback is not None:
-                r.getOutputBuffer(readback)
+            r.renderNextIteration(it, local, radius(it), True, pod)
+            if readback == "blocking":
+                r.getOutputBuffer(host_out[0])
+            elif readback == "async":
+                r.getOutputBufferAsync(host_out[local & 1])   # returns at once; lands while the next iteration renders
+        if readback == "async":
+            r.waitOutput()
         r.join()        # the gather / output of the last iteration run on the renderer's second stream: fold them into `stream`
         if world > 1:
-            with torch.cuda.stream(stream):
-                D.reduce_sum_to_root(D.output_as_tensor(r, dev), dst=0)
+            r.reduce_output(0)      # ncclReduce(sum) on the renderer's stream, into a scratch buffer on rank 0
 
-    # ---- warm-up, then the device-timed region (inputs resident in HBM)
+    def timed(steps, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record()
+        run(steps, **kw)
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    host_out = [torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy() for _ in range(2)]
+
+    # ---- warm-up, then the device-timed region (inputs resident in HBM): the K-step window, `repeats` times back to back
     sampler = ClockSampler(local_rank)
     sampler.start()
-    run(args.warmup, 0)
+    run(args.warmup)
     barrier()
     st0 = r.stats()          # counters are cumulative: everything reported below is the difference over the timed region
     launches0 = st0["launches"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     w0 = sampler.mark()
-    with torch.cuda.stream(stream):
-        e0.record()
-    run(args.steps, args.warmup)
-    with torch.cuda.stream(stream):
-        e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    windows_ms = [timed(args.steps) for _ in range(max(1, args.repeats))]
     sampler.window(w0, sampler.mark())
     st = r.stats()
-    rays = (st["closest_rays"] + st["any_rays"]) - (st0["closest_rays"] + st0["any_rays"])
+    nwin = len(windows_ms)
+    ms = sorted(windows_ms)[nwin // 2]
+    rays = ((st["closest_rays"] + st["any_rays"]) - (st0["closest_rays"] + st0["any_rays"])) / nwin     # per window; the windows differ by < 0.1 %
+    launches_per_window = (st["launches"] - launches0) / nwin
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline of the dominant kernel
     roof = None
@@ -268,8 +316,9 @@ def main():
         r.set_timing(True)
         acc = {}
         for k in range(nprof):
-            local = args.warmup + args.steps + k
-            it = local * world + rank
+            local = cursor[0]
+            cursor[0] += 1
+            it = B + local * world + rank
             r.renderNextIteration(it, local, radius(it), True, pod)
             for name, v in r.timings():
                 acc[name] = acc.get(name, 0.0) + v / nprof
@@ -319,26 +368,45 @@ def main():
                     "others": {k: {"ms": acc[k], "achieved_gbs": alg[k] / (acc[k] * 1e-3) / 1e9, "frac": alg[k] / (acc[k] * 1e-3) / 1e9 / peak}
                                for k in alg if k != name and acc.get(k, 0.0) > 0}}
 
-    # ---- end to end through the C ABI with host buffers: request struct in, W*H*3 floats out every step
-    host_out = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()
-    barrier()
-    st1 = r.stats()
+    # ---- end to end through the C ABI with host buffers: request struct in (120 B), W*H*3 floats out to pinned host memory EVERY step.
+    # (i) the pipelined driver loop: opr_get_output_buffer_async after every iteration (the copy of image i overlaps iteration i+1),
+    # opr_wait_output at the end; (ii) the reference's blocking loop (StandaloneRenderManager.cpp:114-128), reported beside it.
+    def wall(mode):
+        barrier()
+        s0 = r.stats()
+        t0 = time.perf_counter()
+        run(args.steps, readback=mode)
+        barrier()
+        dt = time.perf_counter() - t0
+        s1 = r.stats()
+        return dt, (s1["closest_rays"] + s1["any_rays"]) - (s0["closest_rays"] + s0["any_rays"])
+    run(2, readback="async")      # first use allocates the snapshots
     w1 = sampler.mark()
-    t0 = time.perf_counter()
-    run(args.steps, args.warmup + args.steps + nprof, readback=host_out)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s, rays_e2e = wall("async")
+    e2e_blocking_s, rays_e2e_blocking = wall("blocking")
     sampler.window(w1, sampler.mark())
     clocks = sampler.stop()
-    st2 = r.stats()
-    rays_e2e = (st2["closest_rays"] + st2["any_rays"]) - (st1["closest_rays"] + st1["any_rays"])
 
-    t = torch.tensor([ms, float(rays), e2e_s, float(rays_e2e)], dtype=torch.float64, device="cuda")
+    # ---- the first iterations of a render (large radius: the gather dominates), N = 1 only: round 1 quoted these
+    early = None
+    if world == 1 and args.method == "ppm":
+        cursor[0] = 0
+        run(3, first_iteration=0)
+        st_e0 = r.stats()
+        ms_e = timed(args.steps, first_iteration=0)
+        st_e1 = r.stats()
+        rays_e = (st_e1["closest_rays"] + st_e1["any_rays"]) - (st_e0["closest_rays"] + st_e0["any_rays"])
+        early = {"iterations": "3..%d" % (2 + args.steps), "ms_per_step": ms_e / args.steps, "value": rays_e / (ms_e * 1e-3) / 1e6, "unit": "Mrays/s",
+                 "note": "same workload at the START of a progressive render (radius 1.0-0.6 r0, gather 3-6x the steady-state cost)"}
+
+    t = torch.tensor([ms, float(rays), e2e_s, float(rays_e2e), e2e_blocking_s, float(rays_e2e_blocking)] + windows_ms, dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, e2e_s = float(tmax[0]), float(tmax[2])
-        rays, rays_e2e = float(tsum[1]), float(tsum[3])
+        windows_ms = [float(x) for x in tmax[6:]]            # every window: max over ranks
+        ms = sorted(windows_ms)[nwin // 2]
+        e2e_s, e2e_blocking_s = float(tmax[2]), float(tmax[4])
+        rays, rays_e2e, rays_e2e_blocking = float(tsum[1]), float(tsum[3]), float(tsum[5])
     total_steps = args.steps * world
 
     # ---- optional: time to a target relMSE (BASELINE config 5), iteration-partitioned like everything else
@@ -362,8 +430,9 @@ def main():
             t0e.record()
         reached, done_local, err = None, 0, None
         while done_local < max_local and reached is None:
-            for it, local, rad in part.steps(done_local, check_every):
-                r.renderNextIteration(it, local, rad, True, pod)
+            for local in range(done_local, done_local + check_every):
+                it = local * world + rank
+                r.renderNextIteration(it, local, radius(it), True, pod)
             done_local += check_every
             r.join()
             with torch.cuda.stream(stream):
@@ -398,13 +467,19 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "iterations_per_s": total_steps / (ms * 1e-3), "rays_per_iteration": rays / total_steps,
                 "photons_stored_per_iteration": (st["photons_stored"] - st0["photons_stored"]) / max(1, args.steps),
+                "windows_ms": windows_ms, "repeats": nwin,
                 "e2e": {"value": rays_e2e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.opr_request_details),
                         "d2h_bytes_per_step": W * H * 12, "iterations_per_s": total_steps / e2e_s,
-                        "how": "opr_render_next_iteration + opr_get_output_buffer into pinned host memory every step, wall clock, max over ranks"},
-                "gpu_launches": int(st["launches"] - launches0), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ray_queue": ray_queue, "time_to_relmse": ttt,
+                        "how": "opr_render_next_iteration + opr_get_output_buffer_async into pinned host memory EVERY step (image i is copied out while "
+                               "iteration i+1 renders), opr_wait_output after the last step; wall clock, max over ranks",
+                        "blocking": {"value": rays_e2e_blocking / e2e_blocking_s / 1e6, "iterations_per_s": total_steps / e2e_blocking_s,
+                                     "how": "the reference's driver loop: blocking opr_get_output_buffer after every step"}},
+                "early_iterations": early,
+                "gpu_launches": int(round(launches_per_window)), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ray_queue": ray_queue, "time_to_relmse": ttt,
                 "kernel_ms": kernel_ms, "scene": {"triangles": scene.getNumTriangles(), "meshes": scene.getNumMeshes(), "generate_s": t_scene, "init_scene_s": t_init}}
         print(json.dumps(line))
     if world > 1:
+        r.comm_destroy()
         dist.destroy_process_group()
 
 

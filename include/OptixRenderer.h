@@ -207,6 +207,10 @@ public:
     static const unsigned int EMITTED_PHOTONS_PER_ITERATION = PHOTON_LAUNCH_WIDTH * PHOTON_LAUNCH_HEIGHT;
     static const unsigned int NUM_PHOTONS = EMITTED_PHOTONS_PER_ITERATION * MAX_PHOTON_COUNT;
     static const unsigned int VCM_MAX_PATH_LENGTH = 10u;
+    // OptixRenderer.h:41 declares this member and no translation unit of the reference defines or reads it (the initial radius
+    // comes from IScene::getSceneInitialPPMRadiusEstimate, scene/IScene.cpp:23-31).  Declared for source compatibility; defined
+    // below as 0 so that code naming it links.
+    const static float PPM_INITIAL_RADIUS;
 
     OptixRenderer() : m_r(nullptr) { check(opr_create(&m_r, nullptr)); }
     explicit OptixRenderer(const opr_config& cfg) : m_r(nullptr) { check(opr_create(&m_r, &cfg)); }
@@ -229,5 +233,36 @@ public:
     unsigned int getWidth() const { return opr_get_width(m_r); }
     unsigned int getHeight() const { return opr_get_height(m_r); }
     unsigned int getScreenBufferSizeBytes() const { return opr_get_screen_buffer_size_bytes(m_r); }
+    // additions: read-back that overlaps the next iterations (data must stay valid until waitOutput returns)
+    void getOutputBufferAsync(void* data) { check(opr_get_output_buffer_async(m_r, data)); }
+    void waitOutput() { check(opr_wait_output(m_r)); }
     opr_renderer* handle() const { return m_r; }
+};
+inline const float OptixRenderer::PPM_INITIAL_RADIUS = 0.0f;
+
+// The GPUs of one box behind one object: replaces the client's hand-out loop (Client/DistributedApplication.cpp:96-122) and the
+// render servers' result packets (Server/server/RenderServerRenderer.cpp:154-175).  Global iteration i is rendered by GPU
+// i % size() as its local iteration i / size(), with the radius of the driver's recurrence; getOutputBuffer sums the GPUs'
+// running sums with one NCCL reduce.
+class OptixRendererGroup {
+    opr_group* m_g;
+    static void check(int rc) { if (rc != 0) throw std::runtime_error(opr_last_error()); }
+public:
+    explicit OptixRendererGroup(const std::vector<int>& cudaOrdinals, const opr_config* cfg = nullptr) : m_g(nullptr)
+    { check(opr_group_create(&m_g, (int)cudaOrdinals.size(), cudaOrdinals.data(), cfg)); }
+    ~OptixRendererGroup() { opr_group_destroy(m_g); }
+    OptixRendererGroup(const OptixRendererGroup&) = delete;
+    OptixRendererGroup& operator=(const OptixRendererGroup&) = delete;
+    int size() const { return opr_group_size(m_g); }
+    void initScene(IScene& scene) { check(opr_group_init_scene(m_g, &scene.getSceneDescription())); }
+    void renderNextIterations(unsigned long long firstIteration, unsigned long long count, double initialPPMRadius,
+                              const RenderServerRenderRequestDetails& details)
+    {
+        opr_request_details d; memset(&d, 0, sizeof d);
+        d.camera = details.getCamera(); d.renderMethod = (int)details.getRenderMethod();
+        d.width = details.getWidth(); d.height = details.getHeight(); d.ppmAlpha = (float)details.getPPMAlpha();
+        d.sceneName = details.getSceneName().c_str();
+        check(opr_group_render_next_iterations(m_g, firstIteration, count, initialPPMRadius, details.getPPMAlpha(), &d));
+    }
+    void getOutputBuffer(void* data) { check(opr_group_reduce_output(m_g, data)); }
 };

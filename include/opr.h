@@ -58,6 +58,45 @@ void* opr_get_stream(opr_renderer* r);
  * can render global iterations g, g+G, ... without exchanging radii. */
 double opr_ppm_radius_for_iteration(double initialRadius, uint64_t iteration, double alpha);
 
+/* ---- asynchronous read-back (Standalone/StandaloneRenderManager.cpp:114-128 copies the output after EVERY iteration) --------
+ * opr_get_output_buffer_async snapshots the running sum as of the last opr_render_next_iteration (device copy ordered behind that
+ * iteration only) and streams it to dstHost on the renderer's copy stream while the next iterations render; it returns at once.
+ * dstHost must stay valid until opr_wait_output(r) returns (pinned memory makes the copy truly asynchronous).  Up to two
+ * read-backs may be in flight; a third call first waits for the oldest.  The synchronous opr_get_output_buffer is unchanged. */
+int opr_get_output_buffer_async(opr_renderer* r, void* dstHost);
+int opr_wait_output(opr_renderer* r);
+
+/* ---- multi-GPU behind the C ABI: iteration partition + one NCCL reduce ------------------------------------------------------
+ * Replaces the client's hand-out loop (Client/DistributedApplication.cpp:96-122: the next global iteration number and its
+ * radius go to whichever server is free) and the servers' result packets (Server/server/RenderServerRenderer.cpp:154-175,
+ * summed by the client): global iteration i is rendered by rank i % G as its localIterationNumber i / G with the closed-form
+ * radius opr_ppm_radius_for_iteration(i); the W*H*3-float running sums are combined by ONE ncclReduce(sum) over NVLink into a
+ * scratch buffer on the root (the running sums themselves are never a reduce target, so the call can be repeated).
+ * NCCL is loaded at run time (libnccl.so.2); without it these functions fail with a message, nothing else is affected. */
+/* seed of rank `rank`: disjoint ranges of the per-state seeds `seed + i` (i < 2^28 states) for up to 16 ranks */
+uint32_t opr_group_rank_seed(uint32_t baseSeed, int rank);
+/* (a) one process per GPU (torchrun, MPI): rank 0 makes the 128-byte NCCL id, the launcher transports it, every rank joins */
+int opr_comm_get_unique_id(void* id128);
+int opr_comm_init_rank(opr_renderer* r, const void* id128, int rank, int world);
+int opr_comm_destroy(opr_renderer* r);
+/* ncclReduce(sum) of every rank's running sum onto `root`, queued on opr_get_stream(r) behind everything rendered so far.
+ * dstHost (root only, may be NULL) receives W*H*3 floats and makes the call synchronous; opr_get_reduced_device_ptr(r)
+ * is the device copy of the total on the root. */
+int opr_reduce_output(opr_renderer* r, int root, void* dstHost);
+void* opr_get_reduced_device_ptr(opr_renderer* r);
+/* (b) one process, G GPUs: a group owns one renderer per device and one host thread per renderer */
+typedef struct opr_group opr_group;
+int opr_group_create(opr_group** out, int numDevices, const int* cudaOrdinals, const opr_config* cfg);
+void opr_group_destroy(opr_group* g);
+int opr_group_size(opr_group* g);
+opr_renderer* opr_group_renderer(opr_group* g, int rank);
+int opr_group_init_scene(opr_group* g, const opr_scene_desc* scene);
+/* renders the global iterations [first, first + count) — all ranks in parallel — with radii from (initialRadius, alpha) */
+int opr_group_render_next_iterations(opr_group* g, uint64_t firstIteration, uint64_t count, double initialRadius, double alpha,
+                                     const opr_request_details* details);
+/* sum of all ranks' running sums -> dstHost (W*H*3 floats) through rank 0 */
+int opr_group_reduce_output(opr_group* g, void* dstHost);
+
 /* counters since the last resize: [0] closest-hit rays, [1] any-hit rays, [2] photons stored, [3] kernel launches */
 int opr_get_stats(opr_renderer* r, uint64_t* out, int n);
 /* per-pass CUDA-event timings of the last iteration (opr_set_timing(r,1) first); returns the number written */
@@ -75,7 +114,10 @@ const char* opr_get_timing_name(opr_renderer* r, int index);
  * "direct_sample_mask" (u8 x W*H: bit s = shadow sample s of DirectRadianceEstimation.cu:54-70 was unoccluded and non-zero),
  * "light_vertex_positions" (u32 count + 12 B pad, then {u32 path, float3 hitPoint} per stored light vertex of the last light
  * pass), "connection_counts" (u32 x W*H: contributions that passed isOccluded, vcm.h:43-59, per target pixel, last BDPT
- * iteration; needs opr_debug_set_connection_counts(r, 1) before the iteration). */
+ * iteration; needs opr_debug_set_connection_counts(r, 1) before the iteration), "path_signatures" (u32 x 2*W*H, same switch: per BDPT light subpath, then per camera subpath, a hash of the material kinds it met),
+ * "pt_signature" (u32 x W*H, same switch: hash over
+ * the segments of the last PATH_TRACING iteration's path of (hit flags, light sample contributed, ended by Russian roulette) —
+ * RayGeneratorPT.cu:84-127 draws those decisions from a stream whose final state is discarded, so the RNG state cannot show them). */
 int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t bytes);
 int opr_debug_set_connection_counts(opr_renderer* r, int enabled);
 

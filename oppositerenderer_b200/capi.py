@@ -120,6 +120,21 @@ def _declare(lib):
         "opr_synchronize": (i32, [vp]),
         "opr_join_streams": (i32, [vp]),
         "opr_get_stream": (vp, [vp]),
+        "opr_get_output_buffer_async": (i32, [vp, vp]),
+        "opr_wait_output": (i32, [vp]),
+        "opr_group_rank_seed": (u32, [u32, i32]),
+        "opr_comm_get_unique_id": (i32, [vp]),
+        "opr_comm_init_rank": (i32, [vp, vp, i32, i32]),
+        "opr_comm_destroy": (i32, [vp]),
+        "opr_reduce_output": (i32, [vp, i32, vp]),
+        "opr_get_reduced_device_ptr": (vp, [vp]),
+        "opr_group_create": (i32, [C.POINTER(vp), i32, PI, C.POINTER(opr_config)]),
+        "opr_group_destroy": (None, [vp]),
+        "opr_group_size": (i32, [vp]),
+        "opr_group_renderer": (vp, [vp, i32]),
+        "opr_group_init_scene": (i32, [vp, C.POINTER(opr_scene_desc)]),
+        "opr_group_render_next_iterations": (i32, [vp, u64, u64, C.c_double, C.c_double, C.POINTER(opr_request_details)]),
+        "opr_group_reduce_output": (i32, [vp, vp]),
         "opr_get_stats": (i32, [vp, C.POINTER(C.c_uint64), i32]),
         "opr_get_timings_ms": (i32, [vp, PF, i32]),
         "opr_get_timing_name": (C.c_char_p, [vp, i32]),

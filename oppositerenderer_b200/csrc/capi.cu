@@ -7,9 +7,8 @@
 
 using namespace opr;
 
-struct opr_renderer { Renderer r; };
-
 static thread_local std::string g_lastError;
+extern "C" void opr_set_last_error(const char* msg) { g_lastError = msg ? msg : ""; }   // group.cu reports through the same slot
 #define OPR_TRY(...) try { __VA_ARGS__; return 0; } catch (const std::exception& e) { g_lastError = e.what(); return 1; } catch (...) { g_lastError = "unknown error"; return 1; }
 
 namespace {
@@ -60,7 +59,13 @@ int opr_get_output_buffer(opr_renderer* r, void* dst) { OPR_TRY(r->r.getOutputBu
 uint32_t opr_get_width(opr_renderer* r) { return r->r.width; }
 uint32_t opr_get_height(opr_renderer* r) { return r->r.height; }
 uint32_t opr_get_screen_buffer_size_bytes(opr_renderer* r) { return r->r.width * r->r.height * 3u * (uint32_t)sizeof(float); }
-void* opr_get_output_device_ptr(opr_renderer* r) { try { r->r.joinStreams(); } catch (...) {} return r->r.output; }
+void* opr_get_output_device_ptr(opr_renderer* r)
+{   // the pointer is only handed out once the stream-B work is ordered before `stream`: a caller would otherwise read a half-written sum
+    try { OPR_CUDA_CHECK(cudaSetDevice(r->r.device)); r->r.joinStreams(); return r->r.output; }
+    catch (const std::exception& e) { g_lastError = e.what(); return nullptr; }
+}
+int opr_get_output_buffer_async(opr_renderer* r, void* dst) { OPR_TRY(r->r.getOutputBufferAsync(dst)) }
+int opr_wait_output(opr_renderer* r) { OPR_TRY(r->r.waitOutput()) }
 void* opr_get_stream(opr_renderer* r) { return (void*)r->r.stream; }
 int opr_synchronize(opr_renderer* r) { OPR_TRY({ OPR_CUDA_CHECK(cudaSetDevice(r->r.device)); r->r.joinStreams(); OPR_CUDA_CHECK(cudaStreamSynchronize(r->r.stream)); }) }
 int opr_join_streams(opr_renderer* r) { OPR_TRY({ OPR_CUDA_CHECK(cudaSetDevice(r->r.device)); r->r.joinStreams(); }) }
@@ -173,6 +178,14 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
         } else if (n == "connection_counts") {
             need(px * 4);
             if (R.debugConnectionCountsGet((unsigned*)dst)) throw std::runtime_error("connection counts are off (opr_debug_set_connection_counts) or no BDPT iteration has run");
+        } else if (n == "path_signatures") {
+            need(px * 8);
+            if (R.debugPathSignaturesGet((unsigned*)dst)) throw std::runtime_error("path signatures are off (opr_debug_set_connection_counts) or no BDPT iteration has run");
+        } else if (n == "pt_signature") {
+            need(px * 4);
+            if (!R.ptSignature) throw std::runtime_error("path signatures are off (opr_debug_set_connection_counts) or no PATH_TRACING iteration has run");
+            OPR_CUDA_CHECK(cudaMemcpyAsync(dst, R.ptSignature, px * 4, cudaMemcpyDeviceToHost, st));
+            OPR_CUDA_CHECK(cudaStreamSynchronize(st));
         } else if (n == "direct_sample_mask") {
             // bit s of byte p: shadow sample s of pixel p was cast, unoccluded and non-zero (last PPM iteration)
             need(px);
@@ -219,6 +232,7 @@ int opr_rng_init(uint32_t* states6, uint32_t seed, uint32_t first, uint32_t coun
 {
     OPR_TRY({
         requireDevice();
+        if (count == 0) return 0;
         DevBuf d((size_t)count * 24);
         rng_init_range_kernel<<<(count + 255) / 256, 256>>>(d.as<unsigned>(), seed, first, count);
         OPR_CUDA_CHECK(cudaMemcpy(states6, d.p, (size_t)count * 24, cudaMemcpyDeviceToHost));
@@ -275,7 +289,7 @@ int opr_build_photon_grid(const float* photonsAoS, uint32_t n, float* sortedPhot
         OPR_CUDA_CHECK(cudaMemcpy(dAos.p, photonsAoS, (size_t)n * 36, cudaMemcpyHostToDevice));
         OPR_CUDA_CHECK(cudaMemset(state.p, 0, nPad));
         OPR_CUDA_CHECK(cudaMemset(b.p, 0, (size_t)nPad * 16));
-        photons_aos_to_soa_kernel<<<148 * 4, 256>>>(dAos.as<float>(), n, pb, state.as<unsigned>());
+        photons_aos_to_soa_kernel<<<numSMs() * 4, 256>>>(dAos.as<float>(), n, pb, state.as<unsigned>());
         float init[8] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f, 0.f};
         OPR_CUDA_CHECK(cudaMemcpy(bbox.p, init, 28, cudaMemcpyHostToDevice));
         launch_photon_bbox(pb, state.as<unsigned>(), nPad / MAX_PHOTON_DEPOSITS, bbox.as<float>(), lc);
@@ -299,7 +313,7 @@ int opr_build_photon_grid(const float* photonsAoS, uint32_t n, float* sortedPhot
         const unsigned* sk = flipped ? k1.as<unsigned>() : k0.as<unsigned>();
         const unsigned* sv = flipped ? v1.as<unsigned>() : v0.as<unsigned>();
         launch_photon_reorder(pb, sv, nv, sorted, lc);
-        photons_soa_to_aos_kernel<<<148 * 4, 256>>>(sorted, nv, dAos.as<float>());
+        photons_soa_to_aos_kernel<<<numSMs() * 4, 256>>>(sorted, nv, dAos.as<float>());
         OPR_CUDA_CHECK(cudaDeviceSynchronize());
         OPR_CUDA_CHECK(cudaGetLastError());
         OPR_CUDA_CHECK(cudaMemcpy(sortedPhotonsAoS, dAos.p, (size_t)nv * 36, cudaMemcpyDeviceToHost));
@@ -338,8 +352,8 @@ int opr_gather(uint32_t numPixels, const float* hitpointsAoS, uint32_t numPhoton
         OPR_CUDA_CHECK(cudaMemcpy(dHp.p, hitpointsAoS, (size_t)numPixels * 64, cudaMemcpyHostToDevice));
         OPR_CUDA_CHECK(cudaMemcpy(dPh.p, photonsAoS, (size_t)numPhotons * 36, cudaMemcpyHostToDevice));
         OPR_CUDA_CHECK(cudaMemcpy(dOff.p, offsets, ((size_t)g.numCells + 1) * 4, cudaMemcpyHostToDevice));
-        hitpoints_aos_to_soa_kernel<<<148 * 4, 256>>>(dHp.as<float>(), numPixels, hp);
-        if (numPhotons) photons_aos_to_soa_kernel<<<148 * 4, 256>>>(dPh.as<float>(), numPhotons, pb, state.as<unsigned>());
+        hitpoints_aos_to_soa_kernel<<<numSMs() * 4, 256>>>(dHp.as<float>(), numPixels, hp);
+        if (numPhotons) photons_aos_to_soa_kernel<<<numSMs() * 4, 256>>>(dPh.as<float>(), numPhotons, pb, state.as<unsigned>());
         launch_gather(hp, numPixels, 0, 0, pb, dOff.as<unsigned>(), g, ppmRadius, ppmRadius * ppmRadius, emittedPhotons, dOut.as<float>(), dCounter.as<unsigned>(), lc);
         OPR_CUDA_CHECK(cudaDeviceSynchronize());
         OPR_CUDA_CHECK(cudaGetLastError());
@@ -378,9 +392,9 @@ int opr_trace_closest(opr_renderer* r, const float* rays8, uint32_t n, float* ou
         LaunchCtx lc{R.stream, &R.launches};
         DevBuf dr((size_t)n * 32), o((size_t)n * 16), d((size_t)n * 16), h((size_t)n * 16), t((size_t)n * 4), m((size_t)n * 4), ng((size_t)n * 12);
         OPR_CUDA_CHECK(cudaMemcpyAsync(dr.p, rays8, (size_t)n * 32, cudaMemcpyHostToDevice, R.stream));
-        rays8_to_soa_kernel<<<148 * 4, 256, 0, R.stream>>>(dr.as<float>(), n, o.as<float4>(), d.as<float4>());
+        rays8_to_soa_kernel<<<numSMs() * 4, 256, 0, R.stream>>>(dr.as<float>(), n, o.as<float4>(), d.as<float4>());
         launch_trace_closest_raw(R.scene.view, o.as<float4>(), d.as<float4>(), n, h.as<float4>(), lc);
-        hits_to_host_layout_kernel<<<148 * 4, 256, 0, R.stream>>>(R.scene.view, o.as<float4>(), d.as<float4>(), h.as<float4>(), n, t.as<float>(), m.as<int>(), ng.as<float>());
+        hits_to_host_layout_kernel<<<numSMs() * 4, 256, 0, R.stream>>>(R.scene.view, o.as<float4>(), d.as<float4>(), h.as<float4>(), n, t.as<float>(), m.as<int>(), ng.as<float>());
         OPR_CUDA_CHECK(cudaMemcpyAsync(outT, t.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
         OPR_CUDA_CHECK(cudaMemcpyAsync(outMaterial, m.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
         OPR_CUDA_CHECK(cudaMemcpyAsync(outNg3, ng.p, (size_t)n * 12, cudaMemcpyDeviceToHost, R.stream));
@@ -398,7 +412,7 @@ int opr_trace_any(opr_renderer* r, const float* rays8, uint32_t n, int32_t* outO
         LaunchCtx lc{R.stream, &R.launches};
         DevBuf dr((size_t)n * 32), o((size_t)n * 16), d((size_t)n * 16), occ((size_t)n * 4);
         OPR_CUDA_CHECK(cudaMemcpyAsync(dr.p, rays8, (size_t)n * 32, cudaMemcpyHostToDevice, R.stream));
-        rays8_to_soa_kernel<<<148 * 4, 256, 0, R.stream>>>(dr.as<float>(), n, o.as<float4>(), d.as<float4>());
+        rays8_to_soa_kernel<<<numSMs() * 4, 256, 0, R.stream>>>(dr.as<float>(), n, o.as<float4>(), d.as<float4>());
         launch_trace_any_raw(R.scene.view, o.as<float4>(), d.as<float4>(), n, occ.as<int>(), lc);
         OPR_CUDA_CHECK(cudaMemcpyAsync(outOccluded, occ.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
         OPR_CUDA_CHECK(cudaStreamSynchronize(R.stream));

@@ -238,6 +238,8 @@ void devAlloc(void** out, size_t bytes);
 void devFree(void* p);
 void devSetGuards(bool on);
 int devCheckGuards(int* liveBlocks);
+// multiprocessor count of the current device (cudaDevAttrMultiProcessorCount, cached per device): every grid is sized from it
+int numSMs();
 }
 
 #define OPR_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)

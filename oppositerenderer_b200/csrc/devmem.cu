@@ -77,4 +77,17 @@ int devCheckGuards(int* checkedBlocks)
     return bad;
 }
 
+int numSMs()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;   // B200
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 } // namespace opr

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(BBOX_THREADS) photon_bbox_kernel(PhotonBuf pho
 
 void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc)
 {
-    int blocks = (int)std::min<unsigned>((numThreads + BBOX_THREADS - 1) / BBOX_THREADS, 148 * 8);
+    int blocks = (int)std::min<unsigned>((numThreads + BBOX_THREADS - 1) / BBOX_THREADS, numSMs() * 8);
     photon_bbox_kernel<<<blocks, BBOX_THREADS, 0, lc.st>>>(photons, phState, numThreads, bbox);
     ++*lc.launches;
 }
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) grid_keys_hist_kernel(PhotonBuf photons, 
 
 void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, GridParams g, unsigned* keys, unsigned* hist, LaunchCtx lc)
 {
-    int blocks = (int)std::min<unsigned>((numSlots + 255) / 256, 148 * 16);
+    int blocks = (int)std::min<unsigned>((numSlots + 255) / 256, numSMs() * 16);
     grid_keys_hist_kernel<<<blocks, 256, 0, lc.st>>>(photons, phState, numSlots, g, keys, hist);
     ++*lc.launches;
 }
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) photon_reorder_kernel(PhotonBuf src, cons
 void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned numValid, const PhotonBuf& dst, LaunchCtx lc)
 {
     if (!numValid) return;
-    int blocks = (int)std::min<unsigned>((numValid + 255) / 256, 148 * 16);
+    int blocks = (int)std::min<unsigned>((numValid + 255) / 256, numSMs() * 16);
     photon_reorder_kernel<<<blocks, 256, 0, lc.st>>>(src, sortedSlots, numValid, dst);
     ++*lc.launches;
 }
@@ -328,7 +328,7 @@ void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, un
                    unsigned tilesPerBlock)
 {
     const unsigned numTiles = width ? ((width + 7) / 8) * ((height + 3) / 4) : (numPixels + 31) / 32;
-    int blocks = (int)std::min<unsigned>(numTiles, 148 * std::max(1u, blocksPerSM));
+    int blocks = (int)std::min<unsigned>(numTiles, numSMs() * std::max(1u, blocksPerSM));
     if (tilesPerBlock) blocks = (int)((numTiles + tilesPerBlock - 1) / tilesPerBlock);   // short-lived CTAs: as many resident as fit
     OPR_CUDA_CHECK(cudaMemsetAsync(tileCounter, 0, sizeof(unsigned), lc.st));
     ppm_gather_kernel<<<blocks, GATHER_THREADS, 0, lc.st>>>(hp, numPixels, width, height, sorted, offsets, g, ppmRadius, ppmRadiusSquared, emittedPhotons, indirect,

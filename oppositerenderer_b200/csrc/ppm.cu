@@ -12,7 +12,7 @@
 namespace opr {
 
 constexpr int SHADE_THREADS = 128;
-constexpr int SHADE_BLOCKS_X = 148 * 8;    // per material kind; blocks of empty kinds exit at once (2 per SM left the dominant kind at 12 % occupancy: profiles/r1f)
+#define SHADE_BLOCKS_X (numSMs() * 8)    // per material kind; blocks of empty kinds exit at once (2 per SM left the dominant kind at 12 % occupancy: profiles/r1f)
 
 // ---- helpers -------------------------------------------------------------------------------------------
 OPR_DEV unsigned rng_index(unsigned path, unsigned launchW, unsigned rsW)
@@ -89,7 +89,7 @@ __global__ void rng_init_kernel(RngBuf rng, unsigned seed, size_t n)
 }
 void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc)
 {
-    rng_init_kernel<<<148 * 8, 256, 0, lc.st>>>(rng, seed, n);
+    rng_init_kernel<<<numSMs() * 8, 256, 0, lc.st>>>(rng, seed, n);
     ++*lc.launches;
 }
 
@@ -142,7 +142,7 @@ void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsign
                            const RayQueues& q, LaunchCtx lc)
 {
     unsigned n = w * h;
-    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
+    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, numSMs() * 16);
     ppm_camera_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(cam, w, h, rsW, rng, hp, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters, q.camPending);
     ++*lc.launches;
 }
@@ -329,7 +329,7 @@ void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, cons
 
 void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, LaunchCtx lc)
 {
-    ppm_camera_tail_kernel<<<148 * 4 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.tailO, q.tailD, q.tailPath,
+    ppm_camera_tail_kernel<<<numSMs() * 4 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.tailO, q.tailD, q.tailPath,
                                                                  q.counters + CTR_TAIL_COUNT, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
     ++*lc.launches;
 }
@@ -423,7 +423,7 @@ void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsign
     // keep the camera pass's queue lengths for the occupancy report, then zero the per-bounce counters of this pass
     OPR_CUDA_CHECK(cudaMemcpyAsync(q.counters + CTR_SNAPSHOT, q.counters + CTR_RAYCOUNT, 16 * sizeof(unsigned), cudaMemcpyDeviceToDevice, lc.st));
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_RAYCOUNT, 0, (CTR_TOTAL - CTR_RAYCOUNT) * sizeof(unsigned), lc.st));
-    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
+    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, numSMs() * 16);
     ppm_photon_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, pw, ph, rsW, rng, phPower, phState, q.rayO[0], q.rayD[0], q.rayPath[0], q.counters,
                                                                q.camPending, w, h, q.deferred, q.photonPending, feedsTail ? 1 : 0);
     ++*lc.launches;
@@ -606,7 +606,7 @@ void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, cons
                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc)
 {
     const int cur = bounce & 1;
-    ppm_photon_tail_kernel<<<148 * 8 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
+    ppm_photon_tail_kernel<<<numSMs() * 8 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
                                                                  q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
     ++*lc.launches;
 }
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_late_kernel(SceneVie
 void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState, const PhotonBuf& photons,
                             const RayQueues& q, LaunchCtx lc)
 {
-    ppm_photon_late_kernel<<<148 * 4, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.deferred, q.counters + CTR_DEFERRED_COUNT,
+    ppm_photon_late_kernel<<<numSMs() * 4, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.deferred, q.counters + CTR_DEFERRED_COUNT,
                                                                  q.counters + 16 + STAT_CLOSEST_RAYS);
     ++*lc.launches;
 }
@@ -802,11 +802,11 @@ void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned
     if (!late) {
         OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_SHADOW_COUNT, 0, sizeof(unsigned), lc.st));
         OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_SHADOW2_COUNT, 0, 3 * sizeof(unsigned), lc.st));   // late queue length, cursor, deferred pixels
-        int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
+        int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, numSMs() * 16);
         ppm_direct_gen_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, w, h, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q.counters,
                                                                    part == 1 ? q.camPending : nullptr, q.photonPending, pw, ph, q.directDeferred);
     } else {
-        ppm_direct_late_kernel<<<148 * 4, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q.counters, q.directDeferred);
+        ppm_direct_late_kernel<<<numSMs() * 4, SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q.counters, q.directDeferred);
     }
     ++*lc.launches;
 }
@@ -814,7 +814,7 @@ void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned
 void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const uint2* sampleLight,
                                const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc)
 {
-    int blocks = (int)std::min<unsigned>((n + 255) / 256, 148 * 16);
+    int blocks = (int)std::min<unsigned>((n + 255) / 256, numSMs() * 16);
     ppm_resolve_output_kernel<<<blocks, 256, 0, lc.st>>>(sc, n, hp, sampleFactor, sampleLight, indirect, direct, output, localIteration);
     ++*lc.launches;
 }
@@ -831,7 +831,7 @@ constexpr int PATH_TRACING_RR_START_DEPTH = 3;   // config.h:37
 
 __global__ void __launch_bounds__(SHADE_THREADS) pt_generate_ray_kernel(SceneView sc, opr_camera cam, unsigned w, unsigned h, unsigned rsW, RngBuf rngBuf,
                                                                         HitpointBuf hp, float* __restrict__ output, unsigned localIteration,
-                                                                        unsigned* __restrict__ stats)
+                                                                        unsigned* __restrict__ stats, unsigned* __restrict__ signature)
 {
     const unsigned FULL = 0xffffffffu;
     const unsigned n = w * h;
@@ -874,7 +874,12 @@ __global__ void __launch_bounds__(SHADE_THREADS) pt_generate_ray_kernel(SceneVie
         float3 finalRadiance = f3(0.f);
         bool alive = inImage;
         const int numLights = sc.numLights;
+        // parity diagnostics (null otherwise): per path segment, the hit flags, whether the light sample contributed and whether
+        // Russian roulette ended the path — the discrete decisions of a path, none of which shows in the final RNG state
+        unsigned sig = 0;
         for (int i = 0; i < 5 && __any_sync(FULL, alive); i++) {
+            const bool aliveAtEntry = alive;
+            unsigned code = 0;
             if (alive) hp.pos[p].w = __uint_as_float(PRD_PATH_TRACING);
             // ---- rtTrace(sceneRootObject, ray, radiancePrd): the chain of recursive closest-hit programs
             bool chain = alive;
@@ -899,6 +904,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) pt_generate_ray_kernel(SceneVie
             if (alive) {
                 const float4 pos4 = hp.pos[p];
                 const unsigned flags = __float_as_uint(pos4.w);
+                code = (flags >> 27) & 0x1fu;
                 if (flags & PRD_HIT_EMITTER) {
                     if ((flags & PRD_HIT_SPECULAR) || i == 0) finalRadiance = f3(hp.rad[p]);
                     alive = false;
@@ -947,6 +953,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) pt_generate_ray_kernel(SceneVie
             if (diffuse) {
                 float3 lightContrib = f3(0.f);
                 if (cast) { anyRays++; lightFactor *= occluded ? 0.0f : 1.0f; lightContrib = power * lightFactor; }
+                if (lightContrib.x != 0.f || lightContrib.y != 0.f || lightContrib.z != 0.f) code |= 32u;
                 const float scale = (float)numLights;
                 const float3 accumLightRadiancePreBrdf = f3(0.f) + scale * lightContrib;
                 const float3 directRadiance = attenuation * accumLightRadiancePreBrdf / 1.0f;
@@ -955,10 +962,12 @@ __global__ void __launch_bounds__(SHADE_THREADS) pt_generate_ray_kernel(SceneVie
             if (alive && i >= PATH_TRACING_RR_START_DEPTH) {
                 const float sample = rng_uniform(bufferState);
                 const float probabilityContinue = fmax3(attenuation);
-                if (sample > probabilityContinue) alive = false;
+                if (sample > probabilityContinue) { alive = false; code |= 64u; }
                 else { attenuation /= probabilityContinue; hp.att[p] = make_float4(attenuation.x, attenuation.y, attenuation.z, 0.f); }
             }
+            if (aliveAtEntry) sig = sig * 131u + code + 1u;
         }
+        if (signature && inImage) signature[p] = sig;
         if (inImage && !(finalRadiance.x != finalRadiance.x || finalRadiance.y != finalRadiance.y || finalRadiance.z != finalRadiance.z)) {
             float3 out = finalRadiance;
             if (localIteration != 0) out = f3(output[3 * (size_t)p], output[3 * (size_t)p + 1], output[3 * (size_t)p + 2]) + finalRadiance;
@@ -970,11 +979,11 @@ __global__ void __launch_bounds__(SHADE_THREADS) pt_generate_ray_kernel(SceneVie
 }
 
 void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
-                            float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc)
+                            float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc, unsigned* signature)
 {
     unsigned n = w * h;
-    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, 148 * 16);
-    pt_generate_ray_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, cam, w, h, rsW, rng, hp, output, localIteration, stats);
+    int blocks = (int)std::min<unsigned>((n + SHADE_THREADS - 1) / SHADE_THREADS, numSMs() * 16);
+    pt_generate_ray_kernel<<<blocks, SHADE_THREADS, 0, lc.st>>>(sc, cam, w, h, rsW, rng, hp, output, localIteration, stats, signature);
     ++*lc.launches;
 }
 

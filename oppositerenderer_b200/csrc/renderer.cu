@@ -6,8 +6,13 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
+#include <nvtx3/nvToolsExt.h>
 
 namespace opr {
+
+NvtxRange::NvtxRange(const char* message) { nvtxRangePushA(message); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 void vcm_free(Renderer& r);   // vcm.cu
 
@@ -25,11 +30,13 @@ Renderer::~Renderer()
     dfree(phPower); dfree(phState); dfree(photons.a); dfree(photons.b); dfree(photons.c);
     dfree(sorted.a); dfree(sorted.b); dfree(sorted.c);
     dfree(gridKeys[0]); dfree(gridKeys[1]); dfree(gridVals[0]); dfree(gridVals[1]); dfree(gridHist); dfree(sortTmp); dfree(scanTmp);
-    dfree(gridBBox); dfree(stats64);
+    dfree(gridBBox); dfree(stats64); dfree(reduced);
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
     scene.release();
     if (bboxEvent) cudaEventDestroy(bboxEvent);
     for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone, evPhotonWaves, evVcmShade, evVcmConn[0], evVcmConn[1]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {evOutputReady, evSnapTaken[0], evSnapTaken[1], evSnapCopied[0], evSnapCopied[1]}) if (e) cudaEventDestroy(e);
+    if (streamD) cudaStreamDestroy(streamD);
     if (streamB) cudaStreamDestroy(streamB);
     if (streamC) cudaStreamDestroy(streamC);
     if (stream) cudaStreamDestroy(stream);
@@ -65,6 +72,9 @@ void Renderer::initialize(int cudaOrdinal)
     OPR_CUDA_CHECK(cudaStreamCreateWithPriority(&streamC, cudaStreamNonBlocking, prC));
     for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone, &evPhotonWaves, &evVcmShade, &evVcmConn[0], &evVcmConn[1]})
         OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    OPR_CUDA_CHECK(cudaStreamCreateWithPriority(&streamD, cudaStreamNonBlocking, prLeast));
+    for (cudaEvent_t* e : {&evOutputReady, &evSnapTaken[0], &evSnapTaken[1], &evSnapCopied[0], &evSnapCopied[1]})
+        OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("OPR_VCM_CONNECT_BLOCKS_PER_SM")) vcmConnectBlocksPerSM = (unsigned)std::max(0, atoi(e));
@@ -95,6 +105,7 @@ void Renderer::initScene(const opr_scene_desc* d)
     if (!d || d->numLights == 0) throw std::runtime_error("No lights exists in this scene.");     // :443-447
     OPR_CUDA_CHECK(cudaSetDevice(device));
     lightVertexCountEstimated = false;
+    sceneLoaded = false;      // DeviceScene::load releases the previous scene first: a failed reload must not leave a half-freed scene renderable
     scene.load(d, stream);
     sceneLoaded = true;
 }
@@ -117,7 +128,8 @@ void Renderer::freeBuffers()
     for (int i = 0; i < 2; i++) { dfree(q.rayO[i]); dfree(q.rayD[i]); dfree(q.rayPath[i]); }
     dfree(q.hits); dfree(q.matQueue); dfree(q.counters);
     dfree(q.tailO); dfree(q.tailD); dfree(q.tailPath); dfree(q.camPending); dfree(q.deferred); dfree(q.photonPending); dfree(q.directDeferred);
-    dfree(indirect); dfree(direct); dfree(output);
+    dfree(indirect); dfree(direct); dfree(output); dfree(ptSignature); dfree(outputSnap[0]); dfree(outputSnap[1]);
+    snapTakenPending = snapInFlight[0] = snapInFlight[1] = false;
     dfree(shadowD); dfree(shadowIdx); dfree(shadowD2); dfree(shadowIdx2);
     buffersAllocated = false;
 }
@@ -127,6 +139,7 @@ void Renderer::resizeBuffers(unsigned w, unsigned h)
     OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
     if (streamB) OPR_CUDA_CHECK(cudaStreamSynchronize(streamB));
     if (streamC) OPR_CUDA_CHECK(cudaStreamSynchronize(streamC));
+    if (streamD) OPR_CUDA_CHECK(cudaStreamSynchronize(streamD));
     freeBuffers();
     const size_t px = (size_t)w * h;
     rsW = std::max(photonLaunchWidth, w); rsH = std::max(photonLaunchHeight, h);
@@ -234,6 +247,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     const cudaStream_t stC = sC();
     LaunchCtx lcC{stC, &launches};
     {
+        NvtxRange nv("OptixEntryPoint::RAYTRACE_PASS");
         ScopedTimer t(*this, "ppm.camera");
         { ScopedTimer tg(*this, "camera.gen"); launch_ppm_camera_gen(details.camera, width, height, rsW, rng, hp, q, lc); }
         const unsigned waves = std::max(1u, std::min(cameraWaveBounces, MAX_RADIANCE_TRACE_DEPTH + 1));
@@ -246,6 +260,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     const float ppmRadiusSquared = PPMRadius * PPMRadius;   // :585
     // ---- PPM_PHOTON_PASS (:612)
     {
+        NvtxRange nv("OptixEntryPoint::PHOTON_PASS");
         ScopedTimer t(*this, "ppm.photon");
         // the previous iteration's grid build (stream B) must be done reading the photon slots before they are overwritten
         if (gridDonePending) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evGridDone, 0)); gridDonePending = false; }
@@ -288,6 +303,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     // -> photon pass -> direct pass): with `early`, a pixel's samples are drawn in the first launch only if nothing before them in
     // that order is still running, else in the late one.
     {
+        NvtxRange nv("OptixEntryPoint::PPM_DIRECT_RADIANCE_ESTIMATION_PASS");
         ScopedTimer t(*this, "ppm.direct");
         { ScopedTimer t0(*this, "direct.gen");
           launch_ppm_direct_gen(sc, width, height, rsW, rng, hp, sampleFactor, sampleLight, shadowD, shadowIdx, q, photonLaunchWidth, photonLaunchHeight,
@@ -305,11 +321,12 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         OPR_CUDA_CHECK(cudaEventRecord(evDirectDone, stream));
     }
     // ---- rest of createUniformGridPhotonMap (stream B; the host waits for the bounding box inside)
-    buildPhotonGrid();
+    { NvtxRange nv("Creating photon map"); buildPhotonGrid(); }
     OPR_CUDA_CHECK(cudaEventRecord(evGridDone, stB)); gridDonePending = true;
     LaunchCtx lcB{stB, &launches};
     // ---- PPM_INDIRECT_RADIANCE_ESTIMATION_PASS (:657)
     {
+        NvtxRange nv("OptixEntryPoint::INDIRECT_RADIANCE_ESTIMATION");
         ScopedTimer t(*this, "ppm.gather", stB);
         launch_gather(hp, width * height, width, height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
                       float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lcB, gatherBlocks,
@@ -318,10 +335,13 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     // ---- sum of the light samples + PPM_OUTPUT_PASS (:670)
     {
         OPR_CUDA_CHECK(cudaStreamWaitEvent(stB, evDirectDone, 0));
+        waitSnapshotBeforeOutputWrite(stB);
+        NvtxRange nv("OptixEntryPoint::PPM_OUTPUT_PASS");
         ScopedTimer t(*this, "ppm.resolve_output", stB);
         launch_ppm_resolve_output(sc, width * height, hp, sampleFactor, sampleLight, indirect, keepDebugBuffers ? direct : nullptr, output, localIterationNumber, lcB);
     }
     OPR_CUDA_CHECK(cudaEventRecord(evHpFree[pb], stB)); hpFreePending[pb] = true;
+    outputOnB = overlap;
     (void)iterationNumber;
 }
 
@@ -332,26 +352,34 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber, unsigned 
     if (!sceneLoaded) throw std::runtime_error("Traced before a scene was initialized.");
     OPR_CUDA_CHECK(cudaSetDevice(device));
     if (details.width == 0 || details.height == 0) throw std::runtime_error("zero-sized render request");
+    char rangeName[48];
+    snprintf(rangeName, sizeof rangeName, "OptixRenderer::Trace Iteration %llu", iterationNumber);   // OptixRenderer.cpp:518-520
+    NvtxRange nvIteration(rangeName);
     lastTimings.clear();
     if (!buffersAllocated || details.width != width || details.height != height) resizeBuffers(details.width, details.height);   // :534-537
+    outputOnB = false;
     if (localIterationNumber == 0) {                                                                                             // :540-545
         joinStreams();
+        waitSnapshotBeforeOutputWrite(stream);
         OPR_CUDA_CHECK(cudaMemsetAsync(output, 0, (size_t)width * height * 3 * sizeof(float), stream));
     }
-    if (details.renderMethod != OPR_PROGRESSIVE_PHOTON_MAPPING) joinStreams();   // BDPT accumulates into `output` on `stream`
+    if (details.renderMethod != OPR_PROGRESSIVE_PHOTON_MAPPING) { joinStreams(); waitSnapshotBeforeOutputWrite(stream); }   // BDPT / PT accumulate into `output` on `stream`
 
     if (details.renderMethod == OPR_PROGRESSIVE_PHOTON_MAPPING)
         renderPPM(iterationNumber, (unsigned)localIterationNumber, PPMRadius, details);
     else if (details.renderMethod == OPR_VCM_BIDIRECTIONAL_PATH_TRACING)
         renderVCM(iterationNumber, (unsigned)localIterationNumber, PPMRadius, details);
     else if (details.renderMethod == OPR_PATH_TRACING) {   // :559-567
+        NvtxRange nv("OptixEntryPoint::PT_RAYTRACE_PASS");
         ScopedTimer t(*this, "pt.generateRay");
         LaunchCtx lc{stream, &launches};
+        if (debugConnectionCounts && !ptSignature) dalloc(ptSignature, (size_t)width * height);
         launch_pt_generate_ray(scene.view, details.camera, width, height, rsW, rng, hp, output, (unsigned)localIterationNumber,
-                               q.counters + CTR_STATS, lc);
+                               q.counters + CTR_STATS, lc, debugConnectionCounts ? ptSignature : nullptr);
     } else
         throw std::runtime_error("unknown RenderMethod");
     { LaunchCtx lc{stream, &launches}; launch_stats_fold(q.counters + CTR_STATS, stats64, lc); }   // every ray kernel of an iteration runs on `stream`
+    OPR_CUDA_CHECK(cudaEventRecord(evOutputReady, outputOnB ? streamB : stream));   // the running sum of this iteration is complete behind this event
     OPR_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -362,6 +390,41 @@ void Renderer::getOutputBuffer(void* dst)
     joinStreams();
     OPR_CUDA_CHECK(cudaMemcpyAsync(dst, output, (size_t)width * height * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
     OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+// ---- asynchronous read-back --------------------------------------------------------------------------------------------
+// The driver loop of the reference copies the output after every iteration (Standalone/StandaloneRenderManager.cpp:114-128) and
+// blocks while it does.  Here the copy leaves through a third party: stream D waits for the event behind the iteration's last
+// write to the running sum, snapshots the sum device-to-device (25 MB at 1080p: ~10 us) and sends the snapshot to the host, while
+// streams A / B / C already render the next iterations.  Only the next WRITER of `output` waits — for the snapshot, not the copy.
+void Renderer::waitSnapshotBeforeOutputWrite(cudaStream_t st)
+{
+    if (!snapTakenPending) return;
+    OPR_CUDA_CHECK(cudaStreamWaitEvent(st, evSnapTaken[snapNext ^ 1u], 0));
+    snapTakenPending = false;
+}
+
+void Renderer::getOutputBufferAsync(void* dstHost)
+{
+    if (!buffersAllocated) throw std::runtime_error("getOutputBuffer before the first iteration");
+    OPR_CUDA_CHECK(cudaSetDevice(device));
+    const unsigned s = snapNext;
+    const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+    if (snapInFlight[s]) { OPR_CUDA_CHECK(cudaEventSynchronize(evSnapCopied[s])); snapInFlight[s] = false; }   // third read-back in flight: wait for the oldest
+    if (!outputSnap[s]) dalloc(outputSnap[s], (size_t)width * height * 3);
+    OPR_CUDA_CHECK(cudaStreamWaitEvent(streamD, evOutputReady, 0));
+    OPR_CUDA_CHECK(cudaMemcpyAsync(outputSnap[s], output, bytes, cudaMemcpyDeviceToDevice, streamD));
+    OPR_CUDA_CHECK(cudaEventRecord(evSnapTaken[s], streamD));
+    OPR_CUDA_CHECK(cudaMemcpyAsync(dstHost, outputSnap[s], bytes, cudaMemcpyDeviceToHost, streamD));
+    OPR_CUDA_CHECK(cudaEventRecord(evSnapCopied[s], streamD));
+    snapInFlight[s] = true; snapTakenPending = true;
+    snapNext = s ^ 1u;
+}
+
+void Renderer::waitOutput()
+{
+    OPR_CUDA_CHECK(cudaSetDevice(device));
+    for (unsigned s = 0; s < 2; s++) if (snapInFlight[s]) { OPR_CUDA_CHECK(cudaEventSynchronize(evSnapCopied[s])); snapInFlight[s] = false; }
 }
 
 } // namespace opr

@@ -139,11 +139,28 @@ struct Renderer {
     float* output = nullptr;              // running sum, float3 per pixel == reference outputBuffer
     bool keepDebugBuffers = true;
 
+    // multi-GPU (group.cu): this rank's NCCL communicator and the scratch buffer a reduce lands in on the root
+    void* ncclComm = nullptr; int commRank = 0, commWorld = 1;
+    float* reduced = nullptr; size_t reducedCount = 0;
+    // asynchronous read-back (opr_get_output_buffer_async): device snapshots of the running sum, copied out on `streamD`
+    cudaStream_t streamD = nullptr;
+    float* outputSnap[2] = {nullptr, nullptr};
+    cudaEvent_t evOutputReady = nullptr;            // the last iteration's final write to `output` (on outputStream)
+    cudaEvent_t evSnapTaken[2] = {nullptr, nullptr}, evSnapCopied[2] = {nullptr, nullptr};
+    bool snapTakenPending = false, snapInFlight[2] = {false, false};
+    unsigned snapNext = 0;
+    bool outputOnB = false;                         // the last iteration finished `output` on stream B (PPM) rather than `stream`
+    void getOutputBufferAsync(void* dstHost);
+    void waitOutput();
+    void waitSnapshotBeforeOutputWrite(cudaStream_t st);   // WAR: the next writer of `output` waits for the device snapshot
+
     // VCM state lives in vcm.cu
     struct VcmState* vcm = nullptr;
     int debugLightVertexCounts(unsigned* dstHost);
-    bool debugConnectionCounts = false;   // opr_debug_set_connection_counts
+    bool debugConnectionCounts = false;   // opr_debug_set_connection_counts (BDPT connection counts, PATH_TRACING path signatures)
+    unsigned* ptSignature = nullptr;      // per pixel: hash of the discrete decisions of the last PATH_TRACING iteration's path
     int debugConnectionCountsGet(unsigned* dstHost);
+    int debugPathSignaturesGet(unsigned* dstHost);
     long long debugLightVertexPositions(float* dstHost, size_t capacityVerts);
     bool lightVertexCountEstimated = false;
 
@@ -167,6 +184,14 @@ struct Renderer {
     void photonBBoxAsync(cudaStream_t st);
     void buildPhotonGrid();
     void getOutputBuffer(void* dst);
+};
+
+// NVTX range with the reference's pass names (RenderEngine/renderer/helpers/nsight.h:119-127; call sites OptixRenderer.cpp:520,
+// 562,574,611,624,656,663,669,782,791).  The ranges bracket the host-side ENQUEUE of a pass — the kernels run asynchronously on the
+// renderer's streams — so a timeline shows them next to the kernels they queued.  Header-only NVTX v3: a no-op without a tool.
+struct NvtxRange {
+    explicit NvtxRange(const char* message);
+    ~NvtxRange();
 };
 
 // CUDA-event timer around one pass (enabled by opr_set_timing)
@@ -216,7 +241,7 @@ void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned
 void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
                                float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
 void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
-                            float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc);
+                            float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc, unsigned* signature = nullptr);
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
                                 unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM = 0, unsigned* dbgCount = nullptr);
 void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const uint2* sampleLight,
@@ -232,3 +257,6 @@ void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, un
 bool compute_grid_params(const float lo[3], const float hi[3], GridParams& g);
 
 } // namespace opr
+
+// the C-ABI handle (capi.cu, group.cu)
+struct opr_renderer { opr::Renderer r; };

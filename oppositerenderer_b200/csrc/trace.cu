@@ -107,7 +107,7 @@ static unsigned trace_refill_idle()
 void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc)
 {
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_FETCH_LEGACY, 0, sizeof(unsigned), lc.st));
-    trace_closest_kernel<<<148 * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + cur, q.hits, q.matQueue,
+    trace_closest_kernel<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + cur, q.hits, q.matQueue,
                                                                q.counters + 2, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
                                                                q.counters + CTR_FETCH_LEGACY, trace_refill_idle());
     ++*lc.launches;
@@ -116,7 +116,7 @@ void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, Laun
 void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc)
 {
     const int cur = bounce & 1;
-    trace_closest_kernel<<<148 * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
+    trace_closest_kernel<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
                                                                q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
                                                                q.counters + CTR_FETCH + bounce, trace_refill_idle());
     ++*lc.launches;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shad
 void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
                                float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc)
 {
-    trace_shadow_queue_kernel<<<148 * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, hitPos, shadowD, shadowIdx, count, sampleFactor, fetchCursor, stat, trace_refill_idle());
+    trace_shadow_queue_kernel<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, hitPos, shadowD, shadowIdx, count, sampleFactor, fetchCursor, stat, trace_refill_idle());
     ++*lc.launches;
 }
 
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
                                 unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM, unsigned* dbgCount)
 {
-    const unsigned blocks = 148 * (blocksPerSM ? blocksPerSM : trace_blocks_per_sm());
+    const unsigned blocks = numSMs() * (blocksPerSM ? blocksPerSM : trace_blocks_per_sm());
     trace_connect_queue_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle(), dbgCount);
     ++*lc.launches;
 }
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_any_raw_kernel(SceneView 
 void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, float4* hits, LaunchCtx lc)
 {
     if (!n) return;
-    int blocks = (int)std::min<unsigned>((n + TRACE_THREADS - 1) / TRACE_THREADS, 148 * 16);
+    int blocks = (int)std::min<unsigned>((n + TRACE_THREADS - 1) / TRACE_THREADS, numSMs() * 16);
     trace_closest_raw_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, rayO, rayD, n, hits);
     ++*lc.launches;
 }
@@ -288,7 +288,7 @@ void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const flo
 void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, int* occluded, LaunchCtx lc)
 {
     if (!n) return;
-    int blocks = (int)std::min<unsigned>((n + TRACE_THREADS - 1) / TRACE_THREADS, 148 * 16);
+    int blocks = (int)std::min<unsigned>((n + TRACE_THREADS - 1) / TRACE_THREADS, numSMs() * 16);
     trace_any_raw_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, rayO, rayD, n, occluded);
     ++*lc.launches;
 }

@@ -14,7 +14,7 @@
 namespace opr {
 
 constexpr int VCM_THREADS = 128;
-constexpr int VCM_BLOCKS_X = 148 * 6;
+#define VCM_BLOCKS_X (numSMs() * 6)
 
 struct VcmState {
     float4* state = nullptr;   // per path, one 32-byte record: throughput.xyz, depth (uint bits) | dVCM, dVC, dVM, -
@@ -27,6 +27,7 @@ struct VcmState {
     float4* connC = nullptr;   // contribution.xyz
     float4* conn2[3] = {nullptr, nullptr, nullptr};   // second set: bounce b+1 fills it while stream B still tests the segments of bounce b
     unsigned* dbgConn = nullptr;   // parity diagnostics (opr_debug_set_connection_counts): contributions that passed isOccluded, per target pixel
+    unsigned* dbgSig = nullptr;    // same switch: hash of the material kinds each subpath met (light paths [0, paths), camera paths [paths, 2 paths))
     size_t paths = 0; unsigned maxVerts = 0;
 };
 
@@ -39,7 +40,7 @@ struct VcmParams {
 };
 
 struct VcmBuffers { float4* state; float4* color; unsigned* lvCount; float4* lv; unsigned paths;
-                    float4* connO; float4* connD; float4* connC; unsigned* connCount; unsigned* dbgConn; };
+                    float4* connO; float4* connD; float4* connC; unsigned* connCount; unsigned* dbgConn; unsigned* dbgSig; };
 // path state record: one 256-bit load / store (the shading kernels reach paths in queue order: one sector instead of two each way)
 OPR_DEV void path_load(const VcmBuffers& B, unsigned p, float4& t4, float4& m4)
 {
@@ -62,7 +63,7 @@ void vcm_free(Renderer& r)
     devFree(s->state); devFree(s->color); devFree(s->lvCount);
     devFree(s->connO); devFree(s->connD); devFree(s->connC);
     for (int i = 0; i < 3; i++) devFree(s->conn2[i]);
-    devFree(s->lv); devFree(s->dbgConn);
+    devFree(s->lv); devFree(s->dbgConn); devFree(s->dbgSig);
     delete s; r.vcm = nullptr;
 }
 
@@ -281,6 +282,7 @@ OPR_DEV bool vcm_light_hit(const SceneView& sc, const VcmParams& P, const RngBuf
                            unsigned& connTarget, float3& connOrigin, unsigned& shadowRays)
 {
     bool push = false;
+    if (B.dbgSig) B.dbgSig[p] = B.dbgSig[p] * 131u + (unsigned)kind + 1u;     // parity diagnostics only (null otherwise)
     const Surface sf = eval_surface(sc, hit, o, d);
     const DMaterial& m = sc.materials[sf.material];
     VcmBSDF bsdf; float3 hitNormal, albedo;
@@ -449,6 +451,7 @@ OPR_DEV bool vcm_camera_hit(const SceneView& sc, const VcmParams& P, const RngBu
                             unsigned& shadowRays)
 {
     bool push = false;
+    if (B.dbgSig) B.dbgSig[B.paths + p] = B.dbgSig[B.paths + p] * 131u + (unsigned)kind + 1u;     // parity diagnostics only (null otherwise)
     const Surface sf = eval_surface(sc, hit, o, d);
     const DMaterial& m = sc.materials[sf.material];
     float4 t4, m4;
@@ -713,6 +716,14 @@ int Renderer::debugConnectionCountsGet(unsigned* dstHost)
     return 0;
 }
 
+int Renderer::debugPathSignaturesGet(unsigned* dstHost)
+{
+    if (!vcm || !vcm->dbgSig) return 1;
+    OPR_CUDA_CHECK(cudaMemcpyAsync(dstHost, vcm->dbgSig, vcm->paths * 8, cudaMemcpyDeviceToHost, stream));
+    OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
 int Renderer::debugLightVertexCounts(unsigned* dstHost)
 {
     if (!vcm) return 1;
@@ -751,9 +762,9 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     const SceneView& sc = scene.view;
     vcm_alloc(*this);
     VcmState& S = *vcm;
-    if (debugConnectionCounts && !S.dbgConn) devAlloc((void**)&S.dbgConn, S.paths * 4);
+    if (debugConnectionCounts && !S.dbgConn) { devAlloc((void**)&S.dbgConn, S.paths * 4); devAlloc((void**)&S.dbgSig, S.paths * 8); }
     VcmBuffers B{S.state, S.color, S.lvCount, S.lv, (unsigned)S.paths,
-                 S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, debugConnectionCounts ? S.dbgConn : nullptr};
+                 S.connO, S.connD, S.connC, q.counters + CTR_CONN_COUNT, debugConnectionCounts ? S.dbgConn : nullptr, debugConnectionCounts ? S.dbgSig : nullptr};
     const unsigned lightSubPathCount = width * height;
     const float ppmRadiusSquared = PPMRadius * PPMRadius;
     const float etaVCM = (float(lightSubPathCount) / 1u) * PI_F * ppmRadiusSquared;   // nVM / nVC * pi * r^2 (:687)
@@ -797,11 +808,12 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     };
 
     auto lightPass = [&](const char* name) {
+        NvtxRange nv("OptixEntryPoint::VCM_LIGHT_PASS");
         ScopedTimer t(*this, name);
         unsigned c[2 + NUM_QUEUES] = {0};
         c[0] = width * height;
         OPR_CUDA_CHECK(cudaMemcpyAsync(q.counters, c, sizeof c, cudaMemcpyHostToDevice, stream));
-        int blocks = (int)std::min<unsigned>((c[0] + VCM_THREADS - 1) / VCM_THREADS, 148 * 16);
+        int blocks = (int)std::min<unsigned>((c[0] + VCM_THREADS - 1) / VCM_THREADS, numSMs() * 16);
         vcm_light_gen_kernel<<<blocks, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[0], q.rayD[0], q.rayPath[0]);
         ++launches;
         int cur = 0;
@@ -821,7 +833,7 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             cur ^= 1;
         }
         if (waves <= P.maxPathLen) {
-            vcm_light_tail_kernel<<<148 * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur,
+            vcm_light_tail_kernel<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur,
                                                                        q.counters + CTR_STATS);
             ++launches;
         }
@@ -835,14 +847,15 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         P.estimatePass = 0;
         lightVertexCountEstimated = true;
     }
-    if (B.dbgConn) OPR_CUDA_CHECK(cudaMemsetAsync(B.dbgConn, 0, S.paths * 4, stream));
+    if (B.dbgConn) { OPR_CUDA_CHECK(cudaMemsetAsync(B.dbgConn, 0, S.paths * 4, stream)); OPR_CUDA_CHECK(cudaMemsetAsync(B.dbgSig, 0, S.paths * 8, stream)); }
     lightPass("vcm.light");
     {
+        NvtxRange nv("OptixEntryPoint::VCM_CAMERA_PASS");
         ScopedTimer t(*this, "vcm.camera");
         unsigned c[2 + NUM_QUEUES] = {0};
         c[0] = width * height;
         OPR_CUDA_CHECK(cudaMemcpyAsync(q.counters, c, sizeof c, cudaMemcpyHostToDevice, stream));
-        int blocks = (int)std::min<unsigned>((c[0] + VCM_THREADS - 1) / VCM_THREADS, 148 * 16);
+        int blocks = (int)std::min<unsigned>((c[0] + VCM_THREADS - 1) / VCM_THREADS, numSMs() * 16);
         vcm_camera_gen_kernel<<<blocks, VCM_THREADS, 0, stream>>>(P, rng, B, q.rayO[0], q.rayD[0], q.rayPath[0]);
         ++launches;
         int cur = 0;
@@ -862,7 +875,7 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             cur ^= 1;
         }
         if (waves <= P.maxPathLen) {
-            vcm_camera_tail_kernel<<<148 * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur, q.counters + CTR_STATS);
+            vcm_camera_tail_kernel<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur, q.counters + CTR_STATS);
             ++launches;
         }
         joinConnections();

@@ -14,11 +14,24 @@ Each rank needs its own RNG stream: the reference's servers got that implicitly 
 """
 from . import capi
 
-SEED_STRIDE = 104729   # a prime larger than any launch width, so the per-index seeds `seed + idx` of two ranks interleave differently
+# State i of a renderer is seeded with `seed + i` (rng_init_kernel, OptixRenderer_SpatialHash.cu:310-347), i < rsW * rsH.  Two
+# ranks must therefore differ by MORE than the whole state buffer, or rank r's state j is rank 0's state j + r * stride and both
+# walk the same photon paths.  2^28 states (16384 x 16384) per rank, 16 ranks: disjoint seed ranges modulo 2^32.
+# The same rule lives in C++ (opr_group_rank_seed, csrc/group.cu); tests/test_distributed_cpu.py keeps them equal.
+SEED_STRIDE = 1 << 28
+MAX_RANKS = (1 << 32) // SEED_STRIDE
 
 
 def rank_seed(base_seed, rank):
+    if not (0 <= int(rank) < MAX_RANKS):
+        raise ValueError("rank %d: disjoint per-rank RNG seed ranges exist for %d ranks" % (rank, MAX_RANKS))
     return (int(base_seed) + int(rank) * SEED_STRIDE) & 0xFFFFFFFF
+
+
+def check_state_count(num_states):
+    """Raise unless a state buffer of `num_states` entries keeps the seed ranges of different ranks disjoint."""
+    if int(num_states) > SEED_STRIDE:
+        raise ValueError("%d RNG states exceed the per-rank seed stride %d: ranks would share states" % (num_states, SEED_STRIDE))
 
 
 def global_iteration(rank, world, local_iteration):
@@ -61,14 +74,21 @@ def render_partition(renderer, partition, details, first_local, count, readback=
             renderer.getOutputBuffer(readback)
 
 
-def reduce_sum_to_root(tensor, dst=0, group=None):
-    """One reduce (sum) of the per-rank running-sum buffers onto `dst`; in place on `dst`.  No-op in a world of one.
-    The caller divides by the TOTAL number of iterations (all ranks) afterwards, like RenderWidget.cpp:197."""
+def reduce_sum_to_root(tensor, dst=0, group=None, out=None):
+    """One reduce (sum) of the per-rank running-sum buffers onto `dst`.  The renderer's accumulator is NEVER the target: the sum
+    lands in `out` (or a fresh clone), so the local running sum stays this rank's own and the call can be repeated during a
+    progressive render (a reduce in place would fold the other ranks' earlier sums into rank 0's accumulator and count them again
+    at the next reduce).  Returns the tensor that holds the total on `dst` (undefined content elsewhere).  No-op copy in a world of
+    one.  The caller divides by the TOTAL number of iterations (all ranks) afterwards, like RenderWidget.cpp:197."""
     import torch.distributed as dist
+    if out is None:
+        out = tensor.clone()
+    else:
+        out.copy_(tensor)
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return tensor
-    dist.reduce(tensor, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    return tensor
+        return out
+    dist.reduce(out, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return out
 
 
 def output_as_tensor(renderer, device):

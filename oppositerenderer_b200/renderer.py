@@ -356,6 +356,15 @@ class OptixRenderer:
         self._check(self._lib.opr_get_output_buffer(self._h, data.ctypes.data_as(C.c_void_p)))
         return data
 
+    def getOutputBufferAsync(self, data):
+        """Starts the read-back of the running sum as of the last iteration into `data` (pinned host memory) and returns at once;
+        waitOutput() blocks until every started read-back has landed."""
+        self._check(self._lib.opr_get_output_buffer_async(self._h, data.ctypes.data_as(C.c_void_p)))
+        return data
+
+    def waitOutput(self):
+        self._check(self._lib.opr_wait_output(self._h))
+
     def getWidth(self):
         return self._lib.opr_get_width(self._h)
 
@@ -371,6 +380,23 @@ class OptixRenderer:
 
     def synchronize(self):
         self._check(self._lib.opr_synchronize(self._h))
+
+    # multi-GPU, one process per GPU: the NCCL communicator lives in the C++ library; the launcher only carries the 128-byte id
+    def comm_init_rank(self, unique_id, rank, world):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.opr_comm_init_rank(self._h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._check(self._lib.opr_comm_destroy(self._h))
+
+    def reduce_output(self, root=0, data=None):
+        """ncclReduce(sum) of all ranks' running sums onto `root`, queued on the renderer's stream; with `data` (root only) the
+        total is copied to the host and the call blocks."""
+        self._check(self._lib.opr_reduce_output(self._h, root, data.ctypes.data_as(C.c_void_p) if data is not None else None))
+        return data
+
+    def reduced_device_ptr(self):
+        return self._lib.opr_get_reduced_device_ptr(self._h)
 
     def join(self):
         """Order all queued work (both internal streams) before later work on the renderer's public stream."""
@@ -419,3 +445,60 @@ class OptixRenderer:
         occ = np.empty(n, np.int32)
         self._check(self._lib.opr_trace_any(self._h, rays8.ctypes.data_as(C.POINTER(C.c_float)), n, occ.ctypes.data_as(C.POINTER(C.c_int32))))
         return occ
+
+
+def comm_unique_id():
+    """128-byte NCCL id made by the C++ library (rank 0 calls this; the launcher broadcasts the bytes)."""
+    lib = capi.load_library()
+    buf = C.create_string_buffer(128)
+    if lib.opr_comm_get_unique_id(buf) != 0:
+        raise RuntimeError(lib.opr_last_error().decode(errors="replace"))
+    return buf.raw
+
+
+class RendererGroup:
+    """One process, G GPUs (opr_group_*): the C++ library owns a renderer and a host thread per device; replaces the client's
+    hand-out loop of Client/DistributedApplication.cpp:96-122."""
+
+    def __init__(self, devices, photon_launch=None, vcm_max_path_length=0, seed=None):
+        self._lib = capi.load_library()
+        cfg = capi.opr_config()
+        if photon_launch:
+            cfg.photonLaunchWidth, cfg.photonLaunchHeight = photon_launch
+        cfg.vcmMaxPathLength = vcm_max_path_length
+        if seed is not None:
+            cfg.randomSeed, cfg.seedIsSet = seed, 1
+        self._h = C.c_void_p()
+        devs = (C.c_int32 * len(devices))(*devices)
+        self._check(self._lib.opr_group_create(C.byref(self._h), len(devices), devs, C.byref(cfg)))
+        self._scene = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self._lib.opr_last_error().decode(errors="replace"))
+
+    def size(self):
+        return self._lib.opr_group_size(self._h)
+
+    def initScene(self, scene):
+        self._scene = scene
+        self._check(self._lib.opr_group_init_scene(self._h, scene.getSceneDescription()))
+
+    def renderNextIterations(self, first, count, initial_radius, alpha, details):
+        pod = details.pod() if hasattr(details, "pod") else details
+        self._check(self._lib.opr_group_render_next_iterations(self._h, first, count, initial_radius, alpha, C.byref(pod)))
+
+    def reduceOutput(self, data):
+        self._check(self._lib.opr_group_reduce_output(self._h, data.ctypes.data_as(C.c_void_p)))
+        return data
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.opr_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

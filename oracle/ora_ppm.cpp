@@ -568,11 +568,16 @@ void pt_generateRay(Renderer& r, uint x, uint y)
     const int numShadowSamples = ptDirectLightSampling ? 1 : 0;
     const int numPaths = ptDirectLightSampling ? 5 : 10;
     const std::vector<Light>& lights = r.scene.lights;
+    // parity diagnostics, not part of the reference: per segment (hit flags, light sample contributed, ended by Russian roulette)
+    uint sig = 0;
+    auto sign = [&](uint code) { sig = sig * 131u + code + 1u; };
     for (int i = 0; i < numPaths; i++) {
         prd.flags = PRD_PATH_TRACING;
         traceRadiance(r, ray, prd);
+        uint code = (prd.flags >> 27) & 0x1fu;
         if (prd.flags & PRD_HIT_EMITTER) {
             if ((prd.flags & PRD_HIT_SPECULAR) || i == 0) finalRadiance = prd.radiance;
+            sign(code);
             break;
         } else if (prd.flags & PRD_HIT_NON_SPECULAR) {
             int numLights = (int)lights.size();
@@ -583,22 +588,30 @@ void pt_generateRay(Renderer& r, uint x, uint y)
                 float scale = (float)numLights;
                 float3 lightContrib = scale * getLightContribution(r, light, prd.position, prd.normal, prd.randomState);
                 accumLightRadiancePreBrdf += lightContrib;
+                if (lightContrib.x != 0.f || lightContrib.y != 0.f || lightContrib.z != 0.f) code |= 32u;
             }
             float3 directRadiance = prd.attenuation * accumLightRadiancePreBrdf / (float)numShadowSamples;
             finalRadiance += directRadiance;
             ray.origin = prd.position;
             ray.direction = prd.randomNewDirection;
         } else {
+            sign(code);
             break;
         }
         if (i >= 3) {   // PATH_TRACING_RR_START_DEPTH, config.h:37
             float s = getRandomUniformFloat(&bufferState);
             float probabilityContinue = fmaxf(fmaxf(prd.attenuation.x, prd.attenuation.y), prd.attenuation.z);
-            if (s > probabilityContinue) break;
+            if (s > probabilityContinue) { sign(code | 64u); break; }
             prd.attenuation /= probabilityContinue;
         }
+        sign(code);
     }
     const size_t idx = (size_t)y * r.width + x;
+    if (idx < r.ptSignature.size()) r.ptSignature[idx] = sig;
+    if (idx < r.hitpoints.size()) {     // diagnostics only: the last vertex of the path, where the product's hit-point buffer holds it too
+        Hitpoint& h = r.hitpoints[idx];
+        h.position = prd.position; h.normal = prd.normal; h.attenuation = prd.attenuation; h.radiance = prd.radiance; h.flags = prd.flags;
+    }
     if (!(finalRadiance.x != finalRadiance.x || finalRadiance.y != finalRadiance.y || finalRadiance.z != finalRadiance.z))
         r.output[idx] = r.localIterationNumber == 0 ? finalRadiance : r.output[idx] + finalRadiance;
     r.rs(x, y) = prd.randomState;

@@ -116,9 +116,11 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber_, unsigned
         }
         lightVertexBufferIndex.store(0);                                         // :776-778
         connectionCount.assign((size_t)width * height, 0u);
+        pathSignature.assign((size_t)width * height * 2, 0u);
         launch2D(*this, width, height, vcm_lightPass);                           // :784
         launch2D(*this, width, height, vcm_cameraPass);                          // :793
     } else if (details.renderMethod == OPR_PATH_TRACING) {
+        ptSignature.assign((size_t)width * height, 0);
         launch2D(*this, width, height, pt_generateRay);                          // :559-567
     } else {
         throw std::runtime_error("unknown render method");
@@ -177,6 +179,8 @@ int ora_get_ray_counts(void* h, unsigned long long* closest, unsigned long long*
 { Renderer* r = (Renderer*)h; *closest = r->stats.closest.load(); *any = r->stats.any.load(); return 0; }
 int ora_get_photon_path_lengths(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->photonPathLength.data(), 4 * r->photonPathLength.size()); return 0; }
 int ora_get_direct_sample_mask(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->directSampleMask.data(), r->directSampleMask.size()); return 0; }
+int ora_get_pt_signature(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->ptSignature.data(), 4 * r->ptSignature.size()); return 0; }
+int ora_get_path_signatures(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->pathSignature.data(), 4 * r->pathSignature.size()); return 0; }
 int ora_get_connection_counts(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->connectionCount.data(), 4 * r->connectionCount.size()); return 0; }
 int ora_get_light_vertex_counts(void* h, void* dst) { Renderer* r = (Renderer*)h; memcpy(dst, r->lightSubpathVertexCount.data(), 4 * r->lightSubpathVertexCount.size()); return 0; }
 

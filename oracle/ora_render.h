@@ -31,6 +31,7 @@ struct Renderer {
     PhotonGrid grid{};
     std::vector<float3> indirect, direct, output;
     std::vector<uint> photonPathLength;     // debugPhotonPathLengthBuffer
+    std::vector<uint> ptSignature;                 // parity diagnostics: per-pixel hash of the PATH_TRACING path's discrete decisions
     std::vector<unsigned char> directSampleMask;   // parity diagnostics: bit s = shadow sample s of the pixel was unoccluded and non-zero
 
     // per-iteration context scalars (OptixRenderer.cpp:555-557, 583-589, 616-617)
@@ -52,6 +53,7 @@ struct Renderer {
     std::vector<uint> lightSubpathVertexCount;
     std::vector<uint> lightSubpathVertexIndex;   // [path][vcmMaxPathLength-1]
     uint lightVertexBufferSize = 0;
+    std::vector<uint> pathSignature;             // parity diagnostics: hash of the material kinds a BDPT subpath met, light paths [0, W*H), camera paths [W*H, 2 W*H)
     std::vector<uint> connectionCount;           // parity diagnostics: contributions that passed isOccluded, per target pixel, last iteration
     int vcmUseVC = 1, vcmUseVM = 0;
     int numThreads = 0;                     // 0 = OpenMP default

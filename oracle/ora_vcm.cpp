@@ -727,6 +727,7 @@ static void traceLight(Renderer& r, const Ray& ray, SubpathPRD& prd)
     if (!r.scene.closestHit(ray, hit)) { prd.done = true; return; }   // miss, VCMLightPass.cu:95-98
     const opr_material& m = r.scene.materials[hit.material];
     if (m.kind == OPR_MAT_DIFFUSE_EMITTER) { prd.done = true; return; }   // DiffuseEmitter.cu:76-79
+    if (prd.launchIndex1D < r.pathSignature.size()) { uint& sg = r.pathSignature[prd.launchIndex1D]; sg = sg * 131u + (uint)m.kind + 1u; }   // diagnostics only
     VcmBSDF bsdf; float3 n; bool terminate;
     if (!buildBsdf(r, ray, hit, true, bsdf, n, terminate)) { if (terminate) prd.done = true; return; }
     float3 hitPoint = ray.origin + hit.t * ray.direction;
@@ -739,6 +740,7 @@ static void traceCamera(Renderer& r, const Ray& ray, SubpathPRD& prd)
     r.stats.closest.fetch_add(1, std::memory_order_relaxed);
     if (!r.scene.closestHit(ray, hit)) { prd.done = true; return; }   // miss, VCMCameraPass.cu:87-90
     const opr_material& m = r.scene.materials[hit.material];
+    { const size_t si = (size_t)r.width * r.height + prd.launchIndex1D; if (si < r.pathSignature.size()) { uint& sg = r.pathSignature[si]; sg = sg * 131u + (uint)m.kind + 1u; } }   // diagnostics only
     if (m.kind == OPR_MAT_DIFFUSE_EMITTER) {   // DiffuseEmitter.cu:95-120
         prd.depth++;
         prd.done = true;

@@ -2,7 +2,11 @@
 // (Standalone/StandaloneRenderManager.cpp:60-140): initialize, initScene, the radius-schedule loop, getOutputBuffer.
 //   facade_check rules            -> state rules / error strings that need no GPU
 //   facade_check render W H N out -> N PPM iterations of the built-in Cornell scene, raw float3 sum buffer written to `out`
+//   facade_check group W H N out G -> the same N global iterations handed out over G GPUs (OptixRendererGroup: the client loop of
+//                                     Client/DistributedApplication.cpp:96-122 + one NCCL reduce), summed image written to `out`;
+//                                     read back asynchronously after every hand-out round like the client's preview
 #include "OptixRenderer.h"
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -36,6 +40,28 @@ int main(int argc, char** argv)
     }
     const unsigned W = atoi(argv[2]), H = atoi(argv[3]); const int N = atoi(argv[4]);
     opr_config cfg = {64, 64, 0, 1645301512u, 1};
+    if (OptixRenderer::PPM_INITIAL_RADIUS != 0.0f) return 4;
+    if (mode == "group") {
+        const int G = atoi(argv[6]);
+        std::vector<int> devices;
+        for (int i = 0; i < G; i++) devices.push_back(i);
+        OptixRendererGroup group(devices, &cfg);
+        if (group.size() != G) return 5;
+        Cornell scene;
+        group.initScene(scene);
+        Camera cam = scene.getDefaultCamera();
+        cam.setAspectRatio((float)W / (float)H);
+        RenderServerRenderRequestDetails details(cam, scene.getSceneName(), RenderMethod::PROGRESSIVE_PHOTON_MAPPING, W, H, 2.0 / 3.0);
+        std::vector<float> out((size_t)W * H * 3), preview((size_t)W * H * 3);
+        for (int it = 0; it < N; it += G) {       // one hand-out round: the next G global iterations, one per GPU
+            group.renderNextIterations(it, std::min(G, N - it), scene.getSceneInitialPPMRadiusEstimate(), details);
+            group.getOutputBuffer(preview.data());   // a reduce per round must not disturb the running sums
+        }
+        group.getOutputBuffer(out.data());
+        if (out != preview) return 6;
+        FILE* f = fopen(argv[5], "wb"); fwrite(out.data(), sizeof(float), out.size(), f); fclose(f);
+        return 0;
+    }
     OptixRenderer renderer(cfg);
     renderer.initialize(ComputeDevice(0));
     Cornell scene;
@@ -51,9 +77,12 @@ int main(int argc, char** argv)
         r2 = r2 * (it + ppmAlpha) / (it + 1);
         PPMRadius = sqrt(r2);
     }
-    std::vector<float> out((size_t)W * H * 3);
+    std::vector<float> out((size_t)W * H * 3), async((size_t)W * H * 3);
     if (renderer.getScreenBufferSizeBytes() != out.size() * sizeof(float)) return 3;
+    renderer.getOutputBufferAsync(async.data());
+    renderer.waitOutput();
     renderer.getOutputBuffer(out.data());
+    if (out != async) return 7;
     FILE* f = fopen(argv[5], "wb"); fwrite(out.data(), sizeof(float), out.size(), f); fclose(f);
     return 0;
 }

@@ -51,6 +51,8 @@ def _declare(lib):
         "ora_get_photons_as_emitted": (i32, [vp, vp]),
         "ora_get_direct_sample_mask": (i32, [vp, vp]),
         "ora_get_connection_counts": (i32, [vp, vp]),
+        "ora_get_pt_signature": (i32, [vp, vp]),
+        "ora_get_path_signatures": (i32, [vp, vp]),
         "ora_rng_init": (None, [PU, u32, u32, u32]),
         "ora_rng_uniform": (None, [PU, PF, u32]),
         "ora_build_photon_grid": (i32, [PF, u32, PU, PU, PF, PU, PF, PU]),
@@ -169,6 +171,17 @@ class OracleRenderer:
         """Photon slots before the grid build sorted them (slot = 4 * thread + k), like the product's "photons" buffer."""
         a = np.empty(self.photon_launch[0] * self.photon_launch[1] * 4, PHOTON_DT)
         self.lib.ora_get_photons_as_emitted(self.h, a.ctypes.data_as(C.c_void_p))
+        return a
+
+    def path_signatures(self):
+        """(light paths, camera paths) signature arrays of the last BDPT iteration."""
+        a = np.empty(self.width * self.height * 2, np.uint32)
+        self.lib.ora_get_path_signatures(self.h, a.ctypes.data_as(C.c_void_p))
+        return a[:self.width * self.height], a[self.width * self.height:]
+
+    def pt_signature(self):
+        a = np.empty(self.width * self.height, np.uint32)
+        self.lib.ora_get_pt_signature(self.h, a.ctypes.data_as(C.c_void_p))
         return a
 
     def direct_sample_mask(self):

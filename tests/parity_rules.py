@@ -12,11 +12,20 @@ the measured divergences below, and the fractions are printed.
   state      the final XORWOW state of the pixel's RNG stream differs from the oracle's (the stream is shared by the pixel's camera
              path, the photon thread / light subpath of the same index and the pixel's light samples, OptixRenderer.cpp:368-373), or
              the hit-point flags / position differ;
-  PPM indirect   a photon that exists in only one of the two photon maps (slot-by-slot comparison of the photon buffers as emitted),
-             or differs beyond tolerance, lies within the gather radius of the pixel's hit point; or a photon lies within 1e-4 r of
+  PPM indirect   (quantitative, ppm_indirect_slack) the tolerance of a pixel is widened by the summed |C_gpu - C_oracle| over the photon
+             slots that differ between the two maps and lie in range, C being the slot's contribution evaluated with each
+             renderer's own photon and hit point — and the gather itself is checked against the oracle's gather on the product's
+             own inputs with no exception (gather_stage_exact).  The mask form below is kept for the sum buffer:
+             a photon that exists in only one of the two photon maps (slot-by-slot comparison of the photon buffers as emitted),
+             or differs beyond tolerance (position by more than 2e-4 r — ulps of sinf / cosf grow along a multi-bounce walk, and
+             the gather weight falls to zero at the radius — power by 1e-3, direction by 1e-3), lies within the gather radius of
+             the pixel's hit point; or a photon lies within 1e-4 r of
              the radius sphere itself (accept / reject decided by ulps);
   PPM direct     the set of unoccluded shadow samples of the pixel differs (4-bit mask);
-  BDPT       the number of contributions that passed the occlusion test differs for the pixel (camera-path connections + light
+  PATH_TRACING   the path signature differs: per path segment, the hit flags, whether the light sample contributed (occlusion) and
+             whether Russian roulette ended the path (the reference draws these from a stream whose final state it discards); or the
+             last vertex of the path moved by more than 1e-5 of the scene size (same decisions, drifted geometry);
+  BDPT       the light or camera subpath of the pixel's index met a different sequence of material kinds (path signature); the number of contributions that passed the occlusion test differs for the pixel (camera-path connections + light
              -tracing splats that landed on it), or a light vertex of a diverged path (state) projects onto the pixel in either
              renderer (its splat moved or changed).
 
@@ -66,6 +75,13 @@ class ProductProbe:
     def light_vertex_positions(self):
         return self.r.light_vertex_positions()
 
+    def path_signature(self):
+        return self.r.debug_buffer("pt_signature", np.uint32, self.W * self.H)
+
+    def path_signatures(self):
+        a = self.r.debug_buffer("path_signatures", np.uint32, 2 * self.W * self.H)
+        return a[:self.W * self.H], a[self.W * self.H:]
+
     def output(self):
         return self.r.getOutputBuffer().reshape(-1, 3).copy()
 
@@ -99,6 +115,12 @@ class OracleProbe:
     def light_vertex_positions(self):
         return self.o.light_vertex_positions()
 
+    def path_signature(self):
+        return self.o.pt_signature()
+
+    def path_signatures(self):
+        return self.o.path_signatures()
+
     def output(self):
         return self.o.output().reshape(-1, 3).copy()
 
@@ -131,7 +153,9 @@ def ppm_explained(a, b, radius):
     pa, pb = a.photons_as_emitted(), b.photons_as_emitted()
     va, vb = pa["power"].max(axis=1) > 0, pb["power"].max(axis=1) > 0
     scale = float(np.abs(pb["position"][vb]).max()) if vb.any() else 1.0
-    close = np.isclose(pa["position"], pb["position"], rtol=1e-4, atol=1e-4 * scale).all(axis=1) & \
+    # a photon "differs" when its position moved by more than 2e-4 r: the gather kernel's weight (IndirectRadianceEstimation.cu:59-67)
+    # changes by 2.07 * delta(d^2 / r^2) of the photon's power, so a shift of 5e-4 r already moves a one-photon pixel by 2e-3
+    close = np.isclose(pa["position"], pb["position"], rtol=0, atol=2e-4 * radius).all(axis=1) & \
         np.isclose(pa["power"], pb["power"], rtol=1e-3, atol=1e-6 * float(pb["power"].max() + 1e-30)).all(axis=1) & \
         np.isclose(pa["rayDirection"], pb["rayDirection"], rtol=0, atol=1e-3).all(axis=1)
     same = (va == vb) & (~vb | close)
@@ -151,8 +175,137 @@ def ppm_explained(a, b, radius):
             inner = ptree.query_ball_point(pos, max(radius * (1 - 1e-4) - 2e-6 * scale, 0.0), return_length=True)
             edge[idx] = outer != inner
     mask_diff = a.direct_sample_mask() != b.direct_sample_mask()
-    return dict(camera=cam, indirect=cam | near | edge, direct=cam | (diffuse & mask_diff), photons_differ=int((~same).sum()),
+    return dict(hpa=hpa, hpb=hpb, camera=cam, indirect=cam | near | edge, direct=cam | (diffuse & mask_diff), photons_differ=int((~same).sum()),
                 photons=int(vb.sum()), state=pixel_state_divergence(a, b), near=near, edge=edge, mask=mask_diff & diffuse)
+
+
+# Gaussian filter of the gather (IndirectRadianceEstimation.cu:59-67) and the bound on its slope: |dw/dx| <= 2.07 for x = d^2 / r^2
+_ALPHA, _BETA, _ENB = 1.818, 1.953, 0.141847
+
+
+def _gather_weight(x):
+    return _ALPHA * (1.0 - (1.0 - np.exp(-_BETA * x / 2.0)) / (1.0 - _ENB))
+
+
+def _pair_contribution(hp, ph, pix, slot, valid, radius, emitted):
+    """Contribution of photon `slot` to pixel `pix` (IndirectRadianceEstimation.cu:113-121, :213): the accept tests in float32 in
+    the reference's operation order, the weight in float64."""
+    f = np.float32
+    diff = hp["position"][pix] - ph["position"][slot]
+    d2 = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]
+    n, d = hp["normal"][pix], -ph["rayDirection"][slot]
+    dot = (d[:, 0] * n[:, 0] + d[:, 1] * n[:, 1]) + d[:, 2] * n[:, 2]
+    r2 = f(radius) * f(radius)
+    acc = valid[slot] & (d2 <= r2) & (dot >= 0)
+    w = _gather_weight(d2.astype(np.float64) / float(r2))
+    c = hp["attenuation"][pix].astype(np.float64) / (np.pi * float(r2) * emitted)
+    return np.where(acc[:, None], ph["power"][slot].astype(np.float64) * w[:, None] * c, 0.0)
+
+
+def ppm_indirect_slack(a, b, radius, cam, hpa, hpb):
+    """Quantitative form of the PPM indirect rule.  Photon slots are compared one by one: a slot DIFFERS when it is stored in only
+    one map, or its position moved by more than 5e-5 r, or its power by more than 5e-5 (the slots that agree can together move a
+    pixel by at most 2.07 * 2 * 5e-5 * sum(power) / sum(power * weight) ~ 4e-4 of its value, which the caller adds to the tolerance).
+    For every (pixel, differing slot) pair in range the contribution is evaluated with each renderer's own photon and hit point,
+    and |C_gpu - C_oracle| is summed per pixel: the SLACK by which the measured divergences of the photon maps can move that
+    pixel.  Agreeing slots whose accept / reject is decided by ulps (within 2e-4 r of the radius sphere, or within 1e-4 of the
+    tangent plane) add their full contribution.  Returns (slack (pixels, 3), stats dict)."""
+    W, H = a.W, a.H
+    emitted = float(a.pl[0] * a.pl[1])
+    pa, pb = a.photons_as_emitted(), b.photons_as_emitted()
+    va, vb = pa["power"].max(axis=1) > 0, pb["power"].max(axis=1) > 0
+    dpos = np.abs(pa["position"] - pb["position"]).max(axis=1)
+    dpow = np.abs(pa["power"] - pb["power"]).max(axis=1)
+    differ = (va != vb) | (va & vb & ((dpos > 5e-5 * radius) | (dpow > 5e-5 * pb["power"].max(axis=1))))
+    diffuse = ((hpb["flags"] & ol.PRD_HIT_NON_SPECULAR) != 0) & ~cam
+    pix_ids = np.nonzero(diffuse)[0]
+    slack = np.zeros((W * H, 3), np.float64)
+    stats = dict(photons=int(vb.sum()), differ=int(differ.sum()), only_one=int((va != vb).sum()), pairs=0, edge_pairs=0)
+    if pix_ids.size == 0:
+        return slack, stats
+    ptree = cKDTree(hpb["position"][pix_ids].astype(np.float64))
+
+    def pairs_within(points, dist):
+        if points.shape[0] == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.int64)
+        m = ptree.sparse_distance_matrix(cKDTree(points.astype(np.float64)), dist, output_type="ndarray")
+        return m["i"].astype(np.int64), m["j"].astype(np.int64)
+
+    # (1) differing slots: exact change of the contribution
+    slots = np.nonzero(differ)[0]
+    if slots.size:
+        # every pixel within r of the slot's position in EITHER map (a diverged photon thread stores its photon somewhere else
+        # entirely); the hit points of these pixels agree within `moved`, far below the 1e-3 r margin
+        keys = []
+        for ph, v in ((pa, va), (pb, vb)):
+            sl = slots[v[slots]]
+            i1, j1 = pairs_within(ph["position"][sl], radius * 1.001)
+            keys.append(pix_ids[i1] * np.int64(pa.shape[0]) + sl[j1])
+        key = np.unique(np.concatenate(keys))
+        pix, slot = key // pa.shape[0], key % pa.shape[0]
+        ca = _pair_contribution(hpa, pa, pix, slot, va, radius, emitted)
+        cb = _pair_contribution(hpb, pb, pix, slot, vb, radius, emitted)
+        np.add.at(slack, pix, np.abs(ca - cb))
+        stats["pairs"] = int(pix.size)
+    # (2) agreeing slots on the radius sphere or the tangent plane of a pixel: accept / reject decided by ulps
+    same = np.nonzero(vb & ~differ)[0]
+    if same.size:
+        i2, j2 = pairs_within(pb["position"][same], radius * (1 + 2e-4))
+        pix, slot = pix_ids[i2], same[j2]
+        diff = (hpb["position"][pix] - pb["position"][slot]).astype(np.float64)
+        d = np.sqrt((diff * diff).sum(axis=1))
+        dot = -(pb["rayDirection"][slot].astype(np.float64) * hpb["normal"][pix]).sum(axis=1)
+        dn = np.abs(hpa["normal"][pix].astype(np.float64) - hpb["normal"][pix]).max(axis=1)      # normal-mapped normals differ by the texture unit's 1/256 weights
+        dh = np.abs(hpa["position"][pix].astype(np.float64) - hpb["position"][pix]).max(axis=1)
+        sel = (np.abs(d - radius) <= 2e-4 * radius + 2.0 * dh) | (np.abs(dot) <= 1e-4 + 2.0 * dn)
+        pix, slot = pix[sel], slot[sel]
+        c = hpb["attenuation"][pix].astype(np.float64) / (np.pi * radius * radius * emitted)
+        np.add.at(slack, pix, pb["power"][slot].astype(np.float64) * _ALPHA * c)
+        stats["edge_pairs"] = int(pix.size)
+    # (3) measured drift of the pixel's own inputs: a hit point that moved by dh shifts every distance by at most dh, which changes
+    # sum(P w(d^2/r^2)) by at most 2.07 * 2 dh / r * sum(P) <= 8.33 dh / r of the sum (w >= 0.497 inside the radius); the attenuation
+    # enters as a factor.  Added to the agreeing photons' 5e-5 r.  Returned as a RELATIVE allowance per pixel.
+    dh = np.abs(hpa["position"].astype(np.float64) - hpb["position"]).max(axis=1)
+    att = np.maximum(np.abs(hpb["attenuation"]).max(axis=1).astype(np.float64), 1e-30)
+    datt = np.abs(hpa["attenuation"].astype(np.float64) - hpb["attenuation"]).max(axis=1) / att
+    stats["drift"] = np.where(diffuse, 8.33 * (dh + 5e-5 * radius) / radius + datt, 0.0)
+    return slack, stats
+
+
+def within_tolerance_plus_slack(x, y, slack, drift, rtol=RTOL, atol_rel=ATOL_REL):
+    """Per pixel: |x - y| <= atol + (rtol + drift) |y| + 1.01 slack on every channel; drift is the per-pixel relative allowance.
+    Returns (ok mask, |x - y| / allowed per pixel)."""
+    x, y = x.reshape(-1, 3).astype(np.float64), y.reshape(-1, 3).astype(np.float64)
+    atol = atol_rel * float(np.abs(y).max() + 1e-30)
+    allowed = atol + (rtol + np.asarray(drift, np.float64).reshape(-1, 1)) * np.abs(y) + 1.01 * slack
+    ratio = (np.abs(x - y) / allowed).max(axis=1)
+    return ratio <= 1.0, ratio
+
+
+def gather_stage_exact(a, radius):
+    """(A) of the PPM indirect rule: the product's gather against the ORACLE's gather run on the product's own inputs of the same
+    iteration (its hit points, its sorted photon list, its offset table and grid): identical inputs, no decision can differ, so
+    EVERY pixel must agree within rel 1e-4 (ex2.approx and the summation order).  Returns the worst relative error."""
+    import ctypes as C
+    r, W, H = a.r, a.W, a.H
+    hp = a.hitpoints()
+    g = r.debug_buffer("grid", np.uint32, 8)
+    nv = int(g[7])
+    gs = (C.c_uint32 * 3)(int(g[1]), int(g[2]), int(g[3]))
+    gf = g.view(np.float32)
+    org = (C.c_float * 3)(float(gf[4]), float(gf[5]), float(gf[6]))
+    ncell = int(g[1]) * int(g[2]) * int(g[3])
+    sorted_ph = r.debug_buffer("sorted_photons", ol.PHOTON_DT, max(nv, 1))
+    offsets = r.debug_buffer("offsets", np.uint32, ncell + 1)
+    out0 = np.zeros((W * H, 3), np.float32)
+    rc = ol.load("oracle").ora_gather(W * H, ol.fptr(hp.view(np.float32)), nv, ol.fptr(sorted_ph.view(np.float32)), ol.uptr(offsets), float(gf[0]), gs, org,
+                                      float(radius), float(a.pl[0] * a.pl[1]), ol.fptr(out0))
+    assert rc == 0
+    out = a.indirect()
+    err = np.abs(out - out0) / (np.abs(out0) + 1e-6 * float(out0.max() + 1e-30))
+    assert np.allclose(out, out0, rtol=1e-4, atol=1e-6 * float(out0.max() + 1e-30)), \
+        "gather differs from the oracle's gather on identical inputs: worst relative error %.3e at pixel %d" % (err.max(), int(err.max(axis=1).argmax()))
+    return float(err.max())
 
 
 def project_to_pixel(cam, W, H, points):
@@ -189,13 +342,29 @@ def bdpt_explained(a, b, cam):
     """Per-pixel mask of the BDPT rule after one iteration run on both renderers (connection counts must be enabled)."""
     W, H = a.W, a.H
     state = pixel_state_divergence(a, b)
+    (la, ca), (lb, cb) = a.path_signatures(), b.path_signatures()
+    sig = (la != lb) | (ca != cb)              # the light or the camera subpath of this index met different materials
+    state = state | sig
     count = a.connection_counts() != b.connection_counts()
     splat = np.zeros(W * H, bool)
     for probe in (a, b):
         path, pos = probe.light_vertex_positions()
         sel = state[path]
         _mark_projected(splat, W, H, *project_to_pixel(cam, W, H, pos[sel]))
-    return dict(all=state | count | splat, state=state, count=count, splat=splat)
+    return dict(all=state | count | splat, state=state, count=count, splat=splat, sig=sig)
+
+
+def path_tracing_explained(a, b):
+    """Per-pixel mask of the PATH_TRACING rule: the payload RNG stream ended in a different state, or the path's signature — per
+    segment: hit flags, light sample contributed or not, ended by Russian roulette (decisions RayGeneratorPT.cu:84-127 draws from
+    the stream whose final state it discards) — differs."""
+    div = pixel_state_divergence(a, b) | (a.path_signature() != b.path_signature())
+    # same decisions, but the path itself drifted: ulps of sinf / cosf in a bounce direction grow at every curved or normal-mapped
+    # surface, and after up to five bounces the last vertex sits elsewhere (another texel, another light distance)
+    pa, pb = a.hitpoints()["position"], b.hitpoints()["position"]
+    scale = float(np.abs(pb).max()) + 1e-30
+    moved = np.abs(pa - pb).max(axis=1) > 1e-5 * scale
+    return div | moved
 
 
 def check_explained(name, bad, explained, extra=""):
@@ -215,37 +384,68 @@ def run_lockstep(name, r, o, det, odet, method, W, H, pl, radii, cam_pod, max_ex
     over the iterations).  The explained set must stay below `max_explained` of the image, or the rule would explain anything.
     Returns dict(bad=fraction out of tolerance, explained=fraction explained, lines=[report lines])."""
     a, b = ProductProbe(r, W, H, pl), OracleProbe(o, W, H, pl)
-    if method == 1:
-        r.set_connection_counts(True)
+    if method != 2:
+        r.set_connection_counts(True)     # BDPT connection counts / PATH_TRACING path signatures
     union = np.zeros(W * H, bool)
+    worst_explained = 0.0
     prev_a = prev_b = np.zeros((W * H, 3), np.float32)
+    acc_a = None
     lines = []
     for i, radius in enumerate(radii):
         r.renderNextIteration(i, i, radius, True, det)
         o.render_next_iteration(i, i, radius, odet)
         if method == 2:
             e = ppm_explained(a, b, radius)
-            lines.append(check_explained("%s it%d indirect" % (name, i), out_of_tolerance(a.indirect(), b.indirect()), e["indirect"],
-                                         "; photons differing %d of %d, pixels: state %.4f, suspect photon in range %.4f, photon on the radius sphere %.4f"
-                                         % (e["photons_differ"], e["photons"], e["state"].mean(), e["near"].mean(), e["edge"].mean())))
+            worst = gather_stage_exact(a, radius)       # (A) same inputs -> every pixel, no exception
+            # (B) end to end: in tolerance once the tolerance is widened by what the measured photon-map differences can change
+            slack, st = ppm_indirect_slack(a, b, radius, e["camera"], e["hpa"], e["hpb"])
+            ia, ib = a.indirect(), b.indirect()
+            bad = out_of_tolerance(ia, ib)
+            ok, ratio = within_tolerance_plus_slack(ia, ib, slack, st["drift"])
+            worst_px = np.argsort(-np.where(e["camera"], 0.0, ratio))[:5]
+            lines.append(check_explained("%s it%d indirect" % (name, i), ~ok, e["camera"],
+                                         "; worst |diff| / allowed among pixels with identical camera paths: %s at pixels %s, median relative drift allowance %.1e"
+                                         % (np.round(ratio[worst_px], 3).tolist(), worst_px.tolist(), float(np.median(st["drift"][st["drift"] > 0])) if (st["drift"] > 0).any() else 0.0) +
+                                         "; out of the plain tolerance %.3f %%; gather vs oracle gather on the product's inputs: worst rel %.1e; photon slots differing %d of %d "
+                                         "(%d in one map only), %d (pixel, differing photon) pairs, %d ulp-decided pairs; pixels whose slack exceeds their tolerance %.4f"
+                                         % (100.0 * bad.mean(), worst, st["differ"], st["photons"], st["only_one"], st["pairs"], st["edge_pairs"],
+                                            float((slack > ATOL_REL * float(np.abs(ib).max() + 1e-30) + RTOL * np.abs(ib)).any(axis=1).mean()))))
+            e["indirect"] = e["camera"] | bad
             lines.append(check_explained("%s it%d direct" % (name, i), out_of_tolerance(a.direct(), b.direct()), e["direct"],
                                          "; occlusion mask differs %.4f" % e["mask"].mean()))
             union |= e["indirect"] | e["direct"]
+            worst_explained = max(worst_explained, float((e["indirect"] | e["direct"]).mean()))
+            # PPM_OUTPUT_PASS (ppm/Output.cu:32-37) on the product's own buffers: sum = direct + indirect, added to the running sum
+            inc = a.direct() + ia
+            acc_a = inc if acc_a is None else acc_a + inc
         else:
             if method == 1:
                 e = bdpt_explained(a, b, cam_pod)
                 ex, extra = e["all"], "; state %.4f, connection count %.4f, splat of a diverged path %.4f" % (e["state"].mean(), e["count"].mean(), e["splat"].mean())
             else:
-                ex, extra = pixel_state_divergence(a, b), ""
+                ex = path_tracing_explained(a, b)
+                extra = "; state %.4f, path signature %.4f" % (pixel_state_divergence(a, b).mean(), (a.path_signature() != b.path_signature()).mean())
             oa, ob = a.output(), b.output()
             lines.append(check_explained("%s it%d increment" % (name, i), out_of_tolerance(oa - prev_a, ob - prev_b, rtol=2 * RTOL), ex, extra))
             prev_a, prev_b = oa, ob
             union |= ex
+            worst_explained = max(worst_explained, float(ex.mean()))
         if per_iteration is not None:
             per_iteration(i, a, b)
     oa, ob = a.output(), b.output()
     bad = out_of_tolerance(oa, ob)
+    if acc_a is not None:
+        # the running sum is exactly the sum of the per-iteration buffers checked above (float32, same order of additions)
+        exact = float((acc_a.view(np.uint32) == oa.view(np.uint32)).all(axis=1).mean())
+        lines.append("%s output accumulation over %d iterations: bit-identical to sum(direct + indirect) for %.4f of the pixels" % (name, len(radii), exact))
+        print(lines[-1])
+        assert np.allclose(acc_a, oa, rtol=2e-6, atol=0), "%s: output buffer is not the sum of the per-iteration direct + indirect buffers" % name
     lines.append(check_explained("%s sum buffer after %d iterations" % (name, len(radii)), bad, union))
-    assert union.mean() <= max_explained, "%s: the explained set covers %.1f %% of the image" % (name, 100 * union.mean())
-    rel = float(np.abs(oa - ob).sum() / (np.abs(ob).sum() + 1e-30))
+    # a rule that explains most of the image explains nothing: the cap is on the largest per-iteration explained set (the union over
+    # many iterations grows towards 1 by construction)
+    assert worst_explained <= max_explained, "%s: the explained set of one iteration covers %.1f %% of the image" % (name, 100 * worst_explained)
+    # whole-image relative L1 with both images clipped at the oracle's 99th percentile (a diverged path that reaches the light is a
+    # firefly of a two-iteration render and would otherwise carry the sum)
+    clip = float(np.percentile(ob, 99.0)) + 1e-30
+    rel = float(np.abs(np.minimum(oa, clip) - np.minimum(ob, clip)).sum() / (np.abs(np.minimum(ob, clip)).sum() + 1e-30))
     return dict(bad=float(bad.mean()), explained=float(union.mean()), rel_l1=rel, lines=lines)

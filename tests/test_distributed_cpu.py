@@ -48,9 +48,12 @@ def _worker(rank, world, port, outdir):
     np.save(os.path.join(outdir, "rank%d.npy" % rank), out)
     np.save(os.path.join(outdir, "calls%d.npy" % rank), np.array(calls, np.float64))
     t = torch.from_numpy(out.copy())
-    D.reduce_sum_to_root(t, dst=0)
+    total = D.reduce_sum_to_root(t, dst=0)
+    assert (t.numpy().view(np.uint32) == out.view(np.uint32)).all()      # the local running sum is never a reduce target
+    again = D.reduce_sum_to_root(t, dst=0)                                # ... so a second request during a progressive render gives the same total
     if rank == 0:
-        np.save(os.path.join(outdir, "reduced.npy"), t.numpy())
+        assert (again.numpy().view(np.uint32) == total.numpy().view(np.uint32)).all()
+        np.save(os.path.join(outdir, "reduced.npy"), total.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -88,6 +91,33 @@ def test_closed_form_radius_matches_the_driver_recurrence(product):
 def test_rank_seeds_are_distinct():
     seeds = {D.rank_seed(SEED, r) for r in range(8)}
     assert len(seeds) == 8 and D.rank_seed(SEED, 0) == SEED
+
+
+def test_rank_seed_ranges_are_disjoint_over_the_whole_state_buffer(product):
+    """State i is seeded with seed + i (OptixRenderer_SpatialHash.cu:310-347): two ranks share random streams unless their seeds
+    differ by more than the state count (1920x1080 needs 2.07 M states, 3840x2160 8.3 M).  Python and C++ hold the same rule."""
+    lib = capi.load_library()
+    ns = 3840 * 2160
+    ranges = []
+    for r in range(D.MAX_RANKS):
+        s = D.rank_seed(SEED, r)
+        assert s == lib.opr_group_rank_seed(SEED, r)
+        ranges.append((s, s + ns))
+    for i, (a0, a1) in enumerate(ranges):
+        for b0, b1 in ranges[i + 1:]:
+            for shift in (-(1 << 32), 0, 1 << 32):          # seeds wrap modulo 2^32
+                assert a1 <= b0 + shift or b1 + shift <= a0
+    D.check_state_count(ns)
+    with pytest.raises(ValueError):
+        D.check_state_count(D.SEED_STRIDE + 1)
+    with pytest.raises(ValueError):
+        D.rank_seed(SEED, D.MAX_RANKS)
+    # the first states of two ranks really differ (oracle XORWOW seeding, bit-exact with the CUDA path)
+    a, b = np.zeros(6 * 4, np.uint32), np.zeros(6 * 4, np.uint32)
+    o = ol.load("oracle")
+    o.ora_rng_init(ol.uptr(a), D.rank_seed(SEED, 0), 2_000_000, 4)
+    o.ora_rng_init(ol.uptr(b), D.rank_seed(SEED, 2), 2_000_000 - 2 * 104729, 4)   # the old stride made exactly these states equal
+    assert not np.array_equal(a, b)
 
 
 def test_two_rank_gloo_reduce_equals_sum_of_rank_buffers(oracle, product, tmp_path):
