@@ -368,6 +368,24 @@ def main():
                     "others": {k: {"ms": acc[k], "achieved_gbs": alg[k] / (acc[k] * 1e-3) / 1e9, "frac": alg[k] / (acc[k] * 1e-3) / 1e9 / peak}
                                for k in alg if k != name and acc.get(k, 0.0) > 0}}
 
+    # ---- the overlapped schedule as the device ran it: events on every pass's own stream, no synchronisation (opr_set_timing 2);
+    # the third of four pipelined iterations is reported, times relative to the start of its camera pass
+    timeline = None
+    if args.method == "ppm":
+        barrier()
+        r.set_timing(2)
+        run(4)
+        tl = r.timeline()
+        r.set_timing(0)
+        starts = [i for i, e in enumerate(tl) if e[0] == "camera.gen"]
+        if len(starts) >= 4:
+            t0_, t1_ = tl[starts[2]][2], tl[starts[3]][2]
+            ev = tl[starts[2]:starts[3]]
+            timeline = {"iteration_ms": t1_ - t0_,
+                        "passes": [[n, st_, round(a_ - t0_, 3), round(b_ - t0_, 3)] for n, st_, a_, b_ in ev if n not in ("ppm.camera", "ppm.photon", "ppm.direct")],
+                        "note": "[pass, stream, start, end] in ms from the start of this iteration's camera pass; stream A = RNG-ordered path passes, "
+                                "B = photon grid + gather + output of the same iteration (overlaps the next iteration's A), C = tails"}
+
     # ---- end to end through the C ABI with host buffers: request struct in (120 B), W*H*3 floats out to pinned host memory EVERY step.
     # (i) the pipelined driver loop: opr_get_output_buffer_async after every iteration (the copy of image i overlaps iteration i+1),
     # opr_wait_output at the end; (ii) the reference's blocking loop (StandaloneRenderManager.cpp:114-128), reported beside it.
@@ -474,7 +492,7 @@ def main():
                                "iteration i+1 renders), opr_wait_output after the last step; wall clock, max over ranks",
                         "blocking": {"value": rays_e2e_blocking / e2e_blocking_s / 1e6, "iterations_per_s": total_steps / e2e_blocking_s,
                                      "how": "the reference's driver loop: blocking opr_get_output_buffer after every step"}},
-                "early_iterations": early,
+                "early_iterations": early, "timeline": timeline,
                 "gpu_launches": int(round(launches_per_window)), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "ray_queue": ray_queue, "time_to_relmse": ttt,
                 "kernel_ms": kernel_ms, "scene": {"triangles": scene.getNumTriangles(), "meshes": scene.getNumMeshes(), "generate_s": t_scene, "init_scene_s": t_init}}
         print(json.dumps(line))

@@ -99,7 +99,12 @@ int opr_group_reduce_output(opr_group* g, void* dstHost);
 
 /* counters since the last resize: [0] closest-hit rays, [1] any-hit rays, [2] photons stored, [3] kernel launches */
 int opr_get_stats(opr_renderer* r, uint64_t* out, int n);
-/* per-pass CUDA-event timings of the last iteration (opr_set_timing(r,1) first); returns the number written */
+/* per-pass CUDA-event timings of the last iteration (opr_set_timing(r,1) first); returns the number written.
+ * opr_set_timing(r, 2) = timeline mode: no synchronisation, the passes of all following iterations are bracketed by events on their own
+ * streams; opr_get_timeline synchronises and returns start / end (ms since the first pass) and the stream ('A' path passes, 'B'
+ * grid + gather + output, 'C' tails) of every pass since — the overlapped schedule as the device ran it.  Returns the count (-1: error). */
+int opr_get_timeline(opr_renderer* r, float* startMs, float* endMs, char* streams, int capacity);
+const char* opr_get_timeline_name(opr_renderer* r, int index);
 int opr_set_timing(opr_renderer* r, int enabled);
 int opr_get_timings_ms(opr_renderer* r, float* ms, int capacity);
 const char* opr_get_timing_name(opr_renderer* r, int index);

@@ -139,6 +139,8 @@ def _declare(lib):
         "opr_get_timings_ms": (i32, [vp, PF, i32]),
         "opr_get_timing_name": (C.c_char_p, [vp, i32]),
         "opr_set_timing": (i32, [vp, i32]),
+        "opr_get_timeline": (i32, [vp, PF, PF, C.c_char_p, i32]),
+        "opr_get_timeline_name": (C.c_char_p, [vp, i32]),
         "opr_debug_get_buffer": (i32, [vp, C.c_char_p, vp, u64]),
         "opr_debug_set_connection_counts": (i32, [vp, i32]),
         "opr_debug_set_guards": (None, [i32]),

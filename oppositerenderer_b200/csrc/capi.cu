@@ -87,7 +87,34 @@ int opr_get_stats(opr_renderer* r, uint64_t* out, int n)
     })
 }
 
-int opr_set_timing(opr_renderer* r, int enabled) { r->r.timing = enabled != 0; return 0; }
+int opr_set_timing(opr_renderer* r, int enabled)
+{
+    Renderer& R = r->r;
+    R.timing = enabled == 1; R.timeline = enabled == 2;
+    if (!R.timeline) { for (auto& e : R.timelineEvents) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); } R.timelineEvents.clear(); }
+    return 0;
+}
+int opr_get_timeline(opr_renderer* r, float* startMs, float* endMs, char* streams, int capacity)
+{
+    Renderer& R = r->r;
+    try {
+        OPR_CUDA_CHECK(cudaSetDevice(R.device));
+        OPR_CUDA_CHECK(cudaDeviceSynchronize());
+        const int n = (int)R.timelineEvents.size();
+        for (int i = 0; i < n && i < capacity; i++) {
+            const auto& e = R.timelineEvents[i];
+            OPR_CUDA_CHECK(cudaEventElapsedTime(&startMs[i], R.timelineEvents[0].a, e.a));
+            OPR_CUDA_CHECK(cudaEventElapsedTime(&endMs[i], R.timelineEvents[0].a, e.b));
+            streams[i] = e.stream;
+        }
+        return n;
+    } catch (const std::exception& e) { g_lastError = e.what(); return -1; }
+}
+const char* opr_get_timeline_name(opr_renderer* r, int index)
+{
+    if (index < 0 || index >= (int)r->r.timelineEvents.size()) return "";
+    return r->r.timelineEvents[index].name;
+}
 int opr_get_timings_ms(opr_renderer* r, float* ms, int capacity)
 {
     int n = (int)r->r.lastTimings.size();

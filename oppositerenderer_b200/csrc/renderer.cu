@@ -27,14 +27,15 @@ Renderer::~Renderer()
     if (device >= 0) cudaSetDevice(device);
     vcm_free(*this);
     freeBuffers();
-    dfree(phPower); dfree(phState); dfree(photons.a); dfree(photons.b); dfree(photons.c);
+    dfree(phPower);
+    for (int b = 0; b < 2; b++) { dfree(phStateBuf[b]); dfree(photonsBuf[b].a); dfree(photonsBuf[b].b); dfree(photonsBuf[b].c); }
     dfree(sorted.a); dfree(sorted.b); dfree(sorted.c);
     dfree(gridKeys[0]); dfree(gridKeys[1]); dfree(gridVals[0]); dfree(gridVals[1]); dfree(gridHist); dfree(sortTmp); dfree(scanTmp);
     dfree(gridBBox); dfree(stats64); dfree(reduced);
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
     scene.release();
     if (bboxEvent) cudaEventDestroy(bboxEvent);
-    for (cudaEvent_t e : {evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone, evPhotonWaves, evVcmShade, evVcmConn[0], evVcmConn[1]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {evPhotonsFree[0], evPhotonsFree[1], evGatherDone, evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone, evPhotonWaves, evVcmShade, evVcmConn[0], evVcmConn[1]}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {evOutputReady, evSnapTaken[0], evSnapTaken[1], evSnapCopied[0], evSnapCopied[1]}) if (e) cudaEventDestroy(e);
     if (streamD) cudaStreamDestroy(streamD);
     if (streamB) cudaStreamDestroy(streamB);
@@ -70,12 +71,13 @@ void Renderer::initialize(int cudaOrdinal)
     int prC = prGreatest;
     if (const char* e = getenv("OPR_STREAM_PRIORITY_C")) prC = std::min(prLeast, std::max(prGreatest, prGreatest + atoi(e)));
     OPR_CUDA_CHECK(cudaStreamCreateWithPriority(&streamC, cudaStreamNonBlocking, prC));
-    for (cudaEvent_t* e : {&evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone, &evPhotonWaves, &evVcmShade, &evVcmConn[0], &evVcmConn[1]})
+    for (cudaEvent_t* e : {&evPhotonsFree[0], &evPhotonsFree[1], &evGatherDone, &evHpFree[0], &evHpFree[1], &evGridDone, &evDirectDone, &evJoin, &evCameraWaves, &evPhotonGen, &evTailDone, &evPhotonWaves, &evVcmShade, &evVcmConn[0], &evVcmConn[1]})
         OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     OPR_CUDA_CHECK(cudaStreamCreateWithPriority(&streamD, cudaStreamNonBlocking, prLeast));
     for (cudaEvent_t* e : {&evOutputReady, &evSnapTaken[0], &evSnapTaken[1], &evSnapCopied[0], &evSnapCopied[1]})
         OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
+    if (const char* e = getenv("OPR_GRID_STREAM")) gridOnC = (e[0] == 'C' || e[0] == 'c');
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("OPR_VCM_CONNECT_BLOCKS_PER_SM")) vcmConnectBlocksPerSM = (unsigned)std::max(0, atoi(e));
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM_ALONE")) gatherBlocksPerSMAlone = (unsigned)std::max(1, atoi(e));
@@ -84,8 +86,12 @@ void Renderer::initialize(int cudaOrdinal)
 
     const size_t P = (size_t)photonLaunchWidth * photonLaunchHeight;
     const size_t N = P * MAX_PHOTON_DEPOSITS;
-    dalloc(phPower, P); dalloc(phState, P);
-    dalloc(photons.a, N); dalloc(photons.b, N); dalloc(photons.c, N);
+    dalloc(phPower, P);
+    for (int b = 0; b < 2; b++) {
+        dalloc(phStateBuf[b], P); dalloc(photonsBuf[b].a, N); dalloc(photonsBuf[b].b, N); dalloc(photonsBuf[b].c, N);
+        OPR_CUDA_CHECK(cudaMemsetAsync(phStateBuf[b], 0, P * sizeof(unsigned), stream));
+    }
+    phState = phStateBuf[0]; photons = photonsBuf[0];
     dalloc(sorted.a, N); dalloc(sorted.b, N); dalloc(sorted.c, N);
     dalloc(gridKeys[0], N); dalloc(gridKeys[1], N); dalloc(gridVals[0], N); dalloc(gridVals[1], N);
     dalloc(gridHist, (size_t)PHOTON_GRID_MAX_SIZE + 2);
@@ -95,7 +101,6 @@ void Renderer::initialize(int cudaOrdinal)
     dalloc(stats64, STAT_NUM);
     OPR_CUDA_CHECK(cudaMemsetAsync(stats64, 0, STAT_NUM * sizeof(unsigned long long), stream));
     OPR_CUDA_CHECK(cudaMallocHost((void**)&gridBBoxHost, 16 * sizeof(float)));
-    OPR_CUDA_CHECK(cudaMemsetAsync(phState, 0, P * sizeof(unsigned), stream));
     initialized = true;
 }
 
@@ -125,6 +130,7 @@ void Renderer::freeBuffers()
     for (int b = 0; b < 2; b++) { dfree(hpBuf[b].pos); dfree(hpBuf[b].nrm); dfree(hpBuf[b].att); dfree(hpBuf[b].rad); dfree(sampleFactorBuf[b]); dfree(sampleLightBuf[b]); }
     hp = HitpointBuf{}; sampleFactor = nullptr; sampleLight = nullptr;
     hpFreePending[0] = hpFreePending[1] = gridDonePending = false;
+    photonsFreePending[0] = photonsFreePending[1] = gatherDonePending = false;
     for (int i = 0; i < 2; i++) { dfree(q.rayO[i]); dfree(q.rayD[i]); dfree(q.rayPath[i]); }
     dfree(q.hits); dfree(q.matQueue); dfree(q.counters);
     dfree(q.tailO); dfree(q.tailD); dfree(q.tailPath); dfree(q.camPending); dfree(q.deferred); dfree(q.photonPending); dfree(q.directDeferred);
@@ -184,12 +190,15 @@ void Renderer::photonBBoxAsync(cudaStream_t st)
 
 void Renderer::buildPhotonGrid()
 {   // createUniformGridPhotonMap, OptixRenderer_SpatialHash.cu:209-282
-    const cudaStream_t st = sB();
+    // Stream B by default.  (OPR_GRID_STREAM=C moves it to the greatest-priority stream C: measured, no gain.)
+    const cudaStream_t st = gridStream();
     LaunchCtx lc{st, &launches};
     const unsigned P = photonLaunchWidth * photonLaunchHeight;
     const unsigned N = P * MAX_PHOTON_DEPOSITS;
     OPR_CUDA_CHECK(cudaEventSynchronize(bboxEvent));   // the reference syncs here too (:222)
-    OPR_CUDA_CHECK(cudaStreamWaitEvent(st, bboxEvent, 0));   // stream B starts once the photon pass of this iteration is complete
+    OPR_CUDA_CHECK(cudaStreamWaitEvent(st, bboxEvent, 0));   // the build starts once the photon pass of this iteration is complete
+    // the previous iteration's gather still reads the sorted photons and the offset table this build overwrites
+    if (st != streamB && gatherDonePending) { OPR_CUDA_CHECK(cudaStreamWaitEvent(st, evGatherDone, 0)); gatherDonePending = false; }
     workOnB = true;
     unsigned numValid; memcpy(&numValid, gridBBoxHost + 6, 4);
     float lo[3] = {gridBBoxHost[0], gridBBoxHost[1], gridBBoxHost[2]}, hi[3] = {gridBBoxHost[3], gridBBoxHost[4], gridBBoxHost[5]};
@@ -240,6 +249,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     parity ^= 1u;
     const unsigned pb = parity;
     hp = hpBuf[pb]; sampleFactor = sampleFactorBuf[pb]; sampleLight = sampleLightBuf[pb];
+    photons = photonsBuf[overlap ? pb : 0]; phState = phStateBuf[overlap ? pb : 0];
     if (hpFreePending[pb]) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evHpFree[pb], 0)); hpFreePending[pb] = false; }
     // ---- PPM_RAYTRACE_PASS (:576): wavefront bounces on `stream`; the specular continuations go to the tail queue, which a
     // per-path tail kernel finishes on stream C while the photon wavefronts run (the photon threads whose RNG state those
@@ -263,7 +273,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         NvtxRange nv("OptixEntryPoint::PHOTON_PASS");
         ScopedTimer t(*this, "ppm.photon");
         // the previous iteration's grid build (stream B) must be done reading the photon slots before they are overwritten
-        if (gridDonePending) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evGridDone, 0)); gridDonePending = false; }
+        if (photonsFreePending[pb]) { OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evPhotonsFree[pb], 0)); photonsFreePending[pb] = false; }
         const unsigned waves = std::min(photonWaveBounces, MAX_PHOTON_TRACE_DEPTH + 1);
         { ScopedTimer tg(*this, "photon.gen");
           launch_ppm_photon_gen(sc, photonLaunchWidth, photonLaunchHeight, rsW, rng, phPower, phState, q, width, height, lc, waves == 0); }
@@ -322,7 +332,11 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     }
     // ---- rest of createUniformGridPhotonMap (stream B; the host waits for the bounding box inside)
     { NvtxRange nv("Creating photon map"); buildPhotonGrid(); }
-    OPR_CUDA_CHECK(cudaEventRecord(evGridDone, stB)); gridDonePending = true;
+    OPR_CUDA_CHECK(cudaEventRecord(evPhotonsFree[pb], gridStream())); photonsFreePending[pb] = overlap;
+    if (gridStream() != stB) {   // the gather (stream B) needs the sorted photons and the offset table
+        OPR_CUDA_CHECK(cudaEventRecord(evGridDone, gridStream()));
+        OPR_CUDA_CHECK(cudaStreamWaitEvent(stB, evGridDone, 0));
+    }
     LaunchCtx lcB{stB, &launches};
     // ---- PPM_INDIRECT_RADIANCE_ESTIMATION_PASS (:657)
     {
@@ -332,6 +346,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
                       float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lcB, gatherBlocks,
                       (overlap && gatherBlocks == gatherBlocksPerSM) ? gatherTilesPerBlock : 0u);
     }
+    if (gridStream() != stB) { OPR_CUDA_CHECK(cudaEventRecord(evGatherDone, stB)); gatherDonePending = true; }
     // ---- sum of the light samples + PPM_OUTPUT_PASS (:670)
     {
         OPR_CUDA_CHECK(cudaStreamWaitEvent(stB, evDirectDone, 0));

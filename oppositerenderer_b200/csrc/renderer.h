@@ -97,13 +97,19 @@ struct Renderer {
     bool joinedSinceRender = true;        // the caller consumed the last iteration before asking for the next one (no overlap possible)
     unsigned parity = 0;
     cudaEvent_t evHpFree[2] = {nullptr, nullptr};   // stream B finished with hpBuf[b] / sample buffers b
-    cudaEvent_t evGridDone = nullptr;               // stream B finished reading `photons` / phState
+    cudaEvent_t evGridDone = nullptr;               // the grid build of the latest iteration is complete (sorted photons + offsets ready)
+    cudaEvent_t evPhotonsFree[2] = {nullptr, nullptr};   // the grid build finished reading photonsBuf[b] / phStateBuf[b]
+    cudaEvent_t evGatherDone = nullptr;             // stream B finished reading the sorted photons / offset table (the next build overwrites them)
+    bool photonsFreePending[2] = {false, false}, gatherDonePending = false;
     cudaEvent_t evDirectDone = nullptr;             // stream A finished the light samples of this iteration
     cudaEvent_t evJoin = nullptr;
     // third stream: the camera tail and the photon threads deferred behind it run while `stream` traces the photon wavefronts
     cudaStream_t streamC = nullptr;
     cudaEvent_t evCameraWaves = nullptr, evPhotonGen = nullptr, evTailDone = nullptr, evPhotonWaves = nullptr;
     cudaStream_t sC() const { return overlap ? streamC : stream; }
+    bool gridOnC = false;                 // OPR_GRID_STREAM=C: photon-grid build on stream C (greatest priority) instead of the low-priority stream B (measured: no gain,
+                                          // the build is slowed by the persistent trace kernels holding every register of the SMs, not by its priority)
+    cudaStream_t gridStream() const { return overlap ? (gridOnC ? streamC : streamB) : stream; }
     // BDPT: the occlusion tests of bounce b's connections (stream B) run while `stream` traces and shades bounce b+1
     cudaEvent_t evVcmShade = nullptr, evVcmConn[2] = {nullptr, nullptr};
     bool hpFreePending[2] = {false, false}, gridDonePending = false, workOnB = false;
@@ -111,8 +117,13 @@ struct Renderer {
     void joinStreams();                   // later work on `stream` is ordered after everything queued on stream B
     // photon pass
     float4* phPower = nullptr;            // power.xyz, weight   (PhotonPRD.h:11-12)
-    unsigned* phState = nullptr;          // depth | numStored << 8
-    PhotonBuf photons{};                  // 4*P slots
+    unsigned* phState = nullptr;          // depth | numStored << 8   (= phStateBuf[parity])
+    PhotonBuf photons{};                  // 4*P slots                 (= photonsBuf[parity])
+    // double-buffered: the photon pass of iteration i+1 fills one set while the grid build of iteration i still reads the other.
+    // With one set stream A waited 0.15-0.2 ms per iteration for the build, which runs slowly next to the persistent trace kernels
+    // (timeline in profiles/); 155 MB more of 180 GB.
+    unsigned* phStateBuf[2] = {nullptr, nullptr};
+    PhotonBuf photonsBuf[2]{};
     // photon grid
     unsigned* gridKeys[2] = {nullptr, nullptr};
     unsigned* gridVals[2] = {nullptr, nullptr};
@@ -168,8 +179,10 @@ struct Renderer {
     unsigned long long stats[STAT_NUM] = {0};
     unsigned long long* stats64 = nullptr;   // device: the per-iteration 32-bit counters are folded in here after every iteration
     unsigned long long launches = 0;
-    bool timing = false;
+    bool timing = false, timeline = false;
     std::vector<std::pair<std::string, float>> lastTimings;
+    struct TimelineEntry { const char* name; char stream; cudaEvent_t a, b; };
+    std::vector<TimelineEntry> timelineEvents;      // timeline mode: every pass since the mode was switched on
     std::string lastError;
 
     ~Renderer();
@@ -194,19 +207,26 @@ struct NvtxRange {
     ~NvtxRange();
 };
 
-// CUDA-event timer around one pass (enabled by opr_set_timing)
+// CUDA-event timer around one pass (enabled by opr_set_timing).  Two modes:
+//   timing (opr_set_timing 1): every pass is measured ALONE — the device is synchronised before each one, so the stream pipeline is off;
+//   timeline (opr_set_timing 2): events are recorded on the pass's own stream without any synchronisation and read after the
+//     iterations (opr_get_timeline): start / end of every pass on the device's clock while the three streams overlap as in production.
+//     The start event of a pass is reached when the stream's earlier work is done, so end - start includes waits on other streams
+//     and the slowdown from the kernels that share the SMs.
 struct ScopedTimer {
     Renderer& r; const char* name; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     ScopedTimer(Renderer& r_, const char* n, cudaStream_t st_ = nullptr) : r(r_), name(n), st(st_ ? st_ : r_.stream)
     {
-        if (!r.timing) return;
-        cudaDeviceSynchronize();    // timing mode serialises the two streams: each pass is measured alone
+        if (!r.timing && !r.timeline) return;
+        if (r.timing) cudaDeviceSynchronize();    // timing mode serialises the streams: each pass is measured alone
         cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st);
     }
     ~ScopedTimer()
     {
-        if (!r.timing) return;
-        cudaEventRecord(b, st); cudaEventSynchronize(b);
+        if (!a) return;
+        cudaEventRecord(b, st);
+        if (r.timeline) { r.timelineEvents.push_back(Renderer::TimelineEntry{name, st == r.stream ? 'A' : (st == r.streamB ? 'B' : 'C'), a, b}); return; }
+        cudaEventSynchronize(b);
         float ms = 0; cudaEventElapsedTime(&ms, a, b);
         r.lastTimings.emplace_back(name, ms);
         cudaEventDestroy(a); cudaEventDestroy(b);

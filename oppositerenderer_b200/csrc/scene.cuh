@@ -160,12 +160,18 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t));                  \
         TOUT = tn <= tf ? tn : INF_;                                                                               \
     }
+// The traversal stack of a lane: entries are (subtree ref, entry distance bits).  The default keeps it in local memory
+// (`int2 stack[TRAVERSAL_STACK]`); the wavefront kernels of trace.cu redefine the two accessors to keep the first entries in
+// shared memory (see there).
+#define OPR_STACK_ST(I, V) stack[(I)] = (V);
+#define OPR_STACK_LD(DST, I) DST = stack[(I)];
+#define OPR_STACK_PUSH(R, TB) { OPR_STACK_ST(sp, make_int2((R), (TB))) sp++; }
 #define OPR_CSWAP(TA, RA, TB, RB) { if (TB < TA) { const float tt = TA; TA = TB; TB = tt; const int rr = RA; RA = RB; RB = rr; } }
 // pop the next subtree; those that start behind the closest hit so far are dropped unfetched
 #define OPR_POP(ANYHIT)                                                                                            \
     for (;;) {                                                                                                     \
         if (sp == 0) { cur = TRAVERSAL_DONE; break; }                                                              \
-        const int2 e_ = stack[--sp];                                                                               \
+        int2 e_; --sp; OPR_STACK_LD(e_, sp)                                                                        \
         if ((ANYHIT) || __int_as_float(e_.y) < hit.t) { cur = e_.x; break; }                                       \
     }
 // the four child boxes (lox .. hiz) and child refs (r0 .. r3) of node `cur`
@@ -216,16 +222,16 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
         OPR_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, t3)                                                     \
         OPR_NODE_EMPTY                                                                                             \
         if (ANYHIT) {          /* any order will do for an occlusion query: skip the sorting network */             \
-            if (t1 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r1, 0); else { t0 = t1; r0 = r1; } }               \
-            if (t2 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r2, 0); else { t0 = t2; r0 = r2; } }               \
-            if (t3 < INF_) { if (t0 < INF_) stack[sp++] = make_int2(r3, 0); else { t0 = t3; r0 = r3; } }               \
+            if (t1 < INF_) { if (t0 < INF_) OPR_STACK_PUSH(r1, 0) else { t0 = t1; r0 = r1; } }                         \
+            if (t2 < INF_) { if (t0 < INF_) OPR_STACK_PUSH(r2, 0) else { t0 = t2; r0 = r2; } }                         \
+            if (t3 < INF_) { if (t0 < INF_) OPR_STACK_PUSH(r3, 0) else { t0 = t3; r0 = r3; } }                         \
             if (t0 < INF_) cur = r0; else OPR_POP(true)                                                            \
         } else {                                                                                                   \
             OPR_SORT_CHILDREN                                                                                      \
             if (t0 < INF_) {                                                                                       \
-                if (t3 < INF_) stack[sp++] = make_int2(r3, __float_as_int(t3));                                    \
-                if (t2 < INF_) stack[sp++] = make_int2(r2, __float_as_int(t2));                                    \
-                if (t1 < INF_) stack[sp++] = make_int2(r1, __float_as_int(t1));                                    \
+                if (t3 < INF_) OPR_STACK_PUSH(r3, __float_as_int(t3))                                              \
+                if (t2 < INF_) OPR_STACK_PUSH(r2, __float_as_int(t2))                                              \
+                if (t1 < INF_) OPR_STACK_PUSH(r1, __float_as_int(t1))                                              \
                 cur = r0;                                                                                          \
             } else {                                                                                               \
                 OPR_POP(false)                                                                                     \

@@ -11,6 +11,27 @@ namespace opr {
 
 constexpr int TRACE_THREADS = 128;
 
+// Traversal stack of the wavefront kernels: the first OPR_SSTACK entries of every lane live in shared memory, laid out
+// [entry][thread] so that a lane's bank is its thread index whatever its depth — a push or a pop of a warp whose lanes sit at 17
+// different depths is two shared-memory wavefronts (8-byte entries), where the same access to the per-thread local-memory stack
+// touched two 128-byte lines per DISTINCT depth, on the L1 data pipe that already bounds incoherent traversal (profiles/).  Deeper
+// entries (rare: the bound is 3 * levels + 4) spill to the local array.  0 = everything in local memory.
+#ifndef OPR_SSTACK
+#define OPR_SSTACK 16
+#endif
+#if OPR_SSTACK > 0
+#undef OPR_STACK_ST
+#undef OPR_STACK_LD
+#define OPR_STACK_ST(I, V) { if ((I) < OPR_SSTACK) sstack[(I) * TRACE_THREADS] = (V); else stack[(I) - OPR_SSTACK] = (V); }
+#define OPR_STACK_LD(DST, I) { if ((I) < OPR_SSTACK) DST = sstack[(I) * TRACE_THREADS]; else DST = stack[(I) - OPR_SSTACK]; }
+#define OPR_STACK_DECL                                                                    \
+    __shared__ int2 sstackMem[OPR_SSTACK * TRACE_THREADS];                               \
+    int2* const sstack = sstackMem + threadIdx.x;                                        \
+    int2 stack[TRAVERSAL_STACK - OPR_SSTACK];
+#else
+#define OPR_STACK_DECL int2 stack[TRAVERSAL_STACK];
+#endif
+
 // Closest hit for the rays [0, *count) of a queue; each finished ray is appended to the queue of its material kind
 // (warp-aggregated: one atomicAdd per distinct kind per warp via __match_any_sync), so the shading kernels run sorted by
 // material.
@@ -34,7 +55,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_clos
     float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     float tmin = 0.f;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
-    int2 stack[TRAVERSAL_STACK];
+    OPR_STACK_DECL
     int sp = 0;
     int cur = TRAVERSAL_DONE;
     unsigned ray = NONE;
@@ -136,7 +157,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shad
     float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     const float tmin = 0.0001f;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
-    int2 stack[TRAVERSAL_STACK];
+    OPR_STACK_DECL
     int sp = 0;
     int cur = TRAVERSAL_DONE;
     unsigned idx = 0;
@@ -196,7 +217,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
     float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     const float tmin = EPS_RAY;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
-    int2 stack[TRAVERSAL_STACK];
+    OPR_STACK_DECL
     int sp = 0;
     int cur = TRAVERSAL_DONE;
     unsigned pending = NONE;      // queue index of a finished, unoccluded segment whose contribution is not added yet

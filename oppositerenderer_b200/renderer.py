@@ -408,7 +408,17 @@ class OptixRenderer:
         return dict(closest_rays=a[0], any_rays=a[1], photons_stored=a[2], launches=a[3])
 
     def set_timing(self, on):
-        self._lib.opr_set_timing(self._h, 1 if on else 0)
+        """False / 0: off; True / 1: every pass timed alone (serialised); 2: timeline mode (events only, streams overlap)."""
+        self._lib.opr_set_timing(self._h, int(on))
+
+    def timeline(self):
+        """[(name, stream, start_ms, end_ms)] of every pass since set_timing(2), on the device's clock."""
+        cap = 4096
+        a, b, s = (C.c_float * cap)(), (C.c_float * cap)(), C.create_string_buffer(cap)
+        n = self._lib.opr_get_timeline(self._h, a, b, s, cap)
+        if n < 0:
+            raise RuntimeError(self._lib.opr_last_error().decode(errors="replace"))
+        return [(self._lib.opr_get_timeline_name(self._h, i).decode(), s.raw[i:i + 1].decode(), a[i], b[i]) for i in range(min(n, cap))]
 
     def timings(self):
         ms = (C.c_float * 64)()
