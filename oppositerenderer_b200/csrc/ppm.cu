@@ -65,7 +65,8 @@ OPR_DEV void reset_wave_counters(unsigned* __restrict__ counters, unsigned n)
 }
 
 // tail-kernel shape (measurement knobs): rays per warp = 32 / spread; freeRun = lanes traverse without votes
-static unsigned tail_spread() { static int v = -1; if (v < 0) { const char* e = getenv("OPR_TAIL_SPREAD"); v = e ? atoi(e) : 1; if (v < 1) v = 1; if (v > 32) v = 32; } return (unsigned)v; }
+static unsigned tail_blocks() { static int v = -1; if (v < 0) { const char* e = getenv("OPR_TAIL_BLOCKS_PER_SM"); v = e ? atoi(e) : 4; if (v < 1) v = 1; if (v > 16) v = 16; } return (unsigned)v; }
+static unsigned tail_refill_idle() { static int v = -1; if (v < 0) { const char* e = getenv("OPR_TAIL_REFILL"); v = e ? atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (unsigned)v; }
 static unsigned tail_free() { static int v = -1; if (v < 0) { const char* e = getenv("OPR_TAIL_FREE"); v = e ? atoi(e) : 1; } return (unsigned)v; }
 
 // 32-bit per-iteration ray counters -> 64-bit totals (a long render would wrap 32 bits after a few hundred iterations)
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_gen_kernel(opr_camer
 {
     const unsigned n = w * h;
     reset_wave_counters(counters, n);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[CTR_TAIL_COUNT] = 0u; counters[CTR_DEFERRED_COUNT] = 0u; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[CTR_TAIL_COUNT] = 0u; counters[CTR_DEFERRED_COUNT] = 0u; counters[CTR_TAIL_FETCH] = 0u; counters[CTR_LATE_FETCH] = 0u; }
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         camPending[p] = 0;
         const unsigned x = p % w, y = p / w;
@@ -275,37 +276,60 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneVi
 }
 
 // Tail of the camera pass: the few specular continuation rays left after the wavefront bounces are finished here, one
-// thread per path looping trace -> material program until the path ends (the reference's recursion, unrolled in place).
+// lane per path looping trace -> material program until the path ends (the reference's recursion, unrolled in place).
 // A near-empty wavefront bounce costs a full trace + shade launch pair whose duration is one ray's dependent-load
 // latency; this kernel pays that latency once per path instead of once per bounce.
+//
+// Path regeneration: warps are persistent and pull paths from the queue through a shared cursor; a lane whose path ended
+// takes the next path as soon as `refillIdle` lanes of its warp are idle, instead of idling until the warp's longest path is done
+// (chains of 1 to 9 specular bounces here, 1 to 4 more Russian-roulette bounces in the photon tail: the fixed assignment left warps
+// running with a quarter of their lanes).
+OPR_DEV bool tail_refill(unsigned n, unsigned* __restrict__ cursor, bool alive, bool& exhausted, unsigned refillIdle, unsigned& index)
+{   // returns true for a lane that must load path `index`; all 32 lanes call this together
+    const unsigned FULL = 0xffffffffu;
+    const unsigned idle = __ballot_sync(FULL, !alive);
+    bool take = false;
+    if (!exhausted && (idle == FULL || (unsigned)__popc(idle) >= refillIdle)) {
+        const unsigned lane = threadIdx.x & 31, want = __popc(idle);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(cursor, want);
+        base = __shfl_sync(FULL, base, 0);
+        if (!alive) { index = base + __popc(idle & ((1u << lane) - 1)); take = index < n; }
+        if (base + want >= n) exhausted = true;
+    }
+    return take;
+}
+
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_tail_kernel(SceneView sc, unsigned w, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
                                                                         const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                         const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
-                                                                        unsigned* __restrict__ stat, unsigned spread, unsigned freeRun)
+                                                                        unsigned* __restrict__ stat, unsigned* __restrict__ cursor, unsigned refillIdle, unsigned freeRun)
 {
+    const unsigned FULL = 0xffffffffu;
     const unsigned n = *count;
-    unsigned traced = 0;
-    for (unsigned base = blockIdx.x * blockDim.x; base / spread < n; base += gridDim.x * blockDim.x) {
-        const unsigned i = (base + threadIdx.x) / spread;
-        bool alive = i < n && (threadIdx.x % spread) == 0;
-        const float4 o4 = alive ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = alive ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
-        const unsigned p = alive ? rayPath[i] : 0u;
-        float3 o = f3(o4), d = f3(d4);
-        float tmin = o4.w;
-        while (__any_sync(0xffffffffu, alive)) {
-            HitRec hit;
-            if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
-            else traverse_warp<false>(sc, 0xffffffffu, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
-            if (alive) {
-                traced++;
-                const int kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
-                float3 newO = f3(0.f), newD = f3(0.f);
-                alive = shade_camera_hit(sc, kind, p, o, d, hit, w, rsW, rngBuf, hp, newO, newD);
-                o = newO; d = newD; tmin = 0.0001f;
-            }
+    unsigned traced = 0, p = 0;
+    bool alive = false, exhausted = false;
+    float3 o = f3(0.f), d = f3(0.f, 0.f, 1.f);
+    float tmin = 0.0001f;
+    for (;;) {
+        unsigned i = 0;
+        if (tail_refill(n, cursor, alive, exhausted, refillIdle, i)) {
+            const float4 o4 = rayO[i], d4 = rayD[i];
+            p = rayPath[i]; o = f3(o4); d = f3(d4); tmin = o4.w; alive = true;
+        }
+        if (!__any_sync(FULL, alive)) break;
+        HitRec hit;
+        if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
+        else traverse_warp<false>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+        if (alive) {
+            traced++;
+            const int kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
+            float3 newO = f3(0.f), newD = f3(0.f);
+            alive = shade_camera_hit(sc, kind, p, o, d, hit, w, rsW, rngBuf, hp, newO, newD);
+            o = newO; d = newD; tmin = 0.0001f;
         }
     }
-    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, s);
+    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(FULL, traced, s);
     if ((threadIdx.x & 31) == 0 && traced) atomicAdd(stat, traced);
 }
 
@@ -329,8 +353,9 @@ void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, cons
 
 void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, LaunchCtx lc)
 {
-    ppm_camera_tail_kernel<<<numSMs() * 4 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.tailO, q.tailD, q.tailPath,
-                                                                 q.counters + CTR_TAIL_COUNT, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
+    ppm_camera_tail_kernel<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.tailO, q.tailD, q.tailPath,
+                                                                 q.counters + CTR_TAIL_COUNT, q.counters + 16 + STAT_CLOSEST_RAYS, q.counters + CTR_TAIL_FETCH,
+                                                                 tail_refill_idle(), tail_free());
     ++*lc.launches;
 }
 
@@ -558,36 +583,38 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneVi
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_tail_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf, float4* __restrict__ phPower,
                                                                         unsigned* __restrict__ phState, PhotonBuf photons, const float4* __restrict__ rayO,
                                                                         const float4* __restrict__ rayD, const unsigned* __restrict__ rayPath,
-                                                                        const unsigned* __restrict__ count, unsigned* __restrict__ stat, unsigned spread,
-                                                                        unsigned freeRun)
+                                                                        const unsigned* __restrict__ count, unsigned* __restrict__ stat, unsigned* __restrict__ cursor,
+                                                                        unsigned refillIdle, unsigned freeRun)
 {
+    const unsigned FULL = 0xffffffffu;
     const unsigned n = *count;
-    unsigned traced = 0;
-    for (unsigned base = blockIdx.x * blockDim.x; base / spread < n; base += gridDim.x * blockDim.x) {
-        const unsigned i = (base + threadIdx.x) / spread;
-        bool alive = i < n && (threadIdx.x % spread) == 0;
-        const float4 o4 = alive ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = alive ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
-        const unsigned t = alive ? rayPath[i] : 0u;
-        float3 o = f3(o4), d = f3(d4);
-        float tmin = o4.w;
-        while (__any_sync(0xffffffffu, alive)) {
-            HitRec hit;
-            if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
-            else traverse_warp<false>(sc, 0xffffffffu, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
-            if (alive) {
-                traced++;
-                if (hit.prim < 0) alive = false;   // miss: no-op
-                else {
-                    const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
-                    float3 newO = f3(0.f), newD = f3(0.f);
-                    float newTmin;
-                    alive = shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin);
-                    o = newO; d = newD; tmin = newTmin;
-                }
+    unsigned traced = 0, t = 0;
+    bool alive = false, exhausted = false;
+    float3 o = f3(0.f), d = f3(0.f, 0.f, 1.f);
+    float tmin = 0.0001f;
+    for (;;) {
+        unsigned i = 0;
+        if (tail_refill(n, cursor, alive, exhausted, refillIdle, i)) {     // path regeneration: see ppm_camera_tail_kernel
+            const float4 o4 = rayO[i], d4 = rayD[i];
+            t = rayPath[i]; o = f3(o4); d = f3(d4); tmin = o4.w; alive = true;
+        }
+        if (!__any_sync(FULL, alive)) break;
+        HitRec hit;
+        if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
+        else traverse_warp<false>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+        if (alive) {
+            traced++;
+            if (hit.prim < 0) alive = false;   // miss: no-op
+            else {
+                const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+                float3 newO = f3(0.f), newD = f3(0.f);
+                float newTmin;
+                alive = shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin);
+                o = newO; d = newD; tmin = newTmin;
             }
         }
     }
-    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, s);
+    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(FULL, traced, s);
     if ((threadIdx.x & 31) == 0 && traced) atomicAdd(stat, traced);
 }
 
@@ -606,44 +633,56 @@ void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, cons
                             const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc)
 {
     const int cur = bounce & 1;
-    ppm_photon_tail_kernel<<<numSMs() * 8 * tail_spread(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
-                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS, tail_spread(), tail_free());
+    ppm_photon_tail_kernel<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
+                                                                 q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS, q.counters + CTR_FETCH + bounce,
+                                                                 tail_refill_idle(), tail_free());
     ++*lc.launches;
 }
 
 // The deferred photon threads (see ppm_photon_gen_kernel): emission and the whole random walk, one thread per photon.
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_late_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf, float4* __restrict__ phPower,
                                                                         unsigned* __restrict__ phState, PhotonBuf photons, const unsigned* __restrict__ deferred,
-                                                                        const unsigned* __restrict__ count, unsigned* __restrict__ stat)
+                                                                        const unsigned* __restrict__ count, unsigned* __restrict__ stat, unsigned* __restrict__ cursor,
+                                                                        unsigned refillIdle, unsigned freeRun)
 {
+    const unsigned FULL = 0xffffffffu;
     const unsigned n = *count;
-    unsigned traced = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned t = deferred[i];
-        float3 o, d;
-        photon_emit(sc, t, pw, rsW, rngBuf, phPower, phState, o, d);
-        float tmin = 0.0001f;
-        for (;;) {
-            HitRec hit;
-            traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit);
+    unsigned traced = 0, t = 0;
+    bool alive = false, exhausted = false;
+    float3 o = f3(0.f), d = f3(0.f, 0.f, 1.f);
+    float tmin = 0.0001f;
+    for (;;) {
+        unsigned i = 0;
+        if (tail_refill(n, cursor, alive, exhausted, refillIdle, i)) {     // path regeneration: see ppm_camera_tail_kernel
+            t = deferred[i];
+            photon_emit(sc, t, pw, rsW, rngBuf, phPower, phState, o, d);
+            tmin = 0.0001f; alive = true;
+        }
+        if (!__any_sync(FULL, alive)) break;
+        HitRec hit;
+        if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
+        else traverse_warp<false>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+        if (alive) {
             traced++;
-            if (hit.prim < 0) break;   // miss: no-op
-            const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
-            float3 newO = f3(0.f), newD = f3(0.f);
-            float newTmin;
-            if (!shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin)) break;
-            o = newO; d = newD; tmin = newTmin;
+            if (hit.prim < 0) alive = false;   // miss: no-op
+            else {
+                const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+                float3 newO = f3(0.f), newD = f3(0.f);
+                float newTmin;
+                alive = shade_photon_hit(sc, kind, t, o, d, hit, pw, rsW, rngBuf, phPower, phState, photons, newO, newD, newTmin);
+                o = newO; d = newD; tmin = newTmin;
+            }
         }
     }
-    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, s);
+    for (int s = 16; s > 0; s >>= 1) traced += __shfl_xor_sync(FULL, traced, s);
     if ((threadIdx.x & 31) == 0 && traced) atomicAdd(stat, traced);
 }
 
 void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState, const PhotonBuf& photons,
                             const RayQueues& q, LaunchCtx lc)
 {
-    ppm_photon_late_kernel<<<numSMs() * 4, SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.deferred, q.counters + CTR_DEFERRED_COUNT,
-                                                                 q.counters + 16 + STAT_CLOSEST_RAYS);
+    ppm_photon_late_kernel<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.deferred, q.counters + CTR_DEFERRED_COUNT,
+                                                                 q.counters + 16 + STAT_CLOSEST_RAYS, q.counters + CTR_LATE_FETCH, tail_refill_idle(), tail_free());
     ++*lc.launches;
 }
 

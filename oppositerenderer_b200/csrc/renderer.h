@@ -29,6 +29,8 @@ constexpr int CTR_FETCH_SHADOW2 = 278;
 constexpr int CTR_DIRECT_DEFERRED = 279; // pixels whose direct samples wait for a tail kernel
 constexpr int CTR_CONN2_COUNT = 274; // second BDPT connection queue (vcm.cu): length, -, fetch cursor at 274..276
 constexpr int CTR_CONN2_FETCH = 276;
+constexpr int CTR_TAIL_FETCH = 280;   // path-fetch cursors of the regenerating tail kernels: camera tail, deferred photon threads
+constexpr int CTR_LATE_FETCH = 281;   // (the photon tail's cursor is CTR_FETCH + its first bounce: that bounce has no trace kernel)
 constexpr int CTR_ALLOC = 288;
 
 // Wavefront ray queue state (all device pointers)
