@@ -151,6 +151,9 @@ int opr_gather(uint32_t numPixels, const float* hitpointsAoS, uint32_t numPhoton
 /* closest-hit / any-hit queries against the scene loaded in r.  rays8: n x (o.xyz, tmin, d.xyz, tmax) */
 int opr_trace_closest(opr_renderer* r, const float* rays8, uint32_t n, float* outT, int32_t* outMaterial, float* outGeometricNormal3);
 int opr_trace_any(opr_renderer* r, const float* rays8, uint32_t n, int32_t* outOccluded);
+/* The BVH exists in two node formats (128-byte fp32 nodes for coherent launches, 64-byte quantised nodes for incoherent ones); this
+ * switch makes the two queries above traverse the quantised one, so that both are checked ray by ray against the oracle. */
+int opr_debug_set_trace_nodes(opr_renderer* r, int quantized);
 
 /* ---- host-side pieces of the surface -------------------------------------------------------------------- */
 /* Camera::setup / setAspectRatio (renderer/Camera.cpp:333-345, :294-318) */

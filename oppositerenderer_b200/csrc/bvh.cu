@@ -228,7 +228,7 @@ __global__ void bvh_leaf_tri_kernel(const int* __restrict__ leafPrim, int n, con
     dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// ---- quantised copy of the wide nodes (built only with -DOPR_QBVH=1; measured slower overall) ------------
+// ---- quantised copy of the wide nodes: the incoherent launches traverse it (scene.cuh load_node<true>) -------------------------
 // 64 bytes = 16 words: [0,1] lo.x of children 0..3 as 16-bit values, [2,3] hi.x, [4,5] lo.y, [6,7] hi.y, [8,9] lo.z,
 // [10,11] hi.z, [12..15] child refs.  A value is 0x8000 | q with q in [0, 32767] on the grid origin + q * extent / 32768;
 // lo is rounded down and hi up, each by one further cell, which covers the fp32 error of the decode (2^-23 of the extent).
@@ -374,7 +374,6 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
     const float rootA = (rhi.x - rlo.x) * (rhi.y - rlo.y) + (rhi.y - rlo.y) * (rhi.z - rlo.z) + (rhi.z - rlo.z) * (rhi.x - rlo.x);
     sahCost = rootA > 0.f ? rootCost / rootA : 0.f;
     view.nodes = nodes; view.rootRef = 0; view.leafPrim = leafPrim; view.leafTri = leafTri;
-#if OPR_QBVH
     {   // quantised copy on a grid that frames the root box with a margin of a few cells
         const float3 ext = f3(rhi.x - rlo.x, rhi.y - rlo.y, rhi.z - rlo.z);
         const float big = std::max(std::max(ext.x, ext.y), std::max(ext.z, 1e-20f));
@@ -392,7 +391,6 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
         OPR_CUDA_CHECK(cudaGetLastError());
         view.qnodes = (const float4*)qnodes; view.qOrigin = qo; view.qExtent = qe;
     }
-#endif
     numNodes = numWide; bvhLevels = levels; plocRounds = rounds;
     if (getenv("OPR_BVH_VERBOSE"))
         fprintf(stderr, "[opr] BVH: %d prims, PLOC R=%d %d rounds, %d wide nodes (%.1f MB), %d levels, SAH %.2f\n", n, R, rounds, numWide, numWide * 128.0 / 1e6,

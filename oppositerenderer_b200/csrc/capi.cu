@@ -231,6 +231,7 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
     })
 }
 
+int opr_debug_set_trace_nodes(opr_renderer* r, int quantized) { r->r.rawQuantized = quantized != 0; return 0; }
 int opr_debug_set_connection_counts(opr_renderer* r, int enabled) { r->r.debugConnectionCounts = enabled != 0; return 0; }
 void opr_debug_set_guards(int enabled) { opr::devSetGuards(enabled != 0); }
 int opr_debug_check_guards(int* liveBlocks)
@@ -420,7 +421,7 @@ int opr_trace_closest(opr_renderer* r, const float* rays8, uint32_t n, float* ou
         DevBuf dr((size_t)n * 32), o((size_t)n * 16), d((size_t)n * 16), h((size_t)n * 16), t((size_t)n * 4), m((size_t)n * 4), ng((size_t)n * 12);
         OPR_CUDA_CHECK(cudaMemcpyAsync(dr.p, rays8, (size_t)n * 32, cudaMemcpyHostToDevice, R.stream));
         rays8_to_soa_kernel<<<numSMs() * 4, 256, 0, R.stream>>>(dr.as<float>(), n, o.as<float4>(), d.as<float4>());
-        launch_trace_closest_raw(R.scene.view, o.as<float4>(), d.as<float4>(), n, h.as<float4>(), lc);
+        launch_trace_closest_raw(R.scene.view, o.as<float4>(), d.as<float4>(), n, h.as<float4>(), lc, R.rawQuantized);
         hits_to_host_layout_kernel<<<numSMs() * 4, 256, 0, R.stream>>>(R.scene.view, o.as<float4>(), d.as<float4>(), h.as<float4>(), n, t.as<float>(), m.as<int>(), ng.as<float>());
         OPR_CUDA_CHECK(cudaMemcpyAsync(outT, t.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
         OPR_CUDA_CHECK(cudaMemcpyAsync(outMaterial, m.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
@@ -440,7 +441,7 @@ int opr_trace_any(opr_renderer* r, const float* rays8, uint32_t n, int32_t* outO
         DevBuf dr((size_t)n * 32), o((size_t)n * 16), d((size_t)n * 16), occ((size_t)n * 4);
         OPR_CUDA_CHECK(cudaMemcpyAsync(dr.p, rays8, (size_t)n * 32, cudaMemcpyHostToDevice, R.stream));
         rays8_to_soa_kernel<<<numSMs() * 4, 256, 0, R.stream>>>(dr.as<float>(), n, o.as<float4>(), d.as<float4>());
-        launch_trace_any_raw(R.scene.view, o.as<float4>(), d.as<float4>(), n, occ.as<int>(), lc);
+        launch_trace_any_raw(R.scene.view, o.as<float4>(), d.as<float4>(), n, occ.as<int>(), lc, R.rawQuantized);
         OPR_CUDA_CHECK(cudaMemcpyAsync(outOccluded, occ.p, (size_t)n * 4, cudaMemcpyDeviceToHost, R.stream));
         OPR_CUDA_CHECK(cudaStreamSynchronize(R.stream));
         OPR_CUDA_CHECK(cudaGetLastError());

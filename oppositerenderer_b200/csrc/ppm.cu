@@ -300,6 +300,7 @@ OPR_DEV bool tail_refill(unsigned n, unsigned* __restrict__ cursor, bool alive, 
     return take;
 }
 
+template <bool QN>
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_tail_kernel(SceneView sc, unsigned w, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
                                                                         const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                         const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
@@ -319,8 +320,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_tail_kernel(SceneVie
         }
         if (!__any_sync(FULL, alive)) break;
         HitRec hit;
-        if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
-        else traverse_warp<false>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+        if (freeRun) { if (alive) traverse_free<false, QN>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
+        else traverse_warp<false, QN>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
         if (alive) {
             traced++;
             const int kind = hit.prim < 0 ? QUEUE_MISS : sc.materials[prim_material(sc, hit.prim)].kind;
@@ -351,9 +352,10 @@ void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, cons
     ++*lc.launches;
 }
 
-void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, LaunchCtx lc)
+void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, LaunchCtx lc, bool quantized)
 {
-    ppm_camera_tail_kernel<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.tailO, q.tailD, q.tailPath,
+    auto k = quantized ? ppm_camera_tail_kernel<true> : ppm_camera_tail_kernel<false>;
+    k<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, w, rsW, rng, hp, q.tailO, q.tailD, q.tailPath,
                                                                  q.counters + CTR_TAIL_COUNT, q.counters + 16 + STAT_CLOSEST_RAYS, q.counters + CTR_TAIL_FETCH,
                                                                  tail_refill_idle(), tail_free());
     ++*lc.launches;
@@ -580,6 +582,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_shade_kernel(SceneVi
 
 // Tail of the photon pass (see ppm_camera_tail_kernel): photons still alive after the wavefront bounces finish their
 // random walk here, one thread per photon.
+template <bool QN>
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_tail_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf, float4* __restrict__ phPower,
                                                                         unsigned* __restrict__ phState, PhotonBuf photons, const float4* __restrict__ rayO,
                                                                         const float4* __restrict__ rayD, const unsigned* __restrict__ rayPath,
@@ -600,8 +603,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_tail_kernel(SceneVie
         }
         if (!__any_sync(FULL, alive)) break;
         HitRec hit;
-        if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
-        else traverse_warp<false>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+        if (freeRun) { if (alive) traverse_free<false, QN>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
+        else traverse_warp<false, QN>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
         if (alive) {
             traced++;
             if (hit.prim < 0) alive = false;   // miss: no-op
@@ -630,16 +633,18 @@ void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, con
 }
 
 void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
-                            const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc)
+                            const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc, bool quantized)
 {
     const int cur = bounce & 1;
-    ppm_photon_tail_kernel<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
+    auto k = quantized ? ppm_photon_tail_kernel<true> : ppm_photon_tail_kernel<false>;
+    k<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.rayO[cur], q.rayD[cur], q.rayPath[cur],
                                                                  q.counters + CTR_RAYCOUNT + bounce, q.counters + 16 + STAT_CLOSEST_RAYS, q.counters + CTR_FETCH + bounce,
                                                                  tail_refill_idle(), tail_free());
     ++*lc.launches;
 }
 
 // The deferred photon threads (see ppm_photon_gen_kernel): emission and the whole random walk, one thread per photon.
+template <bool QN>
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_late_kernel(SceneView sc, unsigned pw, unsigned rsW, RngBuf rngBuf, float4* __restrict__ phPower,
                                                                         unsigned* __restrict__ phState, PhotonBuf photons, const unsigned* __restrict__ deferred,
                                                                         const unsigned* __restrict__ count, unsigned* __restrict__ stat, unsigned* __restrict__ cursor,
@@ -660,8 +665,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_late_kernel(SceneVie
         }
         if (!__any_sync(FULL, alive)) break;
         HitRec hit;
-        if (freeRun) { if (alive) traverse_free<false>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
-        else traverse_warp<false>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
+        if (freeRun) { if (alive) traverse_free<false, QN>(sc, o, d, tmin, RT_DEFAULT_MAX, hit); }
+        else traverse_warp<false, QN>(sc, FULL, alive, o, d, tmin, RT_DEFAULT_MAX, hit);
         if (alive) {
             traced++;
             if (hit.prim < 0) alive = false;   // miss: no-op
@@ -679,9 +684,10 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_photon_late_kernel(SceneVie
 }
 
 void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState, const PhotonBuf& photons,
-                            const RayQueues& q, LaunchCtx lc)
+                            const RayQueues& q, LaunchCtx lc, bool quantized)
 {
-    ppm_photon_late_kernel<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.deferred, q.counters + CTR_DEFERRED_COUNT,
+    auto k = quantized ? ppm_photon_late_kernel<true> : ppm_photon_late_kernel<false>;
+    k<<<numSMs() * tail_blocks(), SHADE_THREADS, 0, lc.st>>>(sc, pw, rsW, rng, phPower, phState, photons, q.deferred, q.counters + CTR_DEFERRED_COUNT,
                                                                  q.counters + 16 + STAT_CLOSEST_RAYS, q.counters + CTR_LATE_FETCH, tail_refill_idle(), tail_free());
     ++*lc.launches;
 }

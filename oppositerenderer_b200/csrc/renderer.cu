@@ -77,6 +77,7 @@ void Renderer::initialize(int cudaOrdinal)
     for (cudaEvent_t* e : {&evOutputReady, &evSnapTaken[0], &evSnapTaken[1], &evSnapCopied[0], &evSnapCopied[1]})
         OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
+    if (const char* e = getenv("OPR_QNODES")) qnodeMask = (unsigned)atoi(e);
     if (const char* e = getenv("OPR_GRID_STREAM")) gridOnC = (e[0] == 'C' || e[0] == 'c');
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("OPR_VCM_CONNECT_BLOCKS_PER_SM")) vcmConnectBlocksPerSM = (unsigned)std::max(0, atoi(e));
@@ -262,7 +263,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         { ScopedTimer tg(*this, "camera.gen"); launch_ppm_camera_gen(details.camera, width, height, rsW, rng, hp, q, lc); }
         const unsigned waves = std::max(1u, std::min(cameraWaveBounces, MAX_RADIANCE_TRACE_DEPTH + 1));
         for (unsigned bounce = 0; bounce < waves; bounce++) {
-            { ScopedTimer t0(*this, bounce == 0 ? "trace.camera0" : "trace.camera1+"); launch_trace_closest_bounce(sc, q, bounce, lc); }
+            { ScopedTimer t0(*this, bounce == 0 ? "trace.camera0" : "trace.camera1+"); launch_trace_closest_bounce(sc, q, bounce, lc, (qnodeMask & QN_PRIMARY) != 0); }
             { ScopedTimer t0(*this, bounce == 0 ? "shade.camera0" : "shade.camera1+"); launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, bounce, bounce + 1 == waves, lc); }
         }
         OPR_CUDA_CHECK(cudaEventRecord(evCameraWaves, stream));
@@ -280,13 +281,13 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         OPR_CUDA_CHECK(cudaEventRecord(evPhotonGen, stream));
         // stream C: camera tail, then the deferred photon threads
         OPR_CUDA_CHECK(cudaStreamWaitEvent(stC, evCameraWaves, 0));
-        { ScopedTimer t1(*this, "ppm.camera_tail", stC); launch_ppm_camera_tail(sc, width, rsW, rng, hp, q, lcC); }
+        { ScopedTimer t1(*this, "ppm.camera_tail", stC); launch_ppm_camera_tail(sc, width, rsW, rng, hp, q, lcC, (qnodeMask & QN_CAMERA_TAIL) != 0); }
         OPR_CUDA_CHECK(cudaStreamWaitEvent(stC, evPhotonGen, 0));
-        { ScopedTimer t1(*this, "ppm.photon_late", stC); launch_ppm_photon_late(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, lcC); }
+        { ScopedTimer t1(*this, "ppm.photon_late", stC); launch_ppm_photon_late(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, lcC, (qnodeMask & QN_PHOTON_TAILS) != 0); }
         static const char* tn[] = {"trace.photon0", "trace.photon1", "trace.photon2", "trace.photon3", "trace.photon4+"};
         static const char* sn[] = {"shade.photon0", "shade.photon1", "shade.photon2", "shade.photon3", "shade.photon4+"};
         for (unsigned bounce = 0; bounce < waves; bounce++) {
-            { ScopedTimer t0(*this, tn[std::min(bounce, 4u)]); launch_trace_closest_bounce(sc, q, bounce, lc); }
+            { ScopedTimer t0(*this, tn[std::min(bounce, 4u)]); launch_trace_closest_bounce(sc, q, bounce, lc, (qnodeMask & QN_PHOTON) != 0); }
             { ScopedTimer t0(*this, sn[std::min(bounce, 4u)]);
               launch_ppm_photon_shade(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, bounce, lc, bounce + 1 == waves); }
         }
@@ -299,7 +300,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         }
         if (waves <= MAX_PHOTON_TRACE_DEPTH) {
             ScopedTimer t1(*this, "ppm.photon_tail", early ? stC : stream);
-            launch_ppm_photon_tail(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, waves, early ? lcC : lc);
+            launch_ppm_photon_tail(sc, photonLaunchWidth, rsW, rng, phPower, phState, photons, q, waves, early ? lcC : lc, (qnodeMask & QN_PHOTON_TAILS) != 0);
         }
         if (early) photonBBoxAsync(stC);
         OPR_CUDA_CHECK(cudaEventRecord(evTailDone, stC));
@@ -320,13 +321,13 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
                                 early ? 1 : 0, lc); }
         { ScopedTimer t0(*this, "trace.shadow");
           launch_trace_shadow_queue(sc, hp.pos, shadowD, shadowIdx, q.counters + CTR_SHADOW_COUNT, (float*)sampleFactor, q.counters + CTR_FETCH_SHADOW,
-                                    q.counters + CTR_STATS + STAT_ANY_RAYS, lc); }
+                                    q.counters + CTR_STATS + STAT_ANY_RAYS, lc, (qnodeMask & QN_SHADOW) != 0); }
         if (early) {
             OPR_CUDA_CHECK(cudaStreamWaitEvent(stream, evTailDone, 0));   // hit points, RNG states and photons of the tail paths are complete
             ScopedTimer t0(*this, "direct.late");
             launch_ppm_direct_gen(sc, width, height, rsW, rng, hp, sampleFactor, sampleLight, shadowD2, shadowIdx2, q, photonLaunchWidth, photonLaunchHeight, 2, lc);
             launch_trace_shadow_queue(sc, hp.pos, shadowD2, shadowIdx2, q.counters + CTR_SHADOW2_COUNT, (float*)sampleFactor, q.counters + CTR_FETCH_SHADOW2,
-                                      q.counters + CTR_STATS + STAT_ANY_RAYS, lc);
+                                      q.counters + CTR_STATS + STAT_ANY_RAYS, lc, (qnodeMask & QN_SHADOW) != 0);
         }
         OPR_CUDA_CHECK(cudaEventRecord(evDirectDone, stream));
     }

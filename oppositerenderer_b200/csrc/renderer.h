@@ -109,6 +109,11 @@ struct Renderer {
     cudaStream_t streamC = nullptr;
     cudaEvent_t evCameraWaves = nullptr, evPhotonGen = nullptr, evTailDone = nullptr, evPhotonWaves = nullptr;
     cudaStream_t sC() const { return overlap ? streamC : stream; }
+    // Which launches traverse the quantised nodes (OPR_QNODES, bit mask): 1 photon wavefront bounces, 2 photon tail + deferred photons,
+    // 4 camera tail, 8 primary rays, 16 shadow rays, 32 BDPT bounces >= 1, 64 BDPT connections, 128 BDPT tails.  Default: the incoherent ones.
+    enum { QN_PHOTON = 1, QN_PHOTON_TAILS = 2, QN_CAMERA_TAIL = 4, QN_PRIMARY = 8, QN_SHADOW = 16, QN_VCM_BOUNCES = 32, QN_VCM_CONNECT = 64, QN_VCM_TAILS = 128 };
+    unsigned qnodeMask = QN_PHOTON | QN_PHOTON_TAILS | QN_VCM_BOUNCES | QN_VCM_TAILS;
+    bool rawQuantized = false;            // opr_debug_set_trace_nodes: opr_trace_closest / opr_trace_any traverse the quantised nodes
     bool gridOnC = false;                 // OPR_GRID_STREAM=C: photon-grid build on stream C (greatest priority) instead of the low-priority stream B (measured: no gain,
                                           // the build is slowed by the persistent trace kernels holding every register of the SMs, not by its priority)
     cudaStream_t gridStream() const { return overlap ? (gridOnC ? streamC : streamB) : stream; }
@@ -240,32 +245,34 @@ struct LaunchCtx { cudaStream_t st; unsigned long long* launches; };
 
 void launch_stats_fold(unsigned* counters32, unsigned long long* totals64, LaunchCtx lc);
 void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc);
-void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc);
-void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc);
-void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, float4* hits, LaunchCtx lc);
-void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, int* occluded, LaunchCtx lc);
+// `quantized`: traverse the 64-byte quantised nodes (incoherent rays) instead of the 128-byte fp32 nodes (coherent rays): scene.cuh load_node
+void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc, bool quantized = false);
+void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc, bool quantized = false);
+void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, float4* hits, LaunchCtx lc, bool quantized = false);
+void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, int* occluded, LaunchCtx lc, bool quantized = false);
 
 void launch_ppm_camera_gen(const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                            const RayQueues& q, LaunchCtx lc);
 void launch_ppm_camera_shade(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                              const RayQueues& q, int bounce, bool lastWave, LaunchCtx lc);
-void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, LaunchCtx lc);
+void launch_ppm_camera_tail(const SceneView& sc, unsigned w, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, const RayQueues& q, LaunchCtx lc, bool quantized = false);
 void launch_ppm_photon_late(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState, const PhotonBuf& photons,
-                            const RayQueues& q, LaunchCtx lc);
+                            const RayQueues& q, LaunchCtx lc, bool quantized = false);
 void launch_ppm_photon_gen(const SceneView& sc, unsigned pw, unsigned ph, unsigned rsW, const RngBuf& rng, float4* phPower,
                            unsigned* phState, const RayQueues& q, unsigned w, unsigned h, LaunchCtx lc, bool feedsTail = false);
 void launch_ppm_photon_shade(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
                              const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc, bool lastWave = false);
 void launch_ppm_photon_tail(const SceneView& sc, unsigned pw, unsigned rsW, const RngBuf& rng, float4* phPower, unsigned* phState,
-                            const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc);
+                            const PhotonBuf& photons, const RayQueues& q, int bounce, LaunchCtx lc, bool quantized = false);
 void launch_ppm_direct_gen(const SceneView& sc, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp, float4* sampleFactor,
                            uint2* sampleLight, float4* shadowD, unsigned* shadowIdx, const RayQueues& q, unsigned pw, unsigned ph, int part, LaunchCtx lc);
 void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
-                               float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc);
+                               float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, bool quantized = false);
 void launch_pt_generate_ray(const SceneView& sc, const opr_camera& cam, unsigned w, unsigned h, unsigned rsW, const RngBuf& rng, const HitpointBuf& hp,
                             float* output, unsigned localIteration, unsigned* stats, LaunchCtx lc, unsigned* signature = nullptr);
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
-                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM = 0, unsigned* dbgCount = nullptr);
+                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM = 0, unsigned* dbgCount = nullptr,
+                                bool quantized = false);
 void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const uint2* sampleLight,
                                const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc);
 

@@ -34,11 +34,6 @@ struct DMaterial {
 
 struct DSphere { float3 center; float radius; };
 
-// 1: traverse the 64-byte quantised nodes (two 256-bit loads per node visit instead of four); 0: the 128-byte fp32 nodes
-#ifndef OPR_QBVH
-#define OPR_QBVH 0
-#endif
-
 struct SceneView {
     const float4* nodes; int rootRef;                 // 4-wide BVH (bvh.cu), 8 float4 per node
     const float4* qnodes; float3 qOrigin, qExtent;   // the same tree with child boxes on a 15-bit scene grid, 4 float4 (64 B) per node
@@ -174,31 +169,44 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
         int2 e_; --sp; OPR_STACK_LD(e_, sp)                                                                        \
         if ((ANYHIT) || __int_as_float(e_.y) < hit.t) { cur = e_.x; break; }                                       \
     }
-// the four child boxes (lox .. hiz) and child refs (r0 .. r3) of node `cur`
-#if OPR_QBVH
+// The four child boxes (lox .. hiz) and child refs (r0 .. r3) of node `cur`, in one of two formats chosen per launch (QN):
+//   QN = false  128-byte fp32 nodes (four 256-bit loads);
+//   QN = true   64-byte quantised nodes (two 256-bit loads): child planes as 15-bit values on a scene grid, each decoded by ONE byte
+//               permute into a float in [1, 2), so the slab test stays one FFMA per plane with per-ray constants folded in
+//               (ray_slab_setup).  Boxes are rounded outwards by a cell (bvh.cu), so every primitive the fp32 nodes reach is reached.
+// Measured (1.1 M triangles, profiles/): incoherent rays (photon bounces, tails) 11 % faster on the quantised nodes — half the L1
+// wavefronts per node visit — coherent rays (primary, shadow, specular chains) 11-17 % slower (the decode costs issue slots that the
+// coherent kernels do not have to spare).  Hence per launch, not per build.
 #define OPR_QLO(W) __uint_as_float(__byte_perm(__float_as_uint(W), 0x3F800000u, 0x7104u))
 #define OPR_QHI(W) __uint_as_float(__byte_perm(__float_as_uint(W), 0x3F800000u, 0x7324u))
 #define OPR_Q4(A, B) make_float4(OPR_QLO(A), OPR_QHI(A), OPR_QLO(B), OPR_QHI(B))
-#define OPR_NODE_LOAD                                                                                              \
-        const float4* N_ = sc.qnodes + 4 * (size_t)cur;                                                            \
-        const Float8 na_ = ldg256(N_), nb_ = ldg256(N_ + 2);                                                       \
-        const float4 lox = OPR_Q4(na_.lo.x, na_.lo.y), hix = OPR_Q4(na_.lo.z, na_.lo.w);                          \
-        const float4 loy = OPR_Q4(na_.hi.x, na_.hi.y), hiy = OPR_Q4(na_.hi.z, na_.hi.w);                          \
-        const float4 loz = OPR_Q4(nb_.lo.x, nb_.lo.y), hiz = OPR_Q4(nb_.lo.z, nb_.lo.w), rf = nb_.hi;             \
-        int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
-// an absent child has no box on the grid that every ray misses: recognise it by its ref (child 0 always exists)
-#define OPR_NODE_EMPTY                                                                                             \
-        if (r1 == 0x7fffffff) t1 = INF_;                                                                           \
-        if (r2 == 0x7fffffff) t2 = INF_;                                                                           \
-        if (r3 == 0x7fffffff) t3 = INF_;
-#else
-#define OPR_NODE_LOAD                                                                                              \
-        const float4* N_ = sc.nodes + 8 * (size_t)cur;                                                             \
-        const Float8 nx_ = ldg256(N_), ny_ = ldg256(N_ + 2), nz_ = ldg256(N_ + 4), nr_ = ldg256(N_ + 6);            \
-        const float4 lox = nx_.lo, hix = nx_.hi, loy = ny_.lo, hiy = ny_.hi, loz = nz_.lo, hiz = nz_.hi, rf = nr_.lo; \
-        int r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
-#define OPR_NODE_EMPTY
-#endif
+template <bool QN>
+OPR_DEV void load_node(const SceneView& sc, int cur, float4& lox, float4& hix, float4& loy, float4& hiy, float4& loz, float4& hiz, int& r0, int& r1, int& r2, int& r3)
+{
+    float4 rf;
+    if (QN) {
+        const float4* N_ = sc.qnodes + 4 * (size_t)cur;
+        const Float8 na_ = ldg256(N_), nb_ = ldg256(N_ + 2);
+        lox = OPR_Q4(na_.lo.x, na_.lo.y); hix = OPR_Q4(na_.lo.z, na_.lo.w);
+        loy = OPR_Q4(na_.hi.x, na_.hi.y); hiy = OPR_Q4(na_.hi.z, na_.hi.w);
+        loz = OPR_Q4(nb_.lo.x, nb_.lo.y); hiz = OPR_Q4(nb_.lo.z, nb_.lo.w); rf = nb_.hi;
+    } else {
+        const float4* N_ = sc.nodes + 8 * (size_t)cur;
+        const Float8 nx_ = ldg256(N_), ny_ = ldg256(N_ + 2), nz_ = ldg256(N_ + 4), nr_ = ldg256(N_ + 6);
+        lox = nx_.lo; hix = nx_.hi; loy = ny_.lo; hiy = ny_.hi; loz = nz_.lo; hiz = nz_.hi; rf = nr_.lo;
+    }
+    r0 = __float_as_int(rf.x); r1 = __float_as_int(rf.y); r2 = __float_as_int(rf.z); r3 = __float_as_int(rf.w);
+}
+#define OPR_NODE_LOAD(QN)                                                                                          \
+        float4 lox, hix, loy, hiy, loz, hiz; int r0, r1, r2, r3;                                                   \
+        load_node<QN>(sc, cur, lox, hix, loy, hiy, loz, hiz, r0, r1, r2, r3);
+// a quantised absent child has no box on the grid that every ray misses: recognise it by its ref (child 0 always exists)
+#define OPR_NODE_EMPTY(QN)                                                                                         \
+        if (QN) {                                                                                                  \
+            if (r1 == 0x7fffffff) t1 = INF_;                                                                       \
+            if (r2 == 0x7fffffff) t2 = INF_;                                                                       \
+            if (r3 == 0x7fffffff) t3 = INF_;                                                                       \
+        }
 // Order of the hit children.  Full: 5-comparator network, visit and pop strictly front to back.  OPR_SORT_NEAREST: only the
 // nearest child is found (3 comparators); the others are pushed as they come, each with its entry distance, so a pop still
 // drops the ones behind the closest hit.
@@ -211,16 +219,16 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
 #define OPR_SORT_CHILDREN OPR_CSWAP(t0, r0, t1, r1) OPR_CSWAP(t2, r2, t3, r3) OPR_CSWAP(t0, r0, t2, r2) OPR_CSWAP(t1, r1, t3, r3) OPR_CSWAP(t1, r1, t2, r2)
 #endif
 // one node visit of a lane with cur >= 0
-#define OPR_NODE_STEP(ANYHIT)                                                                                      \
+#define OPR_NODE_STEP(ANYHIT, QN)                                                                                  \
     {                                                                                                              \
         const float INF_ = __int_as_float(0x7f800000);                                                             \
-        OPR_NODE_LOAD                                                                                              \
+        OPR_NODE_LOAD(QN)                                                                                          \
         float t0, t1, t2, t3;                                                                                      \
         OPR_SLAB(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, t0)                                                     \
         OPR_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, t1)                                                     \
         OPR_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, t2)                                                     \
         OPR_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, t3)                                                     \
-        OPR_NODE_EMPTY                                                                                             \
+        OPR_NODE_EMPTY(QN)                                                                                         \
         if (ANYHIT) {          /* any order will do for an occlusion query: skip the sorting network */             \
             if (t1 < INF_) { if (t0 < INF_) OPR_STACK_PUSH(r1, 0) else { t0 = t1; r0 = r1; } }                         \
             if (t2 < INF_) { if (t0 < INF_) OPR_STACK_PUSH(r2, 0) else { t0 = t2; r0 = r2; } }                         \
@@ -274,7 +282,7 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
 #ifndef OPR_VOTE_LEAF
 #define OPR_VOTE_LEAF 1
 #endif
-#define OPR_NODE_PHASE(MASK, ANYHIT)                                                                               \
+#define OPR_NODE_PHASE(MASK, ANYHIT, QN)                                                                           \
     for (;;) {                                                                                                     \
         const unsigned nm_ = __ballot_sync((MASK), cur >= 0);                                                      \
         if (!nm_) break;                                                                                           \
@@ -282,7 +290,7 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
             const unsigned lm_ = __ballot_sync((MASK), cur < 0 && cur != TRAVERSAL_DONE);                          \
             if (__popc(nm_) * OPR_VOTE_NODE < __popc(lm_) * OPR_VOTE_LEAF) break;                                  \
         }                                                                                                          \
-        if (cur >= 0) OPR_NODE_STEP(ANYHIT)                                                                        \
+        if (cur >= 0) OPR_NODE_STEP(ANYHIT, QN)                                                                    \
     }
 
 // 1/d with |d| clamped away from zero: keeps every slab product finite-or-inf (never 0 * inf = NaN)
@@ -292,36 +300,37 @@ OPR_DEV float3 safe_inverse_direction(const float3& d)
               1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z)));
 }
 
-// Per-ray constants of the slab test.  Full-precision nodes: t = plane * idir + ood.  Quantised nodes (OPR_QBVH): a plane is
+// Per-ray constants of the slab test.  Full-precision nodes: t = plane * idir + ood.  Quantised nodes (QN): a plane is
 // stored as q in [0, 32767] on the scene grid, decoded by ONE byte permute into the float v = 1 + q / 32768 (the stored
 // half-word carries the exponent's low bit), and world = qOrigin + (v - 1) * qExtent, so t = v * (qExtent * idir) +
 // (qOrigin - qExtent - o) * idir: the same single FFMA per plane with different per-ray constants.
+template <bool QN>
 OPR_DEV void ray_slab_setup(const SceneView& sc, const float3& o, const float3& d, float3& idir, float3& ood)
 {
     const float3 inv = safe_inverse_direction(d);
-#if OPR_QBVH
-    idir = f3(sc.qExtent.x * inv.x, sc.qExtent.y * inv.y, sc.qExtent.z * inv.z);
-    ood = f3((sc.qOrigin.x - sc.qExtent.x - o.x) * inv.x, (sc.qOrigin.y - sc.qExtent.y - o.y) * inv.y, (sc.qOrigin.z - sc.qExtent.z - o.z) * inv.z);
-#else
-    idir = inv;
-    ood = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
-#endif
+    if (QN) {
+        idir = f3(sc.qExtent.x * inv.x, sc.qExtent.y * inv.y, sc.qExtent.z * inv.z);
+        ood = f3((sc.qOrigin.x - sc.qExtent.x - o.x) * inv.x, (sc.qOrigin.y - sc.qExtent.y - o.y) * inv.y, (sc.qOrigin.z - sc.qExtent.z - o.z) * inv.z);
+    } else {
+        idir = inv;
+        ood = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+    }
 }
 
 // Closest hit (ANY = false) or first accepted intersection (ANY = true: shadow rays, ppm/DirectRadianceEstimation.cu:79-83,
 // bound to every material by material/Material.cpp:18-26) for the lanes of `mask`, which must all make this call together;
 // lanes with active = false ride along.  On return hit.prim = (primIndex << 2) | primType, or -1.
-template <bool ANY>
+template <bool ANY, bool QN = false>
 OPR_DEV bool traverse_warp(const SceneView& sc, unsigned mask, bool active, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
 {
     hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
     float3 idir, ood;
-    ray_slab_setup(sc, o, d, idir, ood);
+    ray_slab_setup<QN>(sc, o, d, idir, ood);
     int2 stack[TRAVERSAL_STACK];
     int sp = 0;
     int cur = active ? sc.rootRef : TRAVERSAL_DONE;
     for (;;) {
-        OPR_NODE_PHASE(mask, ANY)
+        OPR_NODE_PHASE(mask, ANY, QN)
         if (__all_sync(mask, cur == TRAVERSAL_DONE)) break;
         if (cur < 0 && cur != TRAVERSAL_DONE) {
             bool found = false;
@@ -336,17 +345,17 @@ OPR_DEV bool traverse_warp(const SceneView& sc, unsigned mask, bool active, cons
 }
 
 // No votes: every lane runs at its own pace (for latency-bound kernels with a handful of rays per warp).
-template <bool ANY>
+template <bool ANY, bool QN = false>
 OPR_DEV bool traverse_free(const SceneView& sc, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
 {
     hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
     float3 idir, ood;
-    ray_slab_setup(sc, o, d, idir, ood);
+    ray_slab_setup<QN>(sc, o, d, idir, ood);
     int2 stack[TRAVERSAL_STACK];
     int sp = 0;
     int cur = sc.rootRef;
     for (;;) {
-        while (cur >= 0) OPR_NODE_STEP(ANY)
+        while (cur >= 0) OPR_NODE_STEP(ANY, QN)
         if (cur == TRAVERSAL_DONE) break;
         bool found = false;
         OPR_LEAF_STEP(found)

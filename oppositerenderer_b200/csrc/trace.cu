@@ -17,7 +17,7 @@ constexpr int TRACE_THREADS = 128;
 // touched two 128-byte lines per DISTINCT depth, on the L1 data pipe that already bounds incoherent traversal (profiles/).  Deeper
 // entries (rare: the bound is 3 * levels + 4) spill to the local array.  0 = everything in local memory.
 #ifndef OPR_SSTACK
-#define OPR_SSTACK 16
+#define OPR_SSTACK 8
 #endif
 #if OPR_SSTACK > 0
 #undef OPR_STACK_ST
@@ -43,6 +43,7 @@ constexpr int TRACE_THREADS = 128;
 #ifndef OPR_TRACE_MINBLOCKS
 #define OPR_TRACE_MINBLOCKS 1
 #endif
+template <bool QN>
 __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_closest_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       const unsigned* __restrict__ count, float4* __restrict__ hits,
                                                                       unsigned* __restrict__ matQueue, unsigned* __restrict__ matCount,
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_clos
                     if (idx < n) {
                         const float4 o4 = rayO[idx], d4 = rayD[idx];
                         o = f3(o4); d = f3(d4); tmin = o4.w;
-                        ray_slab_setup(sc, o, d, idir, ood);
+                        ray_slab_setup<QN>(sc, o, d, idir, ood);
                         hit.t = d4.w; hit.prim = -1; hit.u = hit.v = 0.f;
                         sp = 0; cur = sc.rootRef; ray = idx;
                     }
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_clos
             }
             if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
         }
-        OPR_NODE_PHASE(FULL, false)
+        OPR_NODE_PHASE(FULL, false, QN)
         if (cur < 0 && cur != TRAVERSAL_DONE) {
             [[maybe_unused]] bool found = false;
             OPR_LEAF_STEP(found)      // a closest-hit query keeps going after an accepted primitive: hit.t only shrinks the search
@@ -125,19 +126,21 @@ static unsigned trace_refill_idle()
 }
 
 // legacy ping-pong counters ([cur] ray count, [2..9) material counts) used by the VCM passes
-void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc)
+void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc, bool quantized)
 {
     OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_FETCH_LEGACY, 0, sizeof(unsigned), lc.st));
-    trace_closest_kernel<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + cur, q.hits, q.matQueue,
+    auto k = quantized ? trace_closest_kernel<true> : trace_closest_kernel<false>;
+    k<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + cur, q.hits, q.matQueue,
                                                                q.counters + 2, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
                                                                q.counters + CTR_FETCH_LEGACY, trace_refill_idle());
     ++*lc.launches;
 }
 
-void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc)
+void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc, bool quantized)
 {
     const int cur = bounce & 1;
-    trace_closest_kernel<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
+    auto k = quantized ? trace_closest_kernel<true> : trace_closest_kernel<false>;
+    k<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
                                                                q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
                                                                q.counters + CTR_FETCH + bounce, trace_refill_idle());
     ++*lc.launches;
@@ -146,6 +149,7 @@ void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bo
 // Any-hit for a compacted queue of shadow rays (ppm/DirectRadianceEstimation.cu:79-83: any intersection in (tmin, tmax)
 // zeroes the sample).  Ray i = (origin = hit point of pixel idx >> 2, direction + tmax = shadowD[i]); an occluded ray
 // clears sampleFactor[idx].  Same persistent / dynamic-fetch / warp-lockstep structure as trace_closest_kernel.
+template <bool QN>
 __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shadow_queue_kernel(SceneView sc, const float4* __restrict__ hitPos, const float4* __restrict__ shadowD,
                                                                            const unsigned* __restrict__ shadowIdx, const unsigned* __restrict__ count,
                                                                            float* __restrict__ sampleFactor, unsigned* __restrict__ fetchCursor,
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shad
                         idx = shadowIdx[i];
                         const float4 d4 = shadowD[i];
                         o = f3(hitPos[idx >> 2]); d = f3(d4);
-                        ray_slab_setup(sc, o, d, idir, ood);
+                        ray_slab_setup<QN>(sc, o, d, idir, ood);
                         hit.t = d4.w; hit.prim = -1;
                         sp = 0; cur = sc.rootRef;
                     }
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shad
             }
             if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
         }
-        OPR_NODE_PHASE(FULL, true)
+        OPR_NODE_PHASE(FULL, true, QN)
         if (cur < 0 && cur != TRAVERSAL_DONE) {
             bool found = false;
             OPR_LEAF_STEP(found)
@@ -197,15 +201,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shad
 }
 
 void launch_trace_shadow_queue(const SceneView& sc, const float4* hitPos, const float4* shadowD, const unsigned* shadowIdx, const unsigned* count,
-                               float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc)
+                               float* sampleFactor, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, bool quantized)
 {
-    trace_shadow_queue_kernel<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, hitPos, shadowD, shadowIdx, count, sampleFactor, fetchCursor, stat, trace_refill_idle());
+    auto k = quantized ? trace_shadow_queue_kernel<true> : trace_shadow_queue_kernel<false>;
+    k<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, hitPos, shadowD, shadowIdx, count, sampleFactor, fetchCursor, stat, trace_refill_idle());
     ++*lc.launches;
 }
 
 // Any-hit for the deferred connections of the BDPT passes (vcm.cu): segment i = (connO[i].xyz, connD[i].xyz) over
 // (EPS_RAY, connO[i].w); when nothing occludes it (isOccluded, vcm/vcm.h:43-59) its contribution connC[i] is added to
 // target[stride * index] (camera-path colour accumulators, or the image for light-tracing splats: vcm.h:159).
+template <bool QN>
 __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_connect_queue_kernel(SceneView sc, const float4* __restrict__ connO, const float4* __restrict__ connD,
                                                                             const float4* __restrict__ connC, const unsigned* __restrict__ count,
                                                                             float* __restrict__ target, unsigned stride, unsigned* __restrict__ fetchCursor,
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
                     if (i < n) {
                         const float4 o4 = connO[i], d4 = connD[i];
                         o = f3(o4); d = f3(d4);
-                        ray_slab_setup(sc, o, d, idir, ood);
+                        ray_slab_setup<QN>(sc, o, d, idir, ood);
                         hit.t = o4.w; hit.prim = -1;
                         sp = 0; cur = sc.rootRef; pending = i;
                     }
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
             }
             if (__all_sync(FULL, cur == TRAVERSAL_DONE)) break;
         }
-        OPR_NODE_PHASE(FULL, true)
+        OPR_NODE_PHASE(FULL, true, QN)
         if (cur < 0 && cur != TRAVERSAL_DONE) {
             bool found = false;
             OPR_LEAF_STEP(found)
@@ -264,14 +270,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
 }
 
 void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const float4* connD, const float4* connC, const unsigned* count, float* target,
-                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM, unsigned* dbgCount)
+                                unsigned stride, unsigned* fetchCursor, unsigned* stat, LaunchCtx lc, unsigned blocksPerSM, unsigned* dbgCount, bool quantized)
 {
     const unsigned blocks = numSMs() * (blocksPerSM ? blocksPerSM : trace_blocks_per_sm());
-    trace_connect_queue_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle(), dbgCount);
+    auto k = quantized ? trace_connect_queue_kernel<true> : trace_connect_queue_kernel<false>;
+    k<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, connO, connD, connC, count, target, stride, fetchCursor, stat, trace_refill_idle(), dbgCount);
     ++*lc.launches;
 }
 
 // Raw entry points over caller-supplied SoA rays (C-ABI opr_trace_closest / opr_trace_any)
+template <bool QN>
 __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_raw_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                           unsigned n, float4* __restrict__ hits)
 {
@@ -280,11 +288,12 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_closest_raw_kernel(SceneV
         const bool active = i < n;
         const float4 o4 = active ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = active ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
         HitRec hit;
-        traverse_warp<false>(sc, 0xffffffffu, active, f3(o4), f3(d4), o4.w, d4.w, hit);
+        traverse_warp<false, QN>(sc, 0xffffffffu, active, f3(o4), f3(d4), o4.w, d4.w, hit);
         if (active) hits[i] = make_float4(hit.t, __int_as_float(hit.prim), hit.u, hit.v);
     }
 }
 
+template <bool QN>
 __global__ void __launch_bounds__(TRACE_THREADS) trace_any_raw_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       unsigned n, int* __restrict__ occluded)
 {
@@ -293,24 +302,26 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_any_raw_kernel(SceneView 
         const bool active = i < n;
         const float4 o4 = active ? rayO[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4 = active ? rayD[i] : make_float4(0.f, 0.f, 1.f, 0.f);
         HitRec hit;
-        const bool occ = traverse_warp<true>(sc, 0xffffffffu, active, f3(o4), f3(d4), o4.w, d4.w, hit);
+        const bool occ = traverse_warp<true, QN>(sc, 0xffffffffu, active, f3(o4), f3(d4), o4.w, d4.w, hit);
         if (active) occluded[i] = occ ? 1 : 0;
     }
 }
 
-void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, float4* hits, LaunchCtx lc)
+void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, float4* hits, LaunchCtx lc, bool quantized)
 {
     if (!n) return;
     int blocks = (int)std::min<unsigned>((n + TRACE_THREADS - 1) / TRACE_THREADS, numSMs() * 16);
-    trace_closest_raw_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, rayO, rayD, n, hits);
+    auto k = quantized ? trace_closest_raw_kernel<true> : trace_closest_raw_kernel<false>;
+    k<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, rayO, rayD, n, hits);
     ++*lc.launches;
 }
 
-void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, int* occluded, LaunchCtx lc)
+void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, int* occluded, LaunchCtx lc, bool quantized)
 {
     if (!n) return;
     int blocks = (int)std::min<unsigned>((n + TRACE_THREADS - 1) / TRACE_THREADS, numSMs() * 16);
-    trace_any_raw_kernel<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, rayO, rayD, n, occluded);
+    auto k = quantized ? trace_any_raw_kernel<true> : trace_any_raw_kernel<false>;
+    k<<<blocks, TRACE_THREADS, 0, lc.st>>>(sc, rayO, rayD, n, occluded);
     ++*lc.launches;
 }
 

@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(VCM_THREADS, OPR_VCM_CAMERA_MINBLOCKS) vcm_cam
 // ---- tails of the two passes: the paths still alive after the wavefront bounces are finished one thread per path (trace ->
 // material program -> connections tested in place), as in the PPM passes (ppm_camera_tail_kernel): late bounces hold a few per
 // cent of the paths, and a wavefront bounce over them costs three launches whose duration is one ray's dependent-load latency.
+template <bool QN>
 __global__ void __launch_bounds__(VCM_THREADS) vcm_light_tail_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B, float* __restrict__ output,
                                                                      const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                      const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_tail_kernel(SceneView s
         float3 o = f3(o4), d = f3(d4);
         for (;;) {
             HitRec hit;
-            traverse_free<false>(sc, o, d, RAY_LEN_MIN, RT_DEFAULT_MAX, hit);
+            traverse_free<false, QN>(sc, o, d, RAY_LEN_MIN, RT_DEFAULT_MAX, hit);
             closest++;
             if (hit.prim < 0) break;                                              // VCMLightPass.cu:95-98
             const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
@@ -672,6 +673,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_light_tail_kernel(SceneView s
     if ((threadIdx.x & 31) == 0) { if (closest) atomicAdd(stats + STAT_CLOSEST_RAYS, closest); if (any) atomicAdd(stats + STAT_ANY_RAYS, any); }
 }
 
+template <bool QN>
 __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_tail_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B,
                                                                       const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
@@ -685,7 +687,7 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_tail_kernel(SceneView 
         float3 o = f3(o4), d = f3(d4);
         for (;;) {
             HitRec hit;
-            traverse_free<false>(sc, o, d, RAY_LEN_MIN, RT_DEFAULT_MAX, hit);
+            traverse_free<false, QN>(sc, o, d, RAY_LEN_MIN, RT_DEFAULT_MAX, hit);
             closest++;
             if (hit.prim < 0) break;                                              // VCMCameraPass.cu:87-90
             const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
@@ -793,13 +795,14 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
     auto traceConnections = [&](float* target, unsigned stride) {
         const VcmBuffers& b = Bq[connSet];
         if (!ov) {
-            launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS, lc, 0, b.dbgConn);
+            launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS, lc, 0, b.dbgConn,
+                                       (qnodeMask & QN_VCM_CONNECT) != 0);
             return;
         }
         OPR_CUDA_CHECK(cudaEventRecord(evVcmShade, stream));
         OPR_CUDA_CHECK(cudaStreamWaitEvent(streamB, evVcmShade, 0));
         launch_trace_connect_queue(sc, b.connO, b.connD, b.connC, b.connCount, target, stride, connFetch[connSet], q.counters + CTR_STATS + STAT_ANY_RAYS,
-                                   LaunchCtx{streamB, &launches}, vcmConnectBlocksPerSM, b.dbgConn);
+                                   LaunchCtx{streamB, &launches}, vcmConnectBlocksPerSM, b.dbgConn, (qnodeMask & QN_VCM_CONNECT) != 0);
         OPR_CUDA_CHECK(cudaEventRecord(evVcmConn[connSet], streamB));
         connBusy[connSet] = true;
     };
@@ -821,7 +824,7 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         for (unsigned bounce = 0; bounce < waves; bounce++) {
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
-            launch_trace_closest(sc, q, cur, lc);
+            launch_trace_closest(sc, q, cur, lc, bounce > 0 && (qnodeMask & QN_VCM_BOUNCES) != 0);
             const VcmBuffers& Bc = beginConnections();
             dim3 grid(VCM_BLOCKS_X, NUM_QUEUES);
             vcm_light_shade_kernel<<<grid, VCM_THREADS, 0, stream>>>(sc, P, rng, Bc, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
@@ -833,7 +836,8 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             cur ^= 1;
         }
         if (waves <= P.maxPathLen) {
-            vcm_light_tail_kernel<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur,
+            auto kt = (qnodeMask & QN_VCM_TAILS) ? vcm_light_tail_kernel<true> : vcm_light_tail_kernel<false>;
+            kt<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur,
                                                                        q.counters + CTR_STATS);
             ++launches;
         }
@@ -863,7 +867,7 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         for (unsigned bounce = 0; bounce < waves; bounce++) {
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + 2, 0, sizeof(unsigned) * NUM_QUEUES, stream));
             OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + (cur ^ 1), 0, sizeof(unsigned), stream));
-            launch_trace_closest(sc, q, cur, lc);
+            launch_trace_closest(sc, q, cur, lc, bounce > 0 && (qnodeMask & QN_VCM_BOUNCES) != 0);
             const VcmBuffers& Bc = beginConnections();
             dim3 grid(VCM_BLOCKS_X, NUM_QUEUES);
             vcm_camera_shade_kernel<<<grid, VCM_THREADS, 0, stream>>>(sc, P, rng, Bc, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.hits, q.matQueue,
@@ -875,7 +879,8 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
             cur ^= 1;
         }
         if (waves <= P.maxPathLen) {
-            vcm_camera_tail_kernel<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur, q.counters + CTR_STATS);
+            auto kt = (qnodeMask & QN_VCM_TAILS) ? vcm_camera_tail_kernel<true> : vcm_camera_tail_kernel<false>;
+            kt<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur, q.counters + CTR_STATS);
             ++launches;
         }
         joinConnections();

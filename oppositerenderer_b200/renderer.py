@@ -430,6 +430,9 @@ class OptixRenderer:
         self._check(self._lib.opr_debug_get_buffer(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.nbytes))
         return a
 
+    def set_trace_nodes(self, quantized):
+        self._check(self._lib.opr_debug_set_trace_nodes(self._h, 1 if quantized else 0))
+
     def set_connection_counts(self, on):
         self._check(self._lib.opr_debug_set_connection_counts(self._h, 1 if on else 0))
 

@@ -116,9 +116,11 @@ def test_traversal_matches_oracle(product, oracle, scene_name, config):
     assert (occ == occ0).mean() > 0.9995
 
 
-def test_traversal_full_size_matches_oracle(product, oracle):
+@pytest.mark.parametrize("quantized", [False, True])
+def test_traversal_full_size_matches_oracle(product, oracle, quantized):
     """The 1.1 M-triangle bench scene (PLOC build, 4-wide collapse, SAH leaves, 17 levels): closest hit and any hit against the
-    oracle's CPU BVH ray by ray — 57.6 K camera rays, 100 K random rays, 100 K shadow segments."""
+    oracle's CPU BVH ray by ray — 57.6 K camera rays, 100 K random rays, 100 K shadow segments — through both node formats (the
+    128-byte fp32 nodes of the coherent launches, the 64-byte quantised nodes of the incoherent ones)."""
     from oppositerenderer_b200 import synthetic
     scene = synthetic.make_scene("sponza", seed=1, detail=1.0, texture_size=64)
     assert scene.num_triangles > 1000000
@@ -127,6 +129,7 @@ def test_traversal_full_size_matches_oracle(product, oracle):
     r = product.OptixRenderer(photon_launch=(16, 16), seed=util.SEED)
     r.initialize(product.ComputeDevice(0))
     r.initScene(scene)
+    r.set_trace_nodes(quantized)
     o = oracle.OracleRenderer("oracle", (16, 16), 10, util.SEED)
     o.init_scene(scene.getSceneDescription())
     rng = np.random.default_rng(5)
