@@ -171,15 +171,37 @@ OPR_DEV float exp2f_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" 
 constexpr int GATHER_THREADS = 128;
 constexpr int GATHER_WARPS = GATHER_THREADS / 32;
 
+// Packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2, PTX *.f32x2).  Measured on B200 (scripts/micro/ffma2.cu): FFMA2 runs at HALF the
+// instruction rate of FFMA, i.e. the same 70 Tflop/s — the FP32 pipe gains nothing, the ISSUE slots do: one slot feeds two lanes'
+// worth of FMAs.  The inner loop of the gather was bound by issue (83 % issue-active: 14 FP32-pipe instructions + 7 others per
+// candidate photon); with two photons per packed instruction it needs ~13 slots per photon for the same 14 pipe cycles, so the
+// FP32 pipe becomes the limit.  Results are those of the scalar IEEE operations, lane by lane (rn, no contraction beyond the
+// fmaf chains the scalar loop already used).
+#ifndef OPR_GATHER_PACKED
+#define OPR_GATHER_PACKED 1
+#endif
+typedef unsigned long long f32x2;
+OPR_DEV f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+OPR_DEV void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+OPR_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+OPR_DEV f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+OPR_DEV f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // 61 registers: 8 CTAs per SM stay resident, which lets the block scheduler interleave the gather with the path passes of the next
 // iteration.  A 96-register build (5 CTAs per SM) is 2 % faster alone on the photon-dense bench scene and 10 % slower on the sparse one.
 __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointBuf hp, unsigned numPixels, unsigned width, unsigned height, PhotonBuf sorted,
                                                                     const unsigned* __restrict__ offsets, GridParams g, float ppmRadius, float ppmRadiusSquared,
                                                                     float emittedPhotons, float* __restrict__ indirect, unsigned* __restrict__ tileCounter, unsigned tilesPerBlock)
 {
+#if OPR_GATHER_PACKED
+    // staged photons as nine component arrays per warp (x y z | dir x y z | power r g b): a 128-bit shared load fetches one component
+    // of FOUR photons as two ready-made packed pairs
+    __shared__ __align__(16) float sP[GATHER_WARPS][9][32];
+#else
     __shared__ float4 sA[GATHER_WARPS][32];
     __shared__ float4 sB[GATHER_WARPS][32];
     __shared__ float sC[GATHER_WARPS][32];
+#endif
     __shared__ float sAcc[GATHER_WARPS][32][3];
     __shared__ unsigned sTile;
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -228,6 +250,12 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
             if (!(x_lo <= x_hi) || !(y_lo <= y_hi) || !(z_lo <= z_hi)) active = false;
         }
         float3 acc = f3(0.f);
+#if OPR_GATHER_PACKED
+        const f32x2 posX2 = pk2(pos.x, pos.x), posY2 = pk2(pos.y, pos.y), posZ2 = pk2(pos.z, pos.z);
+        const f32x2 nrmX2 = pk2(nrm.x, nrm.x), nrmY2 = pk2(nrm.y, nrm.y), nrmZ2 = pk2(nrm.z, nrm.z);
+        const f32x2 kexp2 = pk2(kexp, kexp), w12 = pk2(w1, w1), w02 = pk2(w0, w0);
+        f32x2 accX2 = pk2(0.f, 0.f), accY2 = accX2, accZ2 = accX2;      // even / odd photons of a row chunk
+#endif
         if (__any_sync(0xffffffffu, active)) {
             const unsigned uy_lo = __reduce_min_sync(0xffffffffu, active ? y_lo : 0xffffffffu), uy_hi = __reduce_max_sync(0xffffffffu, active ? y_hi : 0u);
             const unsigned uz_lo = __reduce_min_sync(0xffffffffu, active ? z_lo : 0xffffffffu), uz_hi = __reduce_max_sync(0xffffffffu, active ? z_hi : 0u);
@@ -266,13 +294,47 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
                 float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra; float rc = 0.f;
                 if (begin + lane < end) { ra = __ldg(sorted.a + begin + lane); rb = __ldg(sorted.b + begin + lane); rc = __ldg(sorted.c + begin + lane); }
                 for (unsigned base = begin; base < end; base += 32) {
+#if OPR_GATHER_PACKED
+                    {   // lanes beyond the row's end stage a photon that no pixel accepts (distance2 = inf, zero power)
+                        const bool real = base + lane < end;
+                        sP[w][0][lane] = real ? ra.x : 1e30f; sP[w][1][lane] = ra.y; sP[w][2][lane] = ra.z;
+                        sP[w][3][lane] = ra.w; sP[w][4][lane] = rb.w; sP[w][5][lane] = rc;
+                        sP[w][6][lane] = real ? rb.x : 0.f; sP[w][7][lane] = real ? rb.y : 0.f; sP[w][8][lane] = real ? rb.z : 0.f;
+                    }
+#else
                     sA[w][lane] = ra; sB[w][lane] = rb; sC[w][lane] = rc;
+#endif
                     __syncwarp();
                     const unsigned nxt = base + 32 + lane;
                     if (nxt < end) { ra = __ldg(sorted.a + nxt); rb = __ldg(sorted.b + nxt); rc = __ldg(sorted.c + nxt); }
+                    else { ra = make_float4(0.f, 0.f, 0.f, 0.f); rb = ra; rc = 0.f; }
                     const unsigned cnt = min(32u, end - base);
                     if (need) {
-#if OPR_GATHER_BRANCHFREE
+#if OPR_GATHER_PACKED
+                        // four photons per trip, two per packed instruction; same operations per photon as the scalar loop below
+                        OPR_PRAGMA(unroll 2)
+                        for (unsigned j = 0; j < cnt; j += 4) {
+                            const ulonglong2 X = *(const ulonglong2*)&sP[w][0][j], Y = *(const ulonglong2*)&sP[w][1][j], Z = *(const ulonglong2*)&sP[w][2][j];
+                            const ulonglong2 DX = *(const ulonglong2*)&sP[w][3][j], DY = *(const ulonglong2*)&sP[w][4][j], DZ = *(const ulonglong2*)&sP[w][5][j];
+                            const ulonglong2 PR = *(const ulonglong2*)&sP[w][6][j], PG = *(const ulonglong2*)&sP[w][7][j], PB = *(const ulonglong2*)&sP[w][8][j];
+                            #pragma unroll
+                            for (int h = 0; h < 2; h++) {
+                                const f32x2 x = h ? X.y : X.x, y = h ? Y.y : Y.x, z = h ? Z.y : Z.x;
+                                const f32x2 dx = sub2(posX2, x), dy = sub2(posY2, y), dz = sub2(posZ2, z);
+                                const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                                const f32x2 nd = fma2(h ? DZ.y : DZ.x, nrmZ2, fma2(h ? DY.y : DY.x, nrmY2, mul2(h ? DX.y : DX.x, nrmX2)));
+                                float e0, e1, d20, d21, nd0, nd1;
+                                upk2(mul2(kexp2, d2), e0, e1); upk2(d2, d20, d21); upk2(nd, nd0, nd1);
+                                const f32x2 wgt = fma2(w12, pk2(exp2f_approx(e0), exp2f_approx(e1)), w02);
+                                float wg0, wg1;
+                                upk2(wgt, wg0, wg1);
+                                wg0 = (d20 <= radius2 && nd0 <= 0.f) ? wg0 : 0.f;
+                                wg1 = (d21 <= radius2 && nd1 <= 0.f) ? wg1 : 0.f;
+                                const f32x2 wsel = pk2(wg0, wg1);
+                                accX2 = fma2(h ? PR.y : PR.x, wsel, accX2); accY2 = fma2(h ? PG.y : PG.x, wsel, accY2); accZ2 = fma2(h ? PB.y : PB.x, wsel, accZ2);
+                            }
+                        }
+#elif OPR_GATHER_BRANCHFREE
                         // No branch per photon: both tests are selects, a rejected photon adds an exact zero.  21 instructions per candidate
                         // for every lane instead of 9 + 12 for the ~55 % that pass the distance test — the same issue count once any lane of
                         // the warp accepts, without the divergence bookkeeping and with four candidates in flight (gather 1.94 -> 1.84 ms).
@@ -310,6 +372,9 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
                 }
             }
         }
+#if OPR_GATHER_PACKED
+        { float lo, hi; upk2(accX2, lo, hi); acc.x = lo + hi; upk2(accY2, lo, hi); acc.y = lo + hi; upk2(accZ2, lo, hi); acc.z = lo + hi; }
+#endif
         sAcc[w][lane][0] = acc.x; sAcc[w][lane][1] = acc.y; sAcc[w][lane][2] = acc.z;
         __syncthreads();
         if (w == 0 && inImage) {
