@@ -230,6 +230,25 @@ OPR_DEV unsigned warp_append(unsigned* counter, bool push)
     return base + __popc(mask & ((1u << lane) - 1));
 }
 
+// Path regeneration of the per-path tail kernels (ppm.cu, vcm.cu): persistent warps pull paths from a queue through a shared cursor;
+// a lane whose path ended takes the next one as soon as `refillIdle` lanes of its warp are idle.  Returns true for a lane that must
+// load path `index`; all 32 lanes call this together.
+OPR_DEV bool tail_refill(unsigned n, unsigned* __restrict__ cursor, bool alive, bool& exhausted, unsigned refillIdle, unsigned& index)
+{   // returns true for a lane that must load path `index`; all 32 lanes call this together
+    const unsigned FULL = 0xffffffffu;
+    const unsigned idle = __ballot_sync(FULL, !alive);
+    bool take = false;
+    if (!exhausted && (idle == FULL || (unsigned)__popc(idle) >= refillIdle)) {
+        const unsigned lane = threadIdx.x & 31, want = __popc(idle);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(cursor, want);
+        base = __shfl_sync(FULL, base, 0);
+        if (!alive) { index = base + __popc(idle & ((1u << lane) - 1)); take = index < n; }
+        if (base + want >= n) exhausted = true;
+    }
+    return take;
+}
+
 } // namespace opr
 
 namespace opr {

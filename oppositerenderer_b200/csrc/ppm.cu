@@ -284,22 +284,6 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_shade_kernel(SceneVi
 // takes the next path as soon as `refillIdle` lanes of its warp are idle, instead of idling until the warp's longest path is done
 // (chains of 1 to 9 specular bounces here, 1 to 4 more Russian-roulette bounces in the photon tail: the fixed assignment left warps
 // running with a quarter of their lanes).
-OPR_DEV bool tail_refill(unsigned n, unsigned* __restrict__ cursor, bool alive, bool& exhausted, unsigned refillIdle, unsigned& index)
-{   // returns true for a lane that must load path `index`; all 32 lanes call this together
-    const unsigned FULL = 0xffffffffu;
-    const unsigned idle = __ballot_sync(FULL, !alive);
-    bool take = false;
-    if (!exhausted && (idle == FULL || (unsigned)__popc(idle) >= refillIdle)) {
-        const unsigned lane = threadIdx.x & 31, want = __popc(idle);
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(cursor, want);
-        base = __shfl_sync(FULL, base, 0);
-        if (!alive) { index = base + __popc(idle & ((1u << lane) - 1)); take = index < n; }
-        if (base + want >= n) exhausted = true;
-    }
-    return take;
-}
-
 template <bool QN>
 __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_tail_kernel(SceneView sc, unsigned w, unsigned rsW, RngBuf rngBuf, HitpointBuf hp,
                                                                         const float4* __restrict__ rayO, const float4* __restrict__ rayD,

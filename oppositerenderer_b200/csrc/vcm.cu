@@ -649,27 +649,36 @@ template <bool QN>
 __global__ void __launch_bounds__(VCM_THREADS) vcm_light_tail_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B, float* __restrict__ output,
                                                                      const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                      const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
-                                                                     unsigned* __restrict__ stats)
+                                                                     unsigned* __restrict__ stats, unsigned* __restrict__ cursor, unsigned refillIdle)
 {
+    const unsigned FULL = 0xffffffffu;
     const unsigned n = *count;
-    unsigned closest = 0, any = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o4 = rayO[i], d4 = rayD[i];
-        const unsigned p = rayPath[i];
-        float3 o = f3(o4), d = f3(d4);
-        for (;;) {
+    unsigned closest = 0, any = 0, p = 0;
+    bool alive = false, exhausted = false;
+    float3 o = f3(0.f), d = f3(0.f, 0.f, 1.f);
+    for (;;) {
+        unsigned i = 0;
+        if (tail_refill(n, cursor, alive, exhausted, refillIdle, i)) {     // path regeneration (common.cuh)
+            p = rayPath[i]; o = f3(rayO[i]); d = f3(rayD[i]); alive = true;
+        }
+        if (!__any_sync(FULL, alive)) break;
+        if (alive) {
             HitRec hit;
             traverse_free<false, QN>(sc, o, d, RAY_LEN_MIN, RT_DEFAULT_MAX, hit);
             closest++;
-            if (hit.prim < 0) break;                                              // VCMLightPass.cu:95-98
-            const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
-            if (kind == OPR_MAT_DIFFUSE_EMITTER) break;                           // DiffuseEmitter.cu:76-79
-            Connection conn; unsigned numConn = 0, connTarget = 0; float3 connOrigin = f3(0.f), newO = f3(0.f), newD = f3(0.f);
-            if (!vcm_light_hit<false>(sc, P, rngBuf, B, output, kind, p, o, d, hit, newO, newD, conn, numConn, connTarget, connOrigin, any)) break;
-            o = newO; d = newD;
+            if (hit.prim < 0) alive = false;                                      // VCMLightPass.cu:95-98
+            else {
+                const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+                if (kind == OPR_MAT_DIFFUSE_EMITTER) alive = false;               // DiffuseEmitter.cu:76-79
+                else {
+                    Connection conn; unsigned numConn = 0, connTarget = 0; float3 connOrigin = f3(0.f), newO = f3(0.f), newD = f3(0.f);
+                    alive = vcm_light_hit<false>(sc, P, rngBuf, B, output, kind, p, o, d, hit, newO, newD, conn, numConn, connTarget, connOrigin, any);
+                    o = newO; d = newD;
+                }
+            }
         }
     }
-    for (int s = 16; s > 0; s >>= 1) { closest += __shfl_xor_sync(0xffffffffu, closest, s); any += __shfl_xor_sync(0xffffffffu, any, s); }
+    for (int s = 16; s > 0; s >>= 1) { closest += __shfl_xor_sync(FULL, closest, s); any += __shfl_xor_sync(FULL, any, s); }
     if ((threadIdx.x & 31) == 0) { if (closest) atomicAdd(stats + STAT_CLOSEST_RAYS, closest); if (any) atomicAdd(stats + STAT_ANY_RAYS, any); }
 }
 
@@ -677,26 +686,33 @@ template <bool QN>
 __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_tail_kernel(SceneView sc, VcmParams P, RngBuf rngBuf, VcmBuffers B,
                                                                       const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                       const unsigned* __restrict__ rayPath, const unsigned* __restrict__ count,
-                                                                      unsigned* __restrict__ stats)
+                                                                      unsigned* __restrict__ stats, unsigned* __restrict__ cursor, unsigned refillIdle)
 {
+    const unsigned FULL = 0xffffffffu;
     const unsigned n = *count;
-    unsigned closest = 0, any = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o4 = rayO[i], d4 = rayD[i];
-        const unsigned p = rayPath[i];
-        float3 o = f3(o4), d = f3(d4);
-        for (;;) {
+    unsigned closest = 0, any = 0, p = 0;
+    bool alive = false, exhausted = false;
+    float3 o = f3(0.f), d = f3(0.f, 0.f, 1.f);
+    for (;;) {
+        unsigned i = 0;
+        if (tail_refill(n, cursor, alive, exhausted, refillIdle, i)) {     // path regeneration (common.cuh)
+            p = rayPath[i]; o = f3(rayO[i]); d = f3(rayD[i]); alive = true;
+        }
+        if (!__any_sync(FULL, alive)) break;
+        if (alive) {
             HitRec hit;
             traverse_free<false, QN>(sc, o, d, RAY_LEN_MIN, RT_DEFAULT_MAX, hit);
             closest++;
-            if (hit.prim < 0) break;                                              // VCMCameraPass.cu:87-90
-            const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
-            unsigned numConn = 0; float3 connOrigin = f3(0.f), newO = f3(0.f), newD = f3(0.f);
-            if (!vcm_camera_hit<false>(sc, P, rngBuf, B, kind, p, o, d, hit, newO, newD, nullptr, numConn, connOrigin, any)) break;
-            o = newO; d = newD;
+            if (hit.prim < 0) alive = false;                                      // VCMCameraPass.cu:87-90
+            else {
+                const int kind = sc.materials[prim_material(sc, hit.prim)].kind;
+                unsigned numConn = 0; float3 connOrigin = f3(0.f), newO = f3(0.f), newD = f3(0.f);
+                alive = vcm_camera_hit<false>(sc, P, rngBuf, B, kind, p, o, d, hit, newO, newD, nullptr, numConn, connOrigin, any);
+                o = newO; d = newD;
+            }
         }
     }
-    for (int s = 16; s > 0; s >>= 1) { closest += __shfl_xor_sync(0xffffffffu, closest, s); any += __shfl_xor_sync(0xffffffffu, any, s); }
+    for (int s = 16; s > 0; s >>= 1) { closest += __shfl_xor_sync(FULL, closest, s); any += __shfl_xor_sync(FULL, any, s); }
     if ((threadIdx.x & 31) == 0) { if (closest) atomicAdd(stats + STAT_CLOSEST_RAYS, closest); if (any) atomicAdd(stats + STAT_ANY_RAYS, any); }
 }
 
@@ -837,8 +853,9 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         }
         if (waves <= P.maxPathLen) {
             auto kt = (qnodeMask & QN_VCM_TAILS) ? vcm_light_tail_kernel<true> : vcm_light_tail_kernel<false>;
+            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_TAIL_FETCH, 0, sizeof(unsigned), stream));
             kt<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, output, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur,
-                                                                       q.counters + CTR_STATS);
+                                                                       q.counters + CTR_STATS, q.counters + CTR_TAIL_FETCH, 8u);
             ++launches;
         }
     };
@@ -880,7 +897,9 @@ void Renderer::renderVCM(unsigned long long, unsigned localIterationNumber, floa
         }
         if (waves <= P.maxPathLen) {
             auto kt = (qnodeMask & QN_VCM_TAILS) ? vcm_camera_tail_kernel<true> : vcm_camera_tail_kernel<false>;
-            kt<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur, q.counters + CTR_STATS);
+            OPR_CUDA_CHECK(cudaMemsetAsync(q.counters + CTR_TAIL_FETCH, 0, sizeof(unsigned), stream));
+            kt<<<numSMs() * 4, VCM_THREADS, 0, stream>>>(sc, P, rng, B, q.rayO[cur], q.rayD[cur], q.rayPath[cur], q.counters + cur, q.counters + CTR_STATS,
+                                                                        q.counters + CTR_TAIL_FETCH, 8u);
             ++launches;
         }
         joinConnections();
