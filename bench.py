@@ -484,7 +484,7 @@ def main():
         line = {"metric": METRIC, "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "iterations_per_s": total_steps / (ms * 1e-3), "rays_per_iteration": rays / total_steps,
-                "photons_stored_per_iteration": (st["photons_stored"] - st0["photons_stored"]) / max(1, args.steps),
+                "photons_stored_per_iteration": (st["photons_stored"] - st0["photons_stored"]) / max(1, args.steps * nwin),
                 "windows_ms": windows_ms, "repeats": nwin,
                 "e2e": {"value": rays_e2e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.opr_request_details),
                         "d2h_bytes_per_step": W * H * 12, "iterations_per_s": total_steps / e2e_s,
