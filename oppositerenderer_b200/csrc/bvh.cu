@@ -228,19 +228,33 @@ __global__ void bvh_leaf_tri_kernel(const int* __restrict__ leafPrim, int n, con
     dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// ---- quantised copy of the wide nodes: the incoherent launches traverse it (scene.cuh load_node<true>) -------------------------
-// 64 bytes = 16 words: [0,1] lo.x of children 0..3 as 16-bit values, [2,3] hi.x, [4,5] lo.y, [6,7] hi.y, [8,9] lo.z,
-// [10,11] hi.z, [12..15] child refs.  A value is 0x8000 | q with q in [0, 32767] on the grid origin + q * extent / 32768;
-// lo is rounded down and hi up, each by one further cell, which covers the fp32 error of the decode (2^-23 of the extent).
-__device__ __forceinline__ unsigned quant_lo(float v, float origin, float invCell)
+// ---- final node formats ---------------------------------------------------------------------------------------------------------
+// Both traversal formats store a child box as CENTRE and HALF-EXTENT per axis, not as lo / hi planes: the slab test then is
+//   tc = c * (1/d) - o/d,  t_near = tc - h * |1/d|,  t_far = tc + h * |1/d|
+// — three FFMAs per axis and child on the FP32 pipe (|x| and -x are operand modifiers) instead of two FFMAs and a min + a max on the ALU
+// pipe, which runs at half rate and is what bounds the traversal kernels (ncu: ALU pipe 65 % active, FMA pipe 19 %; profiles/).
+// The boxes stay conservative: h is rounded up so that [c - h, c + h] contains [lo, hi].
+//
+// Quantised copy: 64 bytes = 16 words: [0,1] centre.x of children 0..3 as 16-bit values, [2,3] half.x, [4,5] centre.y, [6,7] half.y,
+// [8,9] centre.z, [10,11] half.z, [12..15] child refs.  A value is 0x8000 | q with q in [0, 32767] in units of extent / 32768 on the
+// scene grid.  lo is rounded down and hi up, each by one further cell (covers the fp32 error of the decode and of the per-ray
+// constants, 2^-22 of the extent), then widened by at most one more cell so that hi - lo is even and the centre lies on the grid.
+__device__ __forceinline__ int quant_lo(float v, float origin, float invCell)
 {
-    const float q = floorf((v - origin) * invCell) - 1.0f;
-    return 0x8000u | (unsigned)fminf(fmaxf(q, 0.0f), 32767.0f);
+    return (int)fminf(fmaxf(floorf((v - origin) * invCell) - 1.0f, 0.0f), 32767.0f);
 }
-__device__ __forceinline__ unsigned quant_hi(float v, float origin, float invCell)
+__device__ __forceinline__ int quant_hi(float v, float origin, float invCell)
 {
-    const float q = ceilf((v - origin) * invCell) + 1.0f;
-    return 0x8000u | (unsigned)fminf(fmaxf(q, 0.0f), 32767.0f);
+    return (int)fminf(fmaxf(ceilf((v - origin) * invCell) + 1.0f, 0.0f), 32767.0f);
+}
+__device__ __forceinline__ void quant_box(float lo, float hi, float origin, float invCell, unsigned& c, unsigned& h)
+{
+    const float INF = __int_as_float(0x7f800000);
+    if (!(lo < INF)) { c = 0x8000u; h = 0x8000u; return; }       // absent child: recognised by its ref in the traversal
+    int ql = quant_lo(lo, origin, invCell), qh = quant_hi(hi, origin, invCell);
+    if ((qh - ql) & 1) { if (qh < 32767) qh++; else ql--; }      // the grid frames the root box with a margin of 8 cells: ql >= 1 here
+    c = 0x8000u | (unsigned)((ql + qh) >> 1);
+    h = 0x8000u | (unsigned)((qh - ql) >> 1);
 }
 __global__ void bvh_quantize_kernel(const float4* __restrict__ wide, int numWide, float3 origin, float3 invCell, uint4* __restrict__ out)
 {
@@ -248,17 +262,40 @@ __global__ void bvh_quantize_kernel(const float4* __restrict__ wide, int numWide
     if (i >= numWide) return;
     const float4* N = wide + 8 * (size_t)i;
     const float4 lox = N[0], hix = N[1], loy = N[2], hiy = N[3], loz = N[4], hiz = N[5], rf = N[6];
-    const float INF = __int_as_float(0x7f800000);
-    auto lo2 = [&](float a, float b, float o, float ic) { return (a < INF ? quant_lo(a, o, ic) : 0x8000u) | ((b < INF ? quant_lo(b, o, ic) : 0x8000u) << 16); };
-    auto hi2 = [&](float a, float b, float o, float ic) { return (a < INF ? quant_hi(a, o, ic) : 0x8000u) | ((b < INF ? quant_hi(b, o, ic) : 0x8000u) << 16); };
+    auto axis = [&](const float4& lo, const float4& hi, float o, float ic) {
+        unsigned c[4], h[4];
+        quant_box(lo.x, hi.x, o, ic, c[0], h[0]); quant_box(lo.y, hi.y, o, ic, c[1], h[1]);
+        quant_box(lo.z, hi.z, o, ic, c[2], h[2]); quant_box(lo.w, hi.w, o, ic, c[3], h[3]);
+        return make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+    };
     uint4* Q = out + 4 * (size_t)i;
-    Q[0] = make_uint4(lo2(lox.x, lox.y, origin.x, invCell.x), lo2(lox.z, lox.w, origin.x, invCell.x),
-                      hi2(hix.x, hix.y, origin.x, invCell.x), hi2(hix.z, hix.w, origin.x, invCell.x));
-    Q[1] = make_uint4(lo2(loy.x, loy.y, origin.y, invCell.y), lo2(loy.z, loy.w, origin.y, invCell.y),
-                      hi2(hiy.x, hiy.y, origin.y, invCell.y), hi2(hiy.z, hiy.w, origin.y, invCell.y));
-    Q[2] = make_uint4(lo2(loz.x, loz.y, origin.z, invCell.z), lo2(loz.z, loz.w, origin.z, invCell.z),
-                      hi2(hiz.x, hiz.y, origin.z, invCell.z), hi2(hiz.z, hiz.w, origin.z, invCell.z));
+    Q[0] = axis(lox, hix, origin.x, invCell.x);
+    Q[1] = axis(loy, hiy, origin.y, invCell.y);
+    Q[2] = axis(loz, hiz, origin.z, invCell.z);
     Q[3] = make_uint4(__float_as_uint(rf.x), __float_as_uint(rf.y), __float_as_uint(rf.z), __float_as_uint(rf.w));
+}
+
+// fp32 nodes, in place: (lo4, hi4) per axis -> (centre4, half4).  An absent child (lo = +inf) becomes c = 0, h = -inf: t_near = +inf,
+// t_far = -inf for every ray (|1/d| is finite and non-zero: safe_inverse_direction).
+__device__ __forceinline__ void centre_half(float lo, float hi, float& c, float& h)
+{
+    const float INF = __int_as_float(0x7f800000);
+    if (!(lo < INF)) { c = 0.f; h = -INF; return; }
+    c = 0.5f * lo + 0.5f * hi;
+    const float e = fmaxf(hi - c, c - lo);                       // each difference is within half an ulp of the true distance to c
+    h = e + (fabsf(c) + fabsf(e)) * 2.4e-7f + 1e-37f;            // two ulps of the larger operand: covers the rounding of c, e and of c +- h
+}
+__global__ void bvh_centre_half_kernel(float4* __restrict__ wide, int numWide)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numWide) return;
+    float4* N = wide + 8 * (size_t)i;
+    for (int a = 0; a < 3; a++) {
+        const float4 lo = N[2 * a], hi = N[2 * a + 1];
+        float4 c, h;
+        centre_half(lo.x, hi.x, c.x, h.x); centre_half(lo.y, hi.y, c.y, h.y); centre_half(lo.z, hi.z, c.z, h.z); centre_half(lo.w, hi.w, c.w, h.w);
+        N[2 * a] = c; N[2 * a + 1] = h;
+    }
 }
 
 // ---- host driver -----------------------------------------------------------------------------------------------------
@@ -387,6 +424,7 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
         uint4* qnodes = nullptr;
         devAlloc((void**)&qnodes, 64 * (size_t)numWide); owned.push_back(qnodes);
         bvh_quantize_kernel<<<(numWide + 255) / 256, 256, 0, st>>>(nodes, numWide, qo, f3(32768.0f / qe.x, 32768.0f / qe.y, 32768.0f / qe.z), qnodes);
+        bvh_centre_half_kernel<<<(numWide + 255) / 256, 256, 0, st>>>(nodes, numWide);      // after the quantiser, which reads lo / hi
         OPR_CUDA_CHECK(cudaStreamSynchronize(st));
         OPR_CUDA_CHECK(cudaGetLastError());
         view.qnodes = (const float4*)qnodes; view.qOrigin = qo; view.qExtent = qe;

@@ -2,7 +2,7 @@
 // OptiX's acceleration structure + rtTrace.
 //
 // HBM layout
-//   nodes      8 x float4 per 4-wide node (128 B = one line): lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4] spare
+//   nodes      8 x float4 per 4-wide node (128 B = one line): centre.x[4] half.x[4] centre.y[4] half.y[4] centre.z[4] half.z[4] refs[4] spare
 //              child ref >= 0: node index; < 0: leaf, ~ref = (firstSlot << 4) | ((count-1) << 1) | mixed; empty: box +inf
 //   leafTri    4 x float4 per leaf slot (48-byte triangle record padded to 64 B; leaf = contiguous run of <= 8 slots)
 //   leafPrim   int per leaf slot: (primIndex << 2) | primType, read once per ray to name the hit
@@ -142,17 +142,28 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
 // The steps are macros over the per-lane variables (o, d, idir, ood, tmin, hit, stack, sp, cur) because the persistent
 // wavefront kernel in trace.cu runs the same steps around its own ray fetch.
 
-// Slab test of one child: entry distance, or +inf when the ray misses the box within (tmin, hit.t).
-// Fused form plane * idir + ood with ood = -o * idir (one FFMA per plane instead of FADD + FMUL).  Its rounding error is
+// Slab test of one child: entry distance, or +inf when the ray misses the box within (tmin, hit.t).  A child box is stored as
+// centre c and half-extent h per axis (bvh.cu): tc = c * idir + ood, t_near = tc - h |idir|, t_far = tc + h |idir| — three FFMAs per
+// axis on the FP32 pipe, no per-axis min / max on the half-rate ALU pipe that bounds these kernels (|x|, -x are operand modifiers).
+// Fused form c * idir + ood with ood = -o * idir (one FFMA instead of FADD + FMUL).  Its rounding error is
 // <= 2^-24 |o| |idir| in t, i.e. 6e-8 * scale in space, against a box inflation of 4e-6 * scale (scene.cu addPrim): the
 // conservatively inflated boxes still never cull a primitive the exact triangle test would accept.
-#define OPR_SLAB(LX, HX, LY, HY, LZ, HZ, TOUT)                                                                     \
+#define OPR_SLAB(QN, CX, HX, CY, HY, CZ, HZ, TOUT)                                                                 \
     {                                                                                                              \
-        const float ax = fmaf((LX), idir.x, ood.x), bx = fmaf((HX), idir.x, ood.x);                                \
-        const float ay = fmaf((LY), idir.y, ood.y), by = fmaf((HY), idir.y, ood.y);                                \
-        const float az = fmaf((LZ), idir.z, ood.z), bz = fmaf((HZ), idir.z, ood.z);                                \
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));                   \
-        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t));                  \
+        float nx, fx, ny, fy, nz, fz;                                                                              \
+        if (QN) {   /* decoded values are 1 + q / 32768: tc carries the +-|idir| of the half-extent's offset */     \
+            const float tx = fmaf((CX), idir.x, ood.x), ty = fmaf((CY), idir.y, ood.y), tz = fmaf((CZ), idir.z, ood.z); \
+            nx = fmaf((HX), -fabsf(idir.x), tx + fabsf(idir.x)); fx = fmaf((HX), fabsf(idir.x), tx - fabsf(idir.x)); \
+            ny = fmaf((HY), -fabsf(idir.y), ty + fabsf(idir.y)); fy = fmaf((HY), fabsf(idir.y), ty - fabsf(idir.y)); \
+            nz = fmaf((HZ), -fabsf(idir.z), tz + fabsf(idir.z)); fz = fmaf((HZ), fabsf(idir.z), tz - fabsf(idir.z)); \
+        } else {                                                                                                   \
+            const float tx = fmaf((CX), idir.x, ood.x), ty = fmaf((CY), idir.y, ood.y), tz = fmaf((CZ), idir.z, ood.z); \
+            nx = fmaf((HX), -fabsf(idir.x), tx); fx = fmaf((HX), fabsf(idir.x), tx);                               \
+            ny = fmaf((HY), -fabsf(idir.y), ty); fy = fmaf((HY), fabsf(idir.y), ty);                               \
+            nz = fmaf((HZ), -fabsf(idir.z), tz); fz = fmaf((HZ), fabsf(idir.z), tz);                               \
+        }                                                                                                          \
+        const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));                                                    \
+        const float tf = fminf(fminf(fx, fy), fminf(fz, hit.t));                                                   \
         TOUT = tn <= tf ? tn : INF_;                                                                               \
     }
 // The traversal stack of a lane: entries are (subtree ref, entry distance bits).  The default keeps it in local memory
@@ -169,9 +180,9 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
         int2 e_; --sp; OPR_STACK_LD(e_, sp)                                                                        \
         if ((ANYHIT) || __int_as_float(e_.y) < hit.t) { cur = e_.x; break; }                                       \
     }
-// The four child boxes (lox .. hiz) and child refs (r0 .. r3) of node `cur`, in one of two formats chosen per launch (QN):
+// The four child boxes (centres cX cY cZ, half-extents hX hY hZ) and child refs (r0 .. r3) of node `cur`, in one of two formats chosen per launch (QN):
 //   QN = false  128-byte fp32 nodes (four 256-bit loads);
-//   QN = true   64-byte quantised nodes (two 256-bit loads): child planes as 15-bit values on a scene grid, each decoded by ONE byte
+//   QN = true   64-byte quantised nodes (two 256-bit loads): box centres and half-extents as 15-bit values on a scene grid, each decoded by ONE byte
 //               permute into a float in [1, 2), so the slab test stays one FFMA per plane with per-ray constants folded in
 //               (ray_slab_setup).  Boxes are rounded outwards by a cell (bvh.cu), so every primitive the fp32 nodes reach is reached.
 // Measured (1.1 M triangles, profiles/): incoherent rays (photon bounces, tails) 11 % faster on the quantised nodes — half the L1
@@ -181,25 +192,25 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
 #define OPR_QHI(W) __uint_as_float(__byte_perm(__float_as_uint(W), 0x3F800000u, 0x7324u))
 #define OPR_Q4(A, B) make_float4(OPR_QLO(A), OPR_QHI(A), OPR_QLO(B), OPR_QHI(B))
 template <bool QN>
-OPR_DEV void load_node(const SceneView& sc, int cur, float4& lox, float4& hix, float4& loy, float4& hiy, float4& loz, float4& hiz, int& r0, int& r1, int& r2, int& r3)
+OPR_DEV void load_node(const SceneView& sc, int cur, float4& cX, float4& hX, float4& cY, float4& hY, float4& cZ, float4& hZ, int& r0, int& r1, int& r2, int& r3)
 {
     float4 rf;
     if (QN) {
         const float4* N_ = sc.qnodes + 4 * (size_t)cur;
         const Float8 na_ = ldg256(N_), nb_ = ldg256(N_ + 2);
-        lox = OPR_Q4(na_.lo.x, na_.lo.y); hix = OPR_Q4(na_.lo.z, na_.lo.w);
-        loy = OPR_Q4(na_.hi.x, na_.hi.y); hiy = OPR_Q4(na_.hi.z, na_.hi.w);
-        loz = OPR_Q4(nb_.lo.x, nb_.lo.y); hiz = OPR_Q4(nb_.lo.z, nb_.lo.w); rf = nb_.hi;
+        cX = OPR_Q4(na_.lo.x, na_.lo.y); hX = OPR_Q4(na_.lo.z, na_.lo.w);
+        cY = OPR_Q4(na_.hi.x, na_.hi.y); hY = OPR_Q4(na_.hi.z, na_.hi.w);
+        cZ = OPR_Q4(nb_.lo.x, nb_.lo.y); hZ = OPR_Q4(nb_.lo.z, nb_.lo.w); rf = nb_.hi;
     } else {
         const float4* N_ = sc.nodes + 8 * (size_t)cur;
         const Float8 nx_ = ldg256(N_), ny_ = ldg256(N_ + 2), nz_ = ldg256(N_ + 4), nr_ = ldg256(N_ + 6);
-        lox = nx_.lo; hix = nx_.hi; loy = ny_.lo; hiy = ny_.hi; loz = nz_.lo; hiz = nz_.hi; rf = nr_.lo;
+        cX = nx_.lo; hX = nx_.hi; cY = ny_.lo; hY = ny_.hi; cZ = nz_.lo; hZ = nz_.hi; rf = nr_.lo;
     }
     r0 = __float_as_int(rf.x); r1 = __float_as_int(rf.y); r2 = __float_as_int(rf.z); r3 = __float_as_int(rf.w);
 }
 #define OPR_NODE_LOAD(QN)                                                                                          \
-        float4 lox, hix, loy, hiy, loz, hiz; int r0, r1, r2, r3;                                                   \
-        load_node<QN>(sc, cur, lox, hix, loy, hiy, loz, hiz, r0, r1, r2, r3);
+        float4 cX, hX, cY, hY, cZ, hZ; int r0, r1, r2, r3;                                                   \
+        load_node<QN>(sc, cur, cX, hX, cY, hY, cZ, hZ, r0, r1, r2, r3);
 // a quantised absent child has no box on the grid that every ray misses: recognise it by its ref (child 0 always exists)
 #define OPR_NODE_EMPTY(QN)                                                                                         \
         if (QN) {                                                                                                  \
@@ -224,10 +235,10 @@ OPR_DEV void load_node(const SceneView& sc, int cur, float4& lox, float4& hix, f
         const float INF_ = __int_as_float(0x7f800000);                                                             \
         OPR_NODE_LOAD(QN)                                                                                          \
         float t0, t1, t2, t3;                                                                                      \
-        OPR_SLAB(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, t0)                                                     \
-        OPR_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, t1)                                                     \
-        OPR_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, t2)                                                     \
-        OPR_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, t3)                                                     \
+        OPR_SLAB(QN, cX.x, hX.x, cY.x, hY.x, cZ.x, hZ.x, t0)                                                 \
+        OPR_SLAB(QN, cX.y, hX.y, cY.y, hY.y, cZ.y, hZ.y, t1)                                                 \
+        OPR_SLAB(QN, cX.z, hX.z, cY.z, hY.z, cZ.z, hZ.z, t2)                                                 \
+        OPR_SLAB(QN, cX.w, hX.w, cY.w, hY.w, cZ.w, hZ.w, t3)                                                 \
         OPR_NODE_EMPTY(QN)                                                                                         \
         if (ANYHIT) {          /* any order will do for an occlusion query: skip the sorting network */             \
             if (t1 < INF_) { if (t0 < INF_) OPR_STACK_PUSH(r1, 0) else { t0 = t1; r0 = r1; } }                         \

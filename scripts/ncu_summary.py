@@ -13,7 +13,12 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit_registers", "sm__inst_executed.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
         "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct",
         "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
-        "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct"]
+        "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "smsp__inst_executed.sum",
+        "launch__occupancy_limit_shared_mem"]
 
 
 def launches(path, out):
@@ -75,7 +80,7 @@ def traffic_one(path, tag, out):
     for vals in rows[2:]:
         kn = vals[hdr.index("Kernel Name")].split("(")[0]
         key = names.get(kn)
-        if kn == "trace_closest_kernel":
+        if kn.startswith("trace_closest_kernel") or kn.startswith("void trace_closest_kernel"):
             key = {0: "trace.camera0", 1: "trace.photon0"}.get(seen_trace)
             seen_trace += 1
         if not key or key in out:
@@ -95,6 +100,9 @@ def traffic_one(path, tag, out):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) < 3 or sys.argv[1].startswith("-"):      # `--help` used to be taken for a tag and wrote profiles/--help_ncu_summary.txt
+        print(__doc__ + "\n       python scripts/ncu_summary.py traffic <summary file name> report.ncu-rep [...]")
+        sys.exit(0 if len(sys.argv) > 1 and sys.argv[1] in ("-h", "--help") else 2)
     if sys.argv[1] == "traffic":
         traffic(sys.argv[3:], sys.argv[2])     # traffic <summary file name> report.ncu-rep [...]
         sys.exit(0)
