@@ -137,3 +137,18 @@ def test_opr_render_tool_runs_the_driver_loop(product, tmp_path):
     data = np.frombuffer(open(bmp, "rb").read()[54:], np.uint8).reshape(40, 48, 3)
     ref = _display_reference(a, 7.0, 2.2)
     assert np.abs(data.astype(int) - ref.astype(int)).max() <= 1
+
+
+@pytest.mark.gpu
+def test_opr_render_tool_distributed_over_one_gpu_equals_standalone(product, tmp_path):
+    """--gpus 1 runs the Client/Server arrangement (DistributedRenderManager -> opr_group_*: hand-out loop, worker thread, reduce) on one
+    GPU: same iterations, same radii (closed form == recurrence in float), same seed -> the same sum buffer as the standalone loop."""
+    exe = os.path.join(ROOT, "oppositerenderer_b200", "csrc", "opr_render")
+    raws = []
+    for extra in ([], ["--gpus", "1"]):
+        raw = str(tmp_path / ("o%d.f32" % len(raws)))
+        out = subprocess.run([exe, "--scene", "Cornell", "--method", "ppm", "--size", "48x40", "--iterations", "6", "--out", str(tmp_path / "o.bmp"), "--raw", raw] + extra,
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr
+        raws.append(np.fromfile(raw, np.float32))
+    assert raws[0].sum() > 0 and np.allclose(raws[0], raws[1], rtol=1e-5, atol=1e-6 * float(raws[0].max()))
