@@ -180,6 +180,13 @@ constexpr int GATHER_WARPS = GATHER_THREADS / 32;
 #ifndef OPR_GATHER_PACKED
 #define OPR_GATHER_PACKED 1
 #endif
+// w if (d2 <= r2 and nd <= 0) else 0, as a chained predicate and ONE select (the compiler emits a select per condition)
+OPR_DEV float keep_if_both(float w, float d2, float r2, float nd)
+{
+    float r;
+    asm("{ .reg .pred p;\n\t setp.le.f32 p, %2, %3;\n\t setp.le.and.f32 p, %4, 0f00000000, p;\n\t selp.f32 %0, %1, 0f00000000, p; }" : "=f"(r) : "f"(w), "f"(d2), "f"(r2), "f"(nd));
+    return r;
+}
 typedef unsigned long long f32x2;
 OPR_DEV f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 OPR_DEV void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -328,8 +335,8 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
                                 const f32x2 wgt = fma2(w12, pk2(exp2f_approx(e0), exp2f_approx(e1)), w02);
                                 float wg0, wg1;
                                 upk2(wgt, wg0, wg1);
-                                wg0 = (d20 <= radius2 && nd0 <= 0.f) ? wg0 : 0.f;
-                                wg1 = (d21 <= radius2 && nd1 <= 0.f) ? wg1 : 0.f;
+                                wg0 = keep_if_both(wg0, d20, radius2, nd0);
+                                wg1 = keep_if_both(wg1, d21, radius2, nd1);
                                 const f32x2 wsel = pk2(wg0, wg1);
                                 accX2 = fma2(h ? PR.y : PR.x, wsel, accX2); accY2 = fma2(h ? PG.y : PG.x, wsel, accY2); accZ2 = fma2(h ? PB.y : PB.x, wsel, accZ2);
                             }

@@ -80,9 +80,15 @@ def traffic_one(path, tag, out):
     for vals in rows[2:]:
         kn = vals[hdr.index("Kernel Name")].split("(")[0]
         key = names.get(kn)
-        if kn.startswith("trace_closest_kernel") or kn.startswith("void trace_closest_kernel"):
-            key = {0: "trace.camera0", 1: "trace.photon0"}.get(seen_trace)
-            seen_trace += 1
+        if "trace_shadow_queue_kernel" in kn:
+            key = "trace.shadow"
+        if "trace_closest_kernel" in kn:
+            # the node format is a template argument: <0> = fp32 nodes (primary rays of an iteration), <1> = quantised nodes (photon bounces);
+            # the first <1> launch after a <0> launch is photon bounce 0 of the same iteration
+            if "<0>" in kn or "(bool)0" in kn:
+                key, seen_trace = "trace.camera0", 1
+            elif seen_trace == 1:
+                key, seen_trace = "trace.photon0", 2
         if not key or key in out:
             continue
         rd, wr = float(vals[hdr.index("dram__bytes_read.sum")]), float(vals[hdr.index("dram__bytes_write.sum")])
