@@ -150,7 +150,7 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
             }
         } else if (n == "photons" || n == "sorted_photons") {
             const bool srt = n == "sorted_photons";
-            const size_t cnt = srt ? R.grid.numValid : P * MAX_PHOTON_DEPOSITS;
+            const size_t cnt = srt ? R.latestGrid().numValid : P * MAX_PHOTON_DEPOSITS;
             need(cnt * 36);
             const PhotonBuf& pb = srt ? R.sorted : R.photons;
             auto a = download(pb.a, cnt, st); auto b = download(pb.b, cnt, st); auto c = download(pb.c, cnt, st);
@@ -167,8 +167,9 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
             OPR_CUDA_CHECK(cudaMemcpyAsync(dst, R.sortedKeys, P * MAX_PHOTON_DEPOSITS * 4, cudaMemcpyDeviceToHost, st));
             OPR_CUDA_CHECK(cudaStreamSynchronize(st));
         } else if (n == "offsets") {
-            need(((size_t)R.grid.numCells + 1) * 4);
-            OPR_CUDA_CHECK(cudaMemcpyAsync(dst, R.gridHist, ((size_t)R.grid.numCells + 1) * 4, cudaMemcpyDeviceToHost, st));
+            const size_t nc = R.latestGrid().numCells;
+            need((nc + 1) * 4);
+            OPR_CUDA_CHECK(cudaMemcpyAsync(dst, R.gridHist, (nc + 1) * 4, cudaMemcpyDeviceToHost, st));
             OPR_CUDA_CHECK(cudaStreamSynchronize(st));
         } else if (n == "indirect" || n == "direct") {
             need(px * 12);
@@ -183,8 +184,9 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
         } else if (n == "grid") {
             need(32);
             float* o = (float*)dst; unsigned* u = (unsigned*)dst;
-            o[0] = R.grid.cellSize; u[1] = R.grid.gridSize.x; u[2] = R.grid.gridSize.y; u[3] = R.grid.gridSize.z;
-            o[4] = R.grid.origo.x; o[5] = R.grid.origo.y; o[6] = R.grid.origo.z; u[7] = R.grid.numValid;
+            const GridParams G = R.latestGrid();
+            o[0] = G.cellSize; u[1] = G.gridSize.x; u[2] = G.gridSize.y; u[3] = G.gridSize.z;
+            o[4] = G.origo.x; o[5] = G.origo.y; o[6] = G.origo.z; u[7] = G.numValid;
         } else if (n == "photon_path_lengths") {
             need(P * 4);
             auto s = download(R.phState, P, st);
@@ -333,14 +335,16 @@ int opr_build_photon_grid(const float* photonsAoS, uint32_t n, float* sortedPhot
         origo3[0] = g.origo.x; origo3[1] = g.origo.y; origo3[2] = g.origo.z; *numValid = nv;
         if (!ok) { g_lastError = "Too many cells in SpatialHash.cu, over defined PHOTON_GRID_MAX_SIZE."; return 2; }
         OPR_CUDA_CHECK(cudaMemset(hist.p, 0, ((size_t)g.numCells + 2) * 4));
-        launch_grid_keys(pb, state.as<unsigned>(), nPad, g, k0.as<unsigned>(), hist.as<unsigned>(), lc);
+        DevBuf gDev(sizeof(GridParams));
+        OPR_CUDA_CHECK(cudaMemcpy(gDev.p, &g, sizeof(GridParams), cudaMemcpyHostToDevice));
+        launch_grid_keys(pb, state.as<unsigned>(), nPad, gDev.as<GridParams>(), k0.as<unsigned>(), hist.as<unsigned>(), lc);
         int bits = 1; while ((1ull << bits) <= (unsigned long long)g.numCells + 1) bits++;
         bool flipped = radix_sort_pairs<unsigned>(k0.as<unsigned>(), v0.as<unsigned>(), k1.as<unsigned>(), v1.as<unsigned>(), nPad, bits,
                                                   sortTmp.as<unsigned>(), true, st);
         exclusive_scan_u32(hist.as<unsigned>(), hist.as<unsigned>(), g.numCells + 1, scanTmp.as<unsigned>(), st);
         const unsigned* sk = flipped ? k1.as<unsigned>() : k0.as<unsigned>();
         const unsigned* sv = flipped ? v1.as<unsigned>() : v0.as<unsigned>();
-        launch_photon_reorder(pb, sv, nv, sorted, lc);
+        launch_photon_reorder(pb, sv, nv, gDev.as<GridParams>(), sorted, lc);
         photons_soa_to_aos_kernel<<<numSMs() * 4, 256>>>(sorted, nv, dAos.as<float>());
         OPR_CUDA_CHECK(cudaDeviceSynchronize());
         OPR_CUDA_CHECK(cudaGetLastError());
@@ -382,7 +386,9 @@ int opr_gather(uint32_t numPixels, const float* hitpointsAoS, uint32_t numPhoton
         OPR_CUDA_CHECK(cudaMemcpy(dOff.p, offsets, ((size_t)g.numCells + 1) * 4, cudaMemcpyHostToDevice));
         hitpoints_aos_to_soa_kernel<<<numSMs() * 4, 256>>>(dHp.as<float>(), numPixels, hp);
         if (numPhotons) photons_aos_to_soa_kernel<<<numSMs() * 4, 256>>>(dPh.as<float>(), numPhotons, pb, state.as<unsigned>());
-        launch_gather(hp, numPixels, 0, 0, pb, dOff.as<unsigned>(), g, ppmRadius, ppmRadius * ppmRadius, emittedPhotons, dOut.as<float>(), dCounter.as<unsigned>(), lc);
+        DevBuf gDev(sizeof(GridParams));
+        OPR_CUDA_CHECK(cudaMemcpy(gDev.p, &g, sizeof(GridParams), cudaMemcpyHostToDevice));
+        launch_gather(hp, numPixels, 0, 0, pb, dOff.as<unsigned>(), gDev.as<GridParams>(), ppmRadius, ppmRadius * ppmRadius, emittedPhotons, dOut.as<float>(), dCounter.as<unsigned>(), lc);
         OPR_CUDA_CHECK(cudaDeviceSynchronize());
         OPR_CUDA_CHECK(cudaGetLastError());
         OPR_CUDA_CHECK(cudaMemcpy(indirectOut, dOut.p, (size_t)numPixels * 12, cudaMemcpyDeviceToHost));

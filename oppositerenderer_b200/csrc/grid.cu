@@ -101,9 +101,10 @@ bool compute_grid_params(const float lo[3], const float hi[3], GridParams& g)
 }
 
 // ---- keys + histogram: calculateHashCellsKernel :152-173, getPhotonGridIndex(1D) ppm/PhotonGrid.h:19-28 ---
-__global__ void __launch_bounds__(256) grid_keys_hist_kernel(PhotonBuf photons, const unsigned* __restrict__ phState, unsigned numSlots, GridParams g,
-                                                             unsigned* __restrict__ keys, unsigned* __restrict__ hist)
+__global__ void __launch_bounds__(256) grid_keys_hist_kernel(PhotonBuf photons, const unsigned* __restrict__ phState, unsigned numSlots,
+                                                             const GridParams* __restrict__ gp, unsigned* __restrict__ keys, unsigned* __restrict__ hist)
 {
+    const GridParams g = *gp;       // written by the host function that precedes this kernel in the stream (renderer.cu)
     const float invCell = 1.f / g.cellSize;
     const unsigned invalidHashCell = g.numCells + 1;
     for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < numSlots; s += gridDim.x * blockDim.x) {
@@ -125,26 +126,27 @@ __global__ void __launch_bounds__(256) grid_keys_hist_kernel(PhotonBuf photons, 
     }
 }
 
-void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, GridParams g, unsigned* keys, unsigned* hist, LaunchCtx lc)
+void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, const GridParams* g, unsigned* keys, unsigned* hist, LaunchCtx lc)
 {
     int blocks = (int)std::min<unsigned>((numSlots + 255) / 256, numSMs() * 16);
     grid_keys_hist_kernel<<<blocks, 256, 0, lc.st>>>(photons, phState, numSlots, g, keys, hist);
     ++*lc.launches;
 }
 
-__global__ void __launch_bounds__(256) photon_reorder_kernel(PhotonBuf src, const unsigned* __restrict__ sortedSlots, unsigned numValid, PhotonBuf dst)
+__global__ void __launch_bounds__(256) photon_reorder_kernel(PhotonBuf src, const unsigned* __restrict__ sortedSlots, const GridParams* __restrict__ gp, PhotonBuf dst)
 {
+    const unsigned numValid = gp->numValid;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < numValid; i += gridDim.x * blockDim.x) {
         const unsigned s = sortedSlots[i];
         dst.a[i] = src.a[s]; dst.b[i] = src.b[s]; dst.c[i] = src.c[s];
     }
 }
 
-void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned numValid, const PhotonBuf& dst, LaunchCtx lc)
+void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned maxValid, const GridParams* g, const PhotonBuf& dst, LaunchCtx lc)
 {
-    if (!numValid) return;
-    int blocks = (int)std::min<unsigned>((numValid + 255) / 256, numSMs() * 16);
-    photon_reorder_kernel<<<blocks, 256, 0, lc.st>>>(src, sortedSlots, numValid, dst);
+    if (!maxValid) return;
+    int blocks = (int)std::min<unsigned>((maxValid + 255) / 256, numSMs() * 16);
+    photon_reorder_kernel<<<blocks, 256, 0, lc.st>>>(src, sortedSlots, g, dst);
     ++*lc.launches;
 }
 
@@ -197,7 +199,7 @@ OPR_DEV f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" :
 // 61 registers: 8 CTAs per SM stay resident, which lets the block scheduler interleave the gather with the path passes of the next
 // iteration.  A 96-register build (5 CTAs per SM) is 2 % faster alone on the photon-dense bench scene and 10 % slower on the sparse one.
 __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointBuf hp, unsigned numPixels, unsigned width, unsigned height, PhotonBuf sorted,
-                                                                    const unsigned* __restrict__ offsets, GridParams g, float ppmRadius, float ppmRadiusSquared,
+                                                                    const unsigned* __restrict__ offsets, const GridParams* __restrict__ gp, float ppmRadius, float ppmRadiusSquared,
                                                                     float emittedPhotons, float* __restrict__ indirect, unsigned* __restrict__ tileCounter, unsigned tilesPerBlock)
 {
 #if OPR_GATHER_PACKED
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
 #endif
     __shared__ float sAcc[GATHER_WARPS][32][3];
     __shared__ unsigned sTile;
+    const GridParams g = *gp;
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned tilesX = width ? (width + 7) / 8 : 0;
     const unsigned numTiles = width ? tilesX * ((height + 3) / 4) : (numPixels + 31) / 32;
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
     }
 }
 
-void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, GridParams g,
+void launch_gather(const HitpointBuf& hp, unsigned numPixels, unsigned width, unsigned height, const PhotonBuf& sorted, const unsigned* offsets, const GridParams* g,
                    float ppmRadius, float ppmRadiusSquared, float emittedPhotons, float* indirect, unsigned* tileCounter, LaunchCtx lc, unsigned blocksPerSM,
                    unsigned tilesPerBlock)
 {

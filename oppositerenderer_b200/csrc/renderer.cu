@@ -33,6 +33,8 @@ Renderer::~Renderer()
     dfree(gridKeys[0]); dfree(gridKeys[1]); dfree(gridVals[0]); dfree(gridVals[1]); dfree(gridHist); dfree(sortTmp); dfree(scanTmp);
     dfree(gridBBox); dfree(stats64); dfree(reduced);
     if (gridBBoxHost) cudaFreeHost(gridBBoxHost);
+    if (gridParamsHost) cudaFreeHost(gridParamsHost);
+    dfree(gridParamsDev);
     scene.release();
     if (bboxEvent) cudaEventDestroy(bboxEvent);
     for (cudaEvent_t e : {evPhotonsFree[0], evPhotonsFree[1], evGatherDone, evHpFree[0], evHpFree[1], evGridDone, evDirectDone, evJoin, evCameraWaves, evPhotonGen, evTailDone, evPhotonWaves, evVcmShade, evVcmConn[0], evVcmConn[1]}) if (e) cudaEventDestroy(e);
@@ -101,7 +103,11 @@ void Renderer::initialize(int cudaOrdinal)
     dalloc(gridBBox, 8);
     dalloc(stats64, STAT_NUM);
     OPR_CUDA_CHECK(cudaMemsetAsync(stats64, 0, STAT_NUM * sizeof(unsigned long long), stream));
-    OPR_CUDA_CHECK(cudaMallocHost((void**)&gridBBoxHost, 16 * sizeof(float)));
+    OPR_CUDA_CHECK(cudaMallocHost((void**)&gridBBoxHost, 2 * 16 * sizeof(float)));      // two sets of (7 results + 7 initial values): by iteration parity
+    OPR_CUDA_CHECK(cudaMallocHost((void**)&gridParamsHost, 2 * sizeof(GridParams)));
+    memset(gridParamsHost, 0, 2 * sizeof(GridParams));
+    dalloc(gridParamsDev, 2);
+    if (const char* e = getenv("OPR_ASYNC_GRID")) asyncGrid = atoi(e) != 0;
     initialized = true;
 }
 
@@ -181,12 +187,36 @@ void Renderer::photonBBoxAsync(cudaStream_t st)
     LaunchCtx lc{st, &launches};
     const unsigned P = photonLaunchWidth * photonLaunchHeight;
     ScopedTimer t(*this, "grid.bbox", st);
-    float* h = gridBBoxHost;
+    float* h = gridBBoxHost + 16 * (overlap ? parity : 0);
     h[8] = FLT_MAX; h[9] = FLT_MAX; h[10] = FLT_MAX; h[11] = -FLT_MAX; h[12] = -FLT_MAX; h[13] = -FLT_MAX; h[14] = 0.f; h[15] = 0.f;
     OPR_CUDA_CHECK(cudaMemcpyAsync(gridBBox, h + 8, 7 * sizeof(float), cudaMemcpyHostToDevice, st));
     launch_photon_bbox(photons, phState, P, gridBBox, lc);
     OPR_CUDA_CHECK(cudaMemcpyAsync(h, gridBBox, 7 * sizeof(float), cudaMemcpyDeviceToHost, st));
     OPR_CUDA_CHECK(cudaEventRecord(bboxEvent, st));
+}
+
+// Host function in the grid stream: the scalar part of createUniformGridPhotonMap (OptixRenderer_SpatialHash.cu:209-250) on the bounding
+// box that the preceding copy left in pinned memory.  Runs on a driver thread; touches only pinned memory and plain host fields.
+static void CUDART_CB grid_scalars_host(void* p)
+{
+    Renderer::GridJob* job = (Renderer::GridJob*)p;
+    const float* h = job->bboxHost;
+    unsigned numValid; memcpy(&numValid, h + 6, 4);
+    float lo[3] = {h[0], h[1], h[2]}, hi[3] = {h[3], h[4], h[5]};
+    if (numValid == 0) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.f; }   // photons[0] is a cleared slot
+    GridParams g;
+    if (!compute_grid_params(lo, hi, g)) { job->self->gridTooLarge = true; g.gridSize = make_uint3(1, 1, 1); g.numCells = 1; }   // :244-248, reported by the next call
+    g.numValid = numValid;
+    *job->paramsHost = g;
+    job->self->stats[STAT_PHOTONS_STORED] += numValid;
+}
+
+const GridParams& Renderer::latestGrid()
+{
+    joinStreams();
+    OPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (asyncGrid) grid = gridParamsHost[overlap ? parity : 0];
+    return grid;
 }
 
 void Renderer::buildPhotonGrid()
@@ -196,27 +226,41 @@ void Renderer::buildPhotonGrid()
     LaunchCtx lc{st, &launches};
     const unsigned P = photonLaunchWidth * photonLaunchHeight;
     const unsigned N = P * MAX_PHOTON_DEPOSITS;
-    OPR_CUDA_CHECK(cudaEventSynchronize(bboxEvent));   // the reference syncs here too (:222)
+    const unsigned pb = overlap ? parity : 0;
+    GridParams* gDev = gridParamsDev + pb;
     OPR_CUDA_CHECK(cudaStreamWaitEvent(st, bboxEvent, 0));   // the build starts once the photon pass of this iteration is complete
     // the previous iteration's gather still reads the sorted photons and the offset table this build overwrites
     if (st != streamB && gatherDonePending) { OPR_CUDA_CHECK(cudaStreamWaitEvent(st, evGatherDone, 0)); gatherDonePending = false; }
     workOnB = true;
-    unsigned numValid; memcpy(&numValid, gridBBoxHost + 6, 4);
-    float lo[3] = {gridBBoxHost[0], gridBBoxHost[1], gridBBoxHost[2]}, hi[3] = {gridBBoxHost[3], gridBBoxHost[4], gridBBoxHost[5]};
-    if (numValid == 0) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.f; }   // photons[0] is a cleared slot
-    if (!compute_grid_params(lo, hi, grid))
-        throw std::runtime_error("Too many cells in SpatialHash.cu, over defined PHOTON_GRID_MAX_SIZE.");   // :246
-    grid.numValid = numValid;
-    stats[STAT_PHOTONS_STORED] += numValid;
+    unsigned numCellsBound = PHOTON_GRID_MAX_SIZE;
+    if (asyncGrid) {
+        // no host wait: the scalars are computed by a host function that the stream runs when the bounding box has landed
+        gridJob[pb] = GridJob{this, gridBBoxHost + 16 * pb, gridParamsHost + pb, pb};
+        OPR_CUDA_CHECK(cudaLaunchHostFunc(st, grid_scalars_host, &gridJob[pb]));
+        OPR_CUDA_CHECK(cudaMemcpyAsync(gDev, gridParamsHost + pb, sizeof(GridParams), cudaMemcpyHostToDevice, st));
+    } else {
+        OPR_CUDA_CHECK(cudaEventSynchronize(bboxEvent));   // the reference syncs here too (:222)
+        const float* h = gridBBoxHost + 16 * pb;
+        unsigned numValid; memcpy(&numValid, h + 6, 4);
+        float lo[3] = {h[0], h[1], h[2]}, hi[3] = {h[3], h[4], h[5]};
+        if (numValid == 0) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.f; }   // photons[0] is a cleared slot
+        if (!compute_grid_params(lo, hi, grid))
+            throw std::runtime_error("Too many cells in SpatialHash.cu, over defined PHOTON_GRID_MAX_SIZE.");   // :246
+        grid.numValid = numValid;
+        stats[STAT_PHOTONS_STORED] += numValid;
+        gridParamsHost[pb] = grid;
+        OPR_CUDA_CHECK(cudaMemcpyAsync(gDev, gridParamsHost + pb, sizeof(GridParams), cudaMemcpyHostToDevice, st));
+        numCellsBound = grid.numCells;
+    }
     {
         ScopedTimer t(*this, "grid.keys", st);
-        OPR_CUDA_CHECK(cudaMemsetAsync(gridHist, 0, ((size_t)grid.numCells + 2) * sizeof(unsigned), st));
-        launch_grid_keys(photons, phState, N, grid, gridKeys[0], gridHist, lc);
+        OPR_CUDA_CHECK(cudaMemsetAsync(gridHist, 0, ((size_t)numCellsBound + 2) * sizeof(unsigned), st));
+        launch_grid_keys(photons, phState, N, gDev, gridKeys[0], gridHist, lc);
     }
     bool flipped;
     {
         ScopedTimer t(*this, "grid.sort", st);
-        int bits = 1; while ((1ull << bits) <= (unsigned long long)grid.numCells + 1) bits++;
+        int bits = 1; while ((1ull << bits) <= (unsigned long long)numCellsBound + 1) bits++;      // 20 bits when the cell count is not known on the host
         int nl = 0;
         flipped = radix_sort_pairs<unsigned>(gridKeys[0], gridVals[0], gridKeys[1], gridVals[1], N, bits, sortTmp, true, st, &nl);
         launches += nl;
@@ -225,12 +269,12 @@ void Renderer::buildPhotonGrid()
     const unsigned* sortedSlots = flipped ? gridVals[1] : gridVals[0];
     {
         ScopedTimer t(*this, "grid.offsets", st);
-        exclusive_scan_u32(gridHist, gridHist, grid.numCells + 1, scanTmp, st);
+        exclusive_scan_u32(gridHist, gridHist, numCellsBound + 1, scanTmp, st);
         launches += 3;
     }
     {
         ScopedTimer t(*this, "grid.reorder", st);
-        launch_photon_reorder(photons, sortedSlots, numValid, sorted, lc);
+        launch_photon_reorder(photons, sortedSlots, N, gDev, sorted, lc);
     }
 }
 
@@ -343,7 +387,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
     {
         NvtxRange nv("OptixEntryPoint::INDIRECT_RADIANCE_ESTIMATION");
         ScopedTimer t(*this, "ppm.gather", stB);
-        launch_gather(hp, width * height, width, height, sorted, gridHist, grid, PPMRadius, ppmRadiusSquared,
+        launch_gather(hp, width * height, width, height, sorted, gridHist, gridParamsDev + (overlap ? parity : 0), PPMRadius, ppmRadiusSquared,
                       float(photonLaunchWidth * photonLaunchHeight), indirect, q.counters + CTR_TILE, lcB, gatherBlocks,
                       (overlap && gatherBlocks == gatherBlocksPerSM) ? gatherTilesPerBlock : 0u);
     }
@@ -368,6 +412,7 @@ void Renderer::renderNextIteration(unsigned long long iterationNumber, unsigned 
     if (!sceneLoaded) throw std::runtime_error("Traced before a scene was initialized.");
     OPR_CUDA_CHECK(cudaSetDevice(device));
     if (details.width == 0 || details.height == 0) throw std::runtime_error("zero-sized render request");
+    if (gridTooLarge) { gridTooLarge = false; throw std::runtime_error("Too many cells in SpatialHash.cu, over defined PHOTON_GRID_MAX_SIZE."); }   // :246, found by the previous iteration's host function
     char rangeName[48];
     snprintf(rangeName, sizeof rangeName, "OptixRenderer::Trace Iteration %llu", iterationNumber);   // OptixRenderer.cpp:518-520
     NvtxRange nvIteration(rangeName);
