@@ -433,6 +433,13 @@ def test_two_stream_pipeline_is_bit_identical_to_serial(product, monkeypatch):
     assert sa["closest_rays"] == sb["closest_rays"] and sa["any_rays"] == sb["any_rays"] and sa["photons_stored"] == sb["photons_stored"]
     assert (a.view(np.uint32) == b.view(np.uint32)).all()
     assert a.sum() > 0
+    # the same with the photon-grid scalars computed by a host function inside the stream (no host wait per iteration) and with the
+    # grid build on the high-priority stream: scheduling switches, not a bit of the image may change
+    for var, val in (("OPR_ASYNC_GRID", "1"), ("OPR_GRID_STREAM", "C")):
+        monkeypatch.setenv(var, val)
+        c, sc = _render_sum(product, True, monkeypatch, scene, cam, W, H, (256, 256), 6, product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING)
+        monkeypatch.delenv(var)
+        assert sc["photons_stored"] == sa["photons_stored"] and (c.view(np.uint32) == a.view(np.uint32)).all(), var
 
 
 def test_full_size_ppm_properties(product):
