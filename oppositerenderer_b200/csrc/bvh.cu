@@ -395,11 +395,15 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
     const int numWide = h[0];
     if (h[2] != n) throw std::runtime_error("BVH build: leaf slots do not cover the primitives");
     if (3 * levels + 4 > TRAVERSAL_STACK) throw std::runtime_error("BVH build: tree deeper than the traversal stack");
-    float4* nodes = nullptr;
-    devAlloc((void**)&nodes, 128 * (size_t)numWide); owned.push_back(nodes);
+    // one allocation: quantised nodes | fp32 nodes | leaf triangle records — what every traversal touches, as ONE address range, so that an
+    // L2 access-policy window can cover it (Renderer::initScene, OPR_L2_PERSIST)
+    const size_t qBytes = 64 * (size_t)numWide, nBytes = 128 * (size_t)numWide, tBytes = sizeof(float4) * LEAF_TRI_STRIDE * (size_t)n;
+    char* block = nullptr;
+    devAlloc((void**)&block, qBytes + nBytes + tBytes); owned.push_back(block);
+    traversalBlock = block; traversalNodeBytes = qBytes + nBytes; traversalBytes = qBytes + nBytes + tBytes;
+    float4* nodes = (float4*)(block + qBytes);
     OPR_CUDA_CHECK(cudaMemcpyAsync(nodes, wideTmp, 128 * (size_t)numWide, cudaMemcpyDeviceToDevice, st));
-    float4* leafTri = nullptr;
-    devAlloc((void**)&leafTri, sizeof(float4) * LEAF_TRI_STRIDE * (size_t)n); owned.push_back(leafTri);
+    float4* leafTri = (float4*)(block + qBytes + nBytes);
     bvh_leaf_tri_kernel<<<B256, 256, 0, st>>>(leafPrim, n, view.triRec, leafTri);
     OPR_CUDA_CHECK(cudaStreamSynchronize(st));
     OPR_CUDA_CHECK(cudaGetLastError());
@@ -421,8 +425,7 @@ void DeviceScene::buildBvh(const std::vector<float4>& primLo, const std::vector<
         };
         float3 qo, qe;
         axis(rlo.x, ext.x, qo.x, qe.x); axis(rlo.y, ext.y, qo.y, qe.y); axis(rlo.z, ext.z, qo.z, qe.z);
-        uint4* qnodes = nullptr;
-        devAlloc((void**)&qnodes, 64 * (size_t)numWide); owned.push_back(qnodes);
+        uint4* qnodes = (uint4*)block;
         bvh_quantize_kernel<<<(numWide + 255) / 256, 256, 0, st>>>(nodes, numWide, qo, f3(32768.0f / qe.x, 32768.0f / qe.y, 32768.0f / qe.z), qnodes);
         bvh_centre_half_kernel<<<(numWide + 255) / 256, 256, 0, st>>>(nodes, numWide);      // after the quantiser, which reads lo / hi
         OPR_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -16,6 +16,8 @@ public:
     float sahCost = 0.f;                                // SAH cost of the binary tree / root area
     float3 aabbMin{}, aabbMax{};
     std::vector<opr_light> hostLights;
+    const void* traversalBlock = nullptr;               // quantised nodes | fp32 nodes | leaf triangles, one allocation
+    size_t traversalNodeBytes = 0, traversalBytes = 0;  // bytes of the two node arrays; of the whole block
 
     DeviceScene() {}
     ~DeviceScene();

@@ -80,6 +80,7 @@ void Renderer::initialize(int cudaOrdinal)
         OPR_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (const char* e = getenv("OPR_OVERLAP")) overlap = atoi(e) != 0;
     if (const char* e = getenv("OPR_QNODES")) qnodeMask = (unsigned)atoi(e);
+    if (const char* e = getenv("OPR_L2_PERSIST")) l2Persist = atoi(e);
     if (const char* e = getenv("OPR_GRID_STREAM")) gridOnC = (e[0] == 'C' || e[0] == 'c');
     if (const char* e = getenv("OPR_GATHER_BLOCKS_PER_SM")) gatherBlocksPerSM = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("OPR_VCM_CONNECT_BLOCKS_PER_SM")) vcmConnectBlocksPerSM = (unsigned)std::max(0, atoi(e));
@@ -120,6 +121,28 @@ void Renderer::initScene(const opr_scene_desc* d)
     sceneLoaded = false;      // DeviceScene::load releases the previous scene first: a failed reload must not leave a half-freed scene renderable
     scene.load(d, stream);
     sceneLoaded = true;
+    // L2 residency of the BVH (OPR_L2_PERSIST: 0 off, 1 the two node arrays, 2 nodes + leaf triangles): an access-policy window on the streams
+    // that trace, over the traversal block, with as much of the L2 set aside as the device allows.  The iteration's streaming buffers (photon
+    // slots, hit points, queues: ~ 400 MB per iteration) otherwise evict the tree between two bounces.
+    if (l2Persist > 0 && scene.traversalBlock) {
+        int maxPersist = 0, maxWindow = 0;
+        OPR_CUDA_CHECK(cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, device));
+        OPR_CUDA_CHECK(cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, device));
+        const size_t want = l2Persist >= 2 ? scene.traversalBytes : scene.traversalNodeBytes;
+        const size_t bytes = std::min<size_t>(want, (size_t)maxWindow);
+        const size_t setAside = std::min<size_t>(bytes, (size_t)maxPersist);
+        if (setAside > 0) {
+            OPR_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside));
+            cudaStreamAttrValue v{};
+            v.accessPolicyWindow.base_ptr = const_cast<void*>(scene.traversalBlock);
+            v.accessPolicyWindow.num_bytes = bytes;
+            v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setAside / (double)bytes);
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            for (cudaStream_t s : {stream, streamC, streamB}) OPR_CUDA_CHECK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v));
+            if (getenv("OPR_BVH_VERBOSE")) fprintf(stderr, "[opr] L2 window: %.1f MB of the traversal block, %.1f MB set aside (device max %.1f MB)\n", bytes / 1e6, setAside / 1e6, maxPersist / 1e6);
+        }
+    }
 }
 
 void Renderer::joinStreams()

@@ -113,6 +113,7 @@ struct Renderer {
     // 4 camera tail, 8 primary rays, 16 shadow rays, 32 BDPT bounces >= 1, 64 BDPT connections, 128 BDPT tails.  Default: the incoherent ones.
     enum { QN_PHOTON = 1, QN_PHOTON_TAILS = 2, QN_CAMERA_TAIL = 4, QN_PRIMARY = 8, QN_SHADOW = 16, QN_VCM_BOUNCES = 32, QN_VCM_CONNECT = 64, QN_VCM_TAILS = 128 };
     unsigned qnodeMask = QN_PHOTON | QN_PHOTON_TAILS | QN_VCM_BOUNCES | QN_VCM_TAILS;
+    int l2Persist = 0;                    // OPR_L2_PERSIST: L2 access-policy window over the BVH (0 off, 1 node arrays, 2 nodes + leaf triangles)
     bool rawQuantized = false;            // opr_debug_set_trace_nodes: opr_trace_closest / opr_trace_any traverse the quantised nodes
     bool gridOnC = false;                 // OPR_GRID_STREAM=C: photon-grid build on stream C (greatest priority) instead of the low-priority stream B (measured: no gain,
                                           // the build is slowed by the persistent trace kernels holding every register of the SMs, not by its priority)
