@@ -331,6 +331,12 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
                             for (int h = 0; h < 2; h++) {
                                 const f32x2 x = h ? X.y : X.x, y = h ? Y.y : Y.x, z = h ? Z.y : Z.x;
                                 const f32x2 dx = sub2(posX2, x), dy = sub2(posY2, y), dz = sub2(posZ2, z);
+                                // dot(a, b) as nvcc compiles the reference's a.x b.x + a.y b.y + a.z b.z for the GPU: one product and two FMAs
+                                // (IndirectRadianceEstimation.cu:54-57,117-118).  The CPU oracle rounds every product, so on a radius sphere or
+                                // tangent plane the last bit of distance2 / the dot decides differently: 2 of 2 073 600 pixels at the full
+                                // configuration hold such a photon, and the stage check names them (tests/parity_rules.py gather_stage_exact).
+                                // (Rounded products are not available at this price: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+                                // whatever -fmad says; packed products with scalar adds cost four more instructions per photon.)
                                 const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
                                 const f32x2 nd = fma2(h ? DZ.y : DZ.x, nrmZ2, fma2(h ? DY.y : DY.x, nrmY2, mul2(h ? DX.y : DX.x, nrmX2)));
                                 float e0, e1, d20, d21, nd0, nd1;
@@ -353,8 +359,8 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
                             const float4 a = sA[w][j], b = sB[w][j];
                             const float c = sC[w][j];
                             const float dx = pos.x - a.x, dy = pos.y - a.y, dz = pos.z - a.z;
-                            const float distance2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            const float ndot = fmaf(c, nrm.z, fmaf(b.w, nrm.y, a.w * nrm.x));
+                            const float distance2 = (dx * dx + dy * dy) + dz * dz;            // the reference's dot(): see the packed loop
+                            const float ndot = (a.w * nrm.x + b.w * nrm.y) + c * nrm.z;
                             float weight = fmaf(w1, exp2f_approx(kexp * distance2), w0);
                             weight = (distance2 <= radius2 && ndot <= 0.f) ? weight : 0.f;
                             acc.x = fmaf(b.x, weight, acc.x); acc.y = fmaf(b.y, weight, acc.y); acc.z = fmaf(b.z, weight, acc.z);
@@ -366,11 +372,11 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) ppm_gather_kernel(HitpointB
                         for (unsigned j = 0; j < cnt; j++) {
                             const float4 a = sA[w][j];
                             const float dx = pos.x - a.x, dy = pos.y - a.y, dz = pos.z - a.z;
-                            const float distance2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            const float distance2 = (dx * dx + dy * dy) + dz * dz;
                             if (distance2 <= radius2) {
                                 const float4 b = sB[w][j];
                                 const float c = sC[w][j];
-                                const float ndot = fmaf(c, nrm.z, fmaf(b.w, nrm.y, a.w * nrm.x));     // dot(-rayDirection, normal) >= 0  <=>  ndot <= 0
+                                const float ndot = (a.w * nrm.x + b.w * nrm.y) + c * nrm.z;           // dot(-rayDirection, normal) >= 0  <=>  ndot <= 0
                                 float weight = fmaf(w1, exp2f_approx(kexp * distance2), w0);
                                 weight = ndot <= 0.f ? weight : 0.f;                                   // a rejected photon adds an exact zero
                                 acc.x = fmaf(b.x, weight, acc.x); acc.y = fmaf(b.y, weight, acc.y); acc.z = fmaf(b.z, weight, acc.z);

@@ -591,14 +591,16 @@ def _rel_mse(a, b, mask):
     return float(np.mean((((a - b) ** 2).sum(-1) / (ref2 + 1e-3 * float(ref2[mask].mean())))[mask]))
 
 
-@pytest.mark.parametrize("method,scene_name,config", [(2, "Cornell", 0), (1, "CornellSmall", 0), (0, "CornellSmall", (1 << 1) | (1 << 9) | (1 << 13))])
-def test_converged_render_within_monte_carlo_noise(product, oracle, method, scene_name, config):
+@pytest.mark.parametrize("method,scene_name,config,size,pl,iters", [(2, "Cornell", 0, 40, 64, 24), (1, "CornellSmall", 0, 40, 64, 24),
+                                                                    (0, "CornellSmall", (1 << 1) | (1 << 9) | (1 << 13), 40, 64, 24),
+                                                                    (2, "Cornell", 0, 128, 160, 64), (1, "CornellSmall", 0, 128, 16, 64)])
+def test_converged_render_within_monte_carlo_noise(product, oracle, method, scene_name, config, size, pl, iters):
     """Independent seeds: the distance of a GPU render from oracle renders must be the Monte Carlo noise floor, i.e. the distance
     between independent oracle renders of the same length (north_star: 'converged relMSE bound below the noise floor').  Three
     oracle seeds give the floor (largest pairwise relMSE); the GPU render (a fourth seed) must be within 1.5 x of it from every
     oracle render, and its mean within the oracle means' spread + 2 %.  Pixels that see the emitter directly are left out: the
     anti-aliased emitter edge has a per-pixel variance hundreds of times that of the rest of the image."""
-    size, pl, iters = 40, (64, 64), 24
+    pl = (pl, pl)
     scene = product.Cornell() if scene_name == "Cornell" else product.CornellSmall(config or None)
     cam = scene.getDefaultCamera()
     cam.setAspectRatio(1.0)

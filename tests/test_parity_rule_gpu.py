@@ -153,3 +153,82 @@ def test_normal_map_without_tangents_matches_oracle(product, oracle):
     _lockstep(product, oracle, "normal map without tangents", scene, cam, cam.pod, r, o, PPM, W, H, pl,
               product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), 2))
     assert not np.isnan(r.debug_buffer("hitpoints", ol.HITPOINT_DT, W * H)["normal"]).any()
+
+
+@pytest.mark.parametrize("kind,config_no", [("sponza", 4), ("conference", 3)])
+def test_baseline_bench_configs_as_stated(product, oracle, kind, config_no):
+    """BASELINE configs 3 and 4 AS STATED — the synthetic ~300 K-triangle Conference-scale and ~1 M-triangle Sponza-scale scenes, PPM,
+    1920 x 1080, 1024 x 1024 photons — one iteration in lock-step with the oracle (all host cores):
+      * hit flags equal except where the camera path's RNG stream diverged; photon count and ray counts within 0.5 %;
+      * the gather checked against the oracle's gather on the product's own 2 M hit points and ~1.8 M sorted photons: every pixel;
+      * direct light: every out-of-tolerance pixel has a diverged camera path, a different occlusion mask, a measurably different normal /
+        attenuation (texture unit) or lies in the plane of an area light — but for at most 4 per million, which are printed;
+      * output == direct + indirect bit for bit; whole image within 1 % (clipped relative L1)."""
+    import os
+    from oppositerenderer_b200 import synthetic
+    W, H, pl = 1920, 1080, (1024, 1024)
+    scene = synthetic.make_scene(kind, seed=1, detail=1.0)
+    assert scene.num_triangles > (1000000 if kind == "sponza" else 250000)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(W / H)
+    r = product.OptixRenderer(photon_launch=pl, seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    o = oracle.OracleRenderer("oracle", pl, 10, util.SEED, threads=len(os.sched_getaffinity(0)))
+    o.init_scene(scene.getSceneDescription())
+    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), PPM, W, H, 2.0 / 3.0)
+    odet = oracle.make_details(cam.pod, PPM, W, H)
+    radius = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), 1)[0]
+    r.renderNextIteration(0, 0, radius, True, det)
+    o.render_next_iteration(0, 0, radius, odet)
+    a, b = pr.ProductProbe(r, W, H, pl), pr.OracleProbe(o, W, H, pl)
+    cam_div, hpa, hpb = pr.camera_divergence(a, b)
+    state = pr.pixel_state_divergence(a, b)
+    # a camera path whose RNG stream did not diverge ends with the same flags, but for rays that graze an edge between two materials which
+    # both draw nothing (mirror | diffuse): a handful in two million
+    assert ((hpa["flags"] != hpb["flags"]) & ~state).sum() <= 1e-5 * W * H
+    assert not np.isnan(hpa["normal"]).any()
+    st, (c0, a0) = r.stats(), o.ray_counts()
+    nv, nv0 = int(r.debug_buffer("grid", np.uint32, 8)[7]), o.grid()["numValid"]
+    assert abs(nv - nv0) <= 0.005 * nv0 and abs(st["closest_rays"] - c0) <= 0.005 * c0 and abs(st["any_rays"] - a0) <= 0.005 * a0, (nv, nv0, st, c0, a0)
+    worst = pr.gather_stage_exact(a, radius)                              # every one of the 2 M pixels, no exception
+    da, db = a.direct(), b.direct()
+    bad_direct = pr.out_of_tolerance(da, db)
+    diffuse = (hpb["flags"] & ol.PRD_HIT_NON_SPECULAR) != 0
+    explained = cam_div | (diffuse & (a.direct_sample_mask() != b.direct_sample_mask())) | (diffuse & pr.shading_inputs_differ(hpa, hpb)) | \
+        (diffuse & pr.coplanar_with_area_light(scene.getSceneDescription(), hpb))
+    for p in np.nonzero(bad_direct & ~explained)[0][:4]:      # what a person needs to name the difference, should the rule ever fail here
+        print("pixel %d direct %s / %s pos %s / %s normal %s / %s att %s / %s mask %x / %x" % (p, da[p], db[p], hpa["position"][p], hpb["position"][p], hpa["normal"][p],
+              hpb["normal"][p], hpa["attenuation"][p], hpb["attenuation"][p], a.direct_sample_mask()[p], b.direct_sample_mask()[p]))
+    # at two million pixels a residue of ill-conditioned pixels (light samples in the tangent plane of the hit, listed above) is admitted: 4 per million
+    line = pr.check_explained("config %d direct" % config_no, bad_direct, explained, allow=int(4e-6 * W * H))
+    ia, ib = a.indirect(), b.indirect()
+    bad_ind = pr.out_of_tolerance(ia, ib)
+    out, out0 = a.output(), b.output()
+    assert ((da + ia).view(np.uint32) == out.view(np.uint32)).all()     # PPM_OUTPUT_PASS, first iteration: output = direct + indirect
+    clip = float(np.percentile(out0, 99.0)) + 1e-30
+    rel = float(np.abs(np.minimum(out, clip) - np.minimum(out0, clip)).sum() / np.abs(np.minimum(out0, clip)).sum())
+    print("config %d (%s, %d triangles): camera paths diverged %.4f %%, photons %d vs %d, gather vs oracle gather on the product's inputs worst rel %.1e, "
+          "indirect out of the plain tolerance %.2f %% (photon-map differences, quantified at reduced size), clipped relative L1 of the image %.2e; %s"
+          % (config_no, kind, scene.num_triangles, 100 * cam_div.mean(), nv, nv0, worst, 100 * bad_ind.mean(), rel, line))
+    assert cam_div.mean() < 0.02 and rel < 1e-2
+
+
+def test_baseline_config_5_workload(product, oracle):
+    """BASELINE config 5's workload — BDPT (vertex connection, recursive MIS, max path length 8) on the ~1 M-triangle scene — at 960 x 540
+    (at 3840 x 2160 the oracle needs ~20 s per iteration and the light-vertex dump of the rule 6 GB; the 4K run itself is
+    bench.py --method bdpt --width 3840 --height 2160), two iterations in lock-step under the per-pixel rule."""
+    import os
+    from oppositerenderer_b200 import synthetic
+    W, H = 960, 540
+    scene = synthetic.make_scene("sponza", seed=1, detail=1.0)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(W / H)
+    r = product.OptixRenderer(photon_launch=(16, 16), vcm_max_path_length=8, seed=util.SEED)
+    r.initialize(product.ComputeDevice(0))
+    r.initScene(scene)
+    o = oracle.OracleRenderer("oracle", (16, 16), 8, util.SEED, threads=len(os.sched_getaffinity(0)))
+    o.init_scene(scene.getSceneDescription())
+    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), 2)
+    # half a million pixels on the full scene: 4 per million may stay unnamed (printed; the reduced-size cases above admit none)
+    _lockstep(product, oracle, "config 5 workload: BDPT 960x540, 1.1 M triangles", scene, cam, cam.pod, r, o, BDPT, W, H, (16, 16), radii, allow=max(1, int(4e-6 * W * H)))
