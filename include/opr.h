@@ -119,7 +119,8 @@ const char* opr_get_timing_name(opr_renderer* r, int index);
  * "direct_sample_mask" (u8 x W*H: bit s = shadow sample s of DirectRadianceEstimation.cu:54-70 was unoccluded and non-zero),
  * "light_vertex_positions" (u32 count + 12 B pad, then {u32 path, float3 hitPoint} per stored light vertex of the last light
  * pass), "connection_counts" (u32 x W*H: contributions that passed isOccluded, vcm.h:43-59, per target pixel, last BDPT
- * iteration; needs opr_debug_set_connection_counts(r, 1) before the iteration), "path_signatures" (u32 x 2*W*H, same switch: per BDPT light subpath, then per camera subpath, a hash of the material kinds it met),
+ * iteration; needs opr_debug_set_connection_counts(r, 1) before the iteration), "sample_factors" (float4 x W*H) and "sample_lights" (4 x u16 x W*H): factor and light index of the four direct-light samples of
+ * DirectRadianceEstimation.cu:54-70 per pixel (0 = not cast or occluded), "path_signatures" (u32 x 2*W*H, same switch: per BDPT light subpath, then per camera subpath, a hash of the material kinds it met),
  * "pt_signature" (u32 x W*H, same switch: hash over
  * the segments of the last PATH_TRACING iteration's path of (hit flags, light sample contributed, ended by Russian roulette) —
  * RayGeneratorPT.cu:84-127 draws those decisions from a stream whose final state is discarded, so the RNG state cannot show them). */

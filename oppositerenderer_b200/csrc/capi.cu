@@ -221,6 +221,15 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
             auto f = download(R.sampleFactor, px, st);
             unsigned char* o = (unsigned char*)dst;
             for (size_t i = 0; i < px; i++) o[i] = (unsigned char)((f[i].x > 0.f) | ((f[i].y > 0.f) << 1) | ((f[i].z > 0.f) << 2) | ((f[i].w > 0.f) << 3));
+        } else if (n == "sample_factors") {
+            // the four light samples of every pixel (last PPM iteration): un-occluded factor (0 = not cast or occluded), 16 B per pixel
+            need(px * 16);
+            OPR_CUDA_CHECK(cudaMemcpyAsync(dst, R.sampleFactor, px * 16, cudaMemcpyDeviceToHost, st));
+            OPR_CUDA_CHECK(cudaStreamSynchronize(st));
+        } else if (n == "sample_lights") {
+            need(px * 8);       // light index of the four samples, 16 bits each
+            OPR_CUDA_CHECK(cudaMemcpyAsync(dst, R.sampleLight, px * 8, cudaMemcpyDeviceToHost, st));
+            OPR_CUDA_CHECK(cudaStreamSynchronize(st));
         } else if (n == "light_vertex_positions") {
             // [0] = number of stored light vertices, then (path, x, y, z) 16-byte records, path-major
             need(16);

@@ -179,6 +179,12 @@ class OracleRenderer:
         self.lib.ora_get_path_signatures(self.h, a.ctypes.data_as(C.c_void_p))
         return a[:self.width * self.height], a[self.width * self.height:]
 
+    def photon_path_lengths(self):
+        """Depth reached by every photon thread of the last photon pass (debugPhotonPathLengthBuffer)."""
+        a = np.empty(self.photon_launch[0] * self.photon_launch[1], np.uint32)
+        self.lib.ora_get_photon_path_lengths(self.h, a.ctypes.data_as(C.c_void_p))
+        return a
+
     def pt_signature(self):
         a = np.empty(self.width * self.height, np.uint32)
         self.lib.ora_get_pt_signature(self.h, a.ctypes.data_as(C.c_void_p))
