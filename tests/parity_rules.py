@@ -533,7 +533,7 @@ def run_lockstep(name, r, o, det, odet, method, W, H, pl, radii, cam_pod, max_ex
         if per_iteration is not None:
             per_iteration(i, a, b)
     oa, ob = a.output(), b.output()
-    bad = out_of_tolerance(oa, ob)
+    bad = out_of_tolerance(oa, ob, rtol=RTOL if acc_a is not None else 2 * RTOL)     # the same tolerance as the increments it is the sum of
     if acc_a is not None:
         # the running sum is exactly the sum of the per-iteration buffers checked above (float32, same order of additions)
         exact = float((acc_a.view(np.uint32) == oa.view(np.uint32)).all(axis=1).mean())

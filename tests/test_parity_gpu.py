@@ -156,58 +156,6 @@ def test_traversal_full_size_matches_oracle(product, oracle, quantized):
     assert (occ == occ0).mean() > 0.9999
 
 
-@pytest.mark.parametrize("scene_name,config,size,pl,iters,minfrac", [
-    ("Cornell", 0, 64, (64, 64), 3, 0.98),
-    ("CornellSmall", 0, 48, (64, 64), 2, 0.97),
-    ("CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 48, (64, 64), 2, 0.95),   # area light, mirror floor, large glass sphere, blocks
-    ("CornellSmall", (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 48, (64, 64), 2, 0.95),   # point light, glossy floor, small mirror + glass spheres
-])
-def test_ppm_stage_parity(product, oracle, scene_name, config, size, pl, iters, minfrac):
-    """One PPM iteration stage by stage (hitpoints, photons, grid, indirect, direct, sum buffer) and the RNG
-    states afterwards, on identical paths (same per-pixel XORWOW seeding)."""
-    scene, cam, r, o, osc = _renderers(product, oracle, scene_name, config, size, pl)
-    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, size, size, 2.0 / 3.0)
-    odet = oracle.make_details(osc.camera(1.0), capi.PROGRESSIVE_PHOTON_MAPPING, size, size)
-    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), iters)
-    if scene_name == "CornellSmall":
-        radii = [0.05 * (x / radii[0]) for x in radii]   # the scene-extent estimate (1.7e-4) finds no photons at this photon count
-    for i in range(iters):
-        r.renderNextIteration(i, i, radii[i], True, det)
-        o.render_next_iteration(i, i, radii[i], odet)
-        hp = r.debug_buffer("hitpoints", ol.HITPOINT_DT, size * size)
-        hp0 = o.hitpoints()
-        same_flags = hp["flags"] == hp0["flags"]
-        assert same_flags.mean() > minfrac
-        m = same_flags & ((hp0["flags"] & ol.PRD_HIT_NON_SPECULAR) != 0)
-        scale = float(np.abs(hp0["position"]).max())
-        assert np.isclose(hp["position"][m], hp0["position"][m], rtol=1e-4, atol=1e-4 * scale).all(axis=1).mean() > minfrac
-        assert np.isclose(hp["attenuation"][m], hp0["attenuation"][m], rtol=1e-5).all(axis=1).mean() > minfrac
-        # photons as emitted (reference layout: thread t owns slots 4t..4t+3)
-        ph = r.debug_buffer("photons", ol.PHOTON_DT, pl[0] * pl[1] * 4)
-        ph0 = o.photons()   # sorted in place by the oracle's grid build: compare as multisets through the sorted lists
-        g = r.debug_buffer("grid", np.uint32, 8)
-        og = o.grid()
-        nv, nv0 = int(g[7]), og["numValid"]
-        assert abs(nv - nv0) <= max(4, 0.02 * nv0)
-        sp = r.debug_buffer("sorted_photons", ol.PHOTON_DT, nv)
-        if nv == nv0 and (g[0:7] == np.concatenate([[og["cellSize"].view(np.uint32)], np.array(og["gridSize"], np.uint32), og["origo"].view(np.uint32)])).all():
-            same = np.isclose(sp["position"], ph0["position"][:nv], rtol=1e-4, atol=1e-3).all(axis=1)
-            assert same.mean() > minfrac
-        assert (ph["power"].max(axis=1) > 0).sum() == nv
-        ind, ind0 = r.debug_buffer("indirect", np.float32, size * size * 3).reshape(size, size, 3), o.indirect()
-        dr, dr0 = r.debug_buffer("direct", np.float32, size * size * 3).reshape(size, size, 3), o.direct()
-        assert util.rel_close_fraction(dr.reshape(-1, 3), dr0.reshape(-1, 3), RTOL, ATOL) > minfrac
-        assert util.rel_close_fraction(ind.reshape(-1, 3), ind0.reshape(-1, 3), 5e-3, 1e-5 * float(ind0.max() + 1e-20)) > minfrac - 0.03
-    out, out0 = r.getOutputBuffer(), o.output()
-    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 1e-5 * float(out0.max()))
-    assert frac > minfrac - 0.03, frac
-    # whole-image agreement far below the Monte Carlo noise of a %d-iteration render
-    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
-    assert rel < 2e-2, rel
-    st = r.stats()
-    assert st["closest_rays"] > 0 and st["any_rays"] > 0 and st["launches"] > 0
-
-
 def test_async_readback_equals_blocking_readback(product):
     """opr_get_output_buffer_async + opr_wait_output (double-buffered device snapshot, copy stream) deliver exactly what the blocking
     getOutputBuffer (OptixRenderer.cpp:860-865) delivers for the same iteration, for every method, while later iterations render."""
@@ -267,36 +215,6 @@ def test_state_rules_gpu(product):
         r.renderNextIteration(0, 0, 7.5, True, bad)
 
 
-@pytest.mark.parametrize("config,maxlen,iters,minfrac", [
-    (0, 8, 3, 0.95),                                            # BASELINE config 2: CornellSmall default, max path length 8
-    ((1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 8, 2, 0.92),   # mirror floor + large glass sphere + blocks
-    ((1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 10, 2, 0.92),  # point light, glossy floor (Lambertian+Phong), mirror + glass spheres
-    ((1 << 5) | (1 << 10), 10, 2, 0.92),                        # distant point light (cone emission), large mirror sphere, no ceiling
-])
-def test_bdpt_parity(product, oracle, config, maxlen, iters, minfrac):
-    """Vertex-connection BDPT (light pass with camera splats, camera pass with S0/S1/vertex connections, recursive MIS)
-    against the oracle on identical paths: per-path stored light-vertex counts, then the sum buffer per pixel."""
-    size = 48
-    scene, cam, r, o, osc = _renderers(product, oracle, "CornellSmall", config, size, (16, 16), maxlen)
-    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.VCM_BIDIRECTIONAL_PATH_TRACING, size, size, 2.0 / 3.0)
-    odet = oracle.make_details(osc.camera(1.0), capi.VCM_BIDIRECTIONAL_PATH_TRACING, size, size)
-    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), iters)
-    for i in range(iters):
-        r.renderNextIteration(i, i, radii[i], True, det)
-        o.render_next_iteration(i, i, radii[i], odet)
-        cnt = r.debug_buffer("light_vertex_counts", np.uint32, size * size)
-        cnt0 = np.zeros(size * size, np.uint32)
-        o.lib.ora_get_light_vertex_counts(o.h, cnt0.ctypes.data_as(C.c_void_p))
-        assert (cnt == cnt0).mean() > minfrac, (cnt == cnt0).mean()
-    out, out0 = r.getOutputBuffer(), o.output()
-    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
-    assert frac > minfrac - 0.07, frac
-    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
-    assert rel < 3e-2, rel
-    st = r.stats()
-    assert st["closest_rays"] > 0 and st["any_rays"] > 0
-
-
 def test_cuda_matches_reference_golden(product):
     """The CUDA path against the committed outputs of the reference's own device programs (tests/golden/*.npz,
     generated by tests/golden/make_golden.py from oracle/_ref): no oracle code runs in this test."""
@@ -329,8 +247,8 @@ def test_cuda_matches_reference_golden(product):
         clip = float(np.percentile(gold["output"], 99.0)) + 1e-30
         rel = np.abs(np.minimum(out, clip) - np.minimum(gold["output"], clip)).sum() / np.abs(np.minimum(gold["output"], clip)).sum()
         print("%s: pixels within rel 5e-3 of the reference golden %.4f, relative L1 (clipped at the 99th percentile) %.2e" % (name, frac, rel))
-        # no oracle runs here, so the divergent paths cannot be named: the per-pixel rule is tests/test_parity_rule_gpu.py;
-        # this test bounds the whole-image error against the reference's own output and the share of untouched pixels
+        # no oracle runs here, so the divergent paths cannot be NAMED — that is tests/test_parity_rule_gpu.py, which admits no pass-fraction;
+        # this test can only bound the whole-image error against the reference's own output and the share of untouched pixels
         # PATH_TRACING: five dependent bounces per path, so more paths flip a decision somewhere (1-2 % of the pixels of these scenes,
         # each named by tests/test_parity_rule_gpu.py), and a flipped path changes its pixel entirely
         assert frac > 0.85 and rel < (6e-2 if method == 0 else 3e-2), (name, frac, rel)
@@ -373,39 +291,6 @@ def test_gather_matches_oracle(product, oracle, npix, nph, radius, coherent):
     assert olib.ora_gather(*args(out0)) == 0
     assert np.allclose(out, out0, rtol=2e-5, atol=1e-7 * float(out0.max() + 1e-30))
     assert (out[hp["flags"] != ol.PRD_HIT_NON_SPECULAR] == 0).all()
-
-
-@pytest.mark.parametrize("kind,detail,minfrac", [("sponza", 0.08, 0.93), ("conference", 0.12, 0.90)])
-def test_synthetic_scene_ppm_parity(product, oracle, kind, detail, minfrac):
-    """The bench workloads (triangle meshes with shading normals / uvs / tangents, Texture materials with RGBA8 bilinear
-    lookups and normal maps, glass + mirror spheres, area + point lights) at reduced tessellation against the oracle:
-    hit flags, photon count, direct, indirect and the sum buffer on identical paths."""
-    from oppositerenderer_b200 import synthetic
-    scene = synthetic.make_scene(kind, seed=1, detail=detail, texture_size=64)
-    cam = scene.getDefaultCamera()
-    W, H, pl, iters = 96, 54, (96, 96), 2
-    cam.setAspectRatio(W / H)
-    r = product.OptixRenderer(photon_launch=pl, seed=util.SEED)
-    r.initialize(product.ComputeDevice(0))
-    r.initScene(scene)
-    o = oracle.OracleRenderer("oracle", pl, 10, util.SEED)
-    o.init_scene(scene.getSceneDescription())
-    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.PROGRESSIVE_PHOTON_MAPPING, W, H, 2.0 / 3.0)
-    odet = oracle.make_details(cam.pod, capi.PROGRESSIVE_PHOTON_MAPPING, W, H)
-    radii = product.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), iters)
-    for i in range(iters):
-        r.renderNextIteration(i, i, radii[i], True, det)
-        o.render_next_iteration(i, i, radii[i], odet)
-        hp, hp0 = r.debug_buffer("hitpoints", ol.HITPOINT_DT, W * H), o.hitpoints()
-        assert (hp["flags"] == hp0["flags"]).mean() > minfrac
-        nv, nv0 = int(r.debug_buffer("grid", np.uint32, 8)[7]), o.grid()["numValid"]
-        assert abs(nv - nv0) <= max(8, 0.03 * nv0), (nv, nv0)
-        dr, dr0 = r.debug_buffer("direct", np.float32, W * H * 3).reshape(-1, 3), o.direct().reshape(-1, 3)
-        assert util.rel_close_fraction(dr, dr0, RTOL, ATOL * float(dr0.max() + 1e-20)) > minfrac
-    out, out0 = r.getOutputBuffer(), o.output()
-    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
-    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
-    assert frac > minfrac - 0.05 and rel < 3e-2, (frac, rel)
 
 
 def _render_sum(product, overlap, monkeypatch, scene, cam, W, H, pl, iters, method):
@@ -482,33 +367,6 @@ def test_full_size_ppm_properties(product):
     assert np.isfinite(second).all() and (second >= first - 1e-6 * np.abs(first)).all() and second.sum() > first.sum()
 
 
-@pytest.mark.parametrize("scene_name,config,minfrac", [("Cornell", 0, 0.97), ("CornellSmall", 0, 0.96),
-                                                       ("CornellSmall", (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), 0.93),
-                                                       ("CornellSmall", (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), 0.93)])
-def test_path_tracing_parity(product, oracle, scene_name, config, minfrac):
-    """RenderMethod::PATH_TRACING (pt/RayGeneratorPT.cu) against the oracle on identical paths, including the reference's two
-    RNG streams per pixel (payload copy vs buffer state) and the final states."""
-    size, iters = 48, 3
-    scene, cam, r, o, osc = _renderers(product, oracle, scene_name, config, size, (16, 16))
-    det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), product.RenderMethod.PATH_TRACING, size, size, 2.0 / 3.0)
-    odet = oracle.make_details(osc.camera(1.0), capi.PATH_TRACING, size, size)
-    for i in range(iters):
-        r.renderNextIteration(i, i, 1.0, True, det)
-        o.render_next_iteration(i, i, 1.0, odet)
-    out, out0 = r.getOutputBuffer(), o.output()
-    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
-    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
-    assert frac > minfrac and rel < 3e-2, (frac, rel)
-    st, (c0, a0) = r.stats(), o.ray_counts()
-    assert abs(st["closest_rays"] - c0) <= 0.02 * c0 and abs(st["any_rays"] - a0) <= 0.02 * a0
-    # RNG write-back: the payload stream survives, the buffer-state draws are discarded (RayGeneratorPT.cu:114)
-    rs = r.debug_buffer("random_states", np.uint32, 6 * 1024 * 1024).reshape(-1, 6)
-    n0 = o.lib.ora_num_random_states(o.h)
-    rs0 = np.zeros((n0, 6), np.uint32)
-    o.lib.ora_get_random_states(o.h, rs0.ctypes.data_as(C.c_void_p), 0, n0)
-    assert (rs[:n0] == rs0).all(axis=1).mean() > minfrac
-
-
 def _quad(p0, e1, e2, material):
     p0, e1, e2 = (np.array(t, np.float32) for t in (p0, e1, e2))
     v = np.stack([p0, p0 + e1, p0 + e1 + e2, p0 + e2]).astype(np.float32)
@@ -538,10 +396,12 @@ def _spot_room(product):
     return SceneDescription("spotroom", (0, 0, 0), (4, 3, 4), mats, [area, spot, point], meshes=meshes, default_camera=cam)
 
 
-@pytest.mark.parametrize("method,minfrac", [(2, 0.93), (1, 0.90)])
-def test_spot_light_dof_and_wide_launch_parity(product, oracle, method, minfrac):
+@pytest.mark.parametrize("method", [2, 1])
+def test_spot_light_dof_and_wide_launch_parity(product, oracle, method):
     """Three light types incl. SPOT photon emission (PhotonGenerator.cu:73-77), depth of field (camera.h:11-27), an image wider
-    than the photon launch and a photon launch taller than the image (RNG buffer max(1024,W) x max(1024,H) indexing)."""
+    than the photon launch and a photon launch taller than the image (RNG buffer max(1024,W) x max(1024,H) indexing) — under the
+    per-pixel rule of tests/parity_rules.py: every pixel in tolerance or accounted for by a measured divergence."""
+    import parity_rules as pr
     scene = _spot_room(product)
     cam = scene.getDefaultCamera()
     W, H, pl, iters = 80, 20, (32, 48), 2
@@ -553,17 +413,15 @@ def test_spot_light_dof_and_wide_launch_parity(product, oracle, method, minfrac)
     o.init_scene(scene.getSceneDescription())
     det = product.RenderServerRenderRequestDetails(cam, scene.getSceneName(), method, W, H, 2.0 / 3.0)
     odet = oracle.make_details(cam.pod, method, W, H)
-    for i in range(iters):
-        r.renderNextIteration(i, i, 0.3, True, det)
-        o.render_next_iteration(i, i, 0.3, odet)
-    out, out0 = r.getOutputBuffer(), o.output()
-    frac = util.rel_close_fraction(out.reshape(-1, 3), out0.reshape(-1, 3), 5e-3, 2e-5 * float(out0.max()))
-    rel = np.abs(out - out0).sum() / np.abs(out0).sum()
-    assert frac > minfrac - 0.05 and rel < 4e-2, (frac, rel)
+    res = pr.run_lockstep("spot room, method %d" % method, r, o, det, odet, method, W, H, pl, [0.3] * iters, cam.pod)
+    assert res["rel_l1"] < 3e-2, res
+    # every RNG state of the 80 x 48 buffer — pixels outside the launch, photon threads outside the image — was advanced exactly as the
+    # reference advances it, unless its own path diverged
     rs = r.debug_buffer("random_states", np.uint32, 6 * 80 * 48).reshape(-1, 6)
     rs0 = np.zeros((80 * 48, 6), np.uint32)
     o.lib.ora_get_random_states(o.h, rs0.ctypes.data_as(C.c_void_p), 0, 80 * 48)
-    assert (rs == rs0).all(axis=1).mean() > minfrac - 0.05      # every state was advanced exactly as the reference advances it
+    print("spot room, method %d: RNG states identical %.4f" % (method, (rs == rs0).all(axis=1).mean()))
+    assert (rs == rs0).all(axis=1).mean() > 0.9
 
 
 def test_resize_reseeds_like_a_fresh_renderer(product):
