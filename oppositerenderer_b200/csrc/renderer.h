@@ -239,6 +239,7 @@ struct ScopedTimer {
     ScopedTimer(Renderer& r_, const char* n, cudaStream_t st_ = nullptr) : r(r_), name(n), st(st_ ? st_ : r_.stream)
     {
         if (!r.timing && !r.timeline) return;
+        if (r.timeline && r.timelineEvents.size() >= 65536) return;     // a forgotten timeline mode must not grow without bound
         if (r.timing) cudaDeviceSynchronize();    // timing mode serialises the streams: each pass is measured alone
         cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st);
     }
