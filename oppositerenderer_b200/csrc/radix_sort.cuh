@@ -1,4 +1,4 @@
-// radix_sort.cuh — stable LSD radix sort (8-bit digits) of (key, uint32 value) pairs and a 3-kernel
+// radix_sort.cuh — stable LSD radix sort (8-bit digits, or 10-bit for keys of 11..20 bits: two passes instead of three) of (key, uint32 value) pairs and a 3-kernel
 // exclusive scan, hand-written for sm_100a.  Replaces thrust::sort_by_key / thrust::exclusive_scan of
 // RenderEngine/renderer/OptixRenderer_SpatialHash.cu:193-207; also sorts Morton codes for the LBVH.
 //
@@ -15,32 +15,34 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
-template <typename Key>
+template <typename Key, int DB>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const Key* __restrict__ keys, unsigned n, int shift,
                                                              unsigned* __restrict__ hist, unsigned numBlocks)
 {
-    __shared__ unsigned sh[256];
-    sh[threadIdx.x] = 0;
+    constexpr unsigned ND = 1u << DB;
+    __shared__ unsigned sh[ND];
+    for (unsigned d = threadIdx.x; d < ND; d += RS_THREADS) sh[d] = 0;
     __syncthreads();
     const unsigned base = blockIdx.x * RS_TILE;
     #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         unsigned i = base + j * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&sh[(unsigned)(keys[i] >> shift) & 255u], 1u);
+        if (i < n) atomicAdd(&sh[(unsigned)(keys[i] >> shift) & (ND - 1)], 1u);
     }
     __syncthreads();
-    hist[threadIdx.x * numBlocks + blockIdx.x] = sh[threadIdx.x];   // digit-major
+    for (unsigned d = threadIdx.x; d < ND; d += RS_THREADS) hist[d * numBlocks + blockIdx.x] = sh[d];   // digit-major
 }
 
-template <typename Key>
+template <typename Key, int DB>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const Key* __restrict__ keysIn, const unsigned* __restrict__ valsIn,
                                                                 Key* __restrict__ keysOut, unsigned* __restrict__ valsOut,
                                                                 unsigned n, int shift, const unsigned* __restrict__ histScanned,
                                                                 unsigned numBlocks)
 {
-    __shared__ unsigned warpCnt[RS_WARPS][256];
+    constexpr unsigned ND = 1u << DB;
+    __shared__ unsigned warpCnt[RS_WARPS][ND];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&warpCnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < RS_WARPS * (int)ND; i += RS_THREADS) (&warpCnt[0][0])[i] = 0;
     __syncthreads();
 
     const unsigned chunkBase = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const Key* __res
         bool valid = i < n;
         key[j] = valid ? keysIn[i] : (Key)0;
         val[j] = valid ? (valsIn ? valsIn[i] : i) : 0u;
-        unsigned digit = (unsigned)(key[j] >> shift) & 255u;
+        unsigned digit = (unsigned)(key[j] >> shift) & (ND - 1);
         unsigned mkey = valid ? digit : (0x80000000u | lane);   // invalid lanes match nobody
         unsigned peers = __match_any_sync(0xffffffffu, mkey);
         unsigned leader = __ffs(peers) - 1;
@@ -64,8 +66,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const Key* __res
         __syncwarp();
     }
     __syncthreads();
-    {   // per digit: exclusive scan over the warps, seeded with this block's global offset
-        unsigned d = threadIdx.x;
+    for (unsigned d = threadIdx.x; d < ND; d += RS_THREADS) {   // per digit: exclusive scan over the warps, seeded with this block's global offset
         unsigned running = histScanned[d * numBlocks + blockIdx.x];
         #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { unsigned c = warpCnt[ww][d]; warpCnt[ww][d] = running; running += c; }
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const Key* __res
     for (int j = 0; j < RS_ITEMS; j++) {
         unsigned i = chunkBase + j * 32 + lane;
         if (i < n) {
-            unsigned digit = (unsigned)(key[j] >> shift) & 255u;
+            unsigned digit = (unsigned)(key[j] >> shift) & (ND - 1);
             unsigned pos = warpCnt[w][digit] + rank[j];
             keysOut[pos] = key[j];
             valsOut[pos] = val[j];
@@ -166,22 +167,33 @@ inline void exclusive_scan_u32(const unsigned* in, unsigned* out, unsigned n, un
 // Sorts n (key,value) pairs by the low `bits` bits of key, stable.  keys/vals are ping-ponged with
 // keysAlt/valsAlt; returns true if the result ended in the Alt buffers.  If valsIn == nullptr on the first
 // pass the values are the input indices 0..n-1.  hist must hold rs_hist_words(n) uint32.
-inline size_t rs_hist_words(unsigned n) { return (size_t)256 * ((n + RS_TILE - 1) / RS_TILE) + scan_tmp_words(256 * ((n + RS_TILE - 1) / RS_TILE)); }
+inline size_t rs_hist_words(unsigned n) { return (size_t)1024 * ((n + RS_TILE - 1) / RS_TILE) + scan_tmp_words(1024 * ((n + RS_TILE - 1) / RS_TILE)); }
 
+template <typename Key, int DB>
+inline void radix_sort_pass(const Key* kin, const unsigned* vin, Key* kout, unsigned* vout, unsigned n, int shift, unsigned* hist, cudaStream_t st)
+{
+    const unsigned blocks = (n + RS_TILE - 1) / RS_TILE;
+    unsigned* scanTmp = hist + (size_t)(1u << DB) * blocks;
+    rs_hist_kernel<Key, DB><<<blocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, blocks);
+    exclusive_scan_u32(hist, hist, (1u << DB) * blocks, scanTmp, st);
+    rs_scatter_kernel<Key, DB><<<blocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist, blocks);
+}
+
+// Digit width: 8 bits, except keys of 11..20 bits (the photon cell keys: <= 10^6 + 1 cells), which are sorted in two 10-bit passes
+// instead of three 8-bit ones (a third less key / value traffic; 32 KB of shared counters per block).
 template <typename Key>
 inline bool radix_sort_pairs(Key* keys, unsigned* vals, Key* keysAlt, unsigned* valsAlt, unsigned n, int bits,
                              unsigned* hist, bool valsAreIndices, cudaStream_t st, int* launches = nullptr)
 {
     if (n == 0) return false;
-    unsigned blocks = (n + RS_TILE - 1) / RS_TILE;
-    unsigned* scanTmp = hist + (size_t)256 * blocks;
+    const int db = (bits > 10 && bits <= 20) ? 10 : 8;
     bool flipped = false;
-    for (int shift = 0; shift < bits; shift += 8) {
+    for (int shift = 0; shift < bits; shift += db) {
         Key* kin = flipped ? keysAlt : keys; Key* kout = flipped ? keys : keysAlt;
         unsigned* vin = flipped ? valsAlt : vals; unsigned* vout = flipped ? vals : valsAlt;
-        rs_hist_kernel<Key><<<blocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, blocks);
-        exclusive_scan_u32(hist, hist, 256 * blocks, scanTmp, st);
-        rs_scatter_kernel<Key><<<blocks, RS_THREADS, 0, st>>>(kin, (shift == 0 && valsAreIndices) ? nullptr : vin, kout, vout, n, shift, hist, blocks);
+        const unsigned* v = (shift == 0 && valsAreIndices) ? nullptr : vin;
+        if (db == 10) radix_sort_pass<Key, 10>(kin, v, kout, vout, n, shift, hist, st);
+        else radix_sort_pass<Key, 8>(kin, v, kout, vout, n, shift, hist, st);
         if (launches) *launches += 5;
         flipped = !flipped;
     }
