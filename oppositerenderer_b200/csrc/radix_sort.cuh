@@ -17,7 +17,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 
 template <typename Key, int DB>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const Key* __restrict__ keys, unsigned n, int shift,
-                                                             unsigned* __restrict__ hist, unsigned numBlocks)
+                                                             unsigned* __restrict__ hist, unsigned numBlocks, bool skip, Key skipKey)
 {
     constexpr unsigned ND = 1u << DB;
     __shared__ unsigned sh[ND];
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const Key* __restri
     #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         unsigned i = base + j * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&sh[(unsigned)(keys[i] >> shift) & (ND - 1)], 1u);
+        if (i < n) { const Key k = keys[i]; if (!skip || k != skipKey) atomicAdd(&sh[(unsigned)(k >> shift) & (ND - 1)], 1u); }
     }
     __syncthreads();
     for (unsigned d = threadIdx.x; d < ND; d += RS_THREADS) hist[d * numBlocks + blockIdx.x] = sh[d];   // digit-major
@@ -37,7 +37,7 @@ template <typename Key, int DB>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const Key* __restrict__ keysIn, const unsigned* __restrict__ valsIn,
                                                                 Key* __restrict__ keysOut, unsigned* __restrict__ valsOut,
                                                                 unsigned n, int shift, const unsigned* __restrict__ histScanned,
-                                                                unsigned numBlocks)
+                                                                unsigned numBlocks, bool skip, Key skipKey)
 {
     constexpr unsigned ND = 1u << DB;
     __shared__ unsigned warpCnt[RS_WARPS][ND];
@@ -49,11 +49,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const Key* __res
     Key key[RS_ITEMS];
     unsigned val[RS_ITEMS];
     unsigned rank[RS_ITEMS];
+    unsigned keep = 0;          // bit j: item j takes part
     #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         unsigned i = chunkBase + j * 32 + lane;
         bool valid = i < n;
         key[j] = valid ? keysIn[i] : (Key)0;
+        if (skip && key[j] == skipKey) valid = false;      // dropped from the sort: this pass compacts
         val[j] = valid ? (valsIn ? valsIn[i] : i) : 0u;
         unsigned digit = (unsigned)(key[j] >> shift) & (ND - 1);
         unsigned mkey = valid ? digit : (0x80000000u | lane);   // invalid lanes match nobody
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const Key* __res
         if (valid && lane == leader) { old = warpCnt[w][digit]; warpCnt[w][digit] = old + __popc(peers); }
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[j] = old + __popc(peers & ((1u << lane) - 1));
+        if (valid) keep |= 1u << j;
         __syncwarp();
     }
     __syncthreads();
@@ -74,8 +77,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const Key* __res
     __syncthreads();
     #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
-        unsigned i = chunkBase + j * 32 + lane;
-        if (i < n) {
+        if (keep & (1u << j)) {
             unsigned digit = (unsigned)(key[j] >> shift) & (ND - 1);
             unsigned pos = warpCnt[w][digit] + rank[j];
             keysOut[pos] = key[j];
@@ -170,32 +172,53 @@ inline void exclusive_scan_u32(const unsigned* in, unsigned* out, unsigned n, un
 inline size_t rs_hist_words(unsigned n) { return (size_t)1024 * ((n + RS_TILE - 1) / RS_TILE) + scan_tmp_words(1024 * ((n + RS_TILE - 1) / RS_TILE)); }
 
 template <typename Key, int DB>
-inline void radix_sort_pass(const Key* kin, const unsigned* vin, Key* kout, unsigned* vout, unsigned n, int shift, unsigned* hist, cudaStream_t st)
+inline void radix_sort_pass(const Key* kin, const unsigned* vin, Key* kout, unsigned* vout, unsigned n, int shift, unsigned* hist, cudaStream_t st,
+                            bool skip = false, Key skipKey = 0)
 {
     const unsigned blocks = (n + RS_TILE - 1) / RS_TILE;
     unsigned* scanTmp = hist + (size_t)(1u << DB) * blocks;
-    rs_hist_kernel<Key, DB><<<blocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, blocks);
+    rs_hist_kernel<Key, DB><<<blocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, blocks, skip, skipKey);
     exclusive_scan_u32(hist, hist, (1u << DB) * blocks, scanTmp, st);
-    rs_scatter_kernel<Key, DB><<<blocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist, blocks);
+    rs_scatter_kernel<Key, DB><<<blocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist, blocks, skip, skipKey);
 }
 
 // Digit width: 8 bits, except keys of 11..20 bits (the photon cell keys: <= 10^6 + 1 cells), which are sorted in two 10-bit passes
 // instead of three 8-bit ones (a third less key / value traffic; 32 KB of shared counters per block).
+// dropKey / numKept (optional): items whose key equals *dropKey take no part — the first pass compacts them away (stable), the later
+// passes run over the numKept items that remain, and the tail [numKept, n) of the result is filled with *dropKey (what a sort of all n
+// items would have left there when *dropKey is the largest key: the invalid photon slots, 58 % of the 4 M slots of an iteration).
+template <typename Key>
+static __global__ void rs_fill_kernel(Key* __restrict__ p, unsigned from, unsigned to, Key v)
+{
+    for (unsigned i = from + blockIdx.x * blockDim.x + threadIdx.x; i < to; i += gridDim.x * blockDim.x) p[i] = v;
+}
+
 template <typename Key>
 inline bool radix_sort_pairs(Key* keys, unsigned* vals, Key* keysAlt, unsigned* valsAlt, unsigned n, int bits,
-                             unsigned* hist, bool valsAreIndices, cudaStream_t st, int* launches = nullptr)
+                             unsigned* hist, bool valsAreIndices, cudaStream_t st, int* launches = nullptr,
+                             const Key* dropKey = nullptr, unsigned numKept = 0)
 {
     if (n == 0) return false;
     const int db = (bits > 10 && bits <= 20) ? 10 : 8;
     bool flipped = false;
+    unsigned m = n;
     for (int shift = 0; shift < bits; shift += db) {
         Key* kin = flipped ? keysAlt : keys; Key* kout = flipped ? keys : keysAlt;
         unsigned* vin = flipped ? valsAlt : vals; unsigned* vout = flipped ? vals : valsAlt;
         const unsigned* v = (shift == 0 && valsAreIndices) ? nullptr : vin;
-        if (db == 10) radix_sort_pass<Key, 10>(kin, v, kout, vout, n, shift, hist, st);
-        else radix_sort_pass<Key, 8>(kin, v, kout, vout, n, shift, hist, st);
+        const bool skip = dropKey && shift == 0;
+        if (m) {
+            if (db == 10) radix_sort_pass<Key, 10>(kin, v, kout, vout, m, shift, hist, st, skip, skip ? *dropKey : (Key)0);
+            else radix_sort_pass<Key, 8>(kin, v, kout, vout, m, shift, hist, st, skip, skip ? *dropKey : (Key)0);
+        }
         if (launches) *launches += 5;
+        if (skip) m = numKept;
         flipped = !flipped;
+    }
+    if (dropKey && numKept < n) {
+        Key* out = flipped ? keysAlt : keys;
+        rs_fill_kernel<Key><<<256, 256, 0, st>>>(out, numKept, n, *dropKey);
+        if (launches) *launches += 1;
     }
     return flipped;
 }

@@ -285,7 +285,10 @@ void Renderer::buildPhotonGrid()
         ScopedTimer t(*this, "grid.sort", st);
         int bits = 1; while ((1ull << bits) <= (unsigned long long)numCellsBound + 1) bits++;      // 20 bits when the cell count is not known on the host
         int nl = 0;
-        flipped = radix_sort_pairs<unsigned>(gridKeys[0], gridVals[0], gridKeys[1], gridVals[1], N, bits, sortTmp, true, st, &nl);
+        // the invalid slots (key numCells + 1, 58 % of the 4 M) are dropped by the first pass when their number is known on the host
+        const unsigned invalidKey = numCellsBound + 1;
+        if (!asyncGrid) flipped = radix_sort_pairs<unsigned>(gridKeys[0], gridVals[0], gridKeys[1], gridVals[1], N, bits, sortTmp, true, st, &nl, &invalidKey, grid.numValid);
+        else flipped = radix_sort_pairs<unsigned>(gridKeys[0], gridVals[0], gridKeys[1], gridVals[1], N, bits, sortTmp, true, st, &nl);
         launches += nl;
     }
     sortedKeys = flipped ? gridKeys[1] : gridKeys[0];
