@@ -66,11 +66,25 @@ __global__ void __launch_bounds__(BBOX_THREADS) photon_bbox_kernel(PhotonBuf pho
     }
 }
 
-void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc)
+// Hands the seven scalars to the host by storing them into mapped pinned memory, and re-arms the device copy for the next iteration.
+// A store over PCIe instead of a cudaMemcpyAsync: the copy engine may be busy with a 25 MB image read-back (opr_get_output_buffer_async),
+// and the host waits for exactly these 28 bytes before it can launch the grid build.
+__global__ void photon_bbox_publish_kernel(float* __restrict__ bbox, volatile float* hostOut)
+{
+    const int i = threadIdx.x;
+    if (i < 7) {
+        hostOut[i] = bbox[i];
+        bbox[i] = i < 3 ? FLT_MAX : (i < 6 ? -FLT_MAX : 0.f);
+    }
+    __threadfence_system();
+}
+
+void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc, float* hostOutMapped)
 {
     int blocks = (int)std::min<unsigned>((numThreads + BBOX_THREADS - 1) / BBOX_THREADS, numSMs() * 8);
     photon_bbox_kernel<<<blocks, BBOX_THREADS, 0, lc.st>>>(photons, phState, numThreads, bbox);
     ++*lc.launches;
+    if (hostOutMapped) { photon_bbox_publish_kernel<<<1, 32, 0, lc.st>>>(bbox, hostOutMapped); ++*lc.launches; }
 }
 
 // ---- host scalars: getSmallestPossibleCellSize :62-71, calculateGridSize :42-50, :229-248 ---------------

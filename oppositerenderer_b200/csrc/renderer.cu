@@ -105,6 +105,12 @@ void Renderer::initialize(int cudaOrdinal)
     dalloc(stats64, STAT_NUM);
     OPR_CUDA_CHECK(cudaMemsetAsync(stats64, 0, STAT_NUM * sizeof(unsigned long long), stream));
     OPR_CUDA_CHECK(cudaMallocHost((void**)&gridBBoxHost, 2 * 16 * sizeof(float)));      // two sets of (7 results + 7 initial values): by iteration parity
+    if (const char* e = getenv("OPR_BBOX_ZEROCOPY")) bboxZeroCopy = atoi(e) != 0;
+    OPR_CUDA_CHECK(cudaHostGetDevicePointer((void**)&gridBBoxHostDev, gridBBoxHost, 0));
+    {
+        const float arm[8] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f, 0.f};
+        OPR_CUDA_CHECK(cudaMemcpy(gridBBox, arm, sizeof arm, cudaMemcpyHostToDevice));
+    }
     OPR_CUDA_CHECK(cudaMallocHost((void**)&gridParamsHost, 2 * sizeof(GridParams)));
     memset(gridParamsHost, 0, 2 * sizeof(GridParams));
     dalloc(gridParamsDev, 2);
@@ -212,9 +218,13 @@ void Renderer::photonBBoxAsync(cudaStream_t st)
     ScopedTimer t(*this, "grid.bbox", st);
     float* h = gridBBoxHost + 16 * (overlap ? parity : 0);
     h[8] = FLT_MAX; h[9] = FLT_MAX; h[10] = FLT_MAX; h[11] = -FLT_MAX; h[12] = -FLT_MAX; h[13] = -FLT_MAX; h[14] = 0.f; h[15] = 0.f;
-    OPR_CUDA_CHECK(cudaMemcpyAsync(gridBBox, h + 8, 7 * sizeof(float), cudaMemcpyHostToDevice, st));
-    launch_photon_bbox(photons, phState, P, gridBBox, lc);
-    OPR_CUDA_CHECK(cudaMemcpyAsync(h, gridBBox, 7 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (bboxZeroCopy) {   // armed at allocation and re-armed by the publish kernel; the result is stored into the pinned block by the device
+        launch_photon_bbox(photons, phState, P, gridBBox, lc, gridBBoxHostDev + (h - gridBBoxHost));
+    } else {
+        OPR_CUDA_CHECK(cudaMemcpyAsync(gridBBox, h + 8, 7 * sizeof(float), cudaMemcpyHostToDevice, st));
+        launch_photon_bbox(photons, phState, P, gridBBox, lc);
+        OPR_CUDA_CHECK(cudaMemcpyAsync(h, gridBBox, 7 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     OPR_CUDA_CHECK(cudaEventRecord(bboxEvent, st));
 }
 

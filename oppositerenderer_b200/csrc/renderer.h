@@ -140,6 +140,8 @@ struct Renderer {
     unsigned* scanTmp = nullptr;
     float* gridBBox = nullptr;            // device: 6 ordered-int floats + valid count
     float* gridBBoxHost = nullptr;        // pinned
+    float* gridBBoxHostDev = nullptr;     // the same memory as the device addresses it (photon_bbox_publish_kernel stores into it)
+    bool bboxZeroCopy = true;             // OPR_BBOX_ZEROCOPY=0: the seven scalars travel by cudaMemcpyAsync instead (queues behind an image read-back)
     PhotonBuf sorted{};                   // compacted + sorted photons
     unsigned* sortedKeys = nullptr;       // alias of gridKeys[x] after the sort
     GridParams grid{};                    // host copy of the latest iteration's scalars: valid after the stream that built the grid was joined and synchronised
@@ -291,7 +293,7 @@ void launch_trace_connect_queue(const SceneView& sc, const float4* connO, const 
 void launch_ppm_resolve_output(const SceneView& sc, unsigned n, const HitpointBuf& hp, const float4* sampleFactor, const uint2* sampleLight,
                                const float* indirect, float* direct, float* output, unsigned localIteration, LaunchCtx lc);
 
-void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc);
+void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc, float* hostOutMapped = nullptr);
 // the grid scalars reach these kernels through a device pointer: they are computed by a host function IN the stream (renderer.cu)
 void launch_grid_keys(const PhotonBuf& photons, const unsigned* phState, unsigned numSlots, const GridParams* g, unsigned* keys, unsigned* hist, LaunchCtx lc);
 void launch_photon_reorder(const PhotonBuf& src, const unsigned* sortedSlots, unsigned maxValid, const GridParams* g, const PhotonBuf& dst, LaunchCtx lc);
