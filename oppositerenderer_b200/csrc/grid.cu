@@ -32,17 +32,20 @@ OPR_DEV void atomicMaxFloat(float* addr, float v)
 
 constexpr int BBOX_THREADS = 256;
 
-// One thread per emitting photon thread; reads its <= 4 deposits.  A photon is valid when it was stored this
-// iteration and fmaxf(power) > 0 (PhotonToAABBConverter :112-119).
+// One thread per photon SLOT (coalesced 16-byte reads; the first version gave a thread the <= 4 deposits of one emitting thread: strided
+// reads in a dependent loop: 0.08 -> 0.05 ms including the hand-over to the host).  A photon is valid when it was stored this iteration and fmaxf(power) > 0
+// (PhotonToAABBConverter :112-119).  min / max / count do not depend on the order: the result is bit-identical.
 __global__ void __launch_bounds__(BBOX_THREADS) photon_bbox_kernel(PhotonBuf photons, const unsigned* __restrict__ phState, unsigned numThreads,
                                                                    float* __restrict__ bbox)
 {
+    __shared__ float sLo[BBOX_THREADS / 32][3], sHi[BBOX_THREADS / 32][3];
+    __shared__ unsigned sCount[BBOX_THREADS / 32];
     float3 lo = f3(FLT_MAX), hi = f3(-FLT_MAX);
     unsigned count = 0;
-    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < numThreads; t += gridDim.x * blockDim.x) {
-        const unsigned numStored = (phState[t] >> 8) & 0xffu;
-        for (unsigned k = 0; k < numStored; k++) {
-            const size_t s = (size_t)t * MAX_PHOTON_DEPOSITS + k;
+    const size_t numSlots = (size_t)numThreads * MAX_PHOTON_DEPOSITS;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < numSlots; s += (size_t)gridDim.x * blockDim.x) {
+        const unsigned numStored = (__ldg(phState + s / MAX_PHOTON_DEPOSITS) >> 8) & 0xffu;
+        if ((unsigned)(s % MAX_PHOTON_DEPOSITS) < numStored) {
             const float4 b = photons.b[s];
             if (fmaxf(fmaxf(b.x, b.y), b.z) > 0) {
                 const float4 a = photons.a[s];
@@ -59,10 +62,18 @@ __global__ void __launch_bounds__(BBOX_THREADS) photon_bbox_kernel(PhotonBuf pho
         hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
         count += __shfl_xor_sync(0xffffffffu, count, o);
     }
-    if ((threadIdx.x & 31) == 0 && count) {
-        atomicMinFloat(bbox + 0, lo.x); atomicMinFloat(bbox + 1, lo.y); atomicMinFloat(bbox + 2, lo.z);
-        atomicMaxFloat(bbox + 3, hi.x); atomicMaxFloat(bbox + 4, hi.y); atomicMaxFloat(bbox + 5, hi.z);
-        atomicAdd((unsigned*)(bbox + 6), count);
+    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sLo[w][0] = lo.x; sLo[w][1] = lo.y; sLo[w][2] = lo.z; sHi[w][0] = hi.x; sHi[w][1] = hi.y; sHi[w][2] = hi.z; sCount[w] = count; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned i = 1; i < BBOX_THREADS / 32; i++) {
+            lo = fmin3(lo, f3(sLo[i][0], sLo[i][1], sLo[i][2])); hi = fmax3(hi, f3(sHi[i][0], sHi[i][1], sHi[i][2])); count += sCount[i];
+        }
+        if (count) {
+            atomicMinFloat(bbox + 0, lo.x); atomicMinFloat(bbox + 1, lo.y); atomicMinFloat(bbox + 2, lo.z);
+            atomicMaxFloat(bbox + 3, hi.x); atomicMaxFloat(bbox + 4, hi.y); atomicMaxFloat(bbox + 5, hi.z);
+            atomicAdd((unsigned*)(bbox + 6), count);
+        }
     }
 }
 
@@ -81,7 +92,8 @@ __global__ void photon_bbox_publish_kernel(float* __restrict__ bbox, volatile fl
 
 void launch_photon_bbox(const PhotonBuf& photons, const unsigned* phState, unsigned numThreads, float* bbox, LaunchCtx lc, float* hostOutMapped)
 {
-    int blocks = (int)std::min<unsigned>((numThreads + BBOX_THREADS - 1) / BBOX_THREADS, numSMs() * 8);
+    const size_t numSlots = (size_t)numThreads * MAX_PHOTON_DEPOSITS;
+    int blocks = (int)std::min<size_t>((numSlots + BBOX_THREADS - 1) / BBOX_THREADS, (size_t)numSMs() * 8);
     photon_bbox_kernel<<<blocks, BBOX_THREADS, 0, lc.st>>>(photons, phState, numThreads, bbox);
     ++*lc.launches;
     if (hostOutMapped) { photon_bbox_publish_kernel<<<1, 32, 0, lc.st>>>(bbox, hostOutMapped); ++*lc.launches; }
