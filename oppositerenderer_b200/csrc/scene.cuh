@@ -151,10 +151,11 @@ constexpr int TRAVERSAL_STACK = 96;    // entries; bvh.cu refuses trees with 3*l
 #define OPR_SLAB(QN, CX, HX, CY, HY, CZ, HZ, TOUT)                                                                 \
     {                                                                                                              \
         float nx, fx, ny, fy, nz, fz;                                                                              \
-        if (QN) {   /* decoded values are 1 + q / 32768: the +-|idir| of the half-extent's offset sits in the two per-ray constants */ \
-            nx = fmaf((HX), -fabsf(idir.x), fmaf((CX), idir.x, ood.x)); fx = fmaf((HX), fabsf(idir.x), fmaf((CX), idir.x, oof.x)); \
-            ny = fmaf((HY), -fabsf(idir.y), fmaf((CY), idir.y, ood.y)); fy = fmaf((HY), fabsf(idir.y), fmaf((CY), idir.y, oof.y)); \
-            nz = fmaf((HZ), -fabsf(idir.z), fmaf((CZ), idir.z, ood.z)); fz = fmaf((HZ), fabsf(idir.z), fmaf((CZ), idir.z, oof.z)); \
+        if (QN) {   /* decoded values are 1 + q / 32768: tc carries the +-|idir| of the half-extent's offset */     \
+            const float tx = fmaf((CX), idir.x, ood.x), ty = fmaf((CY), idir.y, ood.y), tz = fmaf((CZ), idir.z, ood.z); \
+            nx = fmaf((HX), -fabsf(idir.x), tx + fabsf(idir.x)); fx = fmaf((HX), fabsf(idir.x), tx - fabsf(idir.x)); \
+            ny = fmaf((HY), -fabsf(idir.y), ty + fabsf(idir.y)); fy = fmaf((HY), fabsf(idir.y), ty - fabsf(idir.y)); \
+            nz = fmaf((HZ), -fabsf(idir.z), tz + fabsf(idir.z)); fz = fmaf((HZ), fabsf(idir.z), tz - fabsf(idir.z)); \
         } else {                                                                                                   \
             const float tx = fmaf((CX), idir.x, ood.x), ty = fmaf((CY), idir.y, ood.y), tz = fmaf((CZ), idir.z, ood.z); \
             nx = fmaf((HX), -fabsf(idir.x), tx); fx = fmaf((HX), fabsf(idir.x), tx);                               \
@@ -315,20 +316,15 @@ OPR_DEV float3 safe_inverse_direction(const float3& d)
 // half-word carries the exponent's low bit), and world = qOrigin + (v - 1) * qExtent, so t = v * (qExtent * idir) +
 // (qOrigin - qExtent - o) * idir: the same single FFMA per plane with different per-ray constants.
 template <bool QN>
-OPR_DEV void ray_slab_setup(const SceneView& sc, const float3& o, const float3& d, float3& idir, float3& ood, float3& oof)
+OPR_DEV void ray_slab_setup(const SceneView& sc, const float3& o, const float3& d, float3& idir, float3& ood)
 {
     const float3 inv = safe_inverse_direction(d);
     if (QN) {
-        // near = t_centre - (v_h - 1) |idir|, far = t_centre + (v_h - 1) |idir|: the constant parts go into ood (near) and oof (far), which
-        // makes a plane two FFMAs (12 instructions fewer per node than adding |idir| to t_centre per child and axis)
         idir = f3(sc.qExtent.x * inv.x, sc.qExtent.y * inv.y, sc.qExtent.z * inv.z);
-        const float3 base = f3((sc.qOrigin.x - sc.qExtent.x - o.x) * inv.x, (sc.qOrigin.y - sc.qExtent.y - o.y) * inv.y, (sc.qOrigin.z - sc.qExtent.z - o.z) * inv.z);
-        ood = f3(base.x + fabsf(idir.x), base.y + fabsf(idir.y), base.z + fabsf(idir.z));
-        oof = f3(base.x - fabsf(idir.x), base.y - fabsf(idir.y), base.z - fabsf(idir.z));
+        ood = f3((sc.qOrigin.x - sc.qExtent.x - o.x) * inv.x, (sc.qOrigin.y - sc.qExtent.y - o.y) * inv.y, (sc.qOrigin.z - sc.qExtent.z - o.z) * inv.z);
     } else {
         idir = inv;
         ood = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
-        oof = ood;
     }
 }
 
@@ -339,8 +335,8 @@ template <bool ANY, bool QN = false>
 OPR_DEV bool traverse_warp(const SceneView& sc, unsigned mask, bool active, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
 {
     hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
-    float3 idir, ood, oof;
-    ray_slab_setup<QN>(sc, o, d, idir, ood, oof);
+    float3 idir, ood;
+    ray_slab_setup<QN>(sc, o, d, idir, ood);
     int2 stack[TRAVERSAL_STACK];
     int sp = 0;
     int cur = active ? sc.rootRef : TRAVERSAL_DONE;
@@ -364,8 +360,8 @@ template <bool ANY, bool QN = false>
 OPR_DEV bool traverse_free(const SceneView& sc, const float3& o, const float3& d, float tmin, float tmax, HitRec& hit)
 {
     hit.t = tmax; hit.prim = -1; hit.u = hit.v = 0.f;
-    float3 idir, ood, oof;
-    ray_slab_setup<QN>(sc, o, d, idir, ood, oof);
+    float3 idir, ood;
+    ray_slab_setup<QN>(sc, o, d, idir, ood);
     int2 stack[TRAVERSAL_STACK];
     int sp = 0;
     int cur = sc.rootRef;

@@ -41,7 +41,7 @@ constexpr int TRACE_THREADS = 128;
 // pull fresh rays from the shared cursor, so that warps stay full while ray lengths differ by an order of magnitude
 // (incoherent photon bounces).  The node / leaf steps are the warp-lockstep ones of scene.cuh.
 #ifndef OPR_TRACE_MINBLOCKS
-#define OPR_TRACE_MINBLOCKS 7   // 72 registers: what the kernels took unconstrained before the quantised slab test got its second per-ray constant (78 then; no spills at 72)
+#define OPR_TRACE_MINBLOCKS 1
 #endif
 template <bool QN>
 __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_closest_kernel(SceneView sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_clos
     const unsigned FULL = 0xffffffffu, NONE = 0xffffffffu;
     const unsigned n = *count;
     const unsigned lane = threadIdx.x & 31;
-    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f), oof = f3(0.f);
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     float tmin = 0.f;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
     OPR_STACK_DECL
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_clos
                     if (idx < n) {
                         const float4 o4 = rayO[idx], d4 = rayD[idx];
                         o = f3(o4); d = f3(d4); tmin = o4.w;
-                        ray_slab_setup<QN>(sc, o, d, idir, ood, oof);
+                        ray_slab_setup<QN>(sc, o, d, idir, ood);
                         hit.t = d4.w; hit.prim = -1; hit.u = hit.v = 0.f;
                         sp = 0; cur = sc.rootRef; ray = idx;
                     }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shad
     const unsigned FULL = 0xffffffffu;
     const unsigned n = *count;
     const unsigned lane = threadIdx.x & 31;
-    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f), oof = f3(0.f);
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     const float tmin = 0.0001f;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
     OPR_STACK_DECL
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_shad
                         idx = shadowIdx[i];
                         const float4 d4 = shadowD[i];
                         o = f3(hitPos[idx >> 2]); d = f3(d4);
-                        ray_slab_setup<QN>(sc, o, d, idir, ood, oof);
+                        ray_slab_setup<QN>(sc, o, d, idir, ood);
                         hit.t = d4.w; hit.prim = -1;
                         sp = 0; cur = sc.rootRef;
                     }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
     const unsigned FULL = 0xffffffffu, NONE = 0xffffffffu;
     const unsigned n = *count;
     const unsigned lane = threadIdx.x & 31;
-    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f), oof = f3(0.f);
+    float3 o = f3(0.f), d = f3(0.f), idir = f3(0.f), ood = f3(0.f);
     const float tmin = EPS_RAY;
     HitRec hit; hit.t = 0.f; hit.prim = -1; hit.u = hit.v = 0.f;
     OPR_STACK_DECL
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, OPR_TRACE_MINBLOCKS) trace_conn
                     if (i < n) {
                         const float4 o4 = connO[i], d4 = connD[i];
                         o = f3(o4); d = f3(d4);
-                        ray_slab_setup<QN>(sc, o, d, idir, ood, oof);
+                        ray_slab_setup<QN>(sc, o, d, idir, ood);
                         hit.t = o4.w; hit.prim = -1;
                         sp = 0; cur = sc.rootRef; pending = i;
                     }
