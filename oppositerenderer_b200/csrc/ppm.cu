@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_gen_kernel(opr_camer
     const unsigned n = w * h;
     reset_wave_counters(counters, n);
     if (blockIdx.x == 0 && threadIdx.x == 0) { counters[CTR_TAIL_COUNT] = 0u; counters[CTR_DEFERRED_COUNT] = 0u; counters[CTR_TAIL_FETCH] = 0u; counters[CTR_LATE_FETCH] = 0u; }
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const unsigned p = tiled_pixel(s, w, h);
         camPending[p] = 0;
         const unsigned x = p % w, y = p / w;
         const size_t ri = (size_t)y * rsW + x;
@@ -133,9 +134,9 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_camera_gen_kernel(opr_camer
         hp.nrm[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
         hp.att[p] = make_float4(1.f, 1.f, 1.f, 0.f);
         hp.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        rayO[p] = make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, 0.001f);
-        rayD[p] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, RT_DEFAULT_MAX);
-        rayPath[p] = p;
+        rayO[s] = make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, 0.001f);
+        rayD[s] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, RT_DEFAULT_MAX);
+        rayPath[s] = p;
     }
 }
 
@@ -759,8 +760,9 @@ __global__ void __launch_bounds__(SHADE_THREADS) ppm_direct_gen_kernel(SceneView
     const unsigned n = w * h;
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_FETCH_SHADOW] = 0u;     // consumed by the trace kernel that follows
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const unsigned p = base + threadIdx.x;
-        bool inImage = p < n;
+        const bool inRange = base + threadIdx.x < n;
+        const unsigned p = inRange ? tiled_pixel(base + threadIdx.x, w, h) : n;
+        bool inImage = inRange;
         bool wait = false;
         if (inImage) {
             const unsigned x = p % w, y = p / w;
@@ -866,8 +868,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) pt_generate_ray_kernel(SceneVie
     const unsigned n = w * h;
     unsigned closestRays = 0, anyRays = 0;
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const unsigned p = base + threadIdx.x;
-        const bool inImage = p < n;
+        const bool inImage = base + threadIdx.x < n;
+        const unsigned p = inImage ? tiled_pixel(base + threadIdx.x, w, h) : n;
         const unsigned x = inImage ? p % w : 0u, y = inImage ? p / w : 0u;
         const size_t ri = (size_t)y * rsW + x;
         float3 rayOrigin = f3(0.f), rayDirection = f3(0.f, 0.f, 1.f);

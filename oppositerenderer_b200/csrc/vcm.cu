@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_gen_kernel(VcmParams P
                                                                      float4* __restrict__ rayO, float4* __restrict__ rayD, unsigned* __restrict__ rayPath)
 {
     const unsigned n = P.w * P.h;
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const unsigned p = tiled_pixel(s, P.w, P.h);      // the camera path keeps its index (= pixel); only its queue slot moves
         const unsigned x = p % P.w, y = p / P.w;
         const size_t ri = (size_t)y * P.rsW + x;
         Rng rng = rng_load(rngBuf, ri);
@@ -435,9 +436,9 @@ __global__ void __launch_bounds__(VCM_THREADS) vcm_camera_gen_kernel(VcmParams P
         const float cameraPdfW = (1.f / pixelArea) * imageToSolidAngleFactor;
         path_store(B, p, make_float4(1.f, 1.f, 1.f, __uint_as_float(0u)), make_float4(P.lightSubpathCount / cameraPdfW, 0.f, 0.f, 0.f));
         B.color[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        rayO[p] = make_float4(eye.x, eye.y, eye.z, RAY_LEN_MIN);
-        rayD[p] = make_float4(dir.x, dir.y, dir.z, RT_DEFAULT_MAX);
-        rayPath[p] = p;
+        rayO[s] = make_float4(eye.x, eye.y, eye.z, RAY_LEN_MIN);
+        rayD[s] = make_float4(dir.x, dir.y, dir.z, RT_DEFAULT_MAX);
+        rayPath[s] = p;
     }
 }
 
