@@ -343,7 +343,7 @@ void Renderer::renderPPM(unsigned long long iterationNumber, unsigned localItera
         { ScopedTimer tg(*this, "camera.gen"); launch_ppm_camera_gen(details.camera, width, height, rsW, rng, hp, q, lc); }
         const unsigned waves = std::max(1u, std::min(cameraWaveBounces, MAX_RADIANCE_TRACE_DEPTH + 1));
         for (unsigned bounce = 0; bounce < waves; bounce++) {
-            { ScopedTimer t0(*this, bounce == 0 ? "trace.camera0" : "trace.camera1+"); launch_trace_closest_bounce(sc, q, bounce, lc, (qnodeMask & QN_PRIMARY) != 0); }
+            { ScopedTimer t0(*this, bounce == 0 ? "trace.camera0" : "trace.camera1+"); launch_trace_closest_bounce(sc, q, bounce, lc, (qnodeMask & QN_PRIMARY) != 0, bounce == 0); }
             { ScopedTimer t0(*this, bounce == 0 ? "shade.camera0" : "shade.camera1+"); launch_ppm_camera_shade(sc, width, rsW, rng, hp, q, bounce, bounce + 1 == waves, lc); }
         }
         OPR_CUDA_CHECK(cudaEventRecord(evCameraWaves, stream));

@@ -264,7 +264,7 @@ void launch_stats_fold(unsigned* counters32, unsigned long long* totals64, Launc
 void launch_rng_init(const RngBuf& rng, unsigned seed, size_t n, LaunchCtx lc);
 // `quantized`: traverse the 64-byte quantised nodes (incoherent rays) instead of the 128-byte fp32 nodes (coherent rays): scene.cuh load_node
 void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, LaunchCtx lc, bool quantized = false);
-void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc, bool quantized = false);
+void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc, bool quantized = false, bool wholeTiles = false);
 void launch_trace_closest_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, float4* hits, LaunchCtx lc, bool quantized = false);
 void launch_trace_any_raw(const SceneView& sc, const float4* rayO, const float4* rayD, unsigned n, int* occluded, LaunchCtx lc, bool quantized = false);
 

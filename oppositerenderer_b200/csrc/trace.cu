@@ -136,13 +136,15 @@ void launch_trace_closest(const SceneView& sc, const RayQueues& q, int cur, Laun
     ++*lc.launches;
 }
 
-void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc, bool quantized)
+void launch_trace_closest_bounce(const SceneView& sc, const RayQueues& q, int bounce, LaunchCtx lc, bool quantized, bool wholeTiles)
 {
+    // wholeTiles (primary rays, whose 32 consecutive slots are an 8 x 4-pixel tile): a warp takes new rays only when all of its lanes are done, so
+    // it always holds one tile (primary trace 0.381 -> 0.363 ms; the incoherent traces lose 12 % with the same rule and keep the threshold)
     const int cur = bounce & 1;
     auto k = quantized ? trace_closest_kernel<true> : trace_closest_kernel<false>;
     k<<<numSMs() * trace_blocks_per_sm(), TRACE_THREADS, 0, lc.st>>>(sc, q.rayO[cur], q.rayD[cur], q.counters + CTR_RAYCOUNT + bounce, q.hits, q.matQueue,
                                                                q.counters + CTR_MATCOUNT + 8 * bounce, q.capacity, q.counters + CTR_STATS + STAT_CLOSEST_RAYS,
-                                                               q.counters + CTR_FETCH + bounce, trace_refill_idle());
+                                                               q.counters + CTR_FETCH + bounce, wholeTiles ? 32u : trace_refill_idle());
     ++*lc.launches;
 }
 
