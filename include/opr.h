@@ -155,6 +155,10 @@ int opr_trace_any(opr_renderer* r, const float* rays8, uint32_t n, int32_t* outO
 /* The BVH exists in two node formats (128-byte fp32 nodes for coherent launches, 64-byte quantised nodes for incoherent ones); this
  * switch makes the two queries above traverse the quantised one, so that both are checked ray by ray against the oracle. */
 int opr_debug_set_trace_nodes(opr_renderer* r, int quantized);
+/* Pixel index of queue slot `slot` of the primary-ray and direct-light passes of a width x height image: 32 consecutive slots cover an
+ * 8 x 4-pixel tile when the image divides into tiles, else slot == pixel.  Host arithmetic, the function the kernels call (no reference
+ * counterpart: OptiX chooses its own launch-index-to-thread mapping).  Exposed so that the mapping can be checked to be a permutation. */
+uint32_t opr_debug_slot_pixel(uint32_t slot, uint32_t width, uint32_t height);
 
 /* ---- host-side pieces of the surface -------------------------------------------------------------------- */
 /* Camera::setup / setAspectRatio (renderer/Camera.cpp:333-345, :294-318) */

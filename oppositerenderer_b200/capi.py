@@ -144,6 +144,7 @@ def _declare(lib):
         "opr_debug_get_buffer": (i32, [vp, C.c_char_p, vp, u64]),
         "opr_debug_set_connection_counts": (i32, [vp, i32]),
         "opr_debug_set_trace_nodes": (i32, [vp, i32]),
+        "opr_debug_slot_pixel": (u32, [u32, u32, u32]),
         "opr_debug_set_guards": (None, [i32]),
         "opr_debug_check_guards": (i32, [C.POINTER(C.c_int)]),
         "opr_rng_init": (i32, [PU, u32, u32, u32]),

@@ -243,6 +243,7 @@ int opr_debug_get_buffer(opr_renderer* r, const char* name, void* dst, uint64_t 
 }
 
 int opr_debug_set_trace_nodes(opr_renderer* r, int quantized) { r->r.rawQuantized = quantized != 0; return 0; }
+uint32_t opr_debug_slot_pixel(uint32_t slot, uint32_t width, uint32_t height) { return opr::tiled_pixel(slot, width, height); }
 int opr_debug_set_connection_counts(opr_renderer* r, int enabled) { r->r.debugConnectionCounts = enabled != 0; return 0; }
 void opr_debug_set_guards(int enabled) { opr::devSetGuards(enabled != 0); }
 int opr_debug_check_guards(int* liveBlocks)

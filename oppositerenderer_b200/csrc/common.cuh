@@ -252,7 +252,7 @@ OPR_DEV bool tail_refill(unsigned n, unsigned* __restrict__ cursor, bool alive, 
 // Pixel of queue slot s: a warp's 32 consecutive slots cover an 8 x 4 pixel tile instead of a 32 x 1 strip (when the image divides into
 // tiles), so the lanes of a primary-ray or shadow-ray warp start closer together and walk more of the tree side by side.  Per-pixel
 // results do not depend on the slot order.
-OPR_DEV unsigned tiled_pixel(unsigned s, unsigned w, unsigned h)
+OPR_HD unsigned tiled_pixel(unsigned s, unsigned w, unsigned h)
 {
     if ((w & 7u) | (h & 3u)) return s;
     const unsigned tile = s >> 5, l = s & 31u, tilesX = w >> 3;

@@ -147,3 +147,28 @@ def test_scene_description_check_rejects_what_the_device_would_follow(product):
         h = lib.opr_builtin_scene_create(name.encode(), 0)
         assert lib.opr_scene_desc_check(lib.opr_builtin_scene_desc(h), msg, 200) == 0, msg.value
         lib.opr_builtin_scene_destroy(h)
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 2160), (256, 256), (64, 64), (8, 4), (96, 54), (40, 32), (1, 1), (33, 7)])
+def test_queue_slot_order_is_a_permutation_of_the_pixels(product, w, h):
+    """Primary rays and direct-light samples take their pixels in 8 x 4 tiles (32 consecutive slots = one tile) when the image divides
+    into tiles, else row by row; either way every pixel must be named by exactly one slot."""
+    import numpy as np
+    from oppositerenderer_b200 import capi
+    lib = capi.load_library()
+    n = w * h
+    step = 1 if n <= 300000 else 0
+    if step:
+        px = np.array([lib.opr_debug_slot_pixel(s, w, h) for s in range(n)], np.int64)
+        assert np.array_equal(np.sort(px), np.arange(n))
+    else:       # large images: every slot of a sample of whole tile rows (a tile row is a closed set under the mapping) + closed form
+        rows = [0, 1, (h // 4) // 2, h // 4 - 1]
+        for tr in rows:
+            s0 = tr * (w // 8) * 32
+            px = np.array([lib.opr_debug_slot_pixel(s, w, h) for s in range(s0, s0 + (w // 8) * 32)], np.int64)
+            assert np.array_equal(np.sort(px), np.arange(tr * 4 * w, (tr + 1) * 4 * w))
+    if w % 8 == 0 and h % 4 == 0:
+        first = [lib.opr_debug_slot_pixel(s, w, h) for s in range(min(32, n))]
+        assert first == [(l >> 3) * w + (l & 7) for l in range(min(32, n))]          # slot l of tile 0 = pixel (l & 7, l >> 3)
+    else:
+        assert all(lib.opr_debug_slot_pixel(s, w, h) == s for s in range(0, n, max(1, n // 97)))
