@@ -375,7 +375,7 @@ def _quad(p0, e1, e2, material):
     return dict(vertices=v, normals=np.tile(n, (4, 1)), uvs=None, tangents=None, bitangents=None, indices=np.array([[0, 1, 2], [0, 2, 3]], np.int32), material=material)
 
 
-def _spot_room(product):
+def _spot_room(product, with_spot=True):
     """A 4x3x4 box of triangle meshes with an area light, a SPOT light (photon emission only: its direct light factor is 0,
     helpers/light.h:46-50) and a point light; diffuse, glossy and mirror walls."""
     from oppositerenderer_b200.renderer import make_material, SceneDescription
@@ -393,7 +393,7 @@ def _spot_room(product):
     meshes = [_quad((0, 0, 0), (0, 0, 4), (4, 0, 0), 0), _quad((0, 3, 0), (4, 0, 0), (0, 0, 4), 0), _quad((0, 0, 4), (0, 3, 0), (4, 0, 0), 1),
               _quad((0, 0, 0), (0, 3, 0), (0, 0, 4), 2), _quad((4, 0, 0), (0, 0, 4), (0, 3, 0), 0), _quad((1.5, 2.99, 1.5), (0, 0, 1), (1, 0, 0), 3)]
     cam = product.Camera(eye=(2, 1.5, -3.5), lookat=(2, 1.4, 2), up=(0, 1, 0), hfov=50, vfov=50, aperture=0.08, aspectRatioMode=product.Camera.KeepHorizontal)
-    return SceneDescription("spotroom", (0, 0, 0), (4, 3, 4), mats, [area, spot, point], meshes=meshes, default_camera=cam)
+    return SceneDescription("spotroom", (0, 0, 0), (4, 3, 4), mats, [area, spot, point] if with_spot else [area, point], meshes=meshes, default_camera=cam)
 
 
 @pytest.mark.parametrize("method", [2, 1])
