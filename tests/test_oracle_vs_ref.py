@@ -151,3 +151,61 @@ def test_spot_light_in_bdpt_is_a_path_that_misses(oracle, product):
         r.render_next_iteration(i, i, 0.3, det)
     img = r.output()
     assert np.isfinite(img).all() and (img >= 0).all() and img.sum() > 0
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_host_compiled_reference_at_baseline_config_2(oracle):
+    """BASELINE config 2 as stated — CornellSmall, BDPT, max path length 8, 512 x 512 — rendered by the oracle and by the reference's
+    own programs (the latter on one thread: its light-tracing splat is a plain `+=`, vcm.h:159): ray counts identical, image within
+    1e-5.  tests/test_parity_rule_gpu.py::test_baseline_config_2_as_stated compares the CUDA path with this oracle at this size."""
+    a = render("oracle", "CornellSmall", 0, 1, 512, 16, 2, 8, None)
+    b = render("ref", "CornellSmall", 0, 1, 512, 16, 2, 8, None)
+    assert b["output"].sum() > 0
+    _same(a, b)
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("kind,config_no", [("sponza", 4), ("conference", 3)])
+def test_oracle_matches_host_compiled_reference_at_baseline_configs_3_and_4(oracle, kind, config_no):
+    """BASELINE configs 3 and 4 AS STATED — the synthetic Conference-scale (~570 K triangles, glass / mirror) and Sponza-scale (~1.1 M
+    triangles, textured) scenes, PPM, 1920 x 1080, 1024 x 1024 photons, one iteration — rendered by the oracle and by the reference's
+    own programs on all host cores: closest-hit and any-hit ray counts, all 4 M photon cell keys, the offset table and all 2 M hit
+    flags identical, image within 1e-5.  tests/test_parity_rule_gpu.py::test_baseline_bench_configs_as_stated compares the CUDA path
+    with this oracle on exactly these inputs."""
+    from oppositerenderer_b200 import synthetic
+    scene = synthetic.make_scene(kind, seed=1, detail=1.0)
+    W, H, pl = 1920, 1080, (1024, 1024)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(W / H)
+    out = {}
+    for which in ("oracle", "ref"):
+        r = ol.OracleRenderer(which, pl, 10, 1645301512, threads=len(os.sched_getaffinity(0)))
+        r.init_scene(scene.getSceneDescription())
+        r.render_next_iteration(0, 0, scene.getSceneInitialPPMRadiusEstimate(), ol.make_details(cam.pod, 2, W, H))
+        out[which] = dict(output=r.output(), rays=np.array(r.ray_counts(), np.uint64), photon_keys=r.photon_keys(), offsets=r.offsets(),
+                          hitpoint_flags=r.hitpoints()["flags"])
+        del r
+    assert out["ref"]["rays"][0] > W * H + pl[0] * pl[1] and out["ref"]["output"].sum() > 0
+    _same(out["oracle"], out["ref"])
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_host_compiled_reference_on_baseline_config_5_workload(oracle):
+    """BASELINE config 5's workload — BDPT (vertex connection, recursive MIS, max path length 8) on the ~1.1 M-triangle textured scene —
+    at 960 x 540, the size of tests/test_parity_rule_gpu.py::test_baseline_config_5_workload: one iteration by the oracle (all cores) and by
+    the reference's own programs (one thread: its splat is a plain `+=`): ray counts identical, image within 1e-5."""
+    from oppositerenderer_b200 import synthetic
+    scene = synthetic.make_scene("sponza", seed=1, detail=1.0)
+    W, H, pl = 960, 540, (16, 16)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(W / H)
+    radius = float(ol.ppm_radius_schedule(scene.getSceneInitialPPMRadiusEstimate(), 1)[0])
+    out = {}
+    for which in ("oracle", "ref"):
+        r = ol.OracleRenderer(which, pl, 8, 1645301512, threads=1 if which == "ref" else len(os.sched_getaffinity(0)))
+        r.init_scene(scene.getSceneDescription())
+        r.render_next_iteration(0, 0, radius, ol.make_details(cam.pod, 1, W, H))
+        out[which] = dict(output=r.output(), rays=np.array(r.ray_counts(), np.uint64))
+        del r
+    assert out["ref"]["rays"][0] > 2 * W * H and out["ref"]["output"].sum() > 0
+    _same(out["oracle"], out["ref"])

@@ -149,6 +149,36 @@ def test_oracle_renders_the_imported_scene(product, oracle, tmp_path):
     assert ((flags & ol.PRD_HIT_NON_SPECULAR) != 0).mean() > 0.5 and ((flags & ol.PRD_MISS) != 0).mean() < 0.2
 
 
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("method", [2, 1, 0])
+def test_oracle_matches_host_compiled_reference_on_the_imported_scene(product, oracle, tmp_path, method):
+    """CPU: the imported room (glass, mirror, textured + normal-mapped, diffuse and emitter meshes; area + point light) rendered by the
+    oracle and by the reference's own programs (oracle/_ref) with the settings of test_imported_scene_parity: ray counts, photon keys,
+    offsets and hit flags identical, images within 1e-5.  This pins the oracle on the inputs of that GPU test."""
+    path, _ = cf.write_room(str(tmp_path))
+    scene = product.Scene.createFromFile(path)
+    cam = scene.getDefaultCamera()
+    cam.setAspectRatio(1.0)
+    size, pl, iters = 48, (64, 64), 2
+    out = {}
+    for which in ("oracle", "ref"):
+        r = oracle.OracleRenderer(which, pl, 8, util.SEED, threads=1 if (which == "ref" and method == 1) else 0)
+        r.init_scene(scene.getSceneDescription())
+        det = oracle.make_details(cam.pod, method, size, size)
+        for i in range(iters):
+            r.render_next_iteration(i, i, 0.25, det)
+        out[which] = dict(output=r.output(), rays=np.array(r.ray_counts(), np.uint64))
+        if method == 2:
+            out[which].update(photon_keys=r.photon_keys(), offsets=r.offsets(), hitpoint_flags=r.hitpoints()["flags"])
+    a_, b_ = out["oracle"], out["ref"]
+    assert b_["output"].sum() > 0
+    assert (a_["rays"] == b_["rays"]).all(), (a_["rays"], b_["rays"])
+    assert np.allclose(a_["output"], b_["output"], rtol=1e-5, atol=2e-5 * float(b_["output"].max()))
+    if method == 2:
+        for k in ("photon_keys", "offsets", "hitpoint_flags"):
+            assert (a_[k] == b_[k]).all(), k
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("method", [2, 1, 0])
 def test_imported_scene_parity(product, oracle, tmp_path, method):
