@@ -209,3 +209,18 @@ def test_oracle_matches_host_compiled_reference_on_baseline_config_5_workload(or
         del r
     assert out["ref"]["rays"][0] > 2 * W * H and out["ref"]["output"].sum() > 0
     _same(out["oracle"], out["ref"])
+
+
+_CS = [0, (1 << 1) | (1 << 7) | (1 << 11) | (1 << 9), (1 << 3) | (1 << 8) | (1 << 12) | (1 << 13), (1 << 5) | (1 << 10)]   # = test_parity_rule_gpu.CORNELL_SMALL
+_RULE_INPUTS = ([("Cornell", 0, 2, 64, 64, 3, 10, None)] + [("CornellSmall", c, 2, 64, 64, 3, 10, 0.05) for c in _CS] +
+                [("CornellSmall", c, 1, 48, 16, 3, m, None) for c, m in zip(_CS, (8, 8, 10, 10))] +
+                [("Cornell", 0, 0, 48, 16, 3, 10, None), ("CornellSmall", _CS[1], 0, 48, 16, 3, 10, None), ("CornellSmall", _CS[2], 0, 48, 16, 3, 10, None)])
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("case", _RULE_INPUTS, ids=["%s-%d-m%d" % c[:3] for c in _RULE_INPUTS])
+def test_oracle_matches_host_compiled_reference_on_the_inputs_of_the_gpu_rule_tests(oracle, case):
+    """Every built-in-scene case of tests/test_parity_rule_gpu.py (test_ppm_… / test_bdpt_… / test_path_tracing_every_pixel_in_tolerance_
+    or_explained: same scene variant, size, photon launch, iterations, path length and radius), oracle against the reference's own
+    programs: integer results identical, images within 1e-5."""
+    _same(render("oracle", *case), render("ref", *case))
