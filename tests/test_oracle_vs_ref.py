@@ -224,3 +224,13 @@ def test_oracle_matches_host_compiled_reference_on_the_inputs_of_the_gpu_rule_te
     or_explained: same scene variant, size, photon launch, iterations, path length and radius), oracle against the reference's own
     programs: integer results identical, images within 1e-5."""
     _same(render("oracle", *case), render("ref", *case))
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("case", CASES + SYNTH_CASES, ids=[c[0] for c in CASES + SYNTH_CASES])
+def test_golden_fixtures_are_what_the_reference_programs_produce(case):
+    """The committed fixtures are not stale: the reference's own programs (oracle/_ref, built from /root/reference by oracle/refshim)
+    reproduce every one of them now — integer results identical, images within 1e-5 (the light-tracing splat order)."""
+    gold = dict(np.load(os.path.join(GOLDEN, case[0] + ".npz")))
+    got = render("ref", *case[1:]) if case in CASES else render_synthetic("ref", *case[1:])
+    _same(got, gold)
