@@ -3,6 +3,9 @@
 // PARITY PINNED: against oracle/_ref — the reference's own device programs host-compiled from /root/reference by oracle/refshim
 // (tests/test_oracle_vs_ref.py; the same outputs are committed as tests/golden/*.npz) — and, for the XORWOW generator, against
 // NVIDIA's cuRAND host generator (tests/test_oracle_cpu.py).
+// Pinned inputs: every built-in Cornell / CornellSmall case, BASELINE configs 1-4 at their stated sizes, config 5's workload at 960x540,
+// the spot-light / depth-of-field room and the imported COLLADA room of the GPU parity tests (integer results identical, images 1e-5).
+// One case has no pin because the reference is undefined there: a SPOT light in the BDPT passes (helpers/light.h:136-139,208-211).
 //
 // ora_math.h — vector types plus the OptiX SDK 3.5/3.6 `optixu_math_namespace.h` functions the hot
 // path uses.  The OptiX SDK is NOT vendored in /root/reference (SDKs.props:16-17), so these restate
